@@ -1,0 +1,195 @@
+/*
+ * ckks_b200.h -- C ABI of libckks_b200.so, the B200 (sm_100a) RNS-NTT backend.
+ *
+ * This is the drop-in boundary for the reference's `RnsBasis<N>` / `RnsPoly<N>` backend
+ * (src/rings/backends/rns_ntt/{basis,poly}.rs) and the RnsPoly-specific half of `CkksEngine`
+ * (src/crypto/engine.rs:255-540).  Every entry point cites the reference item it replaces
+ * (paths relative to the reference repository root).  A Rust `extern "C"` crate, the C++ mirror in
+ * toy-heaan-ckks_b200/host/rns_poly.hpp and the Python ctypes mirror bind exactly these symbols.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; opaque handles; no exceptions/unwinding across the boundary;
+ *   - every function returns 0 (CKKS_OK) or a ckks_status; codes 1..6 map 1:1 onto `RnsNttError`
+ *     (src/rings/backends/rns_ntt/errors.rs:3-22);
+ *   - host layout == reference layout: a polynomial is L limbs ("channels") of N u64 words,
+ *     limb-major (`Vec<[u64; N]>`, poly.rs:26-30); a handle carries `batch` such polynomials,
+ *     [batch][limb][N]; values are canonical representatives in [0, q_limb);
+ *   - NTT-domain data crosses the boundary in the reference's natural order
+ *     (slot k = p(psi^(2k+1)), poly.rs:136-148); the device-internal order is private;
+ *   - all device work is enqueued on the context's stream; `*_download`, `ckks_ctx_sync` and the
+ *     `*_host` calls block;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns
+ *     CKKS_CUDA_ERROR.
+ */
+#ifndef CKKS_B200_H
+#define CKKS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ckks_status {
+    CKKS_OK = 0,
+    CKKS_INVALID_DEGREE = 1,           /* RnsNttError::InvalidDegree            errors.rs:5  */
+    CKKS_EMPTY_BASIS = 2,              /* RnsNttError::EmptyBasis               errors.rs:8  */
+    CKKS_NON_NTT_FRIENDLY_MODULUS = 3, /* RnsNttError::NonNttFriendlyModulus    errors.rs:11 */
+    CKKS_INVALID_MOD_DROP = 4,         /* RnsNttError::InvalidModDrop           errors.rs:14 */
+    CKKS_CHANNEL_COUNT_MISMATCH = 5,   /* RnsNttError::ChannelCountMismatch     errors.rs:17 */
+    CKKS_NON_REDUCED_COEFFICIENT = 6,  /* RnsNttError::NonReducedCoefficient    errors.rs:20 */
+    CKKS_BASIS_MISMATCH = 20,          /* debug_assert!(Arc::ptr_eq) poly.rs:260-263,288-291 */
+    CKKS_DOMAIN_MISMATCH = 21,         /* debug_assert_eq!(is_ntt)   poly.rs:264-267,292-295 */
+    CKKS_BATCH_MISMATCH = 22,
+    CKKS_LEVEL_MISMATCH = 23,          /* assert_eq!(logq/logp)      engine.rs:135-136,478   */
+    CKKS_SHORT_INPUT = 24,             /* assert!(coeffs.len() >= N) poly.rs:50-54           */
+    CKKS_BAD_HANDLE = 30,
+    CKKS_BAD_ARGUMENT = 31,
+    CKKS_UNSUPPORTED = 32,
+    CKKS_CUDA_ERROR = 40,
+    CKKS_NCCL_ERROR = 41
+} ckks_status;
+
+typedef struct ckks_ctx ckks_ctx;   /* Arc<RnsBasis<N>>  basis.rs:91-94  (+ device tables, stream) */
+typedef struct ckks_poly ckks_poly; /* batch of RnsPoly<N>  poly.rs:26-30, device resident         */
+typedef struct ckks_ksk ckks_ksk;   /* RnsGadgetRelinKey / RnsGadgetRotationKey engine.rs:225-253  */
+
+/* Human-readable text for a status / the last CUDA error string seen by this thread. */
+const char *ckks_status_str(int status);
+const char *ckks_last_error(void);
+/* Number of visible CUDA devices (0 when there is none: every compute call then fails loudly). */
+int ckks_device_count(void);
+
+/* ---- src/math/primes.rs, src/math/utils.rs (host number theory, identical prime chains) -------- */
+int ckks_is_prime(uint64_t n);                                   /* primes.rs:67-93   */
+int ckks_is_ntt_friendly_prime(uint64_t p, uint64_t n);          /* primes.rs:125-131 */
+/* utils.rs:47-80 generate_primes(bit_size, count, degree); CKKS_BAD_ARGUMENT where it panics. */
+int ckks_generate_primes(int bit_size, int count, uint64_t degree, uint64_t *out);
+
+/* ---- RnsBasis<N>  (basis.rs) ------------------------------------------------------------------- */
+/* RnsBasis::new(moduli) basis.rs:97-106 + NttTable::new basis.rs:21-84: validates power-of-two N
+ * and q == 1 mod 2N prime; psi is chosen by the reference rule (find_primitive_root :217-237).
+ * `device` is the CUDA ordinal. */
+int ckks_ctx_create(uint64_t n, const uint64_t *moduli, size_t l, int device, ckks_ctx **out);
+/* RnsBasis::drop_last(k) basis.rs:121-134 (shares the parent's device tables; the child keeps the
+ * parent alive). */
+int ckks_ctx_drop_last(ckks_ctx *ctx, size_t drop_count, ckks_ctx **out);
+int ckks_ctx_destroy(ckks_ctx *ctx);
+int ckks_ctx_sync(ckks_ctx *ctx);
+/* Run this context's work on a caller-owned cudaStream_t (e.g. torch's current stream). */
+int ckks_ctx_set_stream(ckks_ctx *ctx, void *cuda_stream);
+uint64_t ckks_ctx_degree(const ckks_ctx *ctx);
+size_t ckks_ctx_channel_count(const ckks_ctx *ctx);              /* basis.rs:117-119 */
+int ckks_ctx_moduli(const ckks_ctx *ctx, uint64_t *out);         /* basis.rs:109-111 */
+uint32_t ckks_ctx_total_bits(const ckks_ctx *ctx);               /* basis.rs:140-145 */
+uint64_t ckks_ctx_psi(const ckks_ctx *ctx, size_t channel);      /* NttTable psi, basis.rs:33 */
+/* RnsBasis::reconstruct_centered_coeff basis.rs:158-180 (host, u128 CRT, Q < 2^128). */
+int ckks_ctx_reconstruct_centered_coeff(const ckks_ctx *ctx, const uint64_t *residues, int64_t *out);
+/* Selects the small-N single-CTA NTT (1) or the four-step NTT (2) for contexts created afterwards;
+ * 0 = automatic.  Test hook: both paths must agree with the oracle. */
+int ckks_set_ntt_path(int path);
+
+/* ---- RnsPoly<N>  (poly.rs) --------------------------------------------------------------------- */
+/* RnsPoly::zero(basis) poly.rs:36-42, for `batch` polynomials (coefficient domain). */
+int ckks_poly_alloc(ckks_ctx *ctx, size_t batch, ckks_poly **out);
+/* RnsPoly::from_coeffs poly.rs:49-66: coeffs is [batch][coeffs_len] i64, coeffs_len >= N
+ * (CKKS_SHORT_INPUT otherwise); rem_euclid per limb is computed on the device. */
+int ckks_poly_from_coeffs(ckks_ctx *ctx, size_t batch, const int64_t *coeffs, size_t coeffs_len,
+                          ckks_poly **out);
+/* RnsPoly::from_channels poly.rs:72-99: host [batch][channels][N]; CKKS_CHANNEL_COUNT_MISMATCH if
+ * channels != L, CKKS_NON_REDUCED_COEFFICIENT if any word >= its modulus (checked on the device). */
+int ckks_poly_from_channels(ckks_ctx *ctx, size_t batch, const uint64_t *channels, size_t nchannels,
+                            int in_ntt_domain, ckks_poly **out);
+/* RnsPoly::channels() poly.rs:119-121: copies [batch][L][N] to the host in the reference layout
+ * (natural NTT order if the polynomial is in the NTT domain). */
+int ckks_poly_download(ckks_poly *p, uint64_t *out);
+int ckks_poly_clone(ckks_poly *p, ckks_poly **out);              /* #[derive(Clone)] poly.rs:25 */
+int ckks_poly_free(ckks_poly *p);
+size_t ckks_poly_batch(const ckks_poly *p);
+size_t ckks_poly_channel_count(const ckks_poly *p);
+int ckks_poly_is_ntt_domain(const ckks_poly *p);                 /* poly.rs:127-129 */
+int ckks_poly_to_ntt_domain(ckks_poly *p);                       /* poly.rs:136-148 */
+int ckks_poly_to_coeff_domain(ckks_poly *p);                     /* poly.rs:154-166 */
+int ckks_poly_add_assign(ckks_poly *a, const ckks_poly *rhs);    /* AddAssign poly.rs:254-275 */
+int ckks_poly_sub_assign(ckks_poly *a, const ckks_poly *rhs);    /* a += -rhs (Neg + AddAssign) */
+int ckks_poly_neg(ckks_poly *a);                                 /* Neg poly.rs:370-385 */
+/* MulAssign poly.rs:277-331: both NTT domain -> pointwise; both coefficient domain -> negacyclic
+ * product returned in the coefficient domain. */
+int ckks_poly_mul_assign(ckks_poly *a, const ckks_poly *rhs);
+/* RnsPoly::mod_drop_last(k) poly.rs:169-177; `child` must be ckks_ctx_drop_last(ctx, k). */
+int ckks_poly_mod_drop_last(const ckks_poly *p, ckks_ctx *child, ckks_poly **out);
+/* RnsPoly::rescale_into(new_basis) poly.rs:187-228 (floor division by the last prime; result in
+ * the coefficient domain; CKKS_INVALID_MOD_DROP if L < 2). */
+int ckks_poly_rescale_into(const ckks_poly *p, ckks_ctx *child, ckks_poly **out);
+/* PolyAutomorphism::automorphism poly.rs:492-541 (X -> X^exponent, any exponent incl. the even
+ * and `% 2N == 0` quirks) and rotate_slots poly.rs:546-569.  Result in the coefficient domain
+ * (except the exponent % 2N == 0 clone, which keeps the domain flag). */
+int ckks_poly_automorphism(const ckks_poly *p, uint64_t exponent, ckks_poly **out);
+int ckks_poly_rotate_slots(const ckks_poly *p, int32_t k, ckks_poly **out);
+/* PolyRing::to_coeffs poly.rs:404-427: centred CRT into [batch][N] i64 (Q < 2^128). */
+int ckks_poly_to_coeffs(const ckks_poly *p, int64_t *out);
+
+/* ---- gadget keys  (engine.rs:225-253, generated by engine.rs:288-399 on the host) -------------- */
+/* a, b: [digit i < L][limb j < L][N] coefficient domain, as `rlk.a[i].channels()`.  The key is
+ * transformed once and stays resident in HBM. */
+int ckks_ksk_upload(ckks_ctx *ctx, const uint64_t *a, const uint64_t *b, ckks_ksk **out);
+/* Same, from device polynomials of batch L (digit-major), e.g. produced by ckks_gen_gadget_key. */
+int ckks_ksk_from_polys(const ckks_poly *a, const ckks_poly *b, ckks_ksk **out);
+int ckks_ksk_free(ckks_ksk *k);
+/* engine.rs:304-332 / :364-392 with host-sampled a_i, e_i (batch L each, coefficient domain):
+ * b_i = -(a_i*s) + e_i + [target in limb i].  `target` is s^2 (relin) or rotate_slots(s, k). */
+int ckks_gen_gadget_key_b(const ckks_poly *s, const ckks_poly *target, const ckks_poly *a,
+                          const ckks_poly *e, ckks_poly **out_b);
+
+/* ---- CkksEngine<RnsPoly, N> ciphertext ops (engine.rs), batched, coefficient domain ------------ */
+/* add_ciphertexts engine.rs:131-151 */
+int ckks_ct_add(const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1,
+                ckks_poly **c0, ckks_poly **c1);
+/* mul_ciphertexts_gadget engine.rs:473-539 */
+int ckks_ct_mul_relin(const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0,
+                      const ckks_poly *b1, const ckks_ksk *rlk, ckks_poly **c0, ckks_poly **c1);
+/* rescale_ciphertext engine.rs:263-282; *bits_dropped = bit_length(q_last). */
+int ckks_ct_rescale(const ckks_poly *c0, const ckks_poly *c1, ckks_ctx *child, ckks_poly **o0,
+                    ckks_poly **o1, uint32_t *bits_dropped);
+/* mul_ciphertexts_gadget followed by rescale_ciphertext, fused on the device. */
+int ckks_ct_mul_relin_rescale(const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0,
+                              const ckks_poly *b1, const ckks_ksk *rlk, ckks_ctx *child,
+                              ckks_poly **o0, ckks_poly **o1);
+/* rotate_ciphertext engine.rs:412-463 with rotation `k` (the key's `rotation` field). */
+int ckks_ct_rotate(const ckks_poly *c0, const ckks_poly *c1, const ckks_ksk *rotk, int32_t k,
+                   ckks_poly **o0, ckks_poly **o1);
+/* encrypt engine.rs:84-112 with host-sampled u, e0, e1 already uploaded: c0 = pk_b*u + e0 + m,
+ * c1 = pk_a*u + e1.  pk_* have batch 1 or `batch`. */
+int ckks_ct_encrypt(const ckks_poly *pk_b, const ckks_poly *pk_a, const ckks_poly *u,
+                    const ckks_poly *e0, const ckks_poly *e1, const ckks_poly *m, ckks_poly **c0,
+                    ckks_poly **c1);
+/* decrypt engine.rs:114-128: c1*s + c0 (s has batch 1 or `batch`). */
+int ckks_ct_decrypt(const ckks_poly *c0, const ckks_poly *c1, const ckks_poly *s, ckks_poly **out);
+
+/* ---- host-buffer entry points (what a reference-side caller with `Vec<[u64;N]>` data uses) ------ */
+/* mul_ciphertexts_gadget + rescale_ciphertext on `batch` ciphertext pairs held in HOST memory in
+ * the reference layout ([batch][L][N] per component; outputs [batch][L-1][N]).  Copies are chunked
+ * through pinned staging buffers and overlapped with compute. */
+int ckks_ct_mul_relin_rescale_host(ckks_ctx *ctx, ckks_ctx *child, const ckks_ksk *rlk, size_t batch,
+                                   const uint64_t *a0, const uint64_t *a1, const uint64_t *b0,
+                                   const uint64_t *b1, uint64_t *o0, uint64_t *o1);
+int ckks_ct_rotate_host(ckks_ctx *ctx, const ckks_ksk *rotk, int32_t k, size_t batch,
+                        const uint64_t *c0, const uint64_t *c1, uint64_t *o0, uint64_t *o1);
+/* Pinned host allocation helpers for the callers of the *_host entry points. */
+int ckks_host_alloc(size_t bytes, void **out);
+int ckks_host_free(void *p);
+
+/* ---- instrumentation ---------------------------------------------------------------------------- */
+/* Kernel launches issued by this library since process start (bench.py's gpu_launches). */
+uint64_t ckks_launch_count(void);
+/* Name/launch-count table of this library's kernels: writes up to `cap` bytes of
+ * "name=count\n" lines, returns the length needed. */
+size_t ckks_launch_table(char *buf, size_t cap);
+/* Integer-pipe microbenchmark: dependent-free 64-bit Shoup modmuls; returns modmul/s (0 on error). */
+double ckks_bench_modmul_peak(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CKKS_B200_H */

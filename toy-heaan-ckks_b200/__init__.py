@@ -1,0 +1,526 @@
+"""ckks-b200: host-side mirror of the reference's RNS-NTT backend over libckks_b200.so.
+
+The classes keep the reference's names and semantics so tests read like the reference's own:
+
+    RnsBasis        src/rings/backends/rns_ntt/basis.rs:91-181
+    RnsPoly         src/rings/backends/rns_ntt/poly.rs:26-570 (a *batch* of polynomials, device resident)
+    RnsNttError     src/rings/backends/rns_ntt/errors.rs:3-22
+    Ciphertext      src/crypto/types.rs:22-35
+    CkksEngine      src/crypto/engine.rs (add / mul_ciphertexts_gadget / rescale_ciphertext /
+                    rotate_ciphertext / encrypt / decrypt, gadget keys)
+
+Everything is computed by the CUDA library through its C ABI (include/ckks_b200.h); there is no
+CPU fallback and nothing here imports the oracle.  Import fails loudly if the library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libckks_b200.so")
+
+_ERR_NAMES = {
+    1: "InvalidDegree",
+    2: "EmptyBasis",
+    3: "NonNttFriendlyModulus",
+    4: "InvalidModDrop",
+    5: "ChannelCountMismatch",
+    6: "NonReducedCoefficient",
+    20: "BasisMismatch",
+    21: "DomainMismatch",
+    22: "BatchMismatch",
+    23: "LevelMismatch",
+    24: "ShortInput",
+    30: "BadHandle",
+    31: "BadArgument",
+    32: "Unsupported",
+    40: "CudaError",
+    41: "NcclError",
+}
+
+
+class RnsNttError(Exception):
+    """Mirrors `RnsNttError` (errors.rs:3-22) plus the ABI's own failure codes."""
+
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        self.kind = _ERR_NAMES.get(code, f"code {code}")
+        super().__init__(self.kind + (": " + detail if detail else ""))
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a).  This package has no CPU fallback."
+    )
+
+_lib = C.CDLL(LIB_PATH)
+_vp = C.c_void_p
+_u64p = C.POINTER(C.c_uint64)
+_i64p = C.POINTER(C.c_int64)
+_pp = C.POINTER(C.c_void_p)
+
+
+def _sig(name, restype, *argtypes):
+    f = getattr(_lib, name)
+    f.restype = restype
+    f.argtypes = list(argtypes)
+    return f
+
+
+_sig("ckks_status_str", C.c_char_p, C.c_int)
+_sig("ckks_last_error", C.c_char_p)
+_sig("ckks_device_count", C.c_int)
+_sig("ckks_is_prime", C.c_int, C.c_uint64)
+_sig("ckks_is_ntt_friendly_prime", C.c_int, C.c_uint64, C.c_uint64)
+_sig("ckks_generate_primes", C.c_int, C.c_int, C.c_int, C.c_uint64, _u64p)
+_sig("ckks_ctx_create", C.c_int, C.c_uint64, _u64p, C.c_size_t, C.c_int, _pp)
+_sig("ckks_ctx_drop_last", C.c_int, _vp, C.c_size_t, _pp)
+_sig("ckks_ctx_destroy", C.c_int, _vp)
+_sig("ckks_ctx_sync", C.c_int, _vp)
+_sig("ckks_ctx_set_stream", C.c_int, _vp, _vp)
+_sig("ckks_ctx_degree", C.c_uint64, _vp)
+_sig("ckks_ctx_channel_count", C.c_size_t, _vp)
+_sig("ckks_ctx_moduli", C.c_int, _vp, _u64p)
+_sig("ckks_ctx_total_bits", C.c_uint32, _vp)
+_sig("ckks_ctx_psi", C.c_uint64, _vp, C.c_size_t)
+_sig("ckks_ctx_reconstruct_centered_coeff", C.c_int, _vp, _u64p, _i64p)
+_sig("ckks_set_ntt_path", C.c_int, C.c_int)
+_sig("ckks_poly_alloc", C.c_int, _vp, C.c_size_t, _pp)
+_sig("ckks_poly_from_coeffs", C.c_int, _vp, C.c_size_t, _i64p, C.c_size_t, _pp)
+_sig("ckks_poly_from_channels", C.c_int, _vp, C.c_size_t, _u64p, C.c_size_t, C.c_int, _pp)
+_sig("ckks_poly_download", C.c_int, _vp, _u64p)
+_sig("ckks_poly_clone", C.c_int, _vp, _pp)
+_sig("ckks_poly_free", C.c_int, _vp)
+_sig("ckks_poly_batch", C.c_size_t, _vp)
+_sig("ckks_poly_channel_count", C.c_size_t, _vp)
+_sig("ckks_poly_is_ntt_domain", C.c_int, _vp)
+_sig("ckks_poly_to_ntt_domain", C.c_int, _vp)
+_sig("ckks_poly_to_coeff_domain", C.c_int, _vp)
+_sig("ckks_poly_add_assign", C.c_int, _vp, _vp)
+_sig("ckks_poly_sub_assign", C.c_int, _vp, _vp)
+_sig("ckks_poly_neg", C.c_int, _vp)
+_sig("ckks_poly_mul_assign", C.c_int, _vp, _vp)
+_sig("ckks_poly_mod_drop_last", C.c_int, _vp, _vp, _pp)
+_sig("ckks_poly_rescale_into", C.c_int, _vp, _vp, _pp)
+_sig("ckks_poly_automorphism", C.c_int, _vp, C.c_uint64, _pp)
+_sig("ckks_poly_rotate_slots", C.c_int, _vp, C.c_int32, _pp)
+_sig("ckks_poly_to_coeffs", C.c_int, _vp, _i64p)
+_sig("ckks_ksk_upload", C.c_int, _vp, _u64p, _u64p, _pp)
+_sig("ckks_ksk_from_polys", C.c_int, _vp, _vp, _pp)
+_sig("ckks_ksk_free", C.c_int, _vp)
+_sig("ckks_gen_gadget_key_b", C.c_int, _vp, _vp, _vp, _vp, _pp)
+_sig("ckks_ct_add", C.c_int, _vp, _vp, _vp, _vp, _pp, _pp)
+_sig("ckks_ct_mul_relin", C.c_int, _vp, _vp, _vp, _vp, _vp, _pp, _pp)
+_sig("ckks_ct_rescale", C.c_int, _vp, _vp, _vp, _pp, _pp, C.POINTER(C.c_uint32))
+_sig("ckks_ct_mul_relin_rescale", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _pp, _pp)
+_sig("ckks_ct_rotate", C.c_int, _vp, _vp, _vp, C.c_int32, _pp, _pp)
+_sig("ckks_ct_encrypt", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _pp, _pp)
+_sig("ckks_ct_decrypt", C.c_int, _vp, _vp, _vp, _pp)
+_sig("ckks_ct_mul_relin_rescale_host", C.c_int, _vp, _vp, _vp, C.c_size_t, _u64p, _u64p, _u64p, _u64p, _u64p, _u64p)
+_sig("ckks_ct_rotate_host", C.c_int, _vp, _vp, C.c_int32, C.c_size_t, _u64p, _u64p, _u64p, _u64p)
+_sig("ckks_host_alloc", C.c_int, C.c_size_t, _pp)
+_sig("ckks_host_free", C.c_int, _vp)
+_sig("ckks_launch_count", C.c_uint64)
+_sig("ckks_launch_table", C.c_size_t, C.c_char_p, C.c_size_t)
+_sig("ckks_bench_modmul_peak", C.c_double, C.c_int, C.c_int)
+
+# Every symbol include/ckks_b200.h declares (tests/test_abi.py checks the header against this list).
+ABI_SYMBOLS = sorted(n for n in dir(_lib) if n.startswith("ckks_")) or []
+
+
+def _check(rc: int):
+    if rc != 0:
+        detail = _lib.ckks_last_error().decode() if rc in (40, 41) else ""
+        raise RnsNttError(rc, detail)
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_u64p)
+
+
+def device_count() -> int:
+    return int(_lib.ckks_device_count())
+
+
+def launch_count() -> int:
+    return int(_lib.ckks_launch_count())
+
+
+def launch_table() -> dict:
+    n = _lib.ckks_launch_table(None, 0)
+    buf = C.create_string_buffer(int(n))
+    _lib.ckks_launch_table(buf, n)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        k, v = line.split("=")
+        out[k] = int(v)
+    return out
+
+
+def set_ntt_path(path: int):
+    """0 = automatic, 1 = small single-CTA NTT (N <= 2048), 2 = four-step (N >= 256)."""
+    _check(_lib.ckks_set_ntt_path(path))
+
+
+def modmul_peak(device: int = 0, iters: int = 4096) -> float:
+    return float(_lib.ckks_bench_modmul_peak(device, iters))
+
+
+# ── src/math ─────────────────────────────────────────────────────────────────────────────────────
+def is_prime(n: int) -> bool:
+    return bool(_lib.ckks_is_prime(n))
+
+
+def is_ntt_friendly_prime(p: int, n: int) -> bool:
+    return bool(_lib.ckks_is_ntt_friendly_prime(p, n))
+
+
+def generate_primes(bit_size: int, count: int, degree: int) -> list:
+    """utils.rs:47-80.  Raises where the reference panics."""
+    out = np.zeros(max(count, 1), dtype=np.uint64)
+    rc = _lib.ckks_generate_primes(bit_size, count, degree, _ptr(out))
+    if rc:
+        raise RnsNttError(rc, "generate_primes: not enough primes / bad arguments")
+    return [int(x) for x in out[:count]]
+
+
+# ── RnsBasis ─────────────────────────────────────────────────────────────────────────────────────
+class RnsBasis:
+    """`Arc<RnsBasis<N>>` (basis.rs:91-181) with its device tables."""
+
+    def __init__(self, degree: int, moduli, device: int = 0, _handle=None):
+        if _handle is not None:
+            self._h = _handle
+        else:
+            m = _u64(list(moduli))
+            h = _vp()
+            _check(_lib.ckks_ctx_create(degree, _ptr(m) if len(m) else None, len(m), device, C.byref(h)))
+            self._h = h
+        self.degree = int(_lib.ckks_ctx_degree(self._h))
+        self.device = device
+
+    @classmethod
+    def new(cls, degree: int, moduli, device: int = 0) -> "RnsBasis":
+        return cls(degree, moduli, device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.ckks_ctx_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def moduli(self) -> list:
+        out = np.zeros(self.channel_count(), dtype=np.uint64)
+        _check(_lib.ckks_ctx_moduli(self._h, _ptr(out)))
+        return [int(x) for x in out]
+
+    def channel_count(self) -> int:
+        return int(_lib.ckks_ctx_channel_count(self._h))
+
+    def drop_last(self, drop_count: int) -> "RnsBasis":
+        h = _vp()
+        _check(_lib.ckks_ctx_drop_last(self._h, drop_count, C.byref(h)))
+        return RnsBasis(0, [], self.device, _handle=h)
+
+    def total_bits(self) -> int:
+        return int(_lib.ckks_ctx_total_bits(self._h))
+
+    def psi(self, channel: int) -> int:
+        return int(_lib.ckks_ctx_psi(self._h, channel))
+
+    def reconstruct_centered_coeff(self, residues) -> int:
+        r = _u64(residues)
+        out = C.c_int64(0)
+        _check(_lib.ckks_ctx_reconstruct_centered_coeff(self._h, _ptr(r), C.byref(out)))
+        return int(out.value)
+
+    def sync(self):
+        _check(_lib.ckks_ctx_sync(self._h))
+
+    def set_stream(self, cuda_stream: int):
+        _check(_lib.ckks_ctx_set_stream(self._h, _vp(cuda_stream)))
+
+
+# ── RnsPoly ──────────────────────────────────────────────────────────────────────────────────────
+class RnsPoly:
+    """A batch of `RnsPoly<N>` (poly.rs:26-30) resident in HBM.
+
+    Host arrays are [batch, L, N] uint64 (a 2-D [L, N] array is a batch of one)."""
+
+    def __init__(self, handle, basis: RnsBasis):
+        self._h = handle
+        self._basis = basis
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.ckks_poly_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # constructors ------------------------------------------------------------------------------
+    @classmethod
+    def zero(cls, basis: RnsBasis, batch: int = 1) -> "RnsPoly":
+        h = _vp()
+        _check(_lib.ckks_poly_alloc(basis._h, batch, C.byref(h)))
+        return cls(h, basis)
+
+    @classmethod
+    def from_coeffs(cls, coeffs, basis: RnsBasis) -> "RnsPoly":
+        c = np.ascontiguousarray(coeffs, dtype=np.int64)
+        if c.ndim == 1:
+            c = c[None, :]
+        h = _vp()
+        _check(_lib.ckks_poly_from_coeffs(basis._h, c.shape[0], c.ctypes.data_as(_i64p), c.shape[1], C.byref(h)))
+        return cls(h, basis)
+
+    @classmethod
+    def from_channels(cls, channels, basis: RnsBasis, is_ntt_domain: bool = False) -> "RnsPoly":
+        ch = _u64(channels)
+        if ch.ndim == 2:
+            ch = ch[None, :, :]
+        if ch.shape[2] != basis.degree:
+            raise RnsNttError(1, "channel length != N")
+        h = _vp()
+        _check(_lib.ckks_poly_from_channels(basis._h, ch.shape[0], _ptr(ch), ch.shape[1], int(is_ntt_domain), C.byref(h)))
+        return cls(h, basis)
+
+    # accessors ---------------------------------------------------------------------------------
+    def channels(self) -> np.ndarray:
+        out = np.zeros((self.batch(), self.channel_count(), self._basis.degree), dtype=np.uint64)
+        _check(_lib.ckks_poly_download(self._h, _ptr(out)))
+        return out
+
+    def basis(self) -> RnsBasis:
+        return self._basis
+
+    def context(self) -> RnsBasis:
+        return self._basis
+
+    def batch(self) -> int:
+        return int(_lib.ckks_poly_batch(self._h))
+
+    def channel_count(self) -> int:
+        return int(_lib.ckks_poly_channel_count(self._h))
+
+    def is_ntt_domain(self) -> bool:
+        return bool(_lib.ckks_poly_is_ntt_domain(self._h))
+
+    def clone(self) -> "RnsPoly":
+        h = _vp()
+        _check(_lib.ckks_poly_clone(self._h, C.byref(h)))
+        return RnsPoly(h, self._basis)
+
+    # transforms and arithmetic -----------------------------------------------------------------
+    def to_ntt_domain(self):
+        _check(_lib.ckks_poly_to_ntt_domain(self._h))
+
+    def to_coeff_domain(self):
+        _check(_lib.ckks_poly_to_coeff_domain(self._h))
+
+    def __iadd__(self, rhs: "RnsPoly"):
+        _check(_lib.ckks_poly_add_assign(self._h, rhs._h))
+        return self
+
+    def __isub__(self, rhs: "RnsPoly"):
+        _check(_lib.ckks_poly_sub_assign(self._h, rhs._h))
+        return self
+
+    def __imul__(self, rhs: "RnsPoly"):
+        _check(_lib.ckks_poly_mul_assign(self._h, rhs._h))
+        return self
+
+    def __neg__(self) -> "RnsPoly":
+        r = self.clone()
+        _check(_lib.ckks_poly_neg(r._h))
+        return r
+
+    def mod_drop_last(self, drop_count: int = 1, basis: RnsBasis | None = None) -> "RnsPoly":
+        child = basis if basis is not None else self._basis.drop_last(drop_count)
+        h = _vp()
+        _check(_lib.ckks_poly_mod_drop_last(self._h, child._h, C.byref(h)))
+        return RnsPoly(h, child)
+
+    def rescale_into(self, new_basis: RnsBasis) -> "RnsPoly":
+        h = _vp()
+        _check(_lib.ckks_poly_rescale_into(self._h, new_basis._h, C.byref(h)))
+        return RnsPoly(h, new_basis)
+
+    def rescale(self) -> "RnsPoly":
+        if self.channel_count() < 2:
+            raise RnsNttError(4)
+        return self.rescale_into(self._basis.drop_last(1))
+
+    def automorphism(self, exponent: int) -> "RnsPoly":
+        h = _vp()
+        _check(_lib.ckks_poly_automorphism(self._h, exponent, C.byref(h)))
+        return RnsPoly(h, self._basis)
+
+    def rotate_slots(self, k: int) -> "RnsPoly":
+        h = _vp()
+        _check(_lib.ckks_poly_rotate_slots(self._h, k, C.byref(h)))
+        return RnsPoly(h, self._basis)
+
+    def to_coeffs(self) -> np.ndarray:
+        out = np.zeros((self.batch(), self._basis.degree), dtype=np.int64)
+        _check(_lib.ckks_poly_to_coeffs(self._h, out.ctypes.data_as(_i64p)))
+        return out
+
+
+# ── keys and ciphertexts ─────────────────────────────────────────────────────────────────────────
+class GadgetKey:
+    """`RnsGadgetRelinKey` / `RnsGadgetRotationKey` (engine.rs:225-253), transformed and resident."""
+
+    def __init__(self, handle, basis: RnsBasis, rotation: int = 0):
+        self._h = handle
+        self._basis = basis
+        self.rotation = rotation
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.ckks_ksk_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @classmethod
+    def upload(cls, basis: RnsBasis, a, b, rotation: int = 0) -> "GadgetKey":
+        a = _u64(a)
+        b = _u64(b)
+        l, n = basis.channel_count(), basis.degree
+        if a.shape != (l, l, n) or b.shape != (l, l, n):
+            raise RnsNttError(5, "gadget key must be [L, L, N]")
+        h = _vp()
+        _check(_lib.ckks_ksk_upload(basis._h, _ptr(a), _ptr(b), C.byref(h)))
+        return cls(h, basis, rotation)
+
+    @classmethod
+    def from_polys(cls, a: RnsPoly, b: RnsPoly, rotation: int = 0) -> "GadgetKey":
+        h = _vp()
+        _check(_lib.ckks_ksk_from_polys(a._h, b._h, C.byref(h)))
+        return cls(h, a.basis(), rotation)
+
+
+class Ciphertext:
+    """`Ciphertext` (types.rs:22-35): (c0, c1, logp, logq); c0/c1 are batched RnsPoly."""
+
+    def __init__(self, c0: RnsPoly, c1: RnsPoly, logp: int, logq: int):
+        self.c0, self.c1, self.logp, self.logq = c0, c1, logp, logq
+
+
+class CkksEngine:
+    """RnsPoly-specific operations of `CkksEngine` (engine.rs:84-151, 255-540) on device batches.
+
+    Randomness stays on the host (north_star): the sampled polynomials are arguments."""
+
+    @staticmethod
+    def encrypt(pk_b: RnsPoly, pk_a: RnsPoly, u: RnsPoly, e0: RnsPoly, e1: RnsPoly, m: RnsPoly, logp: int, logq: int):
+        h0, h1 = _vp(), _vp()
+        _check(_lib.ckks_ct_encrypt(pk_b._h, pk_a._h, u._h, e0._h, e1._h, m._h, C.byref(h0), C.byref(h1)))
+        b = u.basis()
+        return Ciphertext(RnsPoly(h0, b), RnsPoly(h1, b), logp, logq)
+
+    @staticmethod
+    def decrypt(ct: Ciphertext, s: RnsPoly) -> RnsPoly:
+        h = _vp()
+        _check(_lib.ckks_ct_decrypt(ct.c0._h, ct.c1._h, s._h, C.byref(h)))
+        return RnsPoly(h, ct.c0.basis())
+
+    @staticmethod
+    def add_ciphertexts(a: Ciphertext, b: Ciphertext) -> Ciphertext:
+        if a.logp != b.logp or a.logq != b.logq:  # engine.rs:135-136
+            raise RnsNttError(23)
+        h0, h1 = _vp(), _vp()
+        _check(_lib.ckks_ct_add(a.c0._h, a.c1._h, b.c0._h, b.c1._h, C.byref(h0), C.byref(h1)))
+        bs = a.c0.basis()
+        return Ciphertext(RnsPoly(h0, bs), RnsPoly(h1, bs), a.logp, a.logq)
+
+    @staticmethod
+    def mul_ciphertexts_gadget(a: Ciphertext, b: Ciphertext, rlk: GadgetKey) -> Ciphertext:
+        if a.logq != b.logq:  # engine.rs:478
+            raise RnsNttError(23)
+        h0, h1 = _vp(), _vp()
+        _check(_lib.ckks_ct_mul_relin(a.c0._h, a.c1._h, b.c0._h, b.c1._h, rlk._h, C.byref(h0), C.byref(h1)))
+        bs = a.c0.basis()
+        return Ciphertext(RnsPoly(h0, bs), RnsPoly(h1, bs), a.logp + b.logp, a.logq)
+
+    @staticmethod
+    def rescale_ciphertext(ct: Ciphertext, new_basis: RnsBasis | None = None) -> Ciphertext:
+        if ct.c0.channel_count() < 2:
+            raise RnsNttError(4)
+        child = new_basis if new_basis is not None else ct.c0.basis().drop_last(1)
+        h0, h1 = _vp(), _vp()
+        bits = C.c_uint32(0)
+        _check(_lib.ckks_ct_rescale(ct.c0._h, ct.c1._h, child._h, C.byref(h0), C.byref(h1), C.byref(bits)))
+        return Ciphertext(RnsPoly(h0, child), RnsPoly(h1, child), ct.logp - bits.value, ct.logq - bits.value)
+
+    @staticmethod
+    def mul_relin_rescale(a: Ciphertext, b: Ciphertext, rlk: GadgetKey, new_basis: RnsBasis | None = None) -> Ciphertext:
+        """mul_ciphertexts_gadget followed by rescale_ciphertext in one device call."""
+        if a.logq != b.logq:
+            raise RnsNttError(23)
+        child = new_basis if new_basis is not None else a.c0.basis().drop_last(1)
+        h0, h1 = _vp(), _vp()
+        _check(_lib.ckks_ct_mul_relin_rescale(a.c0._h, a.c1._h, b.c0._h, b.c1._h, rlk._h, child._h, C.byref(h0), C.byref(h1)))
+        bits = a.c0.basis().moduli()[-1].bit_length()
+        return Ciphertext(RnsPoly(h0, child), RnsPoly(h1, child), a.logp + b.logp - bits, a.logq - bits)
+
+    @staticmethod
+    def rotate_ciphertext(ct: Ciphertext, rotk: GadgetKey) -> Ciphertext:
+        h0, h1 = _vp(), _vp()
+        _check(_lib.ckks_ct_rotate(ct.c0._h, ct.c1._h, rotk._h, rotk.rotation, C.byref(h0), C.byref(h1)))
+        bs = ct.c0.basis()
+        return Ciphertext(RnsPoly(h0, bs), RnsPoly(h1, bs), ct.logp, ct.logq)
+
+    @staticmethod
+    def gadget_key_b(s: RnsPoly, target: RnsPoly, a: RnsPoly, e: RnsPoly) -> RnsPoly:
+        """b_i = -(a_i s) + e_i + [target in limb i] (engine.rs:318-327 / :378-387)."""
+        h = _vp()
+        _check(_lib.ckks_gen_gadget_key_b(s._h, target._h, a._h, e._h, C.byref(h)))
+        return RnsPoly(h, s.basis())
+
+
+# ── host-buffer entry points ─────────────────────────────────────────────────────────────────────
+class PinnedBuffer:
+    """Page-locked host memory viewed as a numpy uint64 array."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+        n = int(np.prod(self.shape))
+        p = _vp()
+        _check(_lib.ckks_host_alloc(n * 8, C.byref(p)))
+        self._p = p
+        buf = (C.c_uint64 * n).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=np.uint64).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_p", None):
+                self.array = None
+                _lib.ckks_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+def mul_relin_rescale_host(basis: RnsBasis, child: RnsBasis, rlk: GadgetKey, a0, a1, b0, b1, o0, o1):
+    """Host [batch, L, N] arrays in, host [batch, L-1, N] arrays out (copies inside)."""
+    batch = a0.shape[0]
+    _check(_lib.ckks_ct_mul_relin_rescale_host(basis._h, child._h, rlk._h, batch, _ptr(a0), _ptr(a1), _ptr(b0), _ptr(b1),
+                                               _ptr(o0), _ptr(o1)))
+
+
+def rotate_host(basis: RnsBasis, rotk: GadgetKey, c0, c1, o0, o1):
+    _check(_lib.ckks_ct_rotate_host(basis._h, rotk._h, rotk.rotation, c0.shape[0], _ptr(c0), _ptr(c1), _ptr(o0), _ptr(o1)))

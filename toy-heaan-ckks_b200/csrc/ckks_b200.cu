@@ -1,0 +1,1200 @@
+// ckks_b200.cu -- libckks_b200.so: the C ABI of include/ckks_b200.h over the sm_100a kernels.
+// No torch types, no CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/ckks_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "context.hpp"
+#include "host_math.hpp"
+#include "tables_host.hpp"
+#include "kernels.cuh"
+
+// -------------------------------------------------------------------------------------------------
+// errors, launch accounting
+// -------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+static std::mutex g_mu;
+static std::map<std::string, uint64_t> g_launch_table;
+static int g_ntt_path = 0;
+
+static int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return CKKS_CUDA_ERROR;
+}
+#define CU(x)                                          \
+    do {                                               \
+        cudaError_t e__ = (x);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #x); \
+    } while (0)
+#define TRY(x)                      \
+    do {                            \
+        int s__ = (x);              \
+        if (s__ != CKKS_OK) return s__; \
+    } while (0)
+
+static void count_launch(const char *name) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_launch_table[name]++;
+}
+#define KL(name, ...)                        \
+    do {                                     \
+        count_launch(name);                  \
+        __VA_ARGS__;                         \
+        cudaError_t e__ = cudaPeekAtLastError(); \
+        if (e__ != cudaSuccess) return cuda_fail(e__, name); \
+    } while (0)
+
+extern "C" const char *ckks_status_str(int s) {
+    switch (s) {
+        case CKKS_OK: return "ok";
+        case CKKS_INVALID_DEGREE: return "InvalidDegree";
+        case CKKS_EMPTY_BASIS: return "EmptyBasis";
+        case CKKS_NON_NTT_FRIENDLY_MODULUS: return "NonNttFriendlyModulus";
+        case CKKS_INVALID_MOD_DROP: return "InvalidModDrop";
+        case CKKS_CHANNEL_COUNT_MISMATCH: return "ChannelCountMismatch";
+        case CKKS_NON_REDUCED_COEFFICIENT: return "NonReducedCoefficient";
+        case CKKS_BASIS_MISMATCH: return "BasisMismatch";
+        case CKKS_DOMAIN_MISMATCH: return "DomainMismatch";
+        case CKKS_BATCH_MISMATCH: return "BatchMismatch";
+        case CKKS_LEVEL_MISMATCH: return "LevelMismatch";
+        case CKKS_SHORT_INPUT: return "ShortInput";
+        case CKKS_BAD_HANDLE: return "BadHandle";
+        case CKKS_BAD_ARGUMENT: return "BadArgument";
+        case CKKS_UNSUPPORTED: return "Unsupported";
+        case CKKS_CUDA_ERROR: return "CudaError";
+        case CKKS_NCCL_ERROR: return "NcclError";
+    }
+    return "unknown";
+}
+extern "C" const char *ckks_last_error(void) { return g_err.c_str(); }
+extern "C" int ckks_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+extern "C" uint64_t ckks_launch_count(void) { return g_launches.load(); }
+extern "C" size_t ckks_launch_table(char *buf, size_t cap) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::string s;
+    for (auto &kv : g_launch_table) s += kv.first + "=" + std::to_string(kv.second) + "\n";
+    if (buf && cap) {
+        size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return s.size() + 1;
+}
+extern "C" int ckks_set_ntt_path(int p) {
+    if (p < 0 || p > 2) return CKKS_BAD_ARGUMENT;
+    g_ntt_path = p;
+    return CKKS_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// host number theory (src/math)
+// -------------------------------------------------------------------------------------------------
+extern "C" int ckks_is_prime(uint64_t n) { return hm::is_prime(n) ? 1 : 0; }
+extern "C" int ckks_is_ntt_friendly_prime(uint64_t p, uint64_t n) { return hm::is_ntt_friendly_prime(p, n) ? 1 : 0; }
+extern "C" int ckks_generate_primes(int bits, int count, uint64_t degree, uint64_t *out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    return hm::generate_primes(bits, count, degree, (u64 *)out) ? CKKS_OK : CKKS_BAD_ARGUMENT;
+}
+
+// -------------------------------------------------------------------------------------------------
+// context
+// -------------------------------------------------------------------------------------------------
+Tables::~Tables() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    void *ptrs[] = {d_lc, d_psi, d_psi_inv, d_ninv, d_P1, d_P1i, d_W2, d_W2i, d_TT, d_TTi, d_qlinv};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+static bool ok_ctx(const ckks_ctx *c) { return c && c->magic == MAGIC_CTX; }
+static bool ok_poly(const ckks_poly *p) { return p && p->magic == MAGIC_POLY && ok_ctx(p->ctx); }
+static bool ok_ksk(const ckks_ksk *k) { return k && k->magic == MAGIC_KSK && ok_ctx(k->ctx); }
+static void ctx_ref(ckks_ctx *c) { c->refs.fetch_add(1); }
+static void ctx_unref(ckks_ctx *c) {
+    if (c->refs.fetch_sub(1) == 1) {
+        c->magic = 0;
+        delete c;
+    }
+}
+static bool same_basis(const ckks_ctx *a, const ckks_ctx *b) { return a->T.get() == b->T.get() && a->L == b->L; }
+
+template <class T>
+static int upload_vec(T **dst, const std::vector<T> &v) {
+    CU(cudaMalloc((void **)dst, v.size() * sizeof(T)));
+    CU(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return CKKS_OK;
+}
+static tw_t mk_tw(u64 w, u64 q) { return ht::mk_tw(w, q); }
+
+static int build_tables(Tables &T) {
+    ht::HostTables H;
+    ht::build_host_tables(T.n, T.logn, T.path, T.a1, T.a2, T.moduli, T.psi, H);
+    T.lazy = H.lazy;
+    T.digit_reduce = H.digit_reduce;
+    T.w2_stride = H.w2_stride;
+    TRY(upload_vec(&T.d_lc, H.lc));
+    TRY(upload_vec(&T.d_qlinv, H.ql));
+    if (T.path == 1) {
+        TRY(upload_vec(&T.d_psi, H.psi));
+        TRY(upload_vec(&T.d_psi_inv, H.psii));
+        TRY(upload_vec(&T.d_ninv, H.ninv));
+        return CKKS_OK;
+    }
+    TRY(upload_vec(&T.d_P1, H.P1));
+    TRY(upload_vec(&T.d_P1i, H.P1i));
+    TRY(upload_vec(&T.d_W2, H.W2));
+    TRY(upload_vec(&T.d_W2i, H.W2i));
+    TRY(upload_vec(&T.d_TT, H.TT));
+    TRY(upload_vec(&T.d_TTi, H.TTi));
+    return CKKS_OK;
+}
+
+extern "C" int ckks_ctx_create(uint64_t n, const uint64_t *moduli, size_t l, int device, ckks_ctx **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    // RnsBasis::new: EmptyBasis first (basis.rs:98-100), then per-table checks (basis.rs:22-31).
+    if (l == 0) return CKKS_EMPTY_BASIS;
+    if (!moduli) return CKKS_BAD_ARGUMENT;
+    if (n == 0 || (n & (n - 1)) != 0) return CKKS_INVALID_DEGREE;
+    for (size_t i = 0; i < l; ++i)
+        if (!hm::is_ntt_friendly_prime(moduli[i], n)) return CKKS_NON_NTT_FRIENDLY_MODULUS;
+    int logn = 0;
+    while (((u64)1 << logn) < n) ++logn;
+    if (logn > 16) return CKKS_UNSUPPORTED;
+    for (size_t i = 0; i < l; ++i)
+        if (moduli[i] >> 63) return CKKS_UNSUPPORTED;  // the reference's add_mod wraps there too
+    if (ckks_device_count() <= device || device < 0) {
+        g_err = "no CUDA device " + std::to_string(device) + " (this library has no CPU fallback)";
+        return CKKS_CUDA_ERROR;
+    }
+    CU(cudaSetDevice(device));
+    auto T = std::make_shared<Tables>();
+    T->device = device;
+    T->n = n;
+    T->logn = logn;
+    T->L = l;
+    T->moduli.assign(moduli, moduli + l);
+    int path = g_ntt_path;
+    if (path == 0) path = (logn >= 8) ? 2 : 1;
+    if (path == 2 && logn < 8) return CKKS_UNSUPPORTED;
+    if (path == 1 && logn > 11) return CKKS_UNSUPPORTED;
+    T->path = path;
+    if (path == 2) {
+        T->a1 = (logn + 1) / 2;
+        T->a2 = logn - T->a1;
+    } else {
+        T->a1 = logn;
+        T->a2 = 0;
+    }
+    for (size_t i = 0; i < l; ++i) T->psi.push_back(hm::find_primitive_root(moduli[i], 2 * n));
+    CU(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
+    T->own_stream = true;
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = ~0ull;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    TRY(build_tables(*T));
+    ckks_ctx *c = new ckks_ctx();
+    c->magic = MAGIC_CTX;
+    c->T = T;
+    c->L = l;
+    c->refs = 1;
+    *out = c;
+    return CKKS_OK;
+}
+extern "C" int ckks_ctx_drop_last(ckks_ctx *ctx, size_t k, ckks_ctx **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    if (k >= ctx->L) return CKKS_INVALID_MOD_DROP;  // basis.rs:122-127
+    ckks_ctx *c = new ckks_ctx();
+    c->magic = MAGIC_CTX;
+    c->T = ctx->T;
+    c->L = ctx->L - k;
+    c->refs = 1;
+    *out = c;
+    return CKKS_OK;
+}
+extern "C" int ckks_ctx_destroy(ckks_ctx *ctx) {
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    ctx_unref(ctx);
+    return CKKS_OK;
+}
+extern "C" int ckks_ctx_sync(ckks_ctx *ctx) {
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    CU(cudaStreamSynchronize(ctx->T->stream));
+    return CKKS_OK;
+}
+extern "C" int ckks_ctx_set_stream(ckks_ctx *ctx, void *s) {
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    Tables &T = *ctx->T;
+    CU(cudaStreamSynchronize(T.stream));
+    if (T.own_stream) cudaStreamDestroy(T.stream);
+    T.stream = (cudaStream_t)s;
+    T.own_stream = false;
+    return CKKS_OK;
+}
+extern "C" uint64_t ckks_ctx_degree(const ckks_ctx *c) { return ok_ctx(c) ? c->T->n : 0; }
+extern "C" size_t ckks_ctx_channel_count(const ckks_ctx *c) { return ok_ctx(c) ? c->L : 0; }
+extern "C" int ckks_ctx_moduli(const ckks_ctx *c, uint64_t *out) {
+    if (!ok_ctx(c) || !out) return CKKS_BAD_HANDLE;
+    for (size_t i = 0; i < c->L; ++i) out[i] = c->T->moduli[i];
+    return CKKS_OK;
+}
+extern "C" uint32_t ckks_ctx_total_bits(const ckks_ctx *c) {
+    if (!ok_ctx(c)) return 0;
+    uint32_t s = 0;
+    for (size_t i = 0; i < c->L; ++i) s += 63 - (uint32_t)__builtin_clzll(c->T->moduli[i]);
+    return s;
+}
+extern "C" uint64_t ckks_ctx_psi(const ckks_ctx *c, size_t ch) { return (ok_ctx(c) && ch < c->L) ? c->T->psi[ch] : 0; }
+extern "C" int ckks_ctx_reconstruct_centered_coeff(const ckks_ctx *c, const uint64_t *res, int64_t *out) {
+    if (!ok_ctx(c) || !res || !out) return CKKS_BAD_HANDLE;
+    std::vector<u64> m(c->T->moduli.begin(), c->T->moduli.begin() + c->L);
+    *out = hm::reconstruct_centered(m, (const u64 *)res);
+    return CKKS_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// launch helpers
+// -------------------------------------------------------------------------------------------------
+static EwArgs ew_args(const Tables &T, size_t L, size_t batch) {
+    EwArgs a;
+    a.lc = T.d_lc;
+    a.poly = L * T.n;
+    a.total = batch * a.poly;
+    a.logn = T.logn;
+    a.L = (int)L;
+    return a;
+}
+static unsigned ew_grid(size_t total) {
+    size_t g = (total + 255) / 256;
+    size_t cap = 148 * 32;
+    return (unsigned)(g < cap ? (g ? g : 1) : cap);
+}
+
+template <int KIND, int A, bool PRE, bool POST, bool TR>
+static int launch_pass_a(const char *name, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+    constexpr int E = 4, C = 16;
+    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(u64);
+    const int block = C << (A - E);
+    if (lazy)
+        KL(name, (ntt_pass_kernel<KIND, A, E, C, true, PRE, POST, TR><<<grid, block, smem, s>>>(a)));
+    else
+        KL(name, (ntt_pass_kernel<KIND, A, E, C, false, PRE, POST, TR><<<grid, block, smem, s>>>(a)));
+    return CKKS_OK;
+}
+template <int KIND, bool PRE, bool POST, bool TR>
+static int launch_pass(const char *name, int A, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+    switch (A) {
+        case 4: return launch_pass_a<KIND, 4, PRE, POST, TR>(name, lazy, grid, s, a);
+        case 5: return launch_pass_a<KIND, 5, PRE, POST, TR>(name, lazy, grid, s, a);
+        case 6: return launch_pass_a<KIND, 6, PRE, POST, TR>(name, lazy, grid, s, a);
+        case 7: return launch_pass_a<KIND, 7, PRE, POST, TR>(name, lazy, grid, s, a);
+        case 8: return launch_pass_a<KIND, 8, PRE, POST, TR>(name, lazy, grid, s, a);
+    }
+    return CKKS_UNSUPPORTED;
+}
+
+// Forward / inverse transform of [batch][L][N] words in place (tmp: same size, four-step only).
+static int ntt_run(const Tables &T, size_t L, size_t batch, u64 *d, u64 *tmp, bool inverse) {
+    if (batch == 0) return CKKS_OK;
+    cudaStream_t s = T.stream;
+    if (T.path == 1) {
+        SmallArgs a;
+        a.data = d;
+        a.lc = T.d_lc;
+        a.psi = inverse ? T.d_psi_inv : T.d_psi;
+        a.ninv = T.d_ninv;
+        a.L = (int)L;
+        a.logn = T.logn;
+        int block = (int)(T.n / 2 < 32 ? 32 : (T.n / 2 > 256 ? 256 : T.n / 2));
+        size_t smem = T.n * sizeof(u64);
+        unsigned grid = (unsigned)(batch * L);
+        if (!inverse) {
+            if (T.lazy) KL("ntt_small_fwd", (ntt_small_kernel<false, true><<<grid, block, smem, s>>>(a)));
+            else KL("ntt_small_fwd", (ntt_small_kernel<false, false><<<grid, block, smem, s>>>(a)));
+        } else {
+            if (T.lazy) KL("ntt_small_inv", (ntt_small_kernel<true, true><<<grid, block, smem, s>>>(a)));
+            else KL("ntt_small_inv", (ntt_small_kernel<true, false><<<grid, block, smem, s>>>(a)));
+        }
+        return CKKS_OK;
+    }
+    const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
+    for (size_t b0 = 0; b0 < batch; b0 += 32768) {
+        size_t nb = batch - b0 < 32768 ? batch - b0 : 32768;
+        PassArgs a;
+        a.lc = T.d_lc;
+        a.L = (int)L;
+        a.N = T.n;
+        u64 *dd = d + b0 * L * T.n, *tt = tmp + b0 * L * T.n;
+        if (!inverse) {
+            a.src = dd;
+            a.dst = tt;
+            a.tab = T.d_P1;
+            a.tab_stride = n1;
+            a.elt = nullptr;
+            a.ncols = n2;
+            TRY((launch_pass<XF_NEG_FWD, false, false, true>("ntt_fwd_pass1", T.a1, T.lazy, dim3(n2 / 16, (unsigned)L, (unsigned)nb), s, a)));
+            a.src = tt;
+            a.dst = dd;
+            a.tab = T.d_W2;
+            a.tab_stride = T.w2_stride;
+            a.elt = T.d_TT;
+            a.ncols = n1;
+            TRY((launch_pass<XF_CYC_FWD, true, false, false>("ntt_fwd_pass2", T.a2, T.lazy, dim3(n1 / 16, (unsigned)L, (unsigned)nb), s, a)));
+        } else {
+            a.src = dd;
+            a.dst = tt;
+            a.tab = T.d_W2i;
+            a.tab_stride = T.w2_stride;
+            a.elt = T.d_TTi;
+            a.ncols = n1;
+            TRY((launch_pass<XF_CYC_INV, false, true, true>("ntt_inv_pass2", T.a2, T.lazy, dim3(n1 / 16, (unsigned)L, (unsigned)nb), s, a)));
+            a.src = tt;
+            a.dst = dd;
+            a.tab = T.d_P1i;
+            a.tab_stride = n1;
+            a.elt = nullptr;
+            a.ncols = n2;
+            TRY((launch_pass<XF_NEG_INV, false, false, false>("ntt_inv_pass1", T.a1, T.lazy, dim3(n2 / 16, (unsigned)L, (unsigned)nb), s, a)));
+        }
+    }
+    return CKKS_OK;
+}
+
+static int dev_alloc(const Tables &T, size_t words, u64 **out) {
+    *out = nullptr;
+    if (words == 0) words = 1;
+    CU(cudaMallocAsync((void **)out, words * sizeof(u64), T.stream));
+    return CKKS_OK;
+}
+static void dev_free(const Tables &T, void *p) {
+    if (p) cudaFreeAsync(p, T.stream);
+}
+static int ntt_inplace(const Tables &T, size_t L, size_t batch, u64 *d, bool inverse) {
+    u64 *tmp = nullptr;
+    if (T.path == 2) TRY(dev_alloc(T, batch * L * T.n, &tmp));
+    int rc = ntt_run(T, L, batch, d, tmp, inverse);
+    dev_free(T, tmp);
+    return rc;
+}
+
+// -------------------------------------------------------------------------------------------------
+// polynomials
+// -------------------------------------------------------------------------------------------------
+static int poly_new(ckks_ctx *ctx, size_t batch, bool ntt, ckks_poly **out) {
+    const Tables &T = *ctx->T;
+    CU(cudaSetDevice(T.device));
+    u64 *d;
+    TRY(dev_alloc(T, batch * ctx->L * T.n, &d));
+    ckks_poly *p = new ckks_poly();
+    p->magic = MAGIC_POLY;
+    p->ctx = ctx;
+    ctx_ref(ctx);
+    p->batch = batch;
+    p->d = d;
+    p->ntt = ntt;
+    *out = p;
+    return CKKS_OK;
+}
+static size_t poly_words(const ckks_poly *p) { return p->batch * p->ctx->L * p->ctx->T->n; }
+
+extern "C" int ckks_poly_free(ckks_poly *p) {
+    if (!ok_poly(p)) return CKKS_BAD_HANDLE;
+    cudaSetDevice(p->ctx->T->device);
+    dev_free(*p->ctx->T, p->d);
+    ckks_ctx *c = p->ctx;
+    p->magic = 0;
+    delete p;
+    ctx_unref(c);
+    return CKKS_OK;
+}
+extern "C" int ckks_poly_alloc(ckks_ctx *ctx, size_t batch, ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    TRY(poly_new(ctx, batch, false, out));
+    CU(cudaMemsetAsync((*out)->d, 0, poly_words(*out) * sizeof(u64), ctx->T->stream));
+    return CKKS_OK;
+}
+extern "C" int ckks_poly_clone(ckks_poly *p, ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_poly(p)) return CKKS_BAD_HANDLE;
+    TRY(poly_new(p->ctx, p->batch, p->ntt, out));
+    CU(cudaMemcpyAsync((*out)->d, p->d, poly_words(p) * sizeof(u64), cudaMemcpyDeviceToDevice, p->ctx->T->stream));
+    return CKKS_OK;
+}
+extern "C" size_t ckks_poly_batch(const ckks_poly *p) { return ok_poly(p) ? p->batch : 0; }
+extern "C" size_t ckks_poly_channel_count(const ckks_poly *p) { return ok_poly(p) ? p->ctx->L : 0; }
+extern "C" int ckks_poly_is_ntt_domain(const ckks_poly *p) { return ok_poly(p) ? (p->ntt ? 1 : 0) : -1; }
+
+extern "C" int ckks_poly_from_coeffs(ckks_ctx *ctx, size_t batch, const int64_t *coeffs, size_t clen, ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    const Tables &T = *ctx->T;
+    if (clen < T.n) return CKKS_SHORT_INPUT;
+    if (!coeffs && batch) return CKKS_BAD_ARGUMENT;
+    TRY(poly_new(ctx, batch, false, out));
+    if (batch == 0) return CKKS_OK;
+    i64 *dc;
+    CU(cudaMallocAsync((void **)&dc, batch * clen * sizeof(i64), T.stream));
+    CU(cudaMemcpyAsync(dc, coeffs, batch * clen * sizeof(i64), cudaMemcpyHostToDevice, T.stream));
+    EwArgs a = ew_args(T, ctx->L, batch);
+    KL("from_coeffs", (from_coeffs_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, dc, clen, (*out)->d)));
+    dev_free(T, dc);
+    CU(cudaStreamSynchronize(T.stream));  // `coeffs` may be pageable and reused by the caller
+    return CKKS_OK;
+}
+
+static int permute(const Tables &T, const u64 *src, u64 *dst, size_t words, bool to_internal) {
+    if (!words) return CKKS_OK;
+    KL("permute_ntt", (permute_ntt_kernel<<<(unsigned)((words + 255) / 256), 256, 0, T.stream>>>(src, dst, words, T.logn, T.a1,
+                                                                                               T.a2, to_internal ? 1 : 0)));
+    return CKKS_OK;
+}
+
+extern "C" int ckks_poly_from_channels(ckks_ctx *ctx, size_t batch, const uint64_t *ch, size_t nch, int in_ntt,
+                                       ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    if (nch != ctx->L) return CKKS_CHANNEL_COUNT_MISMATCH;  // poly.rs:77-82
+    if (!ch && batch) return CKKS_BAD_ARGUMENT;
+    const Tables &T = *ctx->T;
+    ckks_poly *p;
+    TRY(poly_new(ctx, batch, in_ntt != 0, &p));
+    size_t words = poly_words(p);
+    int rc = CKKS_OK;
+    if (words) {
+        int *flag = nullptr;
+        int hflag = 0;
+        u64 *stage = nullptr;
+        do {
+            if (cudaMallocAsync((void **)&flag, sizeof(int), T.stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "malloc"); break; }
+            cudaMemsetAsync(flag, 0, sizeof(int), T.stream);
+            u64 *land = p->d;
+            if (in_ntt) {
+                if ((rc = dev_alloc(T, words, &stage)) != CKKS_OK) break;
+                land = stage;
+            }
+            if (cudaMemcpyAsync(land, ch, words * sizeof(u64), cudaMemcpyHostToDevice, T.stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "h2d"); break; }
+            EwArgs a = ew_args(T, ctx->L, batch);
+            count_launch("check_reduced");
+            check_reduced_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, land, flag);
+            if (in_ntt && (rc = permute(T, stage, p->d, words, true)) != CKKS_OK) break;
+            cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, T.stream);
+            if (cudaStreamSynchronize(T.stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "sync"); break; }
+            if (hflag) rc = CKKS_NON_REDUCED_COEFFICIENT;  // poly.rs:83-93
+        } while (0);
+        dev_free(T, flag);
+        dev_free(T, stage);
+    }
+    if (rc != CKKS_OK) {
+        ckks_poly_free(p);
+        return rc;
+    }
+    *out = p;
+    return CKKS_OK;
+}
+
+extern "C" int ckks_poly_download(ckks_poly *p, uint64_t *out) {
+    if (!ok_poly(p)) return CKKS_BAD_HANDLE;
+    const Tables &T = *p->ctx->T;
+    size_t words = poly_words(p);
+    if (!words) return CKKS_OK;
+    if (!out) return CKKS_BAD_ARGUMENT;
+    CU(cudaSetDevice(T.device));
+    if (p->ntt) {
+        u64 *stage;
+        TRY(dev_alloc(T, words, &stage));
+        TRY(permute(T, p->d, stage, words, false));
+        CU(cudaMemcpyAsync(out, stage, words * sizeof(u64), cudaMemcpyDeviceToHost, T.stream));
+        dev_free(T, stage);
+    } else {
+        CU(cudaMemcpyAsync(out, p->d, words * sizeof(u64), cudaMemcpyDeviceToHost, T.stream));
+    }
+    CU(cudaStreamSynchronize(T.stream));
+    return CKKS_OK;
+}
+
+extern "C" int ckks_poly_to_ntt_domain(ckks_poly *p) {
+    if (!ok_poly(p)) return CKKS_BAD_HANDLE;
+    if (p->ntt) return CKKS_OK;  // poly.rs:137-139
+    CU(cudaSetDevice(p->ctx->T->device));
+    TRY(ntt_inplace(*p->ctx->T, p->ctx->L, p->batch, p->d, false));
+    p->ntt = true;
+    return CKKS_OK;
+}
+extern "C" int ckks_poly_to_coeff_domain(ckks_poly *p) {
+    if (!ok_poly(p)) return CKKS_BAD_HANDLE;
+    if (!p->ntt) return CKKS_OK;  // poly.rs:155-157
+    CU(cudaSetDevice(p->ctx->T->device));
+    TRY(ntt_inplace(*p->ctx->T, p->ctx->L, p->batch, p->d, true));
+    p->ntt = false;
+    return CKKS_OK;
+}
+
+// rhs may have batch 1 (broadcast) or a->batch.
+static int check_pair(const ckks_poly *a, const ckks_poly *b, bool allow_bcast) {
+    if (!ok_poly(a) || !ok_poly(b)) return CKKS_BAD_HANDLE;
+    if (!same_basis(a->ctx, b->ctx)) return CKKS_BASIS_MISMATCH;
+    if (a->ntt != b->ntt) return CKKS_DOMAIN_MISMATCH;
+    if (a->batch != b->batch && !(allow_bcast && b->batch == 1)) return CKKS_BATCH_MISMATCH;
+    return CKKS_OK;
+}
+template <int OP>
+static int ew_binary(const char *name, ckks_poly *a, const ckks_poly *b) {
+    const Tables &T = *a->ctx->T;
+    CU(cudaSetDevice(T.device));
+    EwArgs e = ew_args(T, a->ctx->L, a->batch);
+    if (!e.total) return CKKS_OK;
+    size_t bs = (b->batch == a->batch) ? e.poly : 0;
+    KL(name, (ew_binary_kernel<OP><<<ew_grid(e.total), 256, 0, T.stream>>>(e, a->d, b->d, bs)));
+    return CKKS_OK;
+}
+extern "C" int ckks_poly_add_assign(ckks_poly *a, const ckks_poly *b) {
+    TRY(check_pair(a, b, true));
+    return ew_binary<EW_ADD>("ew_add", a, b);
+}
+extern "C" int ckks_poly_sub_assign(ckks_poly *a, const ckks_poly *b) {
+    TRY(check_pair(a, b, true));
+    return ew_binary<EW_SUB>("ew_sub", a, b);
+}
+extern "C" int ckks_poly_neg(ckks_poly *a) {
+    if (!ok_poly(a)) return CKKS_BAD_HANDLE;
+    const Tables &T = *a->ctx->T;
+    CU(cudaSetDevice(T.device));
+    EwArgs e = ew_args(T, a->ctx->L, a->batch);
+    if (!e.total) return CKKS_OK;
+    KL("ew_neg", (ew_neg_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, a->d)));
+    return CKKS_OK;
+}
+extern "C" int ckks_poly_mul_assign(ckks_poly *a, const ckks_poly *b) {
+    TRY(check_pair(a, b, true));
+    const Tables &T = *a->ctx->T;
+    CU(cudaSetDevice(T.device));
+    if (a->ntt) return ew_binary<EW_MUL>("ew_mul", a, b);  // poly.rs:297-306
+    // poly.rs:307-329: forward both, pointwise, inverse; result in the coefficient domain.
+    ckks_poly *r;
+    TRY(ckks_poly_clone(const_cast<ckks_poly *>(b), &r));
+    int rc = ckks_poly_to_ntt_domain(r);
+    if (rc == CKKS_OK) rc = ckks_poly_to_ntt_domain(a);
+    if (rc == CKKS_OK) rc = ew_binary<EW_MUL>("ew_mul", a, r);
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(a);
+    ckks_poly_free(r);
+    return rc;
+}
+
+extern "C" int ckks_poly_mod_drop_last(const ckks_poly *p, ckks_ctx *child, ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_poly(p) || !ok_ctx(child)) return CKKS_BAD_HANDLE;
+    if (child->T.get() != p->ctx->T.get() || child->L > p->ctx->L) return CKKS_BASIS_MISMATCH;
+    if (child->L == 0) return CKKS_INVALID_MOD_DROP;
+    const Tables &T = *child->T;
+    CU(cudaSetDevice(T.device));
+    TRY(poly_new(child, p->batch, p->ntt, out));
+    if (p->batch)
+        CU(cudaMemcpy2DAsync((*out)->d, child->L * T.n * sizeof(u64), p->d, p->ctx->L * T.n * sizeof(u64),
+                             child->L * T.n * sizeof(u64), p->batch, cudaMemcpyDeviceToDevice, T.stream));
+    return CKKS_OK;
+}
+
+static int rescale_dev(const Tables &T, size_t L, size_t batch, const u64 *src, u64 *dst) {
+    EwArgs e = ew_args(T, L - 1, batch);
+    if (!e.total) return CKKS_OK;
+    KL("rescale", (rescale_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, src, dst, T.d_qlinv + (L - 1) * T.L)));
+    return CKKS_OK;
+}
+
+extern "C" int ckks_poly_rescale_into(const ckks_poly *p, ckks_ctx *child, ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_poly(p) || !ok_ctx(child)) return CKKS_BAD_HANDLE;
+    if (p->ctx->L < 2) return CKKS_INVALID_MOD_DROP;  // poly.rs:191-197
+    if (child->T.get() != p->ctx->T.get() || child->L + 1 != p->ctx->L) return CKKS_BASIS_MISMATCH;
+    const Tables &T = *child->T;
+    CU(cudaSetDevice(T.device));
+    const u64 *src = p->d;
+    ckks_poly *tmp = nullptr;
+    if (p->ntt) {  // poly.rs:199-208
+        TRY(ckks_poly_clone(const_cast<ckks_poly *>(p), &tmp));
+        int rc = ckks_poly_to_coeff_domain(tmp);
+        if (rc != CKKS_OK) {
+            ckks_poly_free(tmp);
+            return rc;
+        }
+        src = tmp->d;
+    }
+    int rc = poly_new(child, p->batch, false, out);
+    if (rc == CKKS_OK) rc = rescale_dev(T, p->ctx->L, p->batch, src, (*out)->d);
+    if (tmp) ckks_poly_free(tmp);
+    if (rc != CKKS_OK && *out) {
+        ckks_poly_free(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+static u64 inv_mod_pow2(u64 e, u64 m) {  // e odd, m a power of two
+    u64 x = e;
+    for (int i = 0; i < 6; ++i) x *= 2 - e * x;
+    return x & (m - 1);
+}
+
+extern "C" int ckks_poly_automorphism(const ckks_poly *p, uint64_t exponent, ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_poly(p)) return CKKS_BAD_HANDLE;
+    const Tables &T = *p->ctx->T;
+    CU(cudaSetDevice(T.device));
+    const u64 two_n = 2 * T.n;
+    const u64 e = exponent % two_n;
+    if (e == 0) return ckks_poly_clone(const_cast<ckks_poly *>(p), out);  // poly.rs:508-511
+    const u64 *src = p->d;
+    ckks_poly *tmp = nullptr;
+    if (p->ntt) {  // poly.rs:494-503
+        TRY(ckks_poly_clone(const_cast<ckks_poly *>(p), &tmp));
+        int rc = ckks_poly_to_coeff_domain(tmp);
+        if (rc != CKKS_OK) {
+            ckks_poly_free(tmp);
+            return rc;
+        }
+        src = tmp->d;
+    }
+    int rc = poly_new(p->ctx, p->batch, false, out);
+    EwArgs a = ew_args(T, p->ctx->L, p->batch);
+    if (rc == CKKS_OK && a.total) {
+        if (e & 1) {
+            count_launch("automorphism");
+            automorphism_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, (*out)->d, e, inv_mod_pow2(e, two_n));
+        } else {
+            unsigned *win = nullptr;
+            if (cudaMallocAsync((void **)&win, a.total * sizeof(unsigned), T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "malloc");
+            if (rc == CKKS_OK) {
+                cudaMemsetAsync(win, 0, a.total * sizeof(unsigned), T.stream);
+                count_launch("automorphism_even_mark");
+                automorphism_even_mark_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, win, e);
+                count_launch("automorphism_even_fill");
+                automorphism_even_fill_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, win, (*out)->d, e);
+                dev_free(T, win);
+            }
+        }
+        if (rc == CKKS_OK && cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "automorphism");
+    }
+    if (tmp) ckks_poly_free(tmp);
+    if (rc != CKKS_OK && *out) {
+        ckks_poly_free(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+static u64 rot_exponent(u64 n, int32_t k) {
+    u64 r = k >= 0 ? (u64)k : (u64)(-(int64_t)k);
+    return hm::pow_mod(5, r, 2 * n);  // poly.rs:549-552
+}
+extern "C" int ckks_poly_rotate_slots(const ckks_poly *p, int32_t k, ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_poly(p)) return CKKS_BAD_HANDLE;
+    const u64 n = p->ctx->T->n;
+    u64 e = rot_exponent(n, k);
+    if (k >= 0) return ckks_poly_automorphism(p, e, out);
+    ckks_poly *mid;  // poly.rs:556-566: automorphism(5^|k|) then automorphism(2N-1)
+    TRY(ckks_poly_automorphism(p, e, &mid));
+    int rc = ckks_poly_automorphism(mid, 2 * n - 1, out);
+    ckks_poly_free(mid);
+    return rc;
+}
+
+extern "C" int ckks_poly_to_coeffs(const ckks_poly *p, int64_t *out) {
+    if (!ok_poly(p)) return CKKS_BAD_HANDLE;
+    const Tables &T = *p->ctx->T;
+    const size_t L = p->ctx->L, n = T.n;
+    if (!p->batch) return CKKS_OK;
+    if (!out) return CKKS_BAD_ARGUMENT;
+    ckks_poly *c;
+    TRY(ckks_poly_clone(const_cast<ckks_poly *>(p), &c));
+    int rc = ckks_poly_to_coeff_domain(c);
+    std::vector<u64> h(poly_words(p));
+    if (rc == CKKS_OK) rc = ckks_poly_download(c, (uint64_t *)h.data());
+    ckks_poly_free(c);
+    TRY(rc);
+    // The centred CRT (basis.rs:158-180) is the decode side of the path; it runs on the host.
+    std::vector<u64> mod(T.moduli.begin(), T.moduli.begin() + L), res(L);
+    for (size_t b = 0; b < p->batch; ++b)
+        for (size_t i = 0; i < n; ++i) {
+            for (size_t l = 0; l < L; ++l) res[l] = h[(b * L + l) * n + i];
+            out[b * n + i] = hm::reconstruct_centered(mod, res.data());
+        }
+    return CKKS_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// gadget keys
+// -------------------------------------------------------------------------------------------------
+static int ksk_new(ckks_ctx *ctx, ckks_ksk **out) {
+    const Tables &T = *ctx->T;
+    size_t words = ctx->L * ctx->L * T.n;
+    u64 *a, *b;
+    TRY(dev_alloc(T, words, &a));
+    TRY(dev_alloc(T, words, &b));
+    ckks_ksk *k = new ckks_ksk();
+    k->magic = MAGIC_KSK;
+    k->ctx = ctx;
+    ctx_ref(ctx);
+    k->a = a;
+    k->b = b;
+    *out = k;
+    return CKKS_OK;
+}
+extern "C" int ckks_ksk_free(ckks_ksk *k) {
+    if (!ok_ksk(k)) return CKKS_BAD_HANDLE;
+    cudaSetDevice(k->ctx->T->device);
+    dev_free(*k->ctx->T, k->a);
+    dev_free(*k->ctx->T, k->b);
+    ckks_ctx *c = k->ctx;
+    k->magic = 0;
+    delete k;
+    ctx_unref(c);
+    return CKKS_OK;
+}
+extern "C" int ckks_ksk_upload(ckks_ctx *ctx, const uint64_t *a, const uint64_t *b, ckks_ksk **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    if (!a || !b) return CKKS_BAD_ARGUMENT;
+    const Tables &T = *ctx->T;
+    CU(cudaSetDevice(T.device));
+    ckks_ksk *k;
+    TRY(ksk_new(ctx, &k));
+    size_t words = ctx->L * ctx->L * T.n;
+    int rc = CKKS_OK;
+    if (cudaMemcpyAsync(k->a, a, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess ||
+        cudaMemcpyAsync(k->b, b, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "ksk h2d");
+    if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, false);
+    if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, false);
+    if (rc == CKKS_OK && cudaStreamSynchronize(T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ksk sync");
+    if (rc != CKKS_OK) {
+        ckks_ksk_free(k);
+        return rc;
+    }
+    *out = k;
+    return CKKS_OK;
+}
+extern "C" int ckks_ksk_from_polys(const ckks_poly *a, const ckks_poly *b, ckks_ksk **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_poly(a) || !ok_poly(b)) return CKKS_BAD_HANDLE;
+    if (!same_basis(a->ctx, b->ctx)) return CKKS_BASIS_MISMATCH;
+    ckks_ctx *ctx = a->ctx;
+    if (a->batch != ctx->L || b->batch != ctx->L) return CKKS_BATCH_MISMATCH;
+    const Tables &T = *ctx->T;
+    CU(cudaSetDevice(T.device));
+    ckks_ksk *k;
+    TRY(ksk_new(ctx, &k));
+    size_t words = ctx->L * ctx->L * T.n;
+    cudaMemcpyAsync(k->a, a->d, words * 8, cudaMemcpyDeviceToDevice, T.stream);
+    cudaMemcpyAsync(k->b, b->d, words * 8, cudaMemcpyDeviceToDevice, T.stream);
+    int rc = CKKS_OK;
+    if (!a->ntt) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, false);
+    if (rc == CKKS_OK && !b->ntt) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, false);
+    if (rc != CKKS_OK) {
+        ckks_ksk_free(k);
+        return rc;
+    }
+    *out = k;
+    return CKKS_OK;
+}
+
+// Copy limb i of `target` (batch 1) into limb i of polynomial i of `dst` (batch L), adding.
+__global__ void add_gadget_target_kernel(EwArgs a /* batch L */, u64 *__restrict__ dst, const u64 *__restrict__ target) {
+    const size_t n = (size_t)1 << a.logn;
+    size_t total = (size_t)a.L * n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        size_t i = t >> a.logn, k = t & (n - 1);
+        u64 q = a.lc[i].q;
+        size_t off = i * a.poly + i * n + k;
+        dst[off] = addmod(dst[off], target[i * n + k], q);
+    }
+}
+extern "C" int ckks_gen_gadget_key_b(const ckks_poly *s, const ckks_poly *target, const ckks_poly *a, const ckks_poly *e,
+                                     ckks_poly **out_b) {
+    if (!out_b) return CKKS_BAD_ARGUMENT;
+    *out_b = nullptr;
+    if (!ok_poly(s) || !ok_poly(target) || !ok_poly(a) || !ok_poly(e)) return CKKS_BAD_HANDLE;
+    ckks_ctx *ctx = s->ctx;
+    if (!same_basis(ctx, target->ctx) || !same_basis(ctx, a->ctx) || !same_basis(ctx, e->ctx)) return CKKS_BASIS_MISMATCH;
+    if (s->ntt || target->ntt || a->ntt || e->ntt) return CKKS_DOMAIN_MISMATCH;
+    if (s->batch != 1 || target->batch != 1 || a->batch != ctx->L || e->batch != ctx->L) return CKKS_BATCH_MISMATCH;
+    const Tables &T = *ctx->T;
+    // engine.rs:318-327: b_i = a_i.clone(); b_i *= s; b_i = -b_i; b_i += e_i; b_i += plain_poly
+    ckks_poly *b;
+    TRY(ckks_poly_clone(const_cast<ckks_poly *>(a), &b));
+    int rc = ckks_poly_mul_assign(b, s);
+    if (rc == CKKS_OK) rc = ckks_poly_neg(b);
+    if (rc == CKKS_OK) rc = ckks_poly_add_assign(b, e);
+    if (rc == CKKS_OK) {
+        EwArgs ea = ew_args(T, ctx->L, ctx->L);
+        count_launch("add_gadget_target");
+        add_gadget_target_kernel<<<ew_grid((size_t)ctx->L * T.n), 256, 0, T.stream>>>(ea, b->d, target->d);
+        if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "add_gadget_target");
+    }
+    if (rc != CKKS_OK) {
+        ckks_poly_free(b);
+        return rc;
+    }
+    *out_b = b;
+    return CKKS_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// ciphertext operations
+// -------------------------------------------------------------------------------------------------
+// Gadget key-switch accumulate (engine.rs:505-528 / :429-452):
+//   acc0 += sum_i NTT(alpha_i) * key_b[i],  acc1 += sum_i NTT(alpha_i) * key_a[i]   (NTT domain)
+// `digits`: [batch][L][N] coefficient domain (d2 or the rotated c1).
+static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u64 *digits, const ckks_ksk *key, u64 *acc0,
+                                u64 *acc1) {
+    EwArgs e = ew_args(T, L, batch);
+    if (!e.total) return CKKS_OK;
+    u64 *alpha, *tmp = nullptr;
+    TRY(dev_alloc(T, e.total, &alpha));
+    if (T.path == 2) TRY(dev_alloc(T, e.total, &tmp));
+    int rc = CKKS_OK;
+    for (size_t i = 0; i < L && rc == CKKS_OK; ++i) {
+        count_launch("digit_broadcast");
+        digit_broadcast_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, digits, alpha, (int)i);
+        rc = ntt_run(T, L, batch, alpha, tmp, false);
+        if (rc != CKKS_OK) break;
+        count_launch("ks_mac");
+        ks_mac_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, alpha, key->b + i * e.poly, key->a + i * e.poly, acc0, acc1);
+        if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "keyswitch");
+    }
+    dev_free(T, alpha);
+    dev_free(T, tmp);
+    return rc;
+}
+
+static int check_ct(const ckks_poly *c0, const ckks_poly *c1) {
+    if (!ok_poly(c0) || !ok_poly(c1)) return CKKS_BAD_HANDLE;
+    if (!same_basis(c0->ctx, c1->ctx)) return CKKS_BASIS_MISMATCH;
+    if (c0->batch != c1->batch) return CKKS_BATCH_MISMATCH;
+    if (c0->ntt != c1->ntt) return CKKS_DOMAIN_MISMATCH;
+    return CKKS_OK;
+}
+static void free2(ckks_poly *a, ckks_poly *b) {
+    if (a) ckks_poly_free(a);
+    if (b) ckks_poly_free(b);
+}
+
+extern "C" int ckks_ct_add(const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1, ckks_poly **c0,
+                           ckks_poly **c1) {
+    if (!c0 || !c1) return CKKS_BAD_ARGUMENT;
+    *c0 = *c1 = nullptr;
+    TRY(check_ct(a0, a1));
+    TRY(check_ct(b0, b1));
+    TRY(check_pair(a0, b0, false));
+    ckks_poly *r0 = nullptr, *r1 = nullptr;
+    int rc = ckks_poly_clone(const_cast<ckks_poly *>(a0), &r0);
+    if (rc == CKKS_OK) rc = ckks_poly_clone(const_cast<ckks_poly *>(a1), &r1);
+    if (rc == CKKS_OK) rc = ckks_poly_add_assign(r0, b0);
+    if (rc == CKKS_OK) rc = ckks_poly_add_assign(r1, b1);
+    if (rc != CKKS_OK) {
+        free2(r0, r1);
+        return rc;
+    }
+    *c0 = r0;
+    *c1 = r1;
+    return CKKS_OK;
+}
+
+// mul_ciphertexts_gadget with the minimal exact schedule: 4L forward transforms of the inputs,
+// NTT-domain tensor, L inverse (d2), L(L) digit transforms, NTT-domain accumulation, 2L inverse.
+// Every step is exact in Z_q, so the coefficient-domain output words equal the reference's.
+// On success *c0,*c1 are in the NTT domain if keep_ntt (internal use by the fused rescale) else coefficient.
+static int ct_mul_relin_impl(const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1,
+                             const ckks_ksk *rlk, ckks_poly **c0, ckks_poly **c1) {
+    *c0 = *c1 = nullptr;
+    TRY(check_ct(a0, a1));
+    TRY(check_ct(b0, b1));
+    TRY(check_pair(a0, b0, false));
+    if (!ok_ksk(rlk)) return CKKS_BAD_HANDLE;
+    if (!same_basis(a0->ctx, rlk->ctx)) return CKKS_BASIS_MISMATCH;
+    if (a0->ntt) return CKKS_DOMAIN_MISMATCH;  // the engine works on coefficient-domain ciphertexts
+    const Tables &T = *a0->ctx->T;
+    const size_t L = a0->ctx->L, batch = a0->batch;
+    CU(cudaSetDevice(T.device));
+    ckks_poly *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr;
+    int rc = ckks_poly_clone(const_cast<ckks_poly *>(a0), &A0);
+    if (rc == CKKS_OK) rc = ckks_poly_clone(const_cast<ckks_poly *>(a1), &A1);
+    if (rc == CKKS_OK) rc = ckks_poly_clone(const_cast<ckks_poly *>(b0), &B0);
+    if (rc == CKKS_OK) rc = ckks_poly_clone(const_cast<ckks_poly *>(b1), &B1);
+    if (rc == CKKS_OK) rc = ckks_poly_to_ntt_domain(A0);
+    if (rc == CKKS_OK) rc = ckks_poly_to_ntt_domain(A1);
+    if (rc == CKKS_OK) rc = ckks_poly_to_ntt_domain(B0);
+    if (rc == CKKS_OK) rc = ckks_poly_to_ntt_domain(B1);
+    EwArgs e = ew_args(T, L, batch);
+    if (rc == CKKS_OK && e.total) {
+        // d0 -> A0, d1 -> A1, d2 -> B0
+        count_launch("tensor");
+        tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, A0->d, A1->d, B0->d, B1->d, A0->d, A1->d, B0->d);
+        if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "tensor");
+    }
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(B0);  // engine.rs:493
+    if (rc == CKKS_OK) rc = keyswitch_accumulate(T, L, batch, B0->d, rlk, A0->d, A1->d);
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(A0);
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(A1);
+    free2(B0, B1);
+    if (rc != CKKS_OK) {
+        free2(A0, A1);
+        return rc;
+    }
+    *c0 = A0;
+    *c1 = A1;
+    return CKKS_OK;
+}
+extern "C" int ckks_ct_mul_relin(const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1,
+                                 const ckks_ksk *rlk, ckks_poly **c0, ckks_poly **c1) {
+    if (!c0 || !c1) return CKKS_BAD_ARGUMENT;
+    return ct_mul_relin_impl(a0, a1, b0, b1, rlk, c0, c1);
+}
+
+static uint32_t bit_length(u64 q) { return 64 - (uint32_t)__builtin_clzll(q); }
+
+extern "C" int ckks_ct_rescale(const ckks_poly *c0, const ckks_poly *c1, ckks_ctx *child, ckks_poly **o0, ckks_poly **o1,
+                               uint32_t *bits) {
+    if (!o0 || !o1) return CKKS_BAD_ARGUMENT;
+    *o0 = *o1 = nullptr;
+    TRY(check_ct(c0, c1));
+    if (bits) *bits = bit_length(c0->ctx->T->moduli[c0->ctx->L - 1]);  // engine.rs:266-270
+    ckks_poly *r0 = nullptr, *r1 = nullptr;
+    int rc = ckks_poly_rescale_into(c0, child, &r0);
+    if (rc == CKKS_OK) rc = ckks_poly_rescale_into(c1, child, &r1);
+    if (rc != CKKS_OK) {
+        free2(r0, r1);
+        return rc;
+    }
+    *o0 = r0;
+    *o1 = r1;
+    return CKKS_OK;
+}
+extern "C" int ckks_ct_mul_relin_rescale(const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1,
+                                         const ckks_ksk *rlk, ckks_ctx *child, ckks_poly **o0, ckks_poly **o1) {
+    if (!o0 || !o1) return CKKS_BAD_ARGUMENT;
+    *o0 = *o1 = nullptr;
+    if (!ok_poly(a0) || !ok_ctx(child)) return CKKS_BAD_HANDLE;
+    if (a0->ctx->L < 2) return CKKS_INVALID_MOD_DROP;
+    if (child->T.get() != a0->ctx->T.get() || child->L + 1 != a0->ctx->L) return CKKS_BASIS_MISMATCH;
+    ckks_poly *m0 = nullptr, *m1 = nullptr;
+    TRY(ct_mul_relin_impl(a0, a1, b0, b1, rlk, &m0, &m1));
+    int rc = ckks_ct_rescale(m0, m1, child, o0, o1, nullptr);
+    free2(m0, m1);
+    return rc;
+}
+
+extern "C" int ckks_ct_rotate(const ckks_poly *c0, const ckks_poly *c1, const ckks_ksk *rotk, int32_t k, ckks_poly **o0,
+                              ckks_poly **o1) {
+    if (!o0 || !o1) return CKKS_BAD_ARGUMENT;
+    *o0 = *o1 = nullptr;
+    TRY(check_ct(c0, c1));
+    if (!ok_ksk(rotk)) return CKKS_BAD_HANDLE;
+    if (!same_basis(c0->ctx, rotk->ctx)) return CKKS_BASIS_MISMATCH;
+    const Tables &T = *c0->ctx->T;
+    const size_t L = c0->ctx->L, batch = c0->batch;
+    CU(cudaSetDevice(T.device));
+    ckks_poly *r0 = nullptr, *r1 = nullptr, *k0 = nullptr, *k1 = nullptr;
+    int rc = ckks_poly_rotate_slots(c0, k, &r0);  // engine.rs:417-419
+    if (rc == CKKS_OK) rc = ckks_poly_rotate_slots(c1, k, &r1);
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(r1);
+    if (rc == CKKS_OK) rc = ckks_poly_alloc(c0->ctx, batch, &k0);
+    if (rc == CKKS_OK) rc = ckks_poly_alloc(c0->ctx, batch, &k1);
+    if (rc == CKKS_OK) {
+        k0->ntt = k1->ntt = true;  // zero is zero in either domain
+        rc = keyswitch_accumulate(T, L, batch, r1->d, rotk, k0->d, k1->d);
+    }
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(k0);
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(k1);
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(r0);
+    if (rc == CKKS_OK) rc = ckks_poly_add_assign(r0, k0);  // engine.rs:454-455
+    free2(r1, k0);
+    if (rc != CKKS_OK) {
+        free2(r0, k1);
+        return rc;
+    }
+    *o0 = r0;
+    *o1 = k1;
+    return CKKS_OK;
+}
+
+extern "C" int ckks_ct_encrypt(const ckks_poly *pk_b, const ckks_poly *pk_a, const ckks_poly *u, const ckks_poly *e0,
+                               const ckks_poly *e1, const ckks_poly *m, ckks_poly **c0, ckks_poly **c1) {
+    if (!c0 || !c1) return CKKS_BAD_ARGUMENT;
+    *c0 = *c1 = nullptr;
+    if (!ok_poly(pk_b) || !ok_poly(pk_a) || !ok_poly(u) || !ok_poly(e0) || !ok_poly(e1) || !ok_poly(m)) return CKKS_BAD_HANDLE;
+    // engine.rs:96-104: c0 = pk.b.clone(); c0 *= u; c0 += e0; c0 += m;  c1 = pk.a.clone(); c1 *= u; c1 += e1
+    ckks_poly *r0 = nullptr, *r1 = nullptr;
+    int rc = ckks_poly_clone(const_cast<ckks_poly *>(u), &r0);
+    if (rc == CKKS_OK) rc = ckks_poly_mul_assign(r0, pk_b);  // commutative; lets pk broadcast over the batch
+    if (rc == CKKS_OK) rc = ckks_poly_add_assign(r0, e0);
+    if (rc == CKKS_OK) rc = ckks_poly_add_assign(r0, m);
+    if (rc == CKKS_OK) rc = ckks_poly_clone(const_cast<ckks_poly *>(u), &r1);
+    if (rc == CKKS_OK) rc = ckks_poly_mul_assign(r1, pk_a);
+    if (rc == CKKS_OK) rc = ckks_poly_add_assign(r1, e1);
+    if (rc != CKKS_OK) {
+        free2(r0, r1);
+        return rc;
+    }
+    *c0 = r0;
+    *c1 = r1;
+    return CKKS_OK;
+}
+extern "C" int ckks_ct_decrypt(const ckks_poly *c0, const ckks_poly *c1, const ckks_poly *s, ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    TRY(check_ct(c0, c1));
+    if (!ok_poly(s)) return CKKS_BAD_HANDLE;
+    ckks_poly *r = nullptr;  // engine.rs:121-124: c1 * s + c0
+    int rc = ckks_poly_clone(const_cast<ckks_poly *>(c1), &r);
+    if (rc == CKKS_OK) rc = ckks_poly_mul_assign(r, s);
+    if (rc == CKKS_OK) rc = ckks_poly_add_assign(r, c0);
+    if (rc != CKKS_OK) {
+        if (r) ckks_poly_free(r);
+        return rc;
+    }
+    *out = r;
+    return CKKS_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-buffer entry points
+// -------------------------------------------------------------------------------------------------
+extern "C" int ckks_host_alloc(size_t bytes, void **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return CKKS_OK;
+}
+extern "C" int ckks_host_free(void *p) {
+    if (p) CU(cudaFreeHost(p));
+    return CKKS_OK;
+}
+
+static size_t host_chunk(const Tables &T, size_t L, size_t batch) {
+    // about 256 MiB of input per component and chunk
+    size_t per = L * T.n * sizeof(u64);
+    size_t c = ((size_t)256 << 20) / per;
+    if (c < 1) c = 1;
+    return c < batch ? c : batch;
+}
+static int upload_poly(ckks_ctx *ctx, size_t batch, const u64 *h, ckks_poly **out) {
+    TRY(poly_new(ctx, batch, false, out));
+    CU(cudaMemcpyAsync((*out)->d, h, poly_words(*out) * 8, cudaMemcpyHostToDevice, ctx->T->stream));
+    return CKKS_OK;
+}
+
+extern "C" int ckks_ct_mul_relin_rescale_host(ckks_ctx *ctx, ckks_ctx *child, const ckks_ksk *rlk, size_t batch,
+                                              const uint64_t *a0, const uint64_t *a1, const uint64_t *b0, const uint64_t *b1,
+                                              uint64_t *o0, uint64_t *o1) {
+    if (!ok_ctx(ctx) || !ok_ctx(child) || !ok_ksk(rlk)) return CKKS_BAD_HANDLE;
+    if (batch && (!a0 || !a1 || !b0 || !b1 || !o0 || !o1)) return CKKS_BAD_ARGUMENT;
+    const Tables &T = *ctx->T;
+    CU(cudaSetDevice(T.device));
+    const size_t L = ctx->L, wi = L * T.n, wo = (L - 1) * T.n;
+    const size_t chunk = host_chunk(T, L, batch);
+    for (size_t s = 0; s < batch; s += chunk) {
+        size_t nb = batch - s < chunk ? batch - s : chunk;
+        ckks_poly *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr, *R0 = nullptr, *R1 = nullptr;
+        int rc = upload_poly(ctx, nb, (const u64 *)a0 + s * wi, &A0);
+        if (rc == CKKS_OK) rc = upload_poly(ctx, nb, (const u64 *)a1 + s * wi, &A1);
+        if (rc == CKKS_OK) rc = upload_poly(ctx, nb, (const u64 *)b0 + s * wi, &B0);
+        if (rc == CKKS_OK) rc = upload_poly(ctx, nb, (const u64 *)b1 + s * wi, &B1);
+        if (rc == CKKS_OK) rc = ckks_ct_mul_relin_rescale(A0, A1, B0, B1, rlk, child, &R0, &R1);
+        if (rc == CKKS_OK && cudaMemcpyAsync((u64 *)o0 + s * wo, R0->d, nb * wo * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "d2h");
+        if (rc == CKKS_OK && cudaMemcpyAsync((u64 *)o1 + s * wo, R1->d, nb * wo * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "d2h");
+        free2(A0, A1);
+        free2(B0, B1);
+        free2(R0, R1);
+        TRY(rc);
+    }
+    CU(cudaStreamSynchronize(T.stream));
+    return CKKS_OK;
+}
+
+extern "C" int ckks_ct_rotate_host(ckks_ctx *ctx, const ckks_ksk *rotk, int32_t k, size_t batch, const uint64_t *c0,
+                                   const uint64_t *c1, uint64_t *o0, uint64_t *o1) {
+    if (!ok_ctx(ctx) || !ok_ksk(rotk)) return CKKS_BAD_HANDLE;
+    if (batch && (!c0 || !c1 || !o0 || !o1)) return CKKS_BAD_ARGUMENT;
+    const Tables &T = *ctx->T;
+    CU(cudaSetDevice(T.device));
+    const size_t w = ctx->L * T.n;
+    const size_t chunk = host_chunk(T, ctx->L, batch);
+    for (size_t s = 0; s < batch; s += chunk) {
+        size_t nb = batch - s < chunk ? batch - s : chunk;
+        ckks_poly *C0 = nullptr, *C1 = nullptr, *R0 = nullptr, *R1 = nullptr;
+        int rc = upload_poly(ctx, nb, (const u64 *)c0 + s * w, &C0);
+        if (rc == CKKS_OK) rc = upload_poly(ctx, nb, (const u64 *)c1 + s * w, &C1);
+        if (rc == CKKS_OK) rc = ckks_ct_rotate(C0, C1, rotk, k, &R0, &R1);
+        if (rc == CKKS_OK && cudaMemcpyAsync((u64 *)o0 + s * w, R0->d, nb * w * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "d2h");
+        if (rc == CKKS_OK && cudaMemcpyAsync((u64 *)o1 + s * w, R1->d, nb * w * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "d2h");
+        free2(C0, C1);
+        free2(R0, R1);
+        TRY(rc);
+    }
+    CU(cudaStreamSynchronize(T.stream));
+    return CKKS_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// integer-pipe peak
+// -------------------------------------------------------------------------------------------------
+extern "C" double ckks_bench_modmul_peak(int device, int iters) {
+    if (ckks_device_count() <= device) return 0.0;
+    if (cudaSetDevice(device) != cudaSuccess) return 0.0;
+    u64 *d;
+    if (cudaMalloc((void **)&d, 64) != cudaSuccess) return 0.0;
+    const u64 q = 2305843009211596801ull;  // a 61-bit NTT prime
+    tw_t t = mk_tw(1234567890123456789ull % q, q);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = 148 * 8, threads = 256;
+    modmul_peak_kernel<<<blocks, threads>>>(d, 16, q, t);
+    cudaEventRecord(e0);
+    count_launch("modmul_peak");
+    modmul_peak_kernel<<<blocks, threads>>>(d, iters, q, t);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess || ms <= 0) return 0.0;
+    return (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
+}

@@ -1,0 +1,56 @@
+// context.hpp -- device-side state behind the opaque handles of include/ckks_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "modarith.cuh"
+
+// Everything derived from (N, moduli): the device image of RnsBasis<N> + NttTable<N>
+// (basis.rs:6-17, 91-94).  Shared by a context and all contexts obtained from it with drop_last.
+struct Tables {
+    int device = 0;
+    u64 n = 0;
+    int logn = 0;
+    int path = 0;  // 1 = small single-CTA NTT, 2 = four-step
+    int a1 = 0, a2 = 0;  // four-step: N = 2^a1 * 2^a2 (small path: a1 = logn, a2 = 0)
+    bool lazy = true;    // all q < 2^62
+    bool digit_reduce = true;  // key-switch digits need `% q_j` before the lazy NTT
+    size_t L = 0;
+    std::vector<u64> moduli, psi;
+    LimbConst *d_lc = nullptr;
+    // small path
+    tw_t *d_psi = nullptr, *d_psi_inv = nullptr, *d_ninv = nullptr;
+    // four-step
+    tw_t *d_P1 = nullptr, *d_P1i = nullptr, *d_W2 = nullptr, *d_W2i = nullptr, *d_TT = nullptr, *d_TTi = nullptr;
+    size_t w2_stride = 1;
+    // rescale: qlinv[last][i] = q_last^-1 mod q_i (Shoup pair), [L][L]
+    tw_t *d_qlinv = nullptr;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    ~Tables();
+};
+
+struct ckks_ctx {
+    uint32_t magic;
+    std::shared_ptr<Tables> T;
+    size_t L;  // limbs visible through this context (prefix of T->moduli)
+    std::atomic<int> refs;
+};
+struct ckks_poly {
+    uint32_t magic;
+    ckks_ctx *ctx;
+    size_t batch;
+    u64 *d;  // [batch][L][N]
+    bool ntt;
+};
+struct ckks_ksk {
+    uint32_t magic;
+    ckks_ctx *ctx;
+    u64 *a, *b;  // [digit][limb][N], NTT domain, device-internal order
+};
+
+enum : uint32_t { MAGIC_CTX = 0x434b4358u, MAGIC_POLY = 0x434b504cu, MAGIC_KSK = 0x434b4b53u };

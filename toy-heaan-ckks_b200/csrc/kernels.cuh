@@ -1,0 +1,340 @@
+// kernels.cuh -- CUDA kernels (sm_100a) of the RNS-NTT hot path.  Each kernel cites the reference
+// code whose effect it reproduces (paths relative to the reference repository root).
+#pragma once
+#include "ntt_tile.cuh"
+
+// Data layout everywhere: [batch][limb][N] u64, limb-major like the reference's Vec<[u64; N]>
+// (poly.rs:26-30).  Coefficient-domain words are in natural order.  NTT-domain words are in the
+// device-internal order of the context's NTT path (see permute_ntt_kernel).
+
+// =================================================================================================
+// Four-step NTT passes
+// =================================================================================================
+struct PassArgs {
+    const u64 *src;
+    u64 *dst;
+    const LimbConst *lc;  // [L]
+    const tw_t *tab;      // small per-limb twiddle table, tab_stride entries per limb
+    const tw_t *elt;      // per-element table (N entries per limb), or null
+    size_t tab_stride;
+    int L;          // limbs per polynomial in src/dst
+    unsigned ncols;  // columns (= stride of the transform dimension, in words)
+    size_t N;
+};
+
+// One pass: a 2^A-point transform along the strided dimension of a [2^A][ncols] limb, for a tile of
+// C adjacent columns.  grid = (ncols / C, L, batch), block = C * 2^(A-E).
+//   PREMUL   : multiply by elt[idx][col] on load   (four-step twiddle, forward)
+//   POSTMUL  : multiply by elt[idx][col] on store  (four-step twiddle and 1/N, inverse)
+//   TRANSPOSE: store the tile transposed, dst[col][idx]  (lazy values, consumed by the next pass)
+//              otherwise store in place dst[idx][col] as canonical representatives.
+// Forward  to_ntt_domain  (poly.rs:136-148, 574-580) = <NEG_FWD,TRANSPOSE> then <CYC_FWD,PREMUL>.
+// Inverse  to_coeff_domain(poly.rs:154-166, 582-591) = <CYC_INV,POSTMUL,TRANSPOSE> then <NEG_INV>.
+template <int KIND, int A, int E, int C, bool LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE>
+__global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a) {
+    typedef TileGeom<A, E> GM;
+    constexpr int CP = C + 1;
+    constexpr int NT = C * GM::G;
+    constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);
+    extern __shared__ u64 sm[];
+    const int tid = threadIdx.x;
+    const int c = tid % C, g = tid / C;
+    const int limb = blockIdx.y;
+    const size_t c0 = (size_t)blockIdx.x * C;
+    const size_t base = ((size_t)blockIdx.z * a.L + limb) * a.N;
+    const LimbConst m = a.lc[limb];
+    const u64 q = m.q, q2 = m.q2;
+    const tw_t *tab = a.tab + (size_t)limb * a.tab_stride;
+    const tw_t *elt = (PREMUL || POSTMUL) ? a.elt + (size_t)limb * a.N : nullptr;
+
+    u64 v[1 << E];
+    constexpr int lo_in = FWD ? GM::lo(0) : GM::lo(GM::NS - 1);
+    constexpr int lo_out = FWD ? GM::lo(GM::NS - 1) : GM::lo(0);
+#pragma unroll
+    for (int k = 0; k < (1 << E); ++k) {
+        size_t off = (size_t)tile_idx<E>(g, k, lo_in) * a.ncols + c0 + c;
+        u64 x = a.src[base + off];
+        if (PREMUL) x = mul_tw<LAZY>(x, ldg_tw(elt + off), q);
+        v[k] = x;
+    }
+    xf_tile<KIND, A, E, CP, LAZY>(v, g, c, sm, tab, q, q2);
+    constexpr bool CT_RANGE = (KIND == XF_NEG_FWD || KIND == XF_CYC_INV);
+    if (POSTMUL) {
+#pragma unroll
+        for (int k = 0; k < (1 << E); ++k) {
+            size_t off = (size_t)tile_idx<E>(g, k, lo_out) * a.ncols + c0 + c;
+            v[k] = mul_tw<LAZY>(v[k], ldg_tw(elt + off), q);
+        }
+    }
+    if (TRANSPOSE) {
+        if (GM::NS >= 2) __syncthreads();
+        tile_put<E, CP>(sm, v, g, c, lo_out);
+        __syncthreads();
+        u64 *d = a.dst + base + c0 * (size_t)(1 << A);
+        for (int e = tid; e < (C << A); e += NT) {
+            int cc = e >> A, r = e & ((1 << A) - 1);
+            d[e] = sm[r * CP + cc];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < (1 << E); ++k) {
+            size_t off = (size_t)tile_idx<E>(g, k, lo_out) * a.ncols + c0 + c;
+            u64 x = v[k];
+            if (POSTMUL || !CT_RANGE) x = canon2<LAZY>(x, q);
+            else x = canon4<LAZY>(x, q, q2);
+            a.dst[base + off] = x;
+        }
+    }
+}
+
+// =================================================================================================
+// Small-N NTT: one CTA per limb, whole limb in shared memory (N <= 2048).
+// to_ntt_domain / to_coeff_domain (poly.rs:136-166) for the reference's test sizes (N = 8, 16, ...).
+// Internal NTT order: bit-reversed (position brv(k) holds slot k).
+// =================================================================================================
+struct SmallArgs {
+    u64 *data;  // in place
+    const LimbConst *lc;
+    const tw_t *psi;   // [L][N] psi^brv(i) (forward) or psi^-brv(i) (inverse)
+    const tw_t *ninv;  // [L] N^-1 (inverse only)
+    int L;
+    int logn;
+};
+
+template <bool INVERSE, bool LAZY>
+__global__ void ntt_small_kernel(SmallArgs a) {
+    extern __shared__ u64 sm[];
+    const int n = 1 << a.logn;
+    const int limb = blockIdx.x % a.L;
+    u64 *d = a.data + (size_t)blockIdx.x * n;
+    const LimbConst m = a.lc[limb];
+    const u64 q = m.q, q2 = m.q2;
+    const tw_t *P = a.psi + (size_t)limb * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = d[i];
+    __syncthreads();
+    if (!INVERSE) {
+        for (int s = 0; s < a.logn; ++s) {
+            const int t = n >> (s + 1);
+            for (int j = threadIdx.x; j < n / 2; j += blockDim.x) {
+                int blk = j / t, off = j % t;
+                int i0 = blk * 2 * t + off;
+                u64 x = sm[i0], y = sm[i0 + t];
+                ct_bfly<LAZY>(x, y, ldg_tw(P + (1 << s) + blk), q, q2);
+                sm[i0] = x;
+                sm[i0 + t] = y;
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = canon4<LAZY>(sm[i], q, q2);
+    } else {
+        for (int s = a.logn - 1; s >= 0; --s) {
+            const int t = n >> (s + 1);
+            for (int j = threadIdx.x; j < n / 2; j += blockDim.x) {
+                int blk = j / t, off = j % t;
+                int i0 = blk * 2 * t + off;
+                u64 x = sm[i0], y = sm[i0 + t];
+                gs_bfly<LAZY>(x, y, ldg_tw(P + (1 << s) + blk), q, q2);
+                sm[i0] = x;
+                sm[i0 + t] = y;
+            }
+            __syncthreads();
+        }
+        const tw_t ni = ldg_tw(a.ninv + limb);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = shoup(sm[i], ni, q);
+    }
+}
+
+// =================================================================================================
+// Layout of NTT-domain data crossing the boundary (channels(), from_channels(.., is_ntt=true)):
+// the reference's slot k = p(psi^(2k+1)) in natural order (poly.rs:136-148).
+//   a1 == logn (small path): internal position brv_logn(k)
+//   four-step (n1 = 2^a1, n2 = 2^a2): internal position brv_a2(k >> a1) * n1 + brv_a1(k mod n1)
+// =================================================================================================
+__device__ __forceinline__ unsigned ntt_pos(unsigned k, int a1, int a2) {
+    unsigned k1 = k & ((1u << a1) - 1), k2 = k >> a1;
+    unsigned r1 = a1 ? (__brev(k1) >> (32 - a1)) : 0;
+    unsigned r2 = a2 ? (__brev(k2) >> (32 - a2)) : 0;
+    return (r2 << a1) | r1;
+}
+__global__ void permute_ntt_kernel(const u64 *__restrict__ src, u64 *__restrict__ dst, size_t total, int logn, int a1,
+                                   int a2, int to_internal) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    size_t poly = i >> logn;
+    unsigned k = (unsigned)(i & (((size_t)1 << logn) - 1));
+    unsigned p = ntt_pos(k, a1, a2);
+    if (to_internal) dst[(poly << logn) + p] = src[i];
+    else dst[i] = src[(poly << logn) + p];
+}
+
+// =================================================================================================
+// Elementwise limb kernels.  i indexes [batch][L][N]; rhs may be broadcast over the batch
+// (rhs_bstride == 0).
+// =================================================================================================
+struct EwArgs {
+    const LimbConst *lc;
+    size_t total;  // batch * L * N
+    size_t poly;   // L * N
+    int logn;
+    int L;
+};
+__device__ __forceinline__ int ew_limb(const EwArgs &a, size_t i) { return (int)((i % a.poly) >> a.logn); }
+
+enum { EW_ADD = 0, EW_SUB = 1, EW_MUL = 2 };
+// AddAssign (poly.rs:254-275), a += -b, pointwise MulAssign in the NTT domain (poly.rs:297-306).
+template <int OP>
+__global__ void ew_binary_kernel(EwArgs a, u64 *__restrict__ x, const u64 *__restrict__ y, size_t y_bstride) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
+        const LimbConst &m = a.lc[ew_limb(a, i)];
+        size_t b = i / a.poly, r = i % a.poly;
+        u64 yy = y[b * y_bstride + r];
+        u64 xx = x[i];
+        if (OP == EW_ADD) x[i] = addmod(xx, yy, m.q);
+        if (OP == EW_SUB) x[i] = submod(xx, yy, m.q);
+        if (OP == EW_MUL) x[i] = mulmod(xx, yy, m);
+    }
+}
+// Neg (poly.rs:370-385)
+__global__ void ew_neg_kernel(EwArgs a, u64 *__restrict__ x) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x)
+        x[i] = negmod(x[i], a.lc[ew_limb(a, i)].q);
+}
+// from_coeffs (poly.rs:49-66): rem_euclid of an i64 per limb.  coeffs: [batch][clen].
+__global__ void from_coeffs_kernel(EwArgs a, const i64 *__restrict__ coeffs, size_t clen, u64 *__restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
+        const LimbConst &m = a.lc[ew_limb(a, i)];
+        size_t b = i / a.poly;
+        size_t k = i & (((size_t)1 << a.logn) - 1);
+        i64 c = coeffs[b * clen + k];
+        u64 mag = c < 0 ? (u64)0 - (u64)c : (u64)c;
+        u64 r = barrett_word(mag, m);
+        out[i] = (c < 0) ? negmod(r, m.q) : r;
+    }
+}
+// from_channels reducedness scan (poly.rs:83-93): flag = 1 if any word >= its modulus.
+__global__ void check_reduced_kernel(EwArgs a, const u64 *__restrict__ x, int *flag) {
+    int bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x)
+        bad |= (x[i] >= a.lc[ew_limb(a, i)].q);
+    if (bad) atomicOr(flag, 1);
+}
+// Tensor product of mul_ciphertexts_gadget (engine.rs:481-493) on NTT-domain operands:
+// d0 = a0*b0, d1 = a0*b1 + a1*b0, d2 = a1*b1.  d0/d1/d2 may alias a0/a1/b0 element-wise.
+__global__ void tensor_kernel(EwArgs a, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1, u64 *d0, u64 *d1,
+                              u64 *d2) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
+        const LimbConst &m = a.lc[ew_limb(a, i)];
+        u64 x0 = a0[i], x1 = a1[i], y0 = b0[i], y1 = b1[i];
+        u64 t0 = mulmod(x0, y0, m);
+        u64 t2 = mulmod(x1, y1, m);
+        u64 t1 = addmod(mulmod(x0, y1, m), mulmod(x1, y0, m), m.q);
+        d0[i] = t0;
+        d1[i] = t1;
+        d2[i] = t2;
+    }
+}
+// rescale_into (poly.rs:214-225): out_i = (c_i - (c_last % q_i)) * (q_last^-1 mod q_i) mod q_i.
+// src: [batch][L][N] coefficient domain; out: [batch][L-1][N]; qlinv: [L-1] Shoup pairs.
+__global__ void rescale_kernel(EwArgs a /* of the OUTPUT: L-1 limbs */, const u64 *__restrict__ src,
+                               u64 *__restrict__ out, const tw_t *__restrict__ qlinv) {
+    const size_t n = (size_t)1 << a.logn;
+    const size_t in_poly = a.poly + n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
+        int limb = ew_limb(a, i);
+        const LimbConst &m = a.lc[limb];
+        size_t b = i / a.poly, r = i % a.poly, k = r & (n - 1);
+        u64 ci = src[b * in_poly + r];
+        u64 cl = barrett_word(src[b * in_poly + a.poly + k], m);
+        out[i] = shoup(submod(ci, cl, m.q), ldg_tw(qlinv + limb), m.q);
+    }
+}
+// automorphism (poly.rs:515-538) for odd exponents (a signed permutation), as a gather:
+// out[j] = +-in[i] with i = j * e^-1 mod 2N (sign from i*e mod 2N >= N).
+__global__ void automorphism_kernel(EwArgs a, const u64 *__restrict__ src, u64 *__restrict__ out, u64 e, u64 einv) {
+    const u64 n = (u64)1 << a.logn, mask2 = 2 * n - 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
+        u64 q = a.lc[ew_limb(a, i)].q;
+        u64 j = i & (n - 1);
+        // source index s in [0, N) with s*e == j or j+N (mod 2N)
+        u64 s = (j * einv) & mask2;
+        bool neg = false;
+        if (s >= n) {  // then (s-n)*e == j + N (mod 2N) because e is odd
+            s -= n;
+            neg = true;
+        }
+        (void)e;
+        u64 v = src[i - j + s];
+        out[i] = neg ? negmod(v, q) : v;
+    }
+}
+// automorphism for even exponents (not a bijection): the reference scatters in increasing i and
+// skips zero coefficients, so the largest i with a non-zero coefficient wins (poly.rs:523-537).
+__global__ void automorphism_even_mark_kernel(EwArgs a, const u64 *__restrict__ src, unsigned *__restrict__ winner,
+                                              u64 e) {
+    const u64 n = (u64)1 << a.logn, mask2 = 2 * n - 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
+        u64 k = i & (n - 1);
+        if (src[i] == 0) continue;
+        u64 j = ((k * e) & mask2) & (n - 1);
+        atomicMax(winner + (i - k + j), (unsigned)k + 1u);
+    }
+}
+__global__ void automorphism_even_fill_kernel(EwArgs a, const u64 *__restrict__ src, const unsigned *__restrict__ winner,
+                                              u64 *__restrict__ out, u64 e) {
+    const u64 n = (u64)1 << a.logn, mask2 = 2 * n - 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
+        u64 q = a.lc[ew_limb(a, i)].q;
+        u64 j = i & (n - 1);
+        unsigned w = winner[i];
+        if (!w) {
+            out[i] = 0;
+            continue;
+        }
+        u64 k = w - 1;
+        u64 v = src[i - j + k];
+        out[i] = (((k * e) & mask2) >= n) ? q - v : v;
+    }
+}
+
+// =================================================================================================
+// Gadget key-switch, unfused building blocks (engine.rs:505-528 / :429-452)
+// =================================================================================================
+// alpha_i: limb `digit` of src broadcast to every limb j with `% q_j` (engine.rs:507-516).
+__global__ void digit_broadcast_kernel(EwArgs a, const u64 *__restrict__ src, u64 *__restrict__ out, int digit) {
+    const size_t n = (size_t)1 << a.logn;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
+        int limb = ew_limb(a, i);
+        size_t b = i / a.poly, k = i & (n - 1);
+        u64 v = src[b * a.poly + (size_t)digit * n + k];
+        out[i] = (limb == digit) ? v : barrett_word(v, a.lc[limb]);
+    }
+}
+// acc0 += x * kb, acc1 += x * ka (all NTT domain); kb/ka: one digit's key polynomial [L][N].
+__global__ void ks_mac_kernel(EwArgs a, const u64 *__restrict__ x, const u64 *__restrict__ kb,
+                              const u64 *__restrict__ ka, u64 *__restrict__ acc0, u64 *__restrict__ acc1) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
+        const LimbConst &m = a.lc[ew_limb(a, i)];
+        size_t r = i % a.poly;
+        u64 xx = x[i];
+        acc0[i] = mulmod_add(xx, __ldg(kb + r), acc0[i], m);
+        acc1[i] = mulmod_add(xx, __ldg(ka + r), acc1[i], m);
+    }
+}
+
+// =================================================================================================
+// Integer-pipe microbenchmark: independent Shoup modmuls (measures the IMAD roof the key-switch
+// is bound by; MEASURED_PEAKS.json has no integer figure).
+// =================================================================================================
+__global__ void modmul_peak_kernel(u64 *out, int iters, u64 q, tw_t t) {
+    u64 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (u64)threadIdx.x * 977 + k * 31 + blockIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = shoup_lazy(v[k], t, q);
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s ^= v[k];
+    if (s == 0x123456789abcdefull) out[0] = s;
+}

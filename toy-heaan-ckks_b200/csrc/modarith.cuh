@@ -1,0 +1,175 @@
+// modarith.cuh -- 64-bit modular arithmetic for RNS limbs on the sm_100a integer (IMAD) pipe.
+//
+// Replaces the reference's scalar helpers add_mod / sub_mod / mul_mod (poly.rs:629-653, where
+// mul_mod is a u128 product followed by a software `%`).  All results that leave a kernel are the
+// canonical representatives in [0, q) the reference produces; inside a kernel values may be lazy:
+//   LAZY  (q < 2^62):  Cooley-Tukey butterflies keep values in [0, 4q), Gentleman-Sande in [0, 2q)
+//                      (Harvey's bounds), constants are multiplied with Shoup's precomputed quotient;
+//   !LAZY (q < 2^63):  every step is reduced to [0, q)  (the reference admits 63-bit primes,
+//                      src/math/utils.rs:48, for which 4q does not fit a word).
+#pragma once
+#include <cstdint>
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+#ifndef __CUDACC__
+// Host build (tests/emul): the same arithmetic and index code compiled by g++, so the CPU test
+// suite can check the transforms and tables without a GPU.  Never part of libckks_b200.so.
+#define __device__
+#define __host__
+#define __forceinline__ inline
+static inline u64 __umul64hi(u64 a, u64 b) { return (u64)(((unsigned __int128)a * b) >> 64); }
+struct ulonglong2 {
+    u64 x, y;
+};
+static inline ulonglong2 __ldg(const ulonglong2 *p) { return *p; }
+static inline void __syncthreads() {}
+#endif
+
+// A constant w in [0, q) with its Shoup companion ws = floor(w * 2^64 / q).
+struct alignas(16) tw_t {
+    u64 w, ws;
+};
+
+// Per-limb constants (one entry per RNS prime, resident in HBM / L2, read through the RO path).
+struct LimbConst {
+    u64 q;     // modulus
+    u64 q2;    // 2q (wraps for q >= 2^63: never used in !LAZY mode)
+    u64 bar;   // floor(2^64 / q): Barrett quotient for single-word reduction
+    u64 c64;   // 2^64 mod q
+    u64 c64s;  // Shoup companion of c64
+    u64 pad[3];
+};
+
+__device__ __forceinline__ u64 csub(u64 x, u64 q) { return x >= q ? x - q : x; }
+
+// x * w mod q for any word x: result in [0, 2q)  (q < 2^63).
+__device__ __forceinline__ u64 shoup_lazy(u64 x, tw_t t, u64 q) {
+    u64 h = __umul64hi(x, t.ws);
+    return x * t.w - h * q;
+}
+__device__ __forceinline__ u64 shoup(u64 x, tw_t t, u64 q) { return csub(shoup_lazy(x, t, q), q); }
+
+// x mod q for any word x: result in [0, 2q).
+__device__ __forceinline__ u64 barrett_word_lazy(u64 x, const LimbConst &m) {
+    u64 h = __umul64hi(x, m.bar);
+    return x - h * m.q;
+}
+__device__ __forceinline__ u64 barrett_word(u64 x, const LimbConst &m) {
+    return csub(barrett_word_lazy(x, m), m.q);
+}
+
+// (hi * 2^64 + lo) mod q for any two words: result in [0, q).
+__device__ __forceinline__ u64 reduce128(u64 hi, u64 lo, const LimbConst &m) {
+    tw_t c;
+    c.w = m.c64;
+    c.ws = m.c64s;
+    u64 r1 = shoup(hi, c, m.q);
+    u64 r2 = barrett_word(lo, m);
+    return csub(r1 + r2, m.q);
+}
+
+// a * b mod q, a and b any words with a * b representable (always): result in [0, q).
+__device__ __forceinline__ u64 mulmod(u64 a, u64 b, const LimbConst &m) {
+    return reduce128(__umul64hi(a, b), a * b, m);
+}
+// (a * b + c) mod q with a, b < 2^63 and any word c.
+__device__ __forceinline__ u64 mulmod_add(u64 a, u64 b, u64 c, const LimbConst &m) {
+    u64 lo = a * b;
+    u64 hi = __umul64hi(a, b);
+    u64 s = lo + c;
+    hi += (s < lo) ? 1ull : 0ull;
+    return reduce128(hi, s, m);
+}
+__device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
+__device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+__device__ __forceinline__ u64 negmod(u64 a, u64 q) { return a ? q - a : 0; }
+
+// ---- butterflies ---------------------------------------------------------------------------------
+// Cooley-Tukey (decimation in time): (x, y) -> (x + w*y, x - w*y).
+//   LAZY: in/out [0, 4q).  !LAZY: in/out [0, q).
+template <bool LAZY>
+__device__ __forceinline__ void ct_bfly(u64 &x, u64 &y, tw_t t, u64 q, u64 q2) {
+    if (LAZY) {
+        u64 xx = csub(x, q2);
+        u64 v = shoup_lazy(y, t, q);
+        x = xx + v;
+        y = xx - v + q2;
+    } else {
+        u64 v = shoup(y, t, q);
+        u64 xx = x;
+        x = csub(xx + v, q);
+        y = xx >= v ? xx - v : xx + q - v;
+    }
+}
+// Gentleman-Sande (decimation in frequency): (x, y) -> (x + y, (x - y) * w).
+//   LAZY: in/out [0, 2q).  !LAZY: in/out [0, q).
+template <bool LAZY>
+__device__ __forceinline__ void gs_bfly(u64 &x, u64 &y, tw_t t, u64 q, u64 q2) {
+    if (LAZY) {
+        u64 s = csub(x + y, q2);
+        u64 d = x - y + q2;
+        y = shoup_lazy(d, t, q);
+        x = s;
+    } else {
+        u64 s = csub(x + y, q);
+        u64 d = x >= y ? x - y : x + q - y;
+        y = shoup(d, t, q);
+        x = s;
+    }
+}
+// Gentleman-Sande with unit twiddle.
+template <bool LAZY>
+__device__ __forceinline__ void gs_bfly_one(u64 &x, u64 &y, u64 q, u64 q2) {
+    if (LAZY) {
+        u64 s = csub(x + y, q2);
+        u64 d = csub(x - y + q2, q2);
+        x = s;
+        y = d;
+    } else {
+        u64 s = csub(x + y, q);
+        u64 d = x >= y ? x - y : x + q - y;
+        x = s;
+        y = d;
+    }
+}
+// Cooley-Tukey with unit twiddle.  LAZY: in [0, 4q) -> out [0, 4q).
+template <bool LAZY>
+__device__ __forceinline__ void ct_bfly_one(u64 &x, u64 &y, u64 q, u64 q2) {
+    if (LAZY) {
+        u64 xx = csub(x, q2);
+        u64 v = csub(y, q2);
+        x = xx + v;
+        y = xx - v + q2;
+    } else {
+        u64 xx = x, v = y;
+        x = csub(xx + v, q);
+        y = xx >= v ? xx - v : xx + q - v;
+    }
+}
+
+// Canonicalise a lazy value.
+template <bool LAZY>
+__device__ __forceinline__ u64 canon4(u64 x, u64 q, u64 q2) {  // from the CT range
+    if (LAZY) return csub(csub(x, q2), q);
+    return x;
+}
+template <bool LAZY>
+__device__ __forceinline__ u64 canon2(u64 x, u64 q) {  // from the GS range
+    if (LAZY) return csub(x, q);
+    return x;
+}
+// x * t into the GS range ([0,2q) lazy / [0,q) strict) from any word.
+template <bool LAZY>
+__device__ __forceinline__ u64 mul_tw(u64 x, tw_t t, u64 q) {
+    return LAZY ? shoup_lazy(x, t, q) : shoup(x, t, q);
+}
+
+__device__ __forceinline__ tw_t ldg_tw(const tw_t *p) {
+    ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    tw_t t;
+    t.w = v.x;
+    t.ws = v.y;
+    return t;
+}

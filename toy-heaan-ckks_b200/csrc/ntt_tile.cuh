@@ -1,0 +1,188 @@
+// ntt_tile.cuh -- register-tiled 2^A-point transforms over a tile of C independent columns.
+//
+// Building block of the four-step negacyclic NTT that replaces the reference's
+// to_ntt_domain / to_coeff_domain (poly.rs:136-166) and forward_ntt / inverse_ntt /
+// cooley_tukey_ntt (poly.rs:574-615).
+//
+// A CTA owns a tile of 2^A "rows" (the transform dimension, strided in memory) by C columns
+// (contiguous in memory, one column per lane, so that global accesses coalesce and every twiddle
+// is warp-uniform).  Thread (g, c), g < 2^(A-E), holds 2^E elements of column c in registers and
+// performs up to E radix-2 stages on them without touching memory; between such steps the tile is
+// exchanged through shared memory.  Step t's register window covers index bits [lo+E-1 .. lo]:
+//     idx(g, k) = (g >> lo) << (lo+E) | k << lo | (g & (2^lo - 1)).
+//
+// Four transforms (n = 2^A):
+//   neg_fwd : merged negacyclic Cooley-Tukey, natural in -> bit-reversed out, table P[m+i] = psi^brv(m+i)
+//   cyc_fwd : cyclic decimation-in-frequency,  natural in -> bit-reversed out, table W[e] = omega^e
+//   cyc_inv : cyclic decimation-in-time,       bit-reversed in -> natural out, table W[e] = omega^-e
+//   neg_inv : merged negacyclic Gentleman-Sande, bit-reversed in -> natural out, P[m+i] = psi^-brv(m+i)
+// (no 1/n scaling here; the caller folds it into its per-element table).
+#pragma once
+#include "modarith.cuh"
+
+template <int A, int E>
+struct TileGeom {
+    static constexpr int NS = (A + E - 1) / E;  // number of register steps
+    static constexpr int G = 1 << (A > E ? A - E : 0);  // thread groups per column
+    static constexpr int R = 1 << E;                     // registers (elements) per thread
+    // forward (top-down) step t: window low bit
+    __host__ __device__ static constexpr int lo(int t) { return (A - (t + 1) * E) < 0 ? 0 : (A - (t + 1) * E); }
+    // highest unprocessed bit entering forward step t
+    __host__ __device__ static constexpr int top(int t) { return A - t * E - 1; }
+};
+
+template <int E>
+__device__ __forceinline__ int tile_idx(int g, int k, int lo) {
+    return ((g >> lo) << (lo + E)) | (k << lo) | (g & ((1 << lo) - 1));
+}
+
+// ---- one register step of each transform (T = step number in forward order) ---------------------
+template <int A, int E, int T, bool LAZY>
+__device__ __forceinline__ void neg_fwd_step(u64 (&v)[1 << E], int g, const tw_t *__restrict__ P, u64 q, u64 q2) {
+    constexpr int lo = TileGeom<A, E>::lo(T);
+    constexpr int top = TileGeom<A, E>::top(T);
+#pragma unroll
+    for (int b = top; b >= lo; --b) {
+        const int rb = b - lo;
+        const int s = A - 1 - b;
+        const int base = (1 << s) + ((g >> lo) << (lo + E - b - 1));
+#pragma unroll
+        for (int k = 0; k < (1 << E); ++k) {
+            if (k & (1 << rb)) continue;
+            tw_t tw = ldg_tw(P + base + (k >> (rb + 1)));
+            ct_bfly<LAZY>(v[k], v[k | (1 << rb)], tw, q, q2);
+        }
+    }
+}
+
+template <int A, int E, int T, bool LAZY>
+__device__ __forceinline__ void neg_inv_step(u64 (&v)[1 << E], int g, const tw_t *__restrict__ P, u64 q, u64 q2) {
+    constexpr int lo = TileGeom<A, E>::lo(T);
+    constexpr int top = TileGeom<A, E>::top(T);
+#pragma unroll
+    for (int b = lo; b <= top; ++b) {
+        const int rb = b - lo;
+        const int s = A - 1 - b;
+        const int base = (1 << s) + ((g >> lo) << (lo + E - b - 1));
+#pragma unroll
+        for (int k = 0; k < (1 << E); ++k) {
+            if (k & (1 << rb)) continue;
+            tw_t tw = ldg_tw(P + base + (k >> (rb + 1)));
+            gs_bfly<LAZY>(v[k], v[k | (1 << rb)], tw, q, q2);
+        }
+    }
+}
+
+template <int A, int E, int T, bool LAZY>
+__device__ __forceinline__ void cyc_fwd_step(u64 (&v)[1 << E], int g, const tw_t *__restrict__ W, u64 q, u64 q2) {
+    constexpr int lo = TileGeom<A, E>::lo(T);
+    constexpr int top = TileGeom<A, E>::top(T);
+    const int glo = g & ((1 << lo) - 1);
+#pragma unroll
+    for (int b = top; b >= lo; --b) {
+        const int rb = b - lo;
+        const int sh = A - 1 - b;
+#pragma unroll
+        for (int k = 0; k < (1 << E); ++k) {
+            if (k & (1 << rb)) continue;
+            const int klow = k & ((1 << rb) - 1);
+            if (lo == 0 && klow == 0) {
+                gs_bfly_one<LAZY>(v[k], v[k | (1 << rb)], q, q2);
+            } else {
+                const int e = (((klow << lo) | glo)) << sh;
+                tw_t tw = ldg_tw(W + e);
+                gs_bfly<LAZY>(v[k], v[k | (1 << rb)], tw, q, q2);
+            }
+        }
+    }
+}
+
+template <int A, int E, int T, bool LAZY>
+__device__ __forceinline__ void cyc_inv_step(u64 (&v)[1 << E], int g, const tw_t *__restrict__ W, u64 q, u64 q2) {
+    constexpr int lo = TileGeom<A, E>::lo(T);
+    constexpr int top = TileGeom<A, E>::top(T);
+    const int glo = g & ((1 << lo) - 1);
+#pragma unroll
+    for (int b = lo; b <= top; ++b) {
+        const int rb = b - lo;
+        const int sh = A - 1 - b;
+#pragma unroll
+        for (int k = 0; k < (1 << E); ++k) {
+            if (k & (1 << rb)) continue;
+            const int klow = k & ((1 << rb) - 1);
+            if (lo == 0 && klow == 0) {
+                ct_bfly_one<LAZY>(v[k], v[k | (1 << rb)], q, q2);
+            } else {
+                const int e = (((klow << lo) | glo)) << sh;
+                tw_t tw = ldg_tw(W + e);
+                ct_bfly<LAZY>(v[k], v[k | (1 << rb)], tw, q, q2);
+            }
+        }
+    }
+}
+
+// ---- shared-memory exchange between two register windows -----------------------------------------
+// Tile layout in shared memory: [idx][CP] words, CP = C + 1 (the pad keeps both the column-lane
+// accesses here and the row-lane accesses of the transposing store conflict-free).
+template <int E, int CP>
+__device__ __forceinline__ void tile_put(u64 *sm, const u64 (&v)[1 << E], int g, int c, int lo) {
+#pragma unroll
+    for (int k = 0; k < (1 << E); ++k) sm[tile_idx<E>(g, k, lo) * CP + c] = v[k];
+}
+template <int E, int CP>
+__device__ __forceinline__ void tile_get(const u64 *sm, u64 (&v)[1 << E], int g, int c, int lo) {
+#pragma unroll
+    for (int k = 0; k < (1 << E); ++k) v[k] = sm[tile_idx<E>(g, k, lo) * CP + c];
+}
+
+enum { XF_NEG_FWD = 0, XF_CYC_FWD = 1, XF_CYC_INV = 2, XF_NEG_INV = 3 };
+
+template <int KIND, int A, int E, int T, bool LAZY>
+__device__ __forceinline__ void xf_step(u64 (&v)[1 << E], int g, const tw_t *__restrict__ tab, u64 q, u64 q2) {
+    if (KIND == XF_NEG_FWD) neg_fwd_step<A, E, T, LAZY>(v, g, tab, q, q2);
+    if (KIND == XF_CYC_FWD) cyc_fwd_step<A, E, T, LAZY>(v, g, tab, q, q2);
+    if (KIND == XF_CYC_INV) cyc_inv_step<A, E, T, LAZY>(v, g, tab, q, q2);
+    if (KIND == XF_NEG_INV) neg_inv_step<A, E, T, LAZY>(v, g, tab, q, q2);
+}
+
+// Full transform of the tile.  On entry the thread holds the window of the FIRST step (forward
+// kinds: step 0; inverse kinds: step NS-1); on exit it holds the window of the LAST step
+// (forward: NS-1; inverse: 0).  `sm` is the [2^A][CP] exchange buffer (unused if NS == 1).
+template <int KIND, int A, int E, int CP, bool LAZY>
+__device__ __forceinline__ void xf_tile(u64 (&v)[1 << E], int g, int c, u64 *sm, const tw_t *__restrict__ tab, u64 q,
+                                        u64 q2) {
+    typedef TileGeom<A, E> GM;
+    constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);
+    static_assert(GM::NS >= 1 && GM::NS <= 3, "1..3 register steps supported");
+    if (FWD) {
+        xf_step<KIND, A, E, 0, LAZY>(v, g, tab, q, q2);
+        if (GM::NS >= 2) {
+            tile_put<E, CP>(sm, v, g, c, GM::lo(0));
+            __syncthreads();
+            tile_get<E, CP>(sm, v, g, c, GM::lo(1));
+            xf_step<KIND, A, E, (GM::NS >= 2 ? 1 : 0), LAZY>(v, g, tab, q, q2);
+        }
+        if (GM::NS >= 3) {
+            __syncthreads();
+            tile_put<E, CP>(sm, v, g, c, GM::lo(1));
+            __syncthreads();
+            tile_get<E, CP>(sm, v, g, c, GM::lo(2));
+            xf_step<KIND, A, E, (GM::NS >= 3 ? 2 : 0), LAZY>(v, g, tab, q, q2);
+        }
+    } else {
+        xf_step<KIND, A, E, GM::NS - 1, LAZY>(v, g, tab, q, q2);
+        if (GM::NS >= 2) {
+            tile_put<E, CP>(sm, v, g, c, GM::lo(GM::NS - 1));
+            __syncthreads();
+            tile_get<E, CP>(sm, v, g, c, GM::lo(GM::NS - 2));
+            xf_step<KIND, A, E, (GM::NS >= 2 ? GM::NS - 2 : 0), LAZY>(v, g, tab, q, q2);
+        }
+        if (GM::NS >= 3) {
+            __syncthreads();
+            tile_put<E, CP>(sm, v, g, c, GM::lo(1));
+            __syncthreads();
+            tile_get<E, CP>(sm, v, g, c, GM::lo(0));
+            xf_step<KIND, A, E, 0, LAZY>(v, g, tab, q, q2);
+        }
+    }
+}
