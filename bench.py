@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- ct-mults/s (mul_ciphertexts_gadget + rescale_ciphertext) at N=2^16, L=24.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+One "step" = one pass of the hot path over one batch of synthetic ciphertexts (limbs uniform in
+[0, q_i); BASELINE.json configs[3]: N=65536, L=24 61-bit primes, batch 256 per GPU).  Multi-GPU is
+batch sharding: every rank runs the same per-GPU batch with no collective on the data path
+("scaling": "weak"); value = ciphertexts all ranks processed / max-over-ranks device time.
+
+Keys of the JSON line (see DESIGN.md "Measurement"):
+  value        device-resident throughput (inputs in HBM when the timed region starts)
+  e2e          same metric through the host-buffer C-ABI call, H2D/D2H inside the timed region
+  roofline     dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM peak
+  cpu_baseline the oracle (CPU restatement of the reference schedule) on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (log2 N, L, prime bits, batch per GPU, e2e batch per GPU)
+    "cfg4": (16, 24, 61, 256, 64),
+    "cfg3": (14, 8, 30, 1024, 256),
+    "cfg2": (12, 3, 40, 4096, 1024),
+    "tiny": (12, 3, 40, 8, 8),
+}
+
+
+def algorithmic_bytes_per_ctmult(n: int, l: int, batch: int) -> float:
+    """read both input ciphertexts, write the rescaled one, key once per batch."""
+    return 8.0 * n * (4 * l + 2 * (l - 1)) + 16.0 * l * l * n / batch
+
+
+def modmuls_per_ctmult(n: int, logn: int, l: int) -> float:
+    ntt = n / 2 * logn + n
+    return (4 * l + l * (l - 1) + 3 * l) * ntt + 4 * l * n + 2 * l * l * n + 2 * (l - 1) * n
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    REASONS = {
+        0x0000000000000008: "hw_slowdown",
+        0x0000000000000040: "hw_thermal_slowdown",
+        0x0000000000000020: "sw_thermal_slowdown",
+        0x0000000000000004: "sw_power_cap",
+        0x0000000000000080: "hw_power_brake_slowdown",
+    }
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                r = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        s = sorted(self.samples)
+        return {
+            "sm_mhz": (s[len(s) // 2] if s else None),
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(s),
+        }
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    """The reference algorithm's CPU implementation (oracle port: the Rust crate cannot be built in
+    this image) on this box's host cores.  Rank 0 only."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+
+    logn, l, bits, batch, _ = CONFIGS[args.config]
+    n = 1 << logn
+    cores = os.cpu_count() or 1
+    moduli = orc.generate_primes(bits, l, n)
+    ob = orc.Basis(n, moduli)
+    rng = np.random.default_rng(1234)
+    q = np.array(moduli, dtype=np.uint64)
+    count = max(1, cores // l)  # ciphertext pairs per step; each spreads its limbs over cores/count threads
+
+    def uni(*lead):
+        return (rng.integers(0, 1 << 63, size=(*lead, l, n), dtype=np.uint64) % q[:, None]).astype(np.uint64)
+
+    a0, a1, b0, b1 = uni(count), uni(count), uni(count), uni(count)
+    ka, kb = uni(l), uni(l)
+    for _ in range(args.warmup):
+        ob.bench_mul_rescale(cores, a0[:1], a1[:1], b0[:1], b1[:1], ka, kb)  # warm-up: one unit, all threads
+    total = 0.0
+    for _ in range(args.steps):
+        sec, _, _ = ob.bench_mul_rescale(cores, a0, a1, b0, b1, ka, kb)
+        total += sec
+    value = count * args.steps / total
+    sample = f"{count} ciphertext pair(s) per step at full size N={n}, L={l}; limbs of each spread over {max(1, cores // count)} threads"
+    line = {
+        "impl": "reference",
+        "metric": "ct-mults/sec (mul+relin+rescale)",
+        "value": value,
+        "unit": "ct-mult/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.config}: N=2^{logn}, L={l}, {bits}-bit primes, mul_ciphertexts_gadget+rescale_ciphertext", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "ct-mult/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "ct-mult/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(config, budget_note=""):
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+
+    logn, l, bits, _, _ = CONFIGS[config]
+    n = 1 << logn
+    cores = os.cpu_count() or 1
+    moduli = orc.generate_primes(bits, l, n)
+    ob = orc.Basis(n, moduli)
+    rng = np.random.default_rng(4321)
+    q = np.array(moduli, dtype=np.uint64)
+    count = max(1, cores // l)
+
+    def uni(*lead):
+        return (rng.integers(0, 1 << 63, size=(*lead, l, n), dtype=np.uint64) % q[:, None]).astype(np.uint64)
+
+    a0, a1, b0, b1 = uni(count), uni(count), uni(count), uni(count)
+    ka, kb = uni(l), uni(l)
+    sec, _, _ = ob.bench_mul_rescale(cores, a0, a1, b0, b1, ka, kb)
+    return {
+        "value": count / sec,
+        "unit": "ct-mult/s",
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{count} ciphertext pair(s) at full size N={n}, L={l} ({sec:.1f} s of wall time on {cores} threads); "
+        "oracle = C++ restatement of the reference schedule (the Rust crate cannot be built here)",
+    }
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+
+    g.build_cuda()
+    ck = importlib.import_module("toy-heaan-ckks_b200")
+    logn, l, bits, batch, e2e_batch = CONFIGS[args.config]
+    if args.batch:
+        batch = args.batch
+    if args.e2e_batch:
+        e2e_batch = args.e2e_batch
+    n = 1 << logn
+    moduli = ck.generate_primes(bits, l, n)
+    basis = ck.RnsBasis(n, moduli, device=local)
+    child = basis.drop_last(1)
+    stream = torch.cuda.current_stream()
+    basis.set_stream(stream.cuda_stream)
+    dev = torch.device("cuda", local)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    qt = torch.tensor(moduli, dtype=torch.int64, device=dev)[:, None]
+
+    def uni_poly(b):
+        t = torch.randint(0, 1 << 62, (b, l, n), dtype=torch.int64, device=dev, generator=gen) % qt
+        h = ck._vp()
+        ck._check(ck._lib.ckks_poly_from_device(basis._h, b, ck.C.cast(t.data_ptr(), ck._u64p), 0, ck.C.byref(h)))
+        p = ck.RnsPoly(h, basis)
+        del t
+        return p
+
+    ka, kb = uni_poly(l), uni_poly(l)
+    rlk = ck.GadgetKey.from_polys(ka, kb)
+    del ka, kb
+    cta = ck.Ciphertext(uni_poly(batch), uni_poly(batch), bits, bits * l)
+    ctb = ck.Ciphertext(uni_poly(batch), uni_poly(batch), bits, bits * l)
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step():
+        out = ck.CkksEngine.mul_relin_rescale(cta, ctb, rlk, child)
+        return out
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    ck._lib.ckks_prof_enable(1 if args.prof else 0)
+    launches0 = ck.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ck.launch_count() - launches0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ck._lib.ckks_prof_enable(0)
+    prof = {}
+    if args.prof:
+        need = ck._lib.ckks_prof_collect(None, 0)
+        buf = ck.C.create_string_buffer(int(need) + 65536)
+        ck._lib.ckks_prof_collect(buf, len(buf))
+        for ln in buf.value.decode().splitlines():
+            name, rest = ln.split("=")
+            cnt, ms = rest.split(",")
+            prof[name] = (int(cnt), float(ms))
+    ms_per_step = ms_total / args.steps
+    value = world * batch / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call -------------------------------------------
+    wi, wo = (e2e_batch, l, n), (e2e_batch, l - 1, n)
+    hin = [ck.PinnedBuffer(wi) for _ in range(4)]
+    hout = [ck.PinnedBuffer(wo) for _ in range(2)]
+    e2e_polys = [uni_poly(e2e_batch) for _ in range(4)]
+    for hb, p in zip(hin, e2e_polys):  # host copies of the e2e inputs (outside the timed region)
+        ck._check(ck._lib.ckks_poly_download(p._h, ck._ptr(hb.array)))
+    h2d = 4 * hin[0].array.nbytes
+    d2h = 2 * hout[0].array.nbytes
+
+    def e2e_step():
+        ck.mul_relin_rescale_host(basis, child, rlk, hin[0].array, hin[1].array, hin[2].array, hin[3].array, hout[0].array, hout[1].array)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()  # blocks until the results are in host memory
+    ev1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)) / args.steps
+    e2e_value = world * e2e_batch / (e2e_ms * 1e-3)
+
+    # parity spot check of the e2e output against the device-resident path (same inputs)
+    ref = ck.CkksEngine.mul_relin_rescale(ck.Ciphertext(e2e_polys[0], e2e_polys[1], bits, bits * l),
+                                          ck.Ciphertext(e2e_polys[2], e2e_polys[3], bits, bits * l), rlk, child)
+    assert np.array_equal(ref.c0.channels(), hout[0].array), "host-buffer path and device path disagree"
+    del ref, e2e_polys
+
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_ct = algorithmic_bytes_per_ctmult(n, l, batch)
+    line = {
+        "metric": "ct-mults/sec (mul+relin+rescale)",
+        "value": value,
+        "unit": "ct-mult/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"{args.config}: N=2^{logn}, L={l}, {bits}-bit primes, batch {batch} ciphertext pairs per GPU, "
+            "mul_ciphertexts_gadget+rescale_ciphertext, coefficient-domain in and out",
+            "batch_per_gpu": batch,
+            "e2e_batch_per_gpu": e2e_batch,
+            "parallelism": f"batch-sharded x{world}, no data-path collective",
+            "l2": f"inputs are {4 * batch * l * n * 8 / 2**30:.1f} GiB per step (> 126 MB L2); no flush needed",
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "ct-mult/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+        "gpu_launches": launches,
+        "ctmult": {
+            "algorithmic_bytes": bytes_ct,
+            "hbm_frac": value / world * bytes_ct / (hbm_peak * 1e9),
+            "modmuls": modmuls_per_ctmult(n, logn, l),
+            "modmul_rate": value / world * modmuls_per_ctmult(n, logn, l),
+        },
+    }
+    if args.prof and prof:
+        tot = sum(ms for _, ms in prof.values())
+        top = max(prof.items(), key=lambda kv: kv[1][1])
+        name, (cnt, ms) = top
+        # algorithmic bytes per launch of the dominant kernel (DESIGN.md "Kernels"): an NTT pass is
+        # half of a transform (16 N bytes per limb transform) -> 8 N per limb per pass;
+        # elementwise kernels: the words they must read and write once.
+        per_launch = KERNEL_BYTES.get(name, lambda **kw: None)(n=n, l=l, batch=batch)
+        dur_s = ms * 1e-3 / cnt
+        ach = per_launch / dur_s / 1e9 if per_launch else None
+        line["roofline"] = {
+            "kernel": name,
+            "bound": "hbm",
+            "achieved": ach,
+            "peak": hbm_peak,
+            "unit": "GB/s",
+            "frac": (ach / hbm_peak if ach else None),
+            "traffic": TRAFFIC_NCU.get(name),
+            "peak_kind": peak_kind,
+            "share_of_step": ms / tot,
+            "avg_launch_ms": ms / cnt,
+            "launches": cnt,
+            "algorithmic_bytes_per_launch": per_launch,
+        }
+        line["kernels"] = {k: {"launches": c, "ms": round(m, 3), "share": round(m / tot, 4)} for k, (c, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.config)
+    if args.imad and rank == 0:
+        line["modmul_peak_per_s"] = ck.modmul_peak(local, 4096)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# algorithmic bytes per launch of each kernel as launched by the batched ct-mult
+KERNEL_BYTES = {
+    "ntt_fwd_pass1": lambda n, l, batch: 8.0 * n * l * batch,
+    "ntt_fwd_pass2": lambda n, l, batch: 8.0 * n * l * batch,
+    "ntt_inv_pass1": lambda n, l, batch: 8.0 * n * l * batch,
+    "ntt_inv_pass2": lambda n, l, batch: 8.0 * n * l * batch,
+    "ks_mac": lambda n, l, batch: 8.0 * n * l * batch * 5 + 16.0 * n * l,
+    "digit_broadcast": lambda n, l, batch: 8.0 * n * batch * (l + 1),
+    "tensor": lambda n, l, batch: 8.0 * n * l * batch * 7,
+    "rescale": lambda n, l, batch: 8.0 * n * batch * (2 * l - 1),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/)
+TRAFFIC_NCU = {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="ciphertext pairs per GPU (default: the config's)")
+    ap.add_argument("--e2e-batch", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prof", dest="prof", action="store_false")
+    ap.add_argument("--imad", action="store_true", help="also run the integer-pipe microbenchmark")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

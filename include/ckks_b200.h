@@ -186,6 +186,16 @@ uint64_t ckks_launch_count(void);
 /* Name/launch-count table of this library's kernels: writes up to `cap` bytes of
  * "name=count\n" lines, returns the length needed. */
 size_t ckks_launch_table(char *buf, size_t cap);
+/* Per-kernel timing: while enabled every launch is bracketed by CUDA events on the context's stream;
+ * collect() synchronises and writes "name=launches,total_ms\n" lines (returns the length needed). */
+int ckks_prof_enable(int on);
+size_t ckks_prof_collect(char *buf, size_t cap);
+/* from_channels with the source already in device memory ([batch][L][N], reference layout), and the
+ * raw device pointer of a polynomial (coefficient domain: reference layout; NTT domain: internal
+ * order) for zero-copy interop with the caller's own CUDA code. */
+int ckks_poly_from_device(ckks_ctx *ctx, size_t batch, const uint64_t *dev_channels, int in_ntt_domain,
+                          ckks_poly **out);
+int ckks_poly_device_ptr(ckks_poly *p, uint64_t **out);
 /* Integer-pipe microbenchmark: dependent-free 64-bit Shoup modmuls; returns modmul/s (0 on error). */
 double ckks_bench_modmul_peak(int device, int iters);
 

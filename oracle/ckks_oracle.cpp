@@ -261,6 +261,28 @@ extern "C" i64 orc_reconstruct_centered_coeff(const orc_basis *b, const u64 *res
 }
 
 // ---------------------------------------------------------------------------------------------
+// CPU-baseline threading: the reference is single-threaded; the baseline drivers may spread the
+// independent per-limb transforms of one polynomial over host threads (same arithmetic, same
+// results).  limb_threads == 1 (the default, and what every parity test uses) is purely serial.
+// ---------------------------------------------------------------------------------------------
+static thread_local int limb_threads = 1;
+template <class F>
+static void for_limbs(size_t l, F fn) {
+    int t = limb_threads;
+    if (t <= 1 || l <= 1) {
+        for (size_t c = 0; c < l; ++c) fn(c);
+        return;
+    }
+    if ((size_t)t > l) t = (int)l;
+    std::vector<std::thread> pool;
+    for (int w = 0; w < t; ++w)
+        pool.emplace_back([&, w]() {
+            for (size_t c = (size_t)w; c < l; c += (size_t)t) fn(c);
+        });
+    for (auto &th : pool) th.join();
+}
+
+// ---------------------------------------------------------------------------------------------
 // polynomial kernels -- poly.rs:574-625
 // ---------------------------------------------------------------------------------------------
 static void bit_reverse_permute(u64 *v, u64 n) {  // poly.rs:617-625, basis.rs:257-259
@@ -319,21 +341,21 @@ extern "C" int orc_from_channels_check(const orc_basis *b, const u64 *ch, size_t
 }
 extern "C" void orc_to_ntt_domain(const orc_basis *b, u64 *ch) {  // poly.rs:136-148
     u64 n = b->n;
-    for (size_t c = 0; c < b->moduli.size(); ++c) {
+    for_limbs(b->moduli.size(), [&](size_t c) {
         const NttTable &t = b->tables[c];
         u64 *v = ch + c * n;
         for (u64 j = 0; j < n; ++j) v[j] = mul_mod(v[j], t.twist[j], t.modulus);
         forward_ntt(v, t, n);
-    }
+    });
 }
 extern "C" void orc_to_coeff_domain(const orc_basis *b, u64 *ch) {  // poly.rs:154-166
     u64 n = b->n;
-    for (size_t c = 0; c < b->moduli.size(); ++c) {
+    for_limbs(b->moduli.size(), [&](size_t c) {
         const NttTable &t = b->tables[c];
         u64 *v = ch + c * n;
         inverse_ntt(v, t, n);
         for (u64 j = 0; j < n; ++j) v[j] = mul_mod(v[j], t.untwist[j], t.modulus);
-    }
+    });
 }
 extern "C" void orc_add_assign(const orc_basis *b, u64 *a, const u64 *rhs) {  // poly.rs:254-275
     u64 n = b->n;
@@ -362,16 +384,16 @@ extern "C" void orc_mul_assign(const orc_basis *b, u64 *a, const u64 *rhs, int i
     }
     orc_to_ntt_domain(b, a);                            // :310
     std::vector<u64> rhs_ntt(rhs, rhs + l * n);         // :312 (rhs cloned and re-transformed every time)
-    for (size_t c = 0; c < l; ++c) {                    // :313-319
+    for_limbs(l, [&](size_t c) {                        // :313-319
         const NttTable &t = b->tables[c];
         u64 *v = rhs_ntt.data() + c * n;
         for (u64 j = 0; j < n; ++j) v[j] = mul_mod(v[j], t.twist[j], t.modulus);
         forward_ntt(v, t, n);
-    }
-    for (size_t c = 0; c < l; ++c) {                    // :321-326
+    });
+    for_limbs(l, [&](size_t c) {                        // :321-326
         u64 q = b->moduli[c];
         for (u64 i = 0; i < n; ++i) a[c * n + i] = mul_mod(a[c * n + i], rhs_ntt[c * n + i], q);
-    }
+    });
     orc_to_coeff_domain(b, a);                          // :328
 }
 extern "C" void orc_mul_assign_naive(const orc_basis *b, u64 *a, const u64 *rhs) {  // poly.rs:339-367
@@ -513,10 +535,10 @@ static void gadget_accumulate(const orc_basis *b, const u64 *src, const u64 *key
     std::fill(acc1, acc1 + w, 0);
     std::vector<u64> alpha(w), tb(w), ta(w);
     for (size_t i = 0; i < l; ++i) {
-        for (size_t j = 0; j < l; ++j) {
+        for_limbs(l, [&](size_t j) {
             u64 qj = b->moduli[j];
             for (u64 k = 0; k < n; ++k) alpha[j * n + k] = src[i * n + k] % qj;
-        }
+        });
         (void)orc_from_channels_check(b, alpha.data(), l);  // from_channels O(L*N) scan (:517)
         tb = alpha;
         orc_mul_assign(b, tb.data(), key_b + i * w, 0);
@@ -706,14 +728,21 @@ extern "C" void orc_decode(u64 n, uint32_t scale_bits, const i64 *coeffs, size_t
 // ---------------------------------------------------------------------------------------------
 // CPU baseline drivers
 // ---------------------------------------------------------------------------------------------
+// `count` independent units over `threads` host threads: min(count, threads) outer workers, each
+// spreading the per-limb work of its unit over threads / workers inner threads.
 template <class F>
 static double run_parallel(size_t count, int threads, F fn) {
     if (threads < 1) threads = 1;
+    int outer = (size_t)threads < count ? threads : (int)count;
+    if (outer < 1) outer = 1;
+    int inner = threads / outer;
+    if (inner < 1) inner = 1;
     auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t)
+    for (int t = 0; t < outer; ++t)
         pool.emplace_back([&, t]() {
-            for (size_t k = (size_t)t; k < count; k += (size_t)threads) fn(k);
+            limb_threads = inner;
+            for (size_t k = (size_t)t; k < count; k += (size_t)outer) fn(k);
         });
     for (auto &th : pool) th.join();
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

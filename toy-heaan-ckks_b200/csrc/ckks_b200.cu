@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "context.hpp"
 #include "host_math.hpp"
@@ -44,12 +45,60 @@ static void count_launch(const char *name) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_launch_table[name]++;
 }
-#define KL(name, ...)                        \
-    do {                                     \
-        count_launch(name);                  \
-        __VA_ARGS__;                         \
-        cudaError_t e__ = cudaPeekAtLastError(); \
-        if (e__ != cudaSuccess) return cuda_fail(e__, name); \
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+struct ProfRec {
+    const char *name;
+    cudaEvent_t e0, e1;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_prof_pool.empty()) {
+        e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+struct ProfScope {
+    ProfRec r;
+    cudaStream_t s;
+    bool on;
+    ProfScope(const char *name, cudaStream_t st) : s(st), on(g_prof && g_prof_recs.size() < 400000) {
+        if (on) {
+            r.name = name;
+            r.e0 = prof_event();
+            r.e1 = prof_event();
+            cudaEventRecord(r.e0, s);
+        }
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(r.e1, s);
+            g_prof_recs.push_back(r);
+        }
+    }
+};
+static cudaStream_t g_cur_stream = nullptr;  // stream of the context whose call is running
+#define KL(name, ...)                                            \
+    do {                                                         \
+        count_launch(name);                                      \
+        {                                                        \
+            ProfScope ps__(name, g_cur_stream);                  \
+            __VA_ARGS__;                                         \
+        }                                                        \
+        cudaError_t e__ = cudaPeekAtLastError();                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__, name);     \
+    } while (0)
+// same accounting for the few launches that cannot `return` from the middle of a cleanup path
+#define KLV(name, ...)                           \
+    do {                                         \
+        count_launch(name);                      \
+        ProfScope ps__(name, g_cur_stream);      \
+        __VA_ARGS__;                             \
     } while (0)
 
 extern "C" const char *ckks_status_str(int s) {
@@ -123,7 +172,11 @@ Tables::~Tables() {
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
-static bool ok_ctx(const ckks_ctx *c) { return c && c->magic == MAGIC_CTX; }
+static bool ok_ctx(const ckks_ctx *c) {
+    if (!(c && c->magic == MAGIC_CTX)) return false;
+    g_cur_stream = c->T->stream;
+    return true;
+}
 static bool ok_poly(const ckks_poly *p) { return p && p->magic == MAGIC_POLY && ok_ctx(p->ctx); }
 static bool ok_ksk(const ckks_ksk *k) { return k && k->magic == MAGIC_KSK && ok_ctx(k->ctx); }
 static void ctx_ref(ckks_ctx *c) { c->refs.fetch_add(1); }
@@ -499,8 +552,7 @@ extern "C" int ckks_poly_from_channels(ckks_ctx *ctx, size_t batch, const uint64
             }
             if (cudaMemcpyAsync(land, ch, words * sizeof(u64), cudaMemcpyHostToDevice, T.stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "h2d"); break; }
             EwArgs a = ew_args(T, ctx->L, batch);
-            count_launch("check_reduced");
-            check_reduced_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, land, flag);
+            KLV("check_reduced", (check_reduced_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, land, flag)));
             if (in_ntt && (rc = permute(T, stage, p->d, words, true)) != CKKS_OK) break;
             cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, T.stream);
             if (cudaStreamSynchronize(T.stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "sync"); break; }
@@ -686,17 +738,14 @@ extern "C" int ckks_poly_automorphism(const ckks_poly *p, uint64_t exponent, ckk
     EwArgs a = ew_args(T, p->ctx->L, p->batch);
     if (rc == CKKS_OK && a.total) {
         if (e & 1) {
-            count_launch("automorphism");
-            automorphism_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, (*out)->d, e, inv_mod_pow2(e, two_n));
+            KLV("automorphism", (automorphism_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, (*out)->d, e, inv_mod_pow2(e, two_n))));
         } else {
             unsigned *win = nullptr;
             if (cudaMallocAsync((void **)&win, a.total * sizeof(unsigned), T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "malloc");
             if (rc == CKKS_OK) {
                 cudaMemsetAsync(win, 0, a.total * sizeof(unsigned), T.stream);
-                count_launch("automorphism_even_mark");
-                automorphism_even_mark_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, win, e);
-                count_launch("automorphism_even_fill");
-                automorphism_even_fill_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, win, (*out)->d, e);
+                KLV("automorphism_even_mark", (automorphism_even_mark_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, win, e)));
+                KLV("automorphism_even_fill", (automorphism_even_fill_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, win, (*out)->d, e)));
                 dev_free(T, win);
             }
         }
@@ -858,8 +907,7 @@ extern "C" int ckks_gen_gadget_key_b(const ckks_poly *s, const ckks_poly *target
     if (rc == CKKS_OK) rc = ckks_poly_add_assign(b, e);
     if (rc == CKKS_OK) {
         EwArgs ea = ew_args(T, ctx->L, ctx->L);
-        count_launch("add_gadget_target");
-        add_gadget_target_kernel<<<ew_grid((size_t)ctx->L * T.n), 256, 0, T.stream>>>(ea, b->d, target->d);
+        KLV("add_gadget_target", (add_gadget_target_kernel<<<ew_grid((size_t)ctx->L * T.n), 256, 0, T.stream>>>(ea, b->d, target->d)));
         if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "add_gadget_target");
     }
     if (rc != CKKS_OK) {
@@ -885,12 +933,10 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
     if (T.path == 2) TRY(dev_alloc(T, e.total, &tmp));
     int rc = CKKS_OK;
     for (size_t i = 0; i < L && rc == CKKS_OK; ++i) {
-        count_launch("digit_broadcast");
-        digit_broadcast_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, digits, alpha, (int)i);
+        KLV("digit_broadcast", (digit_broadcast_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, digits, alpha, (int)i)));
         rc = ntt_run(T, L, batch, alpha, tmp, false);
         if (rc != CKKS_OK) break;
-        count_launch("ks_mac");
-        ks_mac_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, alpha, key->b + i * e.poly, key->a + i * e.poly, acc0, acc1);
+        KLV("ks_mac", (ks_mac_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, alpha, key->b + i * e.poly, key->a + i * e.poly, acc0, acc1)));
         if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "keyswitch");
     }
     dev_free(T, alpha);
@@ -959,8 +1005,7 @@ static int ct_mul_relin_impl(const ckks_poly *a0, const ckks_poly *a1, const ckk
     EwArgs e = ew_args(T, L, batch);
     if (rc == CKKS_OK && e.total) {
         // d0 -> A0, d1 -> A1, d2 -> B0
-        count_launch("tensor");
-        tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, A0->d, A1->d, B0->d, B1->d, A0->d, A1->d, B0->d);
+        KLV("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, A0->d, A1->d, B0->d, B1->d, A0->d, A1->d, B0->d)));
         if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "tensor");
     }
     if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(B0);  // engine.rs:493
@@ -1186,8 +1231,7 @@ extern "C" double ckks_bench_modmul_peak(int device, int iters) {
     const int blocks = 148 * 8, threads = 256;
     modmul_peak_kernel<<<blocks, threads>>>(d, 16, q, t);
     cudaEventRecord(e0);
-    count_launch("modmul_peak");
-    modmul_peak_kernel<<<blocks, threads>>>(d, iters, q, t);
+    KLV("modmul_peak", (modmul_peak_kernel<<<blocks, threads>>>(d, iters, q, t)));
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms = 0;
@@ -1197,4 +1241,78 @@ extern "C" double ckks_bench_modmul_peak(int device, int iters) {
     cudaFree(d);
     if (cudaGetLastError() != cudaSuccess || ms <= 0) return 0.0;
     return (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
+}
+
+// -------------------------------------------------------------------------------------------------
+// per-kernel timing, device-pointer interop
+// -------------------------------------------------------------------------------------------------
+extern "C" int ckks_prof_enable(int on) {
+    g_prof = on != 0;
+    return CKKS_OK;
+}
+extern "C" size_t ckks_prof_collect(char *buf, size_t cap) {
+    std::map<std::string, std::pair<uint64_t, double>> agg;
+    for (auto &r : g_prof_recs) {
+        cudaEventSynchronize(r.e1);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            auto &a = agg[r.name];
+            a.first++;
+            a.second += ms;
+        }
+        g_prof_pool.push_back(r.e0);
+        g_prof_pool.push_back(r.e1);
+    }
+    g_prof_recs.clear();
+    cudaGetLastError();
+    std::string s;
+    char line[256];
+    for (auto &kv : agg) {
+        snprintf(line, sizeof line, "%s=%llu,%.6f\n", kv.first.c_str(), (unsigned long long)kv.second.first, kv.second.second);
+        s += line;
+    }
+    if (buf && cap) {
+        size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return s.size() + 1;
+}
+extern "C" int ckks_poly_from_device(ckks_ctx *ctx, size_t batch, const uint64_t *dev, int in_ntt, ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    if (!dev && batch) return CKKS_BAD_ARGUMENT;
+    const Tables &T = *ctx->T;
+    CU(cudaSetDevice(T.device));
+    ckks_poly *p;
+    TRY(poly_new(ctx, batch, in_ntt != 0, &p));
+    size_t words = poly_words(p);
+    int rc = CKKS_OK;
+    if (words) {
+        int *flag = nullptr, hflag = 0;
+        if (cudaMallocAsync((void **)&flag, sizeof(int), T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "malloc");
+        if (rc == CKKS_OK) {
+            cudaMemsetAsync(flag, 0, sizeof(int), T.stream);
+            EwArgs a = ew_args(T, ctx->L, batch);
+            KLV("check_reduced", (check_reduced_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, (const u64 *)dev, flag)));
+            if (in_ntt) rc = permute(T, (const u64 *)dev, p->d, words, true);
+            else if (cudaMemcpyAsync(p->d, dev, words * 8, cudaMemcpyDeviceToDevice, T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "d2d");
+            cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, T.stream);
+            if (cudaStreamSynchronize(T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "sync");
+            if (rc == CKKS_OK && hflag) rc = CKKS_NON_REDUCED_COEFFICIENT;
+        }
+        dev_free(T, flag);
+    }
+    if (rc != CKKS_OK) {
+        ckks_poly_free(p);
+        return rc;
+    }
+    *out = p;
+    return CKKS_OK;
+}
+extern "C" int ckks_poly_device_ptr(ckks_poly *p, uint64_t **out) {
+    if (!ok_poly(p) || !out) return CKKS_BAD_HANDLE;
+    *out = (uint64_t *)p->d;
+    return CKKS_OK;
 }
