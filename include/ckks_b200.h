@@ -89,6 +89,9 @@ int ckks_ctx_reconstruct_centered_coeff(const ckks_ctx *ctx, const uint64_t *res
 /* Selects the small-N single-CTA NTT (1) or the four-step NTT (2) for contexts created afterwards;
  * 0 = automatic.  Test hook: both paths must agree with the oracle. */
 int ckks_set_ntt_path(int path);
+/* Test hook: 1 = run the key-switch from its unfused building blocks (digit broadcast, NTT, MAC);
+ * 0 (default) = fused ks_pass1 / ks_pass2 kernels on the four-step path.  Same results. */
+int ckks_set_unfused(int on);
 
 /* ---- RnsPoly<N>  (poly.rs) --------------------------------------------------------------------- */
 /* RnsPoly::zero(basis) poly.rs:36-42, for `batch` polynomials (coefficient domain). */

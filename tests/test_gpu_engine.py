@@ -112,6 +112,35 @@ def test_rotate_matches_oracle(gpu, orc, n, bits, l, rots):
         assert np.array_equal(o0, h0) and np.array_equal(o1, h1)
 
 
+@pytest.mark.parametrize("n,bits,l", [(256, 30, 3), (4096, 40, 3), (2048, 63, 2), (1024, 62, 2), (8192, 30, 6)])
+def test_unfused_building_blocks_match_fused_and_oracle(gpu, orc, n, bits, l):
+    """The fused ks_pass1/ks_pass2 kernels and the unfused digit-broadcast / NTT / MAC path must both
+    equal the oracle (mixed prime widths exercise the `% q_j` digit reduction)."""
+    moduli = orc.generate_primes(bits, l, n)
+    if bits == 30:  # mixed widths: q_i up to 2^20 times larger than q_j
+        moduli = moduli[:-1] + orc.generate_primes(50, 1, n)
+    gb, ob = gpu.RnsBasis(n, moduli), orc.Basis(n, moduli)
+    rng = np.random.default_rng(300 + n)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, 2) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    key = gpu.GadgetKey.upload(gb, ka, kb, rotation=2)
+    cta, ctb = _ct(gpu, gb, a0, a1, 30, 90), _ct(gpu, gb, b0, b1, 30, 90)
+    m0, m1 = ob.mul_ciphertexts_gadget(a0[1], a1[1], b0[1], b1[1], ka, kb)
+    q0, q1, _ = ob.rescale_ciphertext(m0, m1)
+    r0, r1 = ob.rotate_ciphertext(a0[1], a1[1], ka, kb, 2)
+    for unfused in (False, True):
+        gpu.set_unfused(unfused)
+        try:
+            prod = gpu.CkksEngine.mul_ciphertexts_gadget(cta, ctb, key)
+            fused = gpu.CkksEngine.mul_relin_rescale(cta, ctb, key)
+            rot = gpu.CkksEngine.rotate_ciphertext(cta, key)
+        finally:
+            gpu.set_unfused(False)
+        assert np.array_equal(prod.c0.channels()[1], m0) and np.array_equal(prod.c1.channels()[1], m1), f"unfused={unfused}"
+        assert np.array_equal(fused.c0.channels()[1], q0) and np.array_equal(fused.c1.channels()[1], q1), f"unfused={unfused}"
+        assert np.array_equal(rot.c0.channels()[1], r0) and np.array_equal(rot.c1.channels()[1], r1), f"unfused={unfused}"
+
+
 def test_add_encrypt_decrypt_keygen_match_oracle(gpu, orc):
     n, l = 1024, 3
     moduli = orc.generate_primes(40, l, n)

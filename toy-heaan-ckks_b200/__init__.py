@@ -89,6 +89,11 @@ _sig("ckks_ctx_total_bits", C.c_uint32, _vp)
 _sig("ckks_ctx_psi", C.c_uint64, _vp, C.c_size_t)
 _sig("ckks_ctx_reconstruct_centered_coeff", C.c_int, _vp, _u64p, _i64p)
 _sig("ckks_set_ntt_path", C.c_int, C.c_int)
+_sig("ckks_set_unfused", C.c_int, C.c_int)
+_sig("ckks_prof_enable", C.c_int, C.c_int)
+_sig("ckks_prof_collect", C.c_size_t, C.c_char_p, C.c_size_t)
+_sig("ckks_poly_from_device", C.c_int, _vp, C.c_size_t, _u64p, C.c_int, _pp)
+_sig("ckks_poly_device_ptr", C.c_int, _vp, C.POINTER(_u64p))
 _sig("ckks_poly_alloc", C.c_int, _vp, C.c_size_t, _pp)
 _sig("ckks_poly_from_coeffs", C.c_int, _vp, C.c_size_t, _i64p, C.c_size_t, _pp)
 _sig("ckks_poly_from_channels", C.c_int, _vp, C.c_size_t, _u64p, C.c_size_t, C.c_int, _pp)
@@ -168,6 +173,11 @@ def launch_table() -> dict:
 def set_ntt_path(path: int):
     """0 = automatic, 1 = small single-CTA NTT (N <= 2048), 2 = four-step (N >= 256)."""
     _check(_lib.ckks_set_ntt_path(path))
+
+
+def set_unfused(on: bool):
+    """Test hook: run the key-switch from its unfused building blocks instead of the fused kernels."""
+    _check(_lib.ckks_set_unfused(int(on)))
 
 
 def modmul_peak(device: int = 0, iters: int = 4096) -> float:

@@ -24,6 +24,7 @@ static std::atomic<uint64_t> g_launches{0};
 static std::mutex g_mu;
 static std::map<std::string, uint64_t> g_launch_table;
 static int g_ntt_path = 0;
+static int g_force_unfused = 0;  // test hook: run the unfused key-switch building blocks
 
 static int cuda_fail(cudaError_t e, const char *what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -143,6 +144,10 @@ extern "C" size_t ckks_launch_table(char *buf, size_t cap) {
         buf[n] = 0;
     }
     return s.size() + 1;
+}
+extern "C" int ckks_set_unfused(int on) {
+    g_force_unfused = on != 0;
+    return CKKS_OK;
 }
 extern "C" int ckks_set_ntt_path(int p) {
     if (p < 0 || p > 2) return CKKS_BAD_ARGUMENT;
@@ -366,6 +371,65 @@ static int launch_pass(const char *name, int A, bool lazy, dim3 grid, cudaStream
     return CKKS_UNSUPPORTED;
 }
 
+// ---- four-step pass launchers --------------------------------------------------------------------
+// A "limb range" [limb0, limb0 + nl) of [nb][L][N] words; dst may have a different limb count.
+struct Span {
+    size_t nb;      // polynomials
+    int L;          // limbs per polynomial in src
+    int limb0, nl;  // limbs processed
+    int dstL, dst_limb0;
+};
+static Span whole(size_t nb, size_t L) { return Span{nb, (int)L, 0, (int)L, (int)L, 0}; }
+
+enum { P_FWD1, P_FWD2, P_INV2, P_INV1 };
+static int run_pass(const Tables &T, int which, Span sp, const u64 *src, u64 *dst) {
+    if (sp.nb == 0 || sp.nl == 0) return CKKS_OK;
+    const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
+    cudaStream_t s = T.stream;
+    for (size_t b0 = 0; b0 < sp.nb; b0 += 32768) {
+        size_t nb = sp.nb - b0 < 32768 ? sp.nb - b0 : 32768;
+        PassArgs a;
+        a.lc = T.d_lc;
+        a.L = sp.L;
+        a.N = T.n;
+        a.limb0 = sp.limb0;
+        a.dstL = sp.dstL;
+        a.dst_limb0 = sp.dst_limb0;
+        a.src = src + b0 * sp.L * T.n;
+        a.dst = dst + b0 * sp.dstL * T.n;
+        a.elt = nullptr;
+        switch (which) {
+            case P_FWD1:
+                a.tab = T.d_P1;
+                a.tab_stride = n1;
+                a.ncols = n2;
+                TRY((launch_pass<XF_NEG_FWD, false, false, true>("ntt_fwd_pass1", T.a1, T.lazy, dim3(n2 / 16, sp.nl, (unsigned)nb), s, a)));
+                break;
+            case P_FWD2:
+                a.tab = T.d_W2;
+                a.tab_stride = T.w2_stride;
+                a.elt = T.d_TT;
+                a.ncols = n1;
+                TRY((launch_pass<XF_CYC_FWD, true, false, false>("ntt_fwd_pass2", T.a2, T.lazy, dim3(n1 / 16, sp.nl, (unsigned)nb), s, a)));
+                break;
+            case P_INV2:
+                a.tab = T.d_W2i;
+                a.tab_stride = T.w2_stride;
+                a.elt = T.d_TTi;
+                a.ncols = n1;
+                TRY((launch_pass<XF_CYC_INV, false, true, true>("ntt_inv_pass2", T.a2, T.lazy, dim3(n1 / 16, sp.nl, (unsigned)nb), s, a)));
+                break;
+            case P_INV1:
+                a.tab = T.d_P1i;
+                a.tab_stride = n1;
+                a.ncols = n2;
+                TRY((launch_pass<XF_NEG_INV, false, false, false>("ntt_inv_pass1", T.a1, T.lazy, dim3(n2 / 16, sp.nl, (unsigned)nb), s, a)));
+                break;
+        }
+    }
+    return CKKS_OK;
+}
+
 // Forward / inverse transform of [batch][L][N] words in place (tmp: same size, four-step only).
 static int ntt_run(const Tables &T, size_t L, size_t batch, u64 *d, u64 *tmp, bool inverse) {
     if (batch == 0) return CKKS_OK;
@@ -390,45 +454,13 @@ static int ntt_run(const Tables &T, size_t L, size_t batch, u64 *d, u64 *tmp, bo
         }
         return CKKS_OK;
     }
-    const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
-    for (size_t b0 = 0; b0 < batch; b0 += 32768) {
-        size_t nb = batch - b0 < 32768 ? batch - b0 : 32768;
-        PassArgs a;
-        a.lc = T.d_lc;
-        a.L = (int)L;
-        a.N = T.n;
-        u64 *dd = d + b0 * L * T.n, *tt = tmp + b0 * L * T.n;
-        if (!inverse) {
-            a.src = dd;
-            a.dst = tt;
-            a.tab = T.d_P1;
-            a.tab_stride = n1;
-            a.elt = nullptr;
-            a.ncols = n2;
-            TRY((launch_pass<XF_NEG_FWD, false, false, true>("ntt_fwd_pass1", T.a1, T.lazy, dim3(n2 / 16, (unsigned)L, (unsigned)nb), s, a)));
-            a.src = tt;
-            a.dst = dd;
-            a.tab = T.d_W2;
-            a.tab_stride = T.w2_stride;
-            a.elt = T.d_TT;
-            a.ncols = n1;
-            TRY((launch_pass<XF_CYC_FWD, true, false, false>("ntt_fwd_pass2", T.a2, T.lazy, dim3(n1 / 16, (unsigned)L, (unsigned)nb), s, a)));
-        } else {
-            a.src = dd;
-            a.dst = tt;
-            a.tab = T.d_W2i;
-            a.tab_stride = T.w2_stride;
-            a.elt = T.d_TTi;
-            a.ncols = n1;
-            TRY((launch_pass<XF_CYC_INV, false, true, true>("ntt_inv_pass2", T.a2, T.lazy, dim3(n1 / 16, (unsigned)L, (unsigned)nb), s, a)));
-            a.src = tt;
-            a.dst = dd;
-            a.tab = T.d_P1i;
-            a.tab_stride = n1;
-            a.elt = nullptr;
-            a.ncols = n2;
-            TRY((launch_pass<XF_NEG_INV, false, false, false>("ntt_inv_pass1", T.a1, T.lazy, dim3(n2 / 16, (unsigned)L, (unsigned)nb), s, a)));
-        }
+    Span sp = whole(batch, L);
+    if (!inverse) {
+        TRY(run_pass(T, P_FWD1, sp, d, tmp));
+        TRY(run_pass(T, P_FWD2, sp, tmp, d));
+    } else {
+        TRY(run_pass(T, P_INV2, sp, d, tmp));
+        TRY(run_pass(T, P_INV1, sp, tmp, d));
     }
     return CKKS_OK;
 }
@@ -944,6 +976,206 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
     return rc;
 }
 
+// ---- fused four-step key-switch pipeline -----------------------------------------------------------
+constexpr int KS_E2 = 3, KS_C2 = 16;  // ks_pass2: 8 elements per thread leave room for the 128-bit accumulators
+
+template <int A>
+static int launch_ks1_a(bool lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
+    constexpr int E = 4, C = 16;
+    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(u64);
+    const int block = C << (A - E);
+#define KS1(LZ, RD, DG) KL("ks_pass1", (ks_pass1_kernel<A, E, C, LZ, RD, DG><<<grid, block, smem, s>>>(a)))
+    if (lazy) {
+        if (reduce) { if (diag) KS1(true, true, true); else KS1(true, true, false); }
+        else { if (diag) KS1(true, false, true); else KS1(true, false, false); }
+    } else {
+        if (diag) KS1(false, true, true); else KS1(false, true, false);
+    }
+#undef KS1
+    return CKKS_OK;
+}
+template <int A>
+static int launch_ks2_a(bool lazy, bool mul, dim3 grid, cudaStream_t s, const KsArgs &a) {
+    constexpr int E = KS_E2, C = KS_C2;
+    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(u64);
+    const int block = C << (A - E);
+#define KS2(LZ, MU) KL("ks_pass2", (ks_pass2_kernel<A, E, C, LZ, MU, MU><<<grid, block, smem, s>>>(a)))
+    if (lazy) { if (mul) KS2(true, true); else KS2(true, false); }
+    else { if (mul) KS2(false, true); else KS2(false, false); }
+#undef KS2
+    return CKKS_OK;
+}
+template <int A>
+static int launch_inv1_rescale_a(bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const tw_t *ql) {
+    constexpr int E = 4, C = 16;
+    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(u64);
+    const int block = C << (A - E);
+    if (lazy) KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<A, E, C, true><<<grid, block, smem, s>>>(a, last, ql)));
+    else KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<A, E, C, false><<<grid, block, smem, s>>>(a, last, ql)));
+    return CKKS_OK;
+}
+#define DISPATCH_A(Aval, CALL)                   \
+    switch (Aval) {                              \
+        case 4: { constexpr int AA = 4; CALL; } break; \
+        case 5: { constexpr int AA = 5; CALL; } break; \
+        case 6: { constexpr int AA = 6; CALL; } break; \
+        case 7: { constexpr int AA = 7; CALL; } break; \
+        case 8: { constexpr int AA = 8; CALL; } break; \
+        default: return CKKS_UNSUPPORTED;        \
+    }
+
+static int reduce_every_for(const Tables &T, size_t L) {
+    u64 qmax = 0;
+    for (size_t i = 0; i < L; ++i) qmax = T.moduli[i] > qmax ? T.moduli[i] : qmax;
+    hm::u128 sq = (hm::u128)(qmax - 1) * (qmax - 1);
+    hm::u128 lim = ~(hm::u128)0;
+    hm::u128 t = lim / sq;  // t products of (q-1)^2 fit 128 bits
+    if (t > 1) t -= 1;      // one slot for the carried-in residue
+    return t > 1000000 ? 1000000 : (int)t;
+}
+
+// Key-switch of `cs` polynomials: digits (coefficient domain) [+ dig_ntt] -> transposed inverse-pass-2
+// outputs out0t/out1t (finish with P_INV1).  mul: add d0/d1 and use the NTT-domain limb for i == j.
+static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, const u64 *dig_ntt, const ckks_ksk *key,
+                    const u64 *add0, const u64 *add1, u64 *scratch, u64 *out0t, u64 *out1t, bool mul) {
+    KsArgs a;
+    a.digits = digits;
+    a.dig_ntt = dig_ntt;
+    a.scratch = scratch;
+    a.key_b = key->b;
+    a.key_a = key->a;
+    a.add0 = add0;
+    a.add1 = add1;
+    a.out0 = out0t;
+    a.out1 = out1t;
+    a.lc = T.d_lc;
+    a.P1 = T.d_P1;
+    a.W2 = T.d_W2;
+    a.W2i = T.d_W2i;
+    a.TT = T.d_TT;
+    a.TTi = T.d_TTi;
+    a.w2_stride = T.w2_stride;
+    a.L = (int)L;
+    a.a1 = T.a1;
+    a.a2 = T.a2;
+    a.reduce_every = reduce_every_for(T, L);
+    a.N = T.n;
+    const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
+    cudaStream_t s = T.stream;
+    dim3 g1(n2 / 16, (unsigned)(L * L), (unsigned)cs);
+    DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.lazy, T.digit_reduce, mul, g1, s, a)));
+    dim3 g2(n1 / KS_C2, (unsigned)L, (unsigned)cs);
+    DISPATCH_A(T.a2, TRY(launch_ks2_a<AA>(T.lazy, mul, g2, s, a)));
+    return CKKS_OK;
+}
+
+static size_t ks_chunk(const Tables &T, size_t L, size_t batch) {
+    size_t per = L * L * T.n * sizeof(u64);
+    size_t c = ((size_t)4 << 30) / per;
+    if (c < 1) c = 1;
+    return c < batch ? c : batch;
+}
+
+// mul_ciphertexts_gadget (+ rescale_ciphertext) on coefficient-domain device inputs, four-step path.
+// o0/o1: [batch][L or L-1][N].
+static int fused_mul_relin(const Tables &T, size_t L, size_t batch, const u64 *a0, const u64 *a1, const u64 *b0,
+                           const u64 *b1, const ckks_ksk *rlk, bool rescale, u64 *o0, u64 *o1) {
+    if (!batch) return CKKS_OK;
+    const size_t n = T.n, cs_max = ks_chunk(T, L, batch);
+    const size_t W = cs_max * L * n;
+    u64 *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr, *TMP = nullptr, *SCR = nullptr, *LAST = nullptr;
+    int rc = dev_alloc(T, W, &A0);
+    if (rc == CKKS_OK) rc = dev_alloc(T, W, &A1);
+    if (rc == CKKS_OK) rc = dev_alloc(T, W, &B0);
+    if (rc == CKKS_OK) rc = dev_alloc(T, W, &B1);
+    if (rc == CKKS_OK) rc = dev_alloc(T, W, &TMP);
+    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * L * n, &SCR);
+    if (rc == CKKS_OK && rescale) rc = dev_alloc(T, 2 * cs_max * n, &LAST);
+    const size_t outL = rescale ? L - 1 : L;
+    for (size_t s0 = 0; s0 < batch && rc == CKKS_OK; s0 += cs_max) {
+        const size_t cs = batch - s0 < cs_max ? batch - s0 : cs_max;
+        const size_t off = s0 * L * n;
+        Span sp = whole(cs, L);
+        auto step = [&]() -> int {
+            // forward transforms straight from the caller's (unmodified) inputs
+            const u64 *in[4] = {a0 + off, a1 + off, b0 + off, b1 + off};
+            u64 *nt[4] = {A0, A1, B0, B1};
+            for (int t = 0; t < 4; ++t) {
+                TRY(run_pass(T, P_FWD1, sp, in[t], TMP));
+                TRY(run_pass(T, P_FWD2, sp, TMP, nt[t]));
+            }
+            EwArgs e = ew_args(T, L, cs);
+            KL("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, A0, A1, B0, B1, A0, A1, B0)));  // d0,d1,d2
+            // d2 -> coefficient domain (engine.rs:493); B0 keeps NTT(d2), B1 receives the digits
+            TRY(run_pass(T, P_INV2, sp, B0, TMP));
+            TRY(run_pass(T, P_INV1, sp, TMP, B1));
+            TRY(ks_fused(T, L, cs, B1, B0, rlk, A0, A1, SCR, TMP, B1, true));
+            u64 *d0 = o0 + s0 * outL * n, *d1 = o1 + s0 * outL * n;
+            if (!rescale) {
+                TRY(run_pass(T, P_INV1, sp, TMP, d0));
+                TRY(run_pass(T, P_INV1, sp, B1, d1));
+                return CKKS_OK;
+            }
+            // last limb first, then the others with the rescale epilogue (poly.rs:214-225)
+            Span last{cs, (int)L, (int)L - 1, 1, 1, (int)L - 1};
+            TRY(run_pass(T, P_INV1, last, TMP, LAST));
+            TRY(run_pass(T, P_INV1, last, B1, LAST + cs * n));
+            PassArgs pa;
+            pa.lc = T.d_lc;
+            pa.tab = T.d_P1i;
+            pa.tab_stride = (size_t)1 << T.a1;
+            pa.elt = nullptr;
+            pa.L = (int)L;
+            pa.ncols = 1u << T.a2;
+            pa.N = n;
+            pa.limb0 = 0;
+            pa.dstL = (int)L - 1;
+            pa.dst_limb0 = 0;
+            dim3 g((1u << T.a2) / 16, (unsigned)(L - 1), (unsigned)cs);
+            const tw_t *ql = T.d_qlinv + (L - 1) * T.L;
+            pa.src = TMP;
+            pa.dst = d0;
+            DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.lazy, g, T.stream, pa, LAST, ql)));
+            pa.src = B1;
+            pa.dst = d1;
+            DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.lazy, g, T.stream, pa, LAST + cs * n, ql)));
+            return CKKS_OK;
+        };
+        rc = step();
+    }
+    dev_free(T, A0);
+    dev_free(T, A1);
+    dev_free(T, B0);
+    dev_free(T, B1);
+    dev_free(T, TMP);
+    dev_free(T, SCR);
+    dev_free(T, LAST);
+    return rc;
+}
+
+// Key-switch half of rotate_ciphertext (engine.rs:429-452) on the rotated c1 (coefficient domain):
+// ks0/ks1 receive sum_i alpha_i * key_b[i] / key_a[i] in the coefficient domain.
+static int fused_keyswitch(const Tables &T, size_t L, size_t batch, const u64 *c1r, const ckks_ksk *key, u64 *ks0, u64 *ks1) {
+    if (!batch) return CKKS_OK;
+    const size_t n = T.n, cs_max = ks_chunk(T, L, batch);
+    u64 *T0 = nullptr, *T1 = nullptr, *SCR = nullptr;
+    int rc = dev_alloc(T, cs_max * L * n, &T0);
+    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * n, &T1);
+    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * L * n, &SCR);
+    for (size_t s0 = 0; s0 < batch && rc == CKKS_OK; s0 += cs_max) {
+        const size_t cs = batch - s0 < cs_max ? batch - s0 : cs_max;
+        const size_t off = s0 * L * n;
+        Span sp = whole(cs, L);
+        rc = ks_fused(T, L, cs, c1r + off, nullptr, key, nullptr, nullptr, SCR, T0, T1, false);
+        if (rc == CKKS_OK) rc = run_pass(T, P_INV1, sp, T0, ks0 + off);
+        if (rc == CKKS_OK) rc = run_pass(T, P_INV1, sp, T1, ks1 + off);
+    }
+    dev_free(T, T0);
+    dev_free(T, T1);
+    dev_free(T, SCR);
+    return rc;
+}
+
 static int check_ct(const ckks_poly *c0, const ckks_poly *c1) {
     if (!ok_poly(c0) || !ok_poly(c1)) return CKKS_BAD_HANDLE;
     if (!same_basis(c0->ctx, c1->ctx)) return CKKS_BASIS_MISMATCH;
@@ -993,6 +1225,19 @@ static int ct_mul_relin_impl(const ckks_poly *a0, const ckks_poly *a1, const ckk
     const Tables &T = *a0->ctx->T;
     const size_t L = a0->ctx->L, batch = a0->batch;
     CU(cudaSetDevice(T.device));
+    if (T.path == 2 && !g_force_unfused) {
+        ckks_poly *r0 = nullptr, *r1 = nullptr;
+        int frc = poly_new(a0->ctx, batch, false, &r0);
+        if (frc == CKKS_OK) frc = poly_new(a0->ctx, batch, false, &r1);
+        if (frc == CKKS_OK) frc = fused_mul_relin(T, L, batch, a0->d, a1->d, b0->d, b1->d, rlk, false, r0->d, r1->d);
+        if (frc != CKKS_OK) {
+            free2(r0, r1);
+            return frc;
+        }
+        *c0 = r0;
+        *c1 = r1;
+        return CKKS_OK;
+    }
     ckks_poly *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr;
     int rc = ckks_poly_clone(const_cast<ckks_poly *>(a0), &A0);
     if (rc == CKKS_OK) rc = ckks_poly_clone(const_cast<ckks_poly *>(a1), &A1);
@@ -1053,6 +1298,27 @@ extern "C" int ckks_ct_mul_relin_rescale(const ckks_poly *a0, const ckks_poly *a
     if (!ok_poly(a0) || !ok_ctx(child)) return CKKS_BAD_HANDLE;
     if (a0->ctx->L < 2) return CKKS_INVALID_MOD_DROP;
     if (child->T.get() != a0->ctx->T.get() || child->L + 1 != a0->ctx->L) return CKKS_BASIS_MISMATCH;
+    if (a0->ctx->T->path == 2 && !g_force_unfused) {
+        TRY(check_ct(a0, a1));
+        TRY(check_ct(b0, b1));
+        TRY(check_pair(a0, b0, false));
+        if (!ok_ksk(rlk)) return CKKS_BAD_HANDLE;
+        if (!same_basis(a0->ctx, rlk->ctx)) return CKKS_BASIS_MISMATCH;
+        if (a0->ntt) return CKKS_DOMAIN_MISMATCH;
+        const Tables &T = *a0->ctx->T;
+        CU(cudaSetDevice(T.device));
+        ckks_poly *r0 = nullptr, *r1 = nullptr;
+        int frc = poly_new(child, a0->batch, false, &r0);
+        if (frc == CKKS_OK) frc = poly_new(child, a0->batch, false, &r1);
+        if (frc == CKKS_OK) frc = fused_mul_relin(T, a0->ctx->L, a0->batch, a0->d, a1->d, b0->d, b1->d, rlk, true, r0->d, r1->d);
+        if (frc != CKKS_OK) {
+            free2(r0, r1);
+            return frc;
+        }
+        *o0 = r0;
+        *o1 = r1;
+        return CKKS_OK;
+    }
     ckks_poly *m0 = nullptr, *m1 = nullptr;
     TRY(ct_mul_relin_impl(a0, a1, b0, b1, rlk, &m0, &m1));
     int rc = ckks_ct_rescale(m0, m1, child, o0, o1, nullptr);
@@ -1076,7 +1342,9 @@ extern "C" int ckks_ct_rotate(const ckks_poly *c0, const ckks_poly *c1, const ck
     if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(r1);
     if (rc == CKKS_OK) rc = ckks_poly_alloc(c0->ctx, batch, &k0);
     if (rc == CKKS_OK) rc = ckks_poly_alloc(c0->ctx, batch, &k1);
-    if (rc == CKKS_OK) {
+    if (rc == CKKS_OK && T.path == 2 && !g_force_unfused) {
+        rc = fused_keyswitch(T, L, batch, r1->d, rotk, k0->d, k1->d);
+    } else if (rc == CKKS_OK) {
         k0->ntt = k1->ntt = true;  // zero is zero in either domain
         rc = keyswitch_accumulate(T, L, batch, r1->d, rotk, k0->d, k1->d);
     }

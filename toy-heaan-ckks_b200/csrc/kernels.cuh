@@ -17,9 +17,12 @@ struct PassArgs {
     const tw_t *tab;      // small per-limb twiddle table, tab_stride entries per limb
     const tw_t *elt;      // per-element table (N entries per limb), or null
     size_t tab_stride;
-    int L;          // limbs per polynomial in src/dst
+    int L;          // limbs per polynomial in src
     unsigned ncols;  // columns (= stride of the transform dimension, in words)
     size_t N;
+    int limb0;      // first limb handled (blockIdx.y counts from here)
+    int dstL;       // limbs per polynomial in dst
+    int dst_limb0;  // dst limb index = limb - dst_limb0
 };
 
 // One pass: a 2^A-point transform along the strided dimension of a [2^A][ncols] limb, for a tile of
@@ -39,9 +42,10 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
     extern __shared__ u64 sm[];
     const int tid = threadIdx.x;
     const int c = tid % C, g = tid / C;
-    const int limb = blockIdx.y;
+    const int limb = blockIdx.y + a.limb0;
     const size_t c0 = (size_t)blockIdx.x * C;
     const size_t base = ((size_t)blockIdx.z * a.L + limb) * a.N;
+    const size_t dbase = ((size_t)blockIdx.z * a.dstL + (limb - a.dst_limb0)) * a.N;
     const LimbConst m = a.lc[limb];
     const u64 q = m.q, q2 = m.q2;
     const tw_t *tab = a.tab + (size_t)limb * a.tab_stride;
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
         if (GM::NS >= 2) __syncthreads();
         tile_put<E, CP>(sm, v, g, c, lo_out);
         __syncthreads();
-        u64 *d = a.dst + base + c0 * (size_t)(1 << A);
+        u64 *d = a.dst + dbase + c0 * (size_t)(1 << A);
         for (int e = tid; e < (C << A); e += NT) {
             int cc = e >> A, r = e & ((1 << A) - 1);
             d[e] = sm[r * CP + cc];
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
             u64 x = v[k];
             if (POSTMUL || !CT_RANGE) x = canon2<LAZY>(x, q);
             else x = canon4<LAZY>(x, q, q2);
-            a.dst[base + off] = x;
+            a.dst[dbase + off] = x;
         }
     }
 }
@@ -337,4 +341,205 @@ __global__ void modmul_peak_kernel(u64 *out, int iters, u64 q, tw_t t) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) s ^= v[k];
     if (s == 0x123456789abcdefull) out[0] = s;
+}
+
+// =================================================================================================
+// Fused gadget key-switch for the four-step path (engine.rs:505-528 / :429-452).
+//
+//   ks_pass1: for every (ciphertext, digit i, target limb j != i): first pass of NTT_j(alpha_i),
+//             reading limb i of the coefficient-domain polynomial directly (the `% q_j` of
+//             engine.rs:507-516 is folded into the load, or skipped when 4 q_j > q_i lets the lazy
+//             butterflies absorb it) and writing the transposed intermediate to `scratch`.
+//   ks_pass2: for every (ciphertext, target limb j, tile): loops over the digits i, finishes
+//             NTT_j(alpha_i) in registers, multiplies by key_b[i][j] and key_a[i][j] and accumulates
+//             both sums in 128-bit registers (one reduction per ~L digits); digit i == j is the
+//             NTT-domain limb itself.  The epilogue adds d0 / d1 (or nothing for rotations), runs the
+//             first pass of the inverse transform on the sums while they are still in registers and
+//             stores the transposed intermediate for ntt_inv_pass1.
+// Nothing but the digit polynomial, the keys and the result crosses HBM more than once.
+// =================================================================================================
+struct KsArgs {
+    const u64 *digits;   // [cts][L][N] coefficient domain (d2 or the rotated c1)
+    const u64 *dig_ntt;  // [cts][L][N] NTT domain of the same polynomial (digit i == j shortcut)
+    u64 *scratch;        // [cts][L(j)][L(i)][N] transposed pass-1 output
+    const u64 *key_b, *key_a;  // [L(i)][L(j)][N] NTT domain
+    const u64 *add0, *add1;    // [cts][L][N] NTT domain addends (d0, d1) or null
+    u64 *out0, *out1;          // [cts][L][N] transposed inverse-pass-2 output
+    const LimbConst *lc;
+    const tw_t *P1, *W2, *W2i, *TT, *TTi;
+    size_t w2_stride;
+    int L;
+    int a1, a2;
+    int reduce_every;  // digits between 128-bit accumulator reductions
+    size_t N;
+};
+
+template <int A, int E, int C, bool LAZY, bool REDUCE, bool DIAG>
+__global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
+    typedef TileGeom<A, E> GM;
+    constexpr int CP = C + 1;
+    constexpr int NT = C * GM::G;
+    extern __shared__ u64 sm[];
+    const int L = a.L;
+    const int j = blockIdx.y / L, i = blockIdx.y % L;
+    if (DIAG && i == j) return;  // ks_pass2 takes the NTT-domain limb itself for this digit
+    const int tid = threadIdx.x;
+    const int c = tid % C, g = tid / C;
+    const size_t c0 = (size_t)blockIdx.x * C;
+    const unsigned ncols = 1u << a.a2;
+    const LimbConst m = a.lc[j];
+    const u64 q = m.q, q2 = m.q2;
+    const u64 *src = a.digits + ((size_t)blockIdx.z * L + i) * a.N;
+    u64 *dst = a.scratch + (((size_t)blockIdx.z * L + j) * L + i) * a.N;
+    const tw_t *tab = a.P1 + ((size_t)j << A);
+    u64 v[1 << E];
+#pragma unroll
+    for (int k = 0; k < (1 << E); ++k) {
+        u64 x = src[(size_t)tile_idx<E>(g, k, GM::lo(0)) * ncols + c0 + c];
+        if (REDUCE) x = LAZY ? barrett_word_lazy(x, m) : barrett_word(x, m);
+        v[k] = x;
+    }
+    xf_tile<XF_NEG_FWD, A, E, CP, LAZY>(v, g, c, sm, tab, q, q2);
+    if (GM::NS >= 2) __syncthreads();
+    tile_put<E, CP>(sm, v, g, c, GM::lo(GM::NS - 1));
+    __syncthreads();
+    u64 *d = dst + c0 * (size_t)(1 << A);
+    for (int e = tid; e < (C << A); e += NT) {
+        int cc = e >> A, r = e & ((1 << A) - 1);
+        d[e] = sm[r * CP + cc];
+    }
+}
+
+__device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 x, u64 k) {
+    u64 pl = x * k, ph = __umul64hi(x, k);
+    lo += pl;
+    hi += ph + (lo < pl ? 1ull : 0ull);
+}
+
+template <int A, int E, int C, bool LAZY, bool ADD, bool DIAG>
+__global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
+    typedef TileGeom<A, E> GM;
+    constexpr int CP = C + 1;
+    constexpr int NT = C * GM::G;
+    constexpr int R = 1 << E;
+    extern __shared__ u64 sm[];
+    const int L = a.L;
+    const int j = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int c = tid % C, g = tid / C;
+    const size_t c0 = (size_t)blockIdx.x * C;
+    const unsigned ncols = 1u << a.a1;  // rho runs along the contiguous dimension
+    const LimbConst m = a.lc[j];
+    const u64 q = m.q, q2 = m.q2;
+    const size_t ct = blockIdx.z;
+    const tw_t *W = a.W2 + (size_t)j * a.w2_stride;
+    const tw_t *TT = a.TT + (size_t)j * a.N;
+    constexpr int lo_in = GM::lo(0), lo_out = GM::lo(GM::NS - 1);
+
+    u64 a0l[R], a0h[R], a1l[R], a1h[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) a0l[k] = a0h[k] = a1l[k] = a1h[k] = 0;
+
+    for (int i = 0; i < L; ++i) {
+        u64 v[R];
+        if (DIAG && i == j) {
+            const u64 *src = a.dig_ntt + (ct * L + j) * a.N;
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = src[(size_t)tile_idx<E>(g, k, lo_out) * ncols + c0 + c];
+        } else {
+            const u64 *src = a.scratch + ((ct * L + j) * L + i) * a.N;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                size_t off = (size_t)tile_idx<E>(g, k, lo_in) * ncols + c0 + c;
+                v[k] = mul_tw<LAZY>(src[off], ldg_tw(TT + off), q);
+            }
+            if (GM::NS >= 2) __syncthreads();  // the previous digit's exchange reads are done
+            xf_tile<XF_CYC_FWD, A, E, CP, LAZY>(v, g, c, sm, W, q, q2);
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = canon2<LAZY>(v[k], q);
+        }
+        const u64 *kb = a.key_b + ((size_t)i * L + j) * a.N;
+        const u64 *ka = a.key_a + ((size_t)i * L + j) * a.N;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            size_t off = (size_t)tile_idx<E>(g, k, lo_out) * ncols + c0 + c;
+            mac128(a0l[k], a0h[k], v[k], __ldg(kb + off));
+            mac128(a1l[k], a1h[k], v[k], __ldg(ka + off));
+        }
+        if ((i + 1) % a.reduce_every == 0 && i + 1 < L) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                a0l[k] = reduce128(a0h[k], a0l[k], m);
+                a0h[k] = 0;
+                a1l[k] = reduce128(a1h[k], a1l[k], m);
+                a1h[k] = 0;
+            }
+        }
+    }
+    // epilogue: reduce, add d0 / d1, inverse pass 2 (cyclic DIT + four-step twiddle and 1/N), transposed store
+    const tw_t *Wi = a.W2i + (size_t)j * a.w2_stride;
+    const tw_t *TTi = a.TTi + (size_t)j * a.N;
+#pragma unroll
+    for (int comp = 0; comp < 2; ++comp) {
+        u64 v[R];
+        const u64 *add = comp ? a.add1 : a.add0;
+        u64 *out = (comp ? a.out1 : a.out0) + (ct * L + j) * a.N;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            u64 r = comp ? reduce128(a1h[k], a1l[k], m) : reduce128(a0h[k], a0l[k], m);
+            if (ADD) {
+                size_t off = (size_t)tile_idx<E>(g, k, lo_out) * ncols + c0 + c;
+                r = addmod(r, add[(ct * L + j) * a.N + off], q);
+            }
+            v[k] = r;
+        }
+        __syncthreads();
+        xf_tile<XF_CYC_INV, A, E, CP, LAZY>(v, g, c, sm, Wi, q, q2);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            size_t off = (size_t)tile_idx<E>(g, k, lo_in) * ncols + c0 + c;
+            v[k] = mul_tw<LAZY>(v[k], ldg_tw(TTi + off), q);
+        }
+        if (GM::NS >= 2) __syncthreads();
+        tile_put<E, CP>(sm, v, g, c, lo_in);
+        __syncthreads();
+        u64 *d = out + c0 * (size_t)(1 << A);
+        for (int e = tid; e < (C << A); e += NT) {
+            int cc = e >> A, r = e & ((1 << A) - 1);
+            d[e] = sm[r * CP + cc];
+        }
+    }
+}
+
+// Last pass of the inverse transform (negacyclic GS over rho) fused with rescale_into
+// (poly.rs:214-225): limb i < L-1 of the result is (c_i - (c_last % q_i)) * q_last^-1 mod q_i, where
+// c_last is the already finished coefficient-domain last limb.  src: [cts][L][N] transposed
+// inverse-pass-2 output; last: [cts][N] coefficient domain; dst: [cts][L-1][N].
+template <int A, int E, int C, bool LAZY>
+__global__ void __launch_bounds__(C *(1 << (A - E))) inv_pass1_rescale_kernel(PassArgs a, const u64 *__restrict__ last,
+                                                                               const tw_t *__restrict__ qlinv) {
+    typedef TileGeom<A, E> GM;
+    constexpr int CP = C + 1;
+    extern __shared__ u64 sm[];
+    const int tid = threadIdx.x;
+    const int c = tid % C, g = tid / C;
+    const int limb = blockIdx.y;  // < L-1
+    const size_t c0 = (size_t)blockIdx.x * C;
+    const size_t base_in = ((size_t)blockIdx.z * a.L + limb) * a.N;
+    const size_t base_out = ((size_t)blockIdx.z * (a.L - 1) + limb) * a.N;
+    const LimbConst m = a.lc[limb];
+    const u64 q = m.q, q2 = m.q2;
+    const tw_t *tab = a.tab + (size_t)limb * a.tab_stride;
+    const tw_t qi = ldg_tw(qlinv + limb);
+    u64 v[1 << E];
+#pragma unroll
+    for (int k = 0; k < (1 << E); ++k) v[k] = a.src[base_in + (size_t)tile_idx<E>(g, k, GM::lo(GM::NS - 1)) * a.ncols + c0 + c];
+    xf_tile<XF_NEG_INV, A, E, CP, LAZY>(v, g, c, sm, tab, q, q2);
+#pragma unroll
+    for (int k = 0; k < (1 << E); ++k) {
+        size_t off = (size_t)tile_idx<E>(g, k, GM::lo(0)) * a.ncols + c0 + c;
+        u64 ci = canon2<LAZY>(v[k], q);
+        u64 cl = barrett_word(last[(size_t)blockIdx.z * a.N + off], m);
+        a.dst[base_out + off] = shoup(submod(ci, cl, q), qi, q);
+    }
 }
