@@ -171,7 +171,7 @@ extern "C" int ckks_generate_primes(int bits, int count, uint64_t degree, uint64
 Tables::~Tables() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    void *ptrs[] = {d_lc, d_psi, d_psi_inv, d_ninv, d_P1, d_P1i, d_W2, d_W2i, d_TT, d_TTi, d_qlinv};
+    void *ptrs[] = {d_lc, d_psi, d_psi_inv, d_ninv, d_P1, d_P1i, d_W2, d_W2i, d_TT, d_TTi, d_TTt, d_qlinv};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -221,6 +221,7 @@ static int build_tables(Tables &T) {
     TRY(upload_vec(&T.d_W2i, H.W2i));
     TRY(upload_vec(&T.d_TT, H.TT));
     TRY(upload_vec(&T.d_TTi, H.TTi));
+    TRY(upload_vec(&T.d_TTt, H.TTt));
     return CKKS_OK;
 }
 
@@ -997,9 +998,14 @@ static int launch_ks1_a(bool lazy, bool reduce, bool diag, dim3 grid, cudaStream
 template <int A>
 static int launch_ks2_a(bool lazy, bool mul, dim3 grid, cudaStream_t s, const KsArgs &a) {
     constexpr int E = KS_E2, C = KS_C2;
-    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(u64);
+    const size_t smem = ks2_smem_words<A, C>() * sizeof(u64);
     const int block = C << (A - E);
-#define KS2(LZ, MU) KL("ks_pass2", (ks_pass2_kernel<A, E, C, LZ, MU, MU><<<grid, block, smem, s>>>(a)))
+#define KS2(LZ, MU)                                                                                                     \
+    do {                                                                                                                \
+        if (smem > 48 * 1024)                                                                                           \
+            CU(cudaFuncSetAttribute(ks_pass2_kernel<A, E, C, LZ, MU, MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        KL("ks_pass2", (ks_pass2_kernel<A, E, C, LZ, MU, MU><<<grid, block, smem, s>>>(a)));                             \
+    } while (0)
     if (lazy) { if (mul) KS2(true, true); else KS2(true, false); }
     else { if (mul) KS2(false, true); else KS2(false, false); }
 #undef KS2
@@ -1052,7 +1058,7 @@ static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, con
     a.P1 = T.d_P1;
     a.W2 = T.d_W2;
     a.W2i = T.d_W2i;
-    a.TT = T.d_TT;
+    a.TTt = T.d_TTt;
     a.TTi = T.d_TTi;
     a.w2_stride = T.w2_stride;
     a.L = (int)L;

@@ -25,7 +25,7 @@ struct Tables {
     // small path
     tw_t *d_psi = nullptr, *d_psi_inv = nullptr, *d_ninv = nullptr;
     // four-step
-    tw_t *d_P1 = nullptr, *d_P1i = nullptr, *d_W2 = nullptr, *d_W2i = nullptr, *d_TT = nullptr, *d_TTi = nullptr;
+    tw_t *d_P1 = nullptr, *d_P1i = nullptr, *d_W2 = nullptr, *d_W2i = nullptr, *d_TT = nullptr, *d_TTi = nullptr, *d_TTt = nullptr;
     size_t w2_stride = 1;
     // rescale: qlinv[last][i] = q_last^-1 mod q_i (Shoup pair), [L][L]
     tw_t *d_qlinv = nullptr;

@@ -366,7 +366,7 @@ struct KsArgs {
     const u64 *add0, *add1;    // [cts][L][N] NTT domain addends (d0, d1) or null
     u64 *out0, *out1;          // [cts][L][N] transposed inverse-pass-2 output
     const LimbConst *lc;
-    const tw_t *P1, *W2, *W2i, *TT, *TTi;
+    const tw_t *P1, *W2, *W2i, *TTt, *TTi;
     size_t w2_stride;
     int L;
     int a1, a2;
@@ -400,6 +400,12 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
         v[k] = x;
     }
     xf_tile<XF_NEG_FWD, A, E, CP, LAZY>(v, g, c, sm, tab, q, q2);
+    {  // four-step twiddle psi^(j2 (2 k1 + 1)), table in this pass's [rho][j2] layout
+        const tw_t *TTt = a.TTt + (size_t)j * a.N;
+#pragma unroll
+        for (int k = 0; k < (1 << E); ++k)
+            v[k] = mul_tw<LAZY>(v[k], ldg_tw(TTt + (size_t)tile_idx<E>(g, k, GM::lo(GM::NS - 1)) * ncols + c0 + c), q);
+    }
     if (GM::NS >= 2) __syncthreads();
     tile_put<E, CP>(sm, v, g, c, GM::lo(GM::NS - 1));
     __syncthreads();
@@ -415,6 +421,30 @@ __device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 x, u64 k) {
     lo += pl;
     hi += ph + (lo < pl ? 1ull : 0ull);
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Asynchronous copy of a [2^A][C] word tile (row stride `ncols` words in global memory) into a dense
+// [2^A][C] shared-memory tile, 16 bytes per request (LDGSTS), issued by all NT threads.
+template <int A, int C, int NT>
+__device__ __forceinline__ void stage_tile(u64 *sdst, const u64 *gsrc, unsigned ncols, int tid) {
+    constexpr int CH = C / 2;  // 16-byte chunks per row
+    for (int e = tid; e < (CH << A); e += NT) {
+        int r = e / CH, part = e % CH;
+        cp_async16(sdst + r * C + part * 2, gsrc + (size_t)r * ncols + part * 2);
+    }
+}
+
+// Shared memory of ks_pass2: exchange tile [2^A][C+1], two scratch stages and one key-pair stage
+// of [2^A][C] words each.
+template <int A, int C>
+constexpr size_t ks2_smem_words() {
+    return (size_t)(1 << A) * (C + 1) + 4 * (size_t)(1 << A) * C;
+}
 
 template <int A, int E, int C, bool LAZY, bool ADD, bool DIAG>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
@@ -422,7 +452,12 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
     constexpr int CP = C + 1;
     constexpr int NT = C * GM::G;
     constexpr int R = 1 << E;
-    extern __shared__ u64 sm[];
+    constexpr int TILE = (1 << A) * C;
+    extern __shared__ __align__(16) u64 sm_all[];
+    u64 *stS = sm_all;                 // 2 stages of the digit's pass-1 output
+    u64 *stKb = sm_all + 2 * TILE;     // key_b tile of the current digit
+    u64 *stKa = sm_all + 3 * TILE;     // key_a tile
+    u64 *sm = sm_all + 4 * TILE;       // exchange buffer
     const int L = a.L;
     const int j = blockIdx.y;
     const int tid = threadIdx.x;
@@ -433,40 +468,56 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
     const u64 q = m.q, q2 = m.q2;
     const size_t ct = blockIdx.z;
     const tw_t *W = a.W2 + (size_t)j * a.w2_stride;
-    const tw_t *TT = a.TT + (size_t)j * a.N;
     constexpr int lo_in = GM::lo(0), lo_out = GM::lo(GM::NS - 1);
+    const int nd = DIAG ? L - 1 : L;  // digits that need a transform
+    auto digit_of = [&](int t) { return (DIAG && t >= j) ? t + 1 : t; };
+    const u64 *scr = a.scratch + (ct * L + j) * (size_t)L * a.N + c0;
+    const u64 *kbase_b = a.key_b + (size_t)j * a.N + c0;
+    const u64 *kbase_a = a.key_a + (size_t)j * a.N + c0;
+    const size_t kstride = (size_t)L * a.N;
 
     u64 a0l[R], a0h[R], a1l[R], a1h[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) a0l[k] = a0h[k] = a1l[k] = a1h[k] = 0;
 
-    for (int i = 0; i < L; ++i) {
-        u64 v[R];
-        if (DIAG && i == j) {
-            const u64 *src = a.dig_ntt + (ct * L + j) * a.N;
-#pragma unroll
-            for (int k = 0; k < R; ++k) v[k] = src[(size_t)tile_idx<E>(g, k, lo_out) * ncols + c0 + c];
-        } else {
-            const u64 *src = a.scratch + ((ct * L + j) * L + i) * a.N;
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-                size_t off = (size_t)tile_idx<E>(g, k, lo_in) * ncols + c0 + c;
-                v[k] = mul_tw<LAZY>(src[off], ldg_tw(TT + off), q);
-            }
-            if (GM::NS >= 2) __syncthreads();  // the previous digit's exchange reads are done
-            xf_tile<XF_CYC_FWD, A, E, CP, LAZY>(v, g, c, sm, W, q, q2);
-#pragma unroll
-            for (int k = 0; k < R; ++k) v[k] = canon2<LAZY>(v[k], q);
-        }
-        const u64 *kb = a.key_b + ((size_t)i * L + j) * a.N;
-        const u64 *ka = a.key_a + ((size_t)i * L + j) * a.N;
+    if (nd > 0) {
+        stage_tile<A, C, NT>(stS, scr + (size_t)digit_of(0) * a.N, ncols, tid);
+        cp_async_commit();
+    }
+    if (DIAG) {  // digit i == j: the NTT-domain limb itself
+        const u64 *src = a.dig_ntt + (ct * L + j) * a.N + c0 + c;
+        const u64 *kb = kbase_b + (size_t)j * kstride + c, *ka = kbase_a + (size_t)j * kstride + c;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            size_t off = (size_t)tile_idx<E>(g, k, lo_out) * ncols + c0 + c;
-            mac128(a0l[k], a0h[k], v[k], __ldg(kb + off));
-            mac128(a1l[k], a1h[k], v[k], __ldg(ka + off));
+            size_t off = (size_t)tile_idx<E>(g, k, lo_out) * ncols;
+            u64 x = src[off];
+            mac128(a0l[k], a0h[k], x, __ldg(kb + off));
+            mac128(a1l[k], a1h[k], x, __ldg(ka + off));
         }
-        if ((i + 1) % a.reduce_every == 0 && i + 1 < L) {
+    }
+    for (int t = 0; t < nd; ++t) {
+        const int i = digit_of(t);
+        cp_async_wait_all();
+        __syncthreads();  // scratch(t) landed for everyone; MAC(t-1) finished reading the key stage
+        if (t + 1 < nd) stage_tile<A, C, NT>(stS + ((t + 1) & 1) * TILE, scr + (size_t)digit_of(t + 1) * a.N, ncols, tid);
+        stage_tile<A, C, NT>(stKb, kbase_b + (size_t)i * kstride, ncols, tid);
+        stage_tile<A, C, NT>(stKa, kbase_a + (size_t)i * kstride, ncols, tid);
+        cp_async_commit();
+        u64 v[R];
+        const u64 *S = stS + (t & 1) * TILE;
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = S[tile_idx<E>(g, k, lo_in) * C + c];
+        xf_tile<XF_CYC_FWD, A, E, CP, LAZY>(v, g, c, sm, W, q, q2);
+        cp_async_wait_all();
+        __syncthreads();  // keys(t) (and scratch(t+1)) landed for everyone
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            int so = tile_idx<E>(g, k, lo_out) * C + c;
+            u64 x = canon2<LAZY>(v[k], q);
+            mac128(a0l[k], a0h[k], x, stKb[so]);
+            mac128(a1l[k], a1h[k], x, stKa[so]);
+        }
+        if ((t + 1) % a.reduce_every == 0 && t + 1 < nd) {
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 a0l[k] = reduce128(a0h[k], a0l[k], m);

@@ -15,7 +15,7 @@ struct HostTables {
     std::vector<LimbConst> lc;
     std::vector<tw_t> ql;                   // [L][L] q_last^-1 mod q_i
     std::vector<tw_t> psi, psii, ninv;      // small path
-    std::vector<tw_t> P1, P1i, W2, W2i, TT, TTi;  // four-step
+    std::vector<tw_t> P1, P1i, W2, W2i, TT, TTi, TTt;  // four-step (TTt: TT in [rho][j2] layout)
 };
 inline tw_t mk_tw(u64 w, u64 q) {
     tw_t t;
@@ -79,6 +79,7 @@ inline void build_host_tables(u64 n, int logn, int path, int a1, int a2, const s
     H.W2i.resize(L * H.w2_stride);
     H.TT.resize(L * n);
     H.TTi.resize(L * n);
+    H.TTt.resize(L * n);
     for (size_t j = 0; j < L; ++j) {
         u64 q = moduli[j], ps = psis[j], psinv = hm::inv_mod(ps, q);
         u64 ninv = hm::inv_mod(n % q, q);
@@ -109,6 +110,7 @@ inline void build_host_tables(u64 n, int logn, int path, int a1, int a2, const s
             u64 v = 1, vi = ninv;
             for (u64 j2 = 0; j2 < n2; ++j2) {
                 H.TT[j * n + j2 * n1 + rho] = mk_tw(v, q);
+                H.TTt[j * n + rho * n2 + j2] = H.TT[j * n + j2 * n1 + rho];
                 H.TTi[j * n + j2 * n1 + rho] = mk_tw(vi, q);
                 v = hm::mul_mod(v, gen, q);
                 vi = hm::mul_mod(vi, geni, q);
