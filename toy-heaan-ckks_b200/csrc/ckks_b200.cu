@@ -168,12 +168,14 @@ extern "C" int ckks_generate_primes(int bits, int count, uint64_t degree, uint64
 // -------------------------------------------------------------------------------------------------
 // context
 // -------------------------------------------------------------------------------------------------
+static void destroy_host_pipe(struct HostPipe *p);
 Tables::~Tables() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     void *ptrs[] = {d_lc, d_psi, d_psi_inv, d_ninv, d_P1, d_P1i, d_W2, d_W2i, d_TT, d_TTi, d_TTt, d_qlinv};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    destroy_host_pipe(pipe);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -1420,17 +1422,148 @@ extern "C" int ckks_host_free(void *p) {
     return CKKS_OK;
 }
 
+// Three-stage pipeline over chunks of the batch: H2D on one copy stream, the fused kernels on the
+// context's stream, D2H on a second copy stream, double-buffered, ordered with events.  Host buffers
+// should be page-locked (ckks_host_alloc) for the copies to overlap; pageable memory still works.
+struct HostPipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+    u64 *in[2][4] = {{nullptr}}, *out[2][2] = {{nullptr}};
+    int init(const Tables &T, int n_in, size_t in_words, size_t out_words) {
+        CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&comp_done[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming));
+            for (int t = 0; t < n_in; ++t) CU(cudaMalloc((void **)&in[b][t], in_words * 8));
+            for (int t = 0; t < 2; ++t) CU(cudaMalloc((void **)&out[b][t], out_words * 8));
+        }
+        (void)T;
+        return CKKS_OK;
+    }
+    void destroy() {
+        for (int b = 0; b < 2; ++b) {
+            for (int t = 0; t < 4; ++t)
+                if (in[b][t]) cudaFree(in[b][t]);
+            for (int t = 0; t < 2; ++t)
+                if (out[b][t]) cudaFree(out[b][t]);
+            if (in_done[b]) cudaEventDestroy(in_done[b]);
+            if (comp_done[b]) cudaEventDestroy(comp_done[b]);
+            if (out_done[b]) cudaEventDestroy(out_done[b]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+    }
+};
+
 static size_t host_chunk(const Tables &T, size_t L, size_t batch) {
-    // about 256 MiB of input per component and chunk
+    // about 128 MiB per component and chunk: small enough to pipeline, large enough to fill the GPU
     size_t per = L * T.n * sizeof(u64);
-    size_t c = ((size_t)256 << 20) / per;
+    size_t c = ((size_t)128 << 20) / per;
     if (c < 1) c = 1;
     return c < batch ? c : batch;
 }
-static int upload_poly(ckks_ctx *ctx, size_t batch, const u64 *h, ckks_poly **out) {
-    TRY(poly_new(ctx, batch, false, out));
-    CU(cudaMemcpyAsync((*out)->d, h, poly_words(*out) * 8, cudaMemcpyHostToDevice, ctx->T->stream));
-    return CKKS_OK;
+
+// kind 0: mul_ciphertexts_gadget + rescale_ciphertext (4 inputs, L-1 output limbs); kind 1: rotate (2 inputs).
+static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t rot, size_t batch, const u64 *const *hin,
+                         u64 *const *hout) {
+    const Tables &T = *ctx->T;
+    CU(cudaSetDevice(T.device));
+    if (!batch) return CKKS_OK;
+    const size_t L = ctx->L, n = T.n;
+    const int n_in = kind == 0 ? 4 : 2;
+    const size_t outL = kind == 0 ? L - 1 : L;
+    const size_t wi = L * n, wo = outL * n;
+    const size_t chunk = host_chunk(T, L, batch);
+    if (T.path != 2) {  // small-N path: plain sequential staging through device polynomials
+        for (size_t s = 0; s < batch; s += chunk) {
+            size_t nb = batch - s < chunk ? batch - s : chunk;
+            ckks_poly *P[4] = {nullptr, nullptr, nullptr, nullptr}, *R0 = nullptr, *R1 = nullptr;
+            int rc = CKKS_OK;
+            for (int t = 0; t < n_in && rc == CKKS_OK; ++t) {
+                rc = poly_new(ctx, nb, false, &P[t]);
+                if (rc == CKKS_OK && cudaMemcpyAsync(P[t]->d, hin[t] + s * wi, nb * wi * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess)
+                    rc = cuda_fail(cudaGetLastError(), "h2d");
+            }
+            ckks_ctx *child = nullptr;
+            if (rc == CKKS_OK && kind == 0) rc = ckks_ctx_drop_last(ctx, 1, &child);
+            if (rc == CKKS_OK) rc = kind == 0 ? ckks_ct_mul_relin_rescale(P[0], P[1], P[2], P[3], key, child, &R0, &R1) : ckks_ct_rotate(P[0], P[1], key, rot, &R0, &R1);
+            if (rc == CKKS_OK && (cudaMemcpyAsync(hout[0] + s * wo, R0->d, nb * wo * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess ||
+                                  cudaMemcpyAsync(hout[1] + s * wo, R1->d, nb * wo * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess))
+                rc = cuda_fail(cudaGetLastError(), "d2h");
+            if (cudaStreamSynchronize(T.stream) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
+            for (int t = 0; t < 4; ++t)
+                if (P[t]) ckks_poly_free(P[t]);
+            free2(R0, R1);
+            if (child) ckks_ctx_destroy(child);
+            TRY(rc);
+        }
+        return CKKS_OK;
+    }
+    Tables &TM = *ctx->T;
+    int rc = CKKS_OK;
+    if (!TM.pipe || TM.pipe_nin < n_in || TM.pipe_in_words < chunk * wi || TM.pipe_out_words < chunk * wo) {
+        destroy_host_pipe(TM.pipe);
+        TM.pipe = new HostPipe();
+        rc = TM.pipe->init(T, n_in, chunk * wi, chunk * wo);
+        TM.pipe_nin = n_in;
+        TM.pipe_in_words = chunk * wi;
+        TM.pipe_out_words = chunk * wo;
+    }
+    HostPipe &hp = *TM.pipe;
+    const u64 e1 = rot >= 0 ? rot_exponent(n, rot) : (rot_exponent(n, rot) * (2 * n - 1)) % (2 * n);
+    u64 *rot0 = nullptr, *rot1 = nullptr;
+    if (rc == CKKS_OK && kind == 1) {
+        rc = dev_alloc(T, chunk * wi, &rot0);
+        if (rc == CKKS_OK) rc = dev_alloc(T, chunk * wi, &rot1);
+    }
+    size_t c = 0;
+    for (size_t s = 0; s < batch && rc == CKKS_OK; s += chunk, ++c) {
+        const size_t nb = batch - s < chunk ? batch - s : chunk;
+        const int b = (int)(c & 1);
+        auto step = [&]() -> int {
+            if (c >= 2) CU(cudaStreamWaitEvent(hp.s_in, hp.comp_done[b], 0));  // compute of chunk c-2 has released in[b]
+            for (int t = 0; t < n_in; ++t)
+                CU(cudaMemcpyAsync(hp.in[b][t], hin[t] + s * wi, nb * wi * 8, cudaMemcpyHostToDevice, hp.s_in));
+            CU(cudaEventRecord(hp.in_done[b], hp.s_in));
+            CU(cudaStreamWaitEvent(T.stream, hp.in_done[b], 0));
+            if (c >= 2) CU(cudaStreamWaitEvent(T.stream, hp.out_done[b], 0));  // D2H of chunk c-2 has drained out[b]
+            if (kind == 0) {
+                TRY(fused_mul_relin(T, L, nb, hp.in[b][0], hp.in[b][1], hp.in[b][2], hp.in[b][3], key, true, hp.out[b][0], hp.out[b][1]));
+            } else {
+                // rotate_ciphertext (engine.rs:412-463): signed permutation of both components, key-switch of c1
+                EwArgs ea = ew_args(T, L, nb);
+                const u64 einv = inv_mod_pow2(e1, 2 * n);
+                KL("automorphism", (automorphism_kernel<<<ew_grid(ea.total), 256, 0, T.stream>>>(ea, hp.in[b][0], rot0, e1, einv)));
+                KL("automorphism", (automorphism_kernel<<<ew_grid(ea.total), 256, 0, T.stream>>>(ea, hp.in[b][1], rot1, e1, einv)));
+                TRY(fused_keyswitch(T, L, nb, rot1, key, hp.out[b][0], hp.out[b][1]));
+                KL("ew_add", (ew_binary_kernel<EW_ADD><<<ew_grid(ea.total), 256, 0, T.stream>>>(ea, hp.out[b][0], rot0, ea.poly)));
+            }
+            CU(cudaEventRecord(hp.comp_done[b], T.stream));
+            CU(cudaStreamWaitEvent(hp.s_out, hp.comp_done[b], 0));
+            CU(cudaMemcpyAsync(hout[0] + s * wo, hp.out[b][0], nb * wo * 8, cudaMemcpyDeviceToHost, hp.s_out));
+            CU(cudaMemcpyAsync(hout[1] + s * wo, hp.out[b][1], nb * wo * 8, cudaMemcpyDeviceToHost, hp.s_out));
+            CU(cudaEventRecord(hp.out_done[b], hp.s_out));
+            return CKKS_OK;
+        };
+        rc = step();
+    }
+    cudaStreamSynchronize(hp.s_in);
+    if (cudaStreamSynchronize(T.stream) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
+    if (cudaStreamSynchronize(hp.s_out) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
+    dev_free(T, rot0);
+    dev_free(T, rot1);
+    if (rc != CKKS_OK) {  // do not keep a pipeline whose events may be in an unknown state
+        destroy_host_pipe(TM.pipe);
+        TM.pipe = nullptr;
+    }
+    return rc;
+}
+static void destroy_host_pipe(HostPipe *p) {
+    if (!p) return;
+    p->destroy();
+    delete p;
 }
 
 extern "C" int ckks_ct_mul_relin_rescale_host(ckks_ctx *ctx, ckks_ctx *child, const ckks_ksk *rlk, size_t batch,
@@ -1438,55 +1571,22 @@ extern "C" int ckks_ct_mul_relin_rescale_host(ckks_ctx *ctx, ckks_ctx *child, co
                                               uint64_t *o0, uint64_t *o1) {
     if (!ok_ctx(ctx) || !ok_ctx(child) || !ok_ksk(rlk)) return CKKS_BAD_HANDLE;
     if (batch && (!a0 || !a1 || !b0 || !b1 || !o0 || !o1)) return CKKS_BAD_ARGUMENT;
-    const Tables &T = *ctx->T;
-    CU(cudaSetDevice(T.device));
-    const size_t L = ctx->L, wi = L * T.n, wo = (L - 1) * T.n;
-    const size_t chunk = host_chunk(T, L, batch);
-    for (size_t s = 0; s < batch; s += chunk) {
-        size_t nb = batch - s < chunk ? batch - s : chunk;
-        ckks_poly *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr, *R0 = nullptr, *R1 = nullptr;
-        int rc = upload_poly(ctx, nb, (const u64 *)a0 + s * wi, &A0);
-        if (rc == CKKS_OK) rc = upload_poly(ctx, nb, (const u64 *)a1 + s * wi, &A1);
-        if (rc == CKKS_OK) rc = upload_poly(ctx, nb, (const u64 *)b0 + s * wi, &B0);
-        if (rc == CKKS_OK) rc = upload_poly(ctx, nb, (const u64 *)b1 + s * wi, &B1);
-        if (rc == CKKS_OK) rc = ckks_ct_mul_relin_rescale(A0, A1, B0, B1, rlk, child, &R0, &R1);
-        if (rc == CKKS_OK && cudaMemcpyAsync((u64 *)o0 + s * wo, R0->d, nb * wo * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess)
-            rc = cuda_fail(cudaGetLastError(), "d2h");
-        if (rc == CKKS_OK && cudaMemcpyAsync((u64 *)o1 + s * wo, R1->d, nb * wo * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess)
-            rc = cuda_fail(cudaGetLastError(), "d2h");
-        free2(A0, A1);
-        free2(B0, B1);
-        free2(R0, R1);
-        TRY(rc);
-    }
-    CU(cudaStreamSynchronize(T.stream));
-    return CKKS_OK;
+    if (ctx->L < 2) return CKKS_INVALID_MOD_DROP;
+    if (child->T.get() != ctx->T.get() || child->L + 1 != ctx->L) return CKKS_BASIS_MISMATCH;
+    if (!same_basis(ctx, rlk->ctx)) return CKKS_BASIS_MISMATCH;
+    const u64 *hin[4] = {(const u64 *)a0, (const u64 *)a1, (const u64 *)b0, (const u64 *)b1};
+    u64 *hout[2] = {(u64 *)o0, (u64 *)o1};
+    return host_pipeline(ctx, 0, rlk, 0, batch, hin, hout);
 }
 
 extern "C" int ckks_ct_rotate_host(ckks_ctx *ctx, const ckks_ksk *rotk, int32_t k, size_t batch, const uint64_t *c0,
                                    const uint64_t *c1, uint64_t *o0, uint64_t *o1) {
     if (!ok_ctx(ctx) || !ok_ksk(rotk)) return CKKS_BAD_HANDLE;
     if (batch && (!c0 || !c1 || !o0 || !o1)) return CKKS_BAD_ARGUMENT;
-    const Tables &T = *ctx->T;
-    CU(cudaSetDevice(T.device));
-    const size_t w = ctx->L * T.n;
-    const size_t chunk = host_chunk(T, ctx->L, batch);
-    for (size_t s = 0; s < batch; s += chunk) {
-        size_t nb = batch - s < chunk ? batch - s : chunk;
-        ckks_poly *C0 = nullptr, *C1 = nullptr, *R0 = nullptr, *R1 = nullptr;
-        int rc = upload_poly(ctx, nb, (const u64 *)c0 + s * w, &C0);
-        if (rc == CKKS_OK) rc = upload_poly(ctx, nb, (const u64 *)c1 + s * w, &C1);
-        if (rc == CKKS_OK) rc = ckks_ct_rotate(C0, C1, rotk, k, &R0, &R1);
-        if (rc == CKKS_OK && cudaMemcpyAsync((u64 *)o0 + s * w, R0->d, nb * w * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess)
-            rc = cuda_fail(cudaGetLastError(), "d2h");
-        if (rc == CKKS_OK && cudaMemcpyAsync((u64 *)o1 + s * w, R1->d, nb * w * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess)
-            rc = cuda_fail(cudaGetLastError(), "d2h");
-        free2(C0, C1);
-        free2(R0, R1);
-        TRY(rc);
-    }
-    CU(cudaStreamSynchronize(T.stream));
-    return CKKS_OK;
+    if (!same_basis(ctx, rotk->ctx)) return CKKS_BASIS_MISMATCH;
+    const u64 *hin[4] = {(const u64 *)c0, (const u64 *)c1, nullptr, nullptr};
+    u64 *hout[2] = {(u64 *)o0, (u64 *)o1};
+    return host_pipeline(ctx, 1, rotk, k, batch, hin, hout);
 }
 
 // -------------------------------------------------------------------------------------------------

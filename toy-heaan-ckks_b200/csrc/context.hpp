@@ -31,6 +31,10 @@ struct Tables {
     tw_t *d_qlinv = nullptr;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // cached staging buffers / copy streams of the host-buffer entry points
+    struct HostPipe *pipe = nullptr;
+    int pipe_nin = 0;
+    size_t pipe_in_words = 0, pipe_out_words = 0;
     ~Tables();
 };
 
