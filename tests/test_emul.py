@@ -1,0 +1,57 @@
+"""CPU emulation of the device transform code (tests/emul/ntt_emul.cpp compiles csrc/ntt_tile.cuh,
+csrc/modarith.cuh and csrc/tables_host.hpp with g++): the four-step index math, twiddle tables and
+lazy-range invariants are checked against the oracle without a GPU."""
+import ctypes as C
+import os
+import random
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emul(built):
+    lib = C.CDLL(os.path.join(HERE, "emul", "libntt_emul.so"))
+    lib.emul_ntt_4step.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int]
+    lib.emul_ntt_pos.argtypes = [C.c_uint32, C.c_int, C.c_int]
+    lib.emul_ntt_pos.restype = C.c_uint32
+    lib.emul_psi.argtypes = [C.c_uint64, C.c_uint64]
+    lib.emul_psi.restype = C.c_uint64
+    for name, nargs in (("emul_mulmod", 3), ("emul_mulmod_add", 4), ("emul_barrett_word", 2)):
+        f = getattr(lib, name)
+        f.argtypes = [C.c_uint64] * nargs
+        f.restype = C.c_uint64
+    return lib
+
+
+@pytest.mark.parametrize("logn,bits,strict", [(8, 30, 0), (9, 61, 0), (10, 62, 0), (11, 63, 0), (12, 40, 0), (12, 40, 1), (13, 61, 0), (14, 30, 0), (16, 61, 0)])
+def test_four_step_matches_oracle(emul, orc, logn, bits, strict):
+    n = 1 << logn
+    q = orc.generate_primes(bits, 1, n)[0]
+    ob = orc.Basis(n, [q])
+    assert emul.emul_psi(n, q) == ob.psi(0)  # same root selection as basis.rs:217-237
+    rng = np.random.default_rng(logn * 100 + bits)
+    x = rng.integers(0, q, n, dtype=np.uint64)
+    x[:3] = [q - 1, 0, 1]
+    ref = ob.to_ntt(x[None, :])[0]
+    d = x.copy()
+    assert emul.emul_ntt_4step(n, q, d.ctypes.data_as(C.POINTER(C.c_uint64)), 0, strict) == 0, "lazy range violated"
+    a1 = (logn + 1) // 2
+    pos = np.array([emul.emul_ntt_pos(k, a1, logn - a1) for k in range(n)])
+    assert np.array_equal(d[pos], ref)
+    assert emul.emul_ntt_4step(n, q, d.ctypes.data_as(C.POINTER(C.c_uint64)), 1, strict) == 0
+    assert np.array_equal(d, x)
+
+
+def test_modarith_against_python_integers(emul):
+    rnd = random.Random(5)
+    qs = [17, 97, 1073741441, 1099511592961, 2305843009211596801, 4611686018427365377, 9223372036854744577]
+    for q in qs:
+        cases = [(0, 0, 0), (q - 1, q - 1, q - 1), (1, q - 1, 2**64 - 1), (2**63 - 1, 2**63 - 1, 2**64 - 1)]
+        cases += [(rnd.randrange(2**63), rnd.randrange(2**63), rnd.randrange(2**64)) for _ in range(300)]
+        for a, b, c in cases:
+            assert emul.emul_mulmod(a, b, q) == (a * b) % q
+            assert emul.emul_mulmod_add(a, b, c, q) == (a * b + c) % q
+            assert emul.emul_barrett_word(c, q) == c % q
