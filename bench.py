@@ -30,9 +30,9 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # name: (log2 N, L, prime bits, batch per GPU, e2e batch per GPU)
-    "cfg4": (16, 24, 61, 256, 64),
-    "cfg3": (14, 8, 30, 1024, 256),
-    "cfg2": (12, 3, 40, 4096, 1024),
+    "cfg4": (16, 24, 61, 256, 64),    # BASELINE.json configs[3]: the metric's configuration (default)
+    "cfg3": (14, 8, 30, 1024, 256),   # configs[2]: rotation (automorphism + key-switch), see --op
+    "cfg2": (12, 3, 40, 4096, 1024),  # configs[1]
     "tiny": (12, 3, 40, 8, 8),
 }
 
@@ -262,9 +262,13 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    op = args.op or ("rotate" if args.config == "cfg3" else "mul")
+    rlk.rotation = 1
+
     def step():
-        out = ck.CkksEngine.mul_relin_rescale(cta, ctb, rlk, child)
-        return out
+        if op == "rotate":
+            return ck.CkksEngine.rotate_ciphertext(cta, rlk)
+        return ck.CkksEngine.mul_relin_rescale(cta, ctb, rlk, child)
 
     for _ in range(args.warmup):
         step()
@@ -296,7 +300,7 @@ def run_b200(args):
     value = world * batch / (ms_per_step * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------
-    wi, wo = (e2e_batch, l, n), (e2e_batch, l - 1, n)
+    wi, wo = (e2e_batch, l, n), (e2e_batch, l - 1 if op == "mul" else l, n)
     hin = [ck.PinnedBuffer(wi) for _ in range(4)]
     hout = [ck.PinnedBuffer(wo) for _ in range(2)]
     e2e_polys = [uni_poly(e2e_batch) for _ in range(4)]
@@ -305,8 +309,14 @@ def run_b200(args):
     h2d = 4 * hin[0].array.nbytes
     d2h = 2 * hout[0].array.nbytes
 
+    if op == "rotate":
+        h2d //= 2
+
     def e2e_step():
-        ck.mul_relin_rescale_host(basis, child, rlk, hin[0].array, hin[1].array, hin[2].array, hin[3].array, hout[0].array, hout[1].array)
+        if op == "rotate":
+            ck.rotate_host(basis, rlk, hin[0].array, hin[1].array, hout[0].array, hout[1].array)
+        else:
+            ck.mul_relin_rescale_host(basis, child, rlk, hin[0].array, hin[1].array, hin[2].array, hin[3].array, hout[0].array, hout[1].array)
 
     e2e_step()
     barrier()
@@ -320,8 +330,8 @@ def run_b200(args):
     e2e_value = world * e2e_batch / (e2e_ms * 1e-3)
 
     # parity spot check of the e2e output against the device-resident path (same inputs)
-    ref = ck.CkksEngine.mul_relin_rescale(ck.Ciphertext(e2e_polys[0], e2e_polys[1], bits, bits * l),
-                                          ck.Ciphertext(e2e_polys[2], e2e_polys[3], bits, bits * l), rlk, child)
+    ea, eb = ck.Ciphertext(e2e_polys[0], e2e_polys[1], bits, bits * l), ck.Ciphertext(e2e_polys[2], e2e_polys[3], bits, bits * l)
+    ref = ck.CkksEngine.rotate_ciphertext(ea, rlk) if op == "rotate" else ck.CkksEngine.mul_relin_rescale(ea, eb, rlk, child)
     assert np.array_equal(ref.c0.channels(), hout[0].array), "host-buffer path and device path disagree"
     del ref, e2e_polys
 
@@ -329,9 +339,9 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     bytes_ct = algorithmic_bytes_per_ctmult(n, l, batch)
     line = {
-        "metric": "ct-mults/sec (mul+relin+rescale)",
+        "metric": "ct-mults/sec (mul+relin+rescale)" if op == "mul" else "rotations/sec (automorphism + gadget key-switch)",
         "value": value,
-        "unit": "ct-mult/s",
+        "unit": "ct-mult/s" if op == "mul" else "rotation/s",
         "n_gpus": world,
         "steps": args.steps,
         "warmup": args.warmup,
@@ -343,7 +353,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": {
             "workload": f"{args.config}: N=2^{logn}, L={l}, {bits}-bit primes, batch {batch} ciphertext pairs per GPU, "
-            "mul_ciphertexts_gadget+rescale_ciphertext, coefficient-domain in and out",
+            + ("mul_ciphertexts_gadget+rescale_ciphertext" if op == "mul" else "rotate_ciphertext(k=1)") + ", coefficient-domain in and out",
             "batch_per_gpu": batch,
             "e2e_batch_per_gpu": e2e_batch,
             "parallelism": f"batch-sharded x{world}, no data-path collective",
@@ -394,6 +404,71 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_ntt_sweep(args):
+    """BASELINE.json configs[4]: standalone limb-batched NTT / INTT, N = 2^12..2^16, L in {1, 8, 24, 32},
+    30-bit and 61-bit chains; batch sized to ~1 GiB of limbs.  transforms/s and achieved GB/s
+    (algorithmic 16 N bytes per limb transform) against the measured HBM peak."""
+    import torch
+
+    import __graft_entry__ as g
+
+    g.build_cuda()
+    ck = importlib.import_module("toy-heaan-ckks_b200")
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    rows = []
+    for bits in (30, 61):
+        for logn in (12, 13, 14, 15, 16):
+            for l in (1, 8, 24, 32):
+                n = 1 << logn
+                try:
+                    moduli = ck.generate_primes(bits, l, n)
+                except ck.RnsNttError:
+                    continue
+                basis = ck.RnsBasis(n, moduli)
+                basis.set_stream(stream.cuda_stream)
+                batch = max(1, (1 << 30) // (l * n * 8))
+                qt = torch.tensor(moduli, dtype=torch.int64, device=dev)[:, None]
+                t = torch.randint(0, 1 << 62, (batch, l, n), dtype=torch.int64, device=dev) % qt
+                h = ck._vp()
+                ck._check(ck._lib.ckks_poly_from_device(basis._h, batch, ck.C.cast(t.data_ptr(), ck._u64p), 0, ck.C.byref(h)))
+                p = ck.RnsPoly(h, basis)
+                del t
+                res = {}
+                for name in ("fwd", "inv"):
+                    fn = p.to_ntt_domain if name == "fwd" else p.to_coeff_domain
+                    other = p.to_coeff_domain if name == "fwd" else p.to_ntt_domain
+                    if name == "inv":
+                        p.to_ntt_domain()
+                    for _ in range(args.warmup):
+                        fn()
+                        other()
+                    times = []
+                    for _ in range(max(args.steps, 3)):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(stream)
+                        fn()
+                        e1.record(stream)
+                        torch.cuda.synchronize()
+                        times.append(e0.elapsed_time(e1))
+                        other()
+                    ms = sorted(times)[len(times) // 2]
+                    tr = batch * l / (ms * 1e-3)
+                    res[name] = {"ms": ms, "transforms_per_s": tr, "gbs": tr * 16.0 * n / 1e9, "frac": tr * 16.0 * n / 1e9 / hbm_peak}
+                    if name == "inv":
+                        p.to_coeff_domain()
+                rows.append({"bits": bits, "logn": logn, "L": l, "batch": batch, **{k + "_" + kk: vv for k, v in res.items() for kk, vv in v.items()}})
+                del p, basis
+                torch.cuda.empty_cache()
+    best = max(rows, key=lambda r: r["fwd_gbs"])
+    print(json.dumps({"metric": "limb NTT achieved HBM GB/s (16 N bytes per transform)", "value": best["fwd_gbs"], "unit": "GB/s", "n_gpus": 1,
+                      "peak": hbm_peak, "peak_kind": peak_kind, "frac": best["fwd_frac"], "best": best, "sweep": rows,
+                      "config": {"workload": "NTT/INTT sweep N=2^12..2^16, L in {1,8,24,32}, 30- and 61-bit chains, ~1 GiB of limbs per point (> L2)"}}), flush=True)
+
+
 # algorithmic bytes per launch of each kernel as launched by the batched ct-mult (see DESIGN.md)
 KERNEL_BYTES = {
     "ntt_fwd_pass1": lambda n, l, batch: 8.0 * n * l * batch,
@@ -421,8 +496,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prof", dest="prof", action="store_false")
     ap.add_argument("--imad", action="store_true", help="also run the integer-pipe microbenchmark")
+    ap.add_argument("--op", default="", choices=["", "mul", "rotate"], help="hot-path operation (default: mul; rotate for cfg3)")
+    ap.add_argument("--ntt-sweep", action="store_true", help="BASELINE.json configs[4]: limb-batched NTT/INTT sweep instead of the ct-mult bench")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.ntt_sweep:
+        run_ntt_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -92,6 +92,9 @@ int ckks_set_ntt_path(int path);
 /* Test hook: 1 = run the key-switch from its unfused building blocks (digit broadcast, NTT, MAC);
  * 0 (default) = fused ks_pass1 / ks_pass2 kernels on the four-step path.  Same results. */
 int ckks_set_unfused(int on);
+/* Test hook: contexts created afterwards with all moduli < 2^31 use 32-bit butterflies, tables and
+ * scratch on the four-step path (1, default) or the generic 64-bit code (0).  Same results. */
+int ckks_set_word32(int on);
 
 /* ---- RnsPoly<N>  (poly.rs) --------------------------------------------------------------------- */
 /* RnsPoly::zero(basis) poly.rs:36-42, for `batch` polynomials (coefficient domain). */

@@ -13,66 +13,66 @@
 namespace {
 constexpr int E = 4, C = 16, CP = C + 1;
 
-template <int KIND, int A, int T, bool LAZY>
-void step_all(std::vector<std::array<u64, 16>> &regs, const tw_t *tab, u64 q, u64 q2) {
+template <int KIND, int A, int T, bool LAZY, typename WD, typename TW>
+void step_all(std::vector<std::array<WD, 16>> &regs, const TW *tab, WD q, WD q2) {
     const int G = TileGeom<A, E>::G;
     for (int g = 0; g < G; ++g)
         for (int c = 0; c < C; ++c) {
-            u64(&v)[16] = *reinterpret_cast<u64(*)[16]>(regs[g * C + c].data());
+            WD(&v)[16] = *reinterpret_cast<WD(*)[16]>(regs[g * C + c].data());
             xf_step<KIND, A, E, T, LAZY>(v, g, tab, q, q2);
         }
 }
-template <int A>
-void exchange(std::vector<std::array<u64, 16>> &regs, std::vector<u64> &sm, int lo_from, int lo_to) {
+template <int A, typename WD>
+void exchange(std::vector<std::array<WD, 16>> &regs, std::vector<WD> &sm, int lo_from, int lo_to) {
     const int G = TileGeom<A, E>::G;
     for (int g = 0; g < G; ++g)
         for (int c = 0; c < C; ++c) {
-            u64(&v)[16] = *reinterpret_cast<u64(*)[16]>(regs[g * C + c].data());
+            WD(&v)[16] = *reinterpret_cast<WD(*)[16]>(regs[g * C + c].data());
             tile_put<E, CP>(sm.data(), v, g, c, lo_from);
         }
     for (int g = 0; g < G; ++g)
         for (int c = 0; c < C; ++c) {
-            u64(&v)[16] = *reinterpret_cast<u64(*)[16]>(regs[g * C + c].data());
+            WD(&v)[16] = *reinterpret_cast<WD(*)[16]>(regs[g * C + c].data());
             tile_get<E, CP>(sm.data(), v, g, c, lo_to);
         }
 }
 
-template <int KIND, int A, bool LAZY, bool PRE, bool POST, bool TR>
-void pass(const u64 *src, u64 *dst, const LimbConst &m, const tw_t *tab, const tw_t *elt, unsigned ncols, int *range_bad) {
+template <int KIND, int A, bool LAZY, bool PRE, bool POST, bool TR, typename WD, typename TW>
+void pass(const u64 *src, u64 *dst, const LimbConst &m, const TW *tab, const TW *elt, unsigned ncols, int *range_bad, WD) {
     typedef TileGeom<A, E> GM;
     constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);
     constexpr int lo_in = FWD ? GM::lo(0) : GM::lo(GM::NS - 1);
     constexpr int lo_out = FWD ? GM::lo(GM::NS - 1) : GM::lo(0);
-    const u64 q = m.q, q2 = m.q2;
-    std::vector<u64> sm((size_t)(1 << A) * CP);
+    const WD q = (WD)m.q, q2 = (WD)m.q2;
+    std::vector<WD> sm((size_t)(1 << A) * CP);
     for (unsigned c0 = 0; c0 < ncols; c0 += C) {
-        std::vector<std::array<u64, 16>> regs(GM::G * C);
+        std::vector<std::array<WD, 16>> regs(GM::G * C);
         for (int g = 0; g < GM::G; ++g)
             for (int c = 0; c < C; ++c)
                 for (int k = 0; k < 16; ++k) {
                     size_t off = (size_t)tile_idx<E>(g, k, lo_in) * ncols + c0 + c;
-                    u64 x = src[off];
+                    WD x = (WD)src[off];
                     if (PRE) x = mul_tw<LAZY>(x, elt[off], q);
                     regs[g * C + c][k] = x;
                 }
         if (FWD) {
             step_all<KIND, A, 0, LAZY>(regs, tab, q, q2);
             if (GM::NS >= 2) {
-                exchange<A>(regs, sm, GM::lo(0), GM::lo(1));
+                exchange<A, WD>(regs, sm, GM::lo(0), GM::lo(1));
                 step_all<KIND, A, (GM::NS >= 2 ? 1 : 0), LAZY>(regs, tab, q, q2);
             }
             if (GM::NS >= 3) {
-                exchange<A>(regs, sm, GM::lo(1), GM::lo(2));
+                exchange<A, WD>(regs, sm, GM::lo(1), GM::lo(2));
                 step_all<KIND, A, (GM::NS >= 3 ? 2 : 0), LAZY>(regs, tab, q, q2);
             }
         } else {
             step_all<KIND, A, GM::NS - 1, LAZY>(regs, tab, q, q2);
             if (GM::NS >= 2) {
-                exchange<A>(regs, sm, GM::lo(GM::NS - 1), GM::lo(GM::NS - 2));
+                exchange<A, WD>(regs, sm, GM::lo(GM::NS - 1), GM::lo(GM::NS - 2));
                 step_all<KIND, A, (GM::NS >= 2 ? GM::NS - 2 : 0), LAZY>(regs, tab, q, q2);
             }
             if (GM::NS >= 3) {
-                exchange<A>(regs, sm, GM::lo(1), GM::lo(0));
+                exchange<A, WD>(regs, sm, GM::lo(1), GM::lo(0));
                 step_all<KIND, A, 0, LAZY>(regs, tab, q, q2);
             }
         }
@@ -82,42 +82,44 @@ void pass(const u64 *src, u64 *dst, const LimbConst &m, const tw_t *tab, const t
                 for (int k = 0; k < 16; ++k) {
                     int idx = tile_idx<E>(g, k, lo_out);
                     size_t off = (size_t)idx * ncols + c0 + c;
-                    u64 x = regs[g * C + c][k];
+                    WD x = regs[g * C + c][k];
                     // lazy-range audit: CT kinds must stay below 4q, GS kinds below 2q
-                    if (LAZY && x >= (CT_RANGE ? 4 * q : 2 * q)) *range_bad = 1;
+                    if (LAZY && (u64)x >= (CT_RANGE ? 4 * (u64)q : 2 * (u64)q)) *range_bad = 1;
                     if (!LAZY && x >= q) *range_bad = 1;
                     if (POST) x = mul_tw<LAZY>(x, elt[off], q);
                     if (TR) {
-                        dst[(size_t)(c0 + c) * (1 << A) + idx] = x;
+                        dst[(size_t)(c0 + c) * (1 << A) + idx] = (u64)x;
                     } else {
                         if (POST || !CT_RANGE) x = canon2<LAZY>(x, q);
                         else x = canon4<LAZY>(x, q, q2);
-                        dst[off] = x;
+                        dst[off] = (u64)x;
                     }
                 }
     }
 }
 
-template <int KIND, bool LAZY, bool PRE, bool POST, bool TR>
-void pass_a(int A, const u64 *src, u64 *dst, const LimbConst &m, const tw_t *tab, const tw_t *elt, unsigned ncols, int *bad) {
+template <int KIND, bool LAZY, bool PRE, bool POST, bool TR, typename WD, typename TW>
+void pass_a(int A, const u64 *src, u64 *dst, const LimbConst &m, const TW *tab, const TW *elt, unsigned ncols, int *bad, WD w) {
     switch (A) {
-        case 4: pass<KIND, 4, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad); break;
-        case 5: pass<KIND, 5, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad); break;
-        case 6: pass<KIND, 6, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad); break;
-        case 7: pass<KIND, 7, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad); break;
-        case 8: pass<KIND, 8, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad); break;
+        case 4: pass<KIND, 4, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad, w); break;
+        case 5: pass<KIND, 5, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad, w); break;
+        case 6: pass<KIND, 6, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad, w); break;
+        case 7: pass<KIND, 7, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad, w); break;
+        case 8: pass<KIND, 8, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad, w); break;
     }
 }
-template <bool LAZY>
-void run(const ht::HostTables &H, u64 n, int a1, int a2, u64 *d, int inverse, int *bad) {
+template <bool LAZY, typename WD, typename TW>
+void run(const LimbConst &lc, const TW *P1, const TW *P1i, const TW *W2, const TW *W2i, const TW *TT, const TW *TTi, u64 n, int a1,
+         int a2, u64 *d, int inverse, int *bad, WD w) {
     std::vector<u64> tmp(n);
     unsigned n1 = 1u << a1, n2 = 1u << a2;
+    const TW *none = nullptr;
     if (!inverse) {
-        pass_a<XF_NEG_FWD, LAZY, false, false, true>(a1, d, tmp.data(), H.lc[0], H.P1.data(), nullptr, n2, bad);
-        pass_a<XF_CYC_FWD, LAZY, true, false, false>(a2, tmp.data(), d, H.lc[0], H.W2.data(), H.TT.data(), n1, bad);
+        pass_a<XF_NEG_FWD, LAZY, false, false, true>(a1, d, tmp.data(), lc, P1, none, n2, bad, w);
+        pass_a<XF_CYC_FWD, LAZY, true, false, false>(a2, tmp.data(), d, lc, W2, TT, n1, bad, w);
     } else {
-        pass_a<XF_CYC_INV, LAZY, false, true, true>(a2, d, tmp.data(), H.lc[0], H.W2i.data(), H.TTi.data(), n1, bad);
-        pass_a<XF_NEG_INV, LAZY, false, false, false>(a1, tmp.data(), d, H.lc[0], H.P1i.data(), nullptr, n2, bad);
+        pass_a<XF_CYC_INV, LAZY, false, true, true>(a2, d, tmp.data(), lc, W2i, TTi, n1, bad, w);
+        pass_a<XF_NEG_INV, LAZY, false, false, false>(a1, tmp.data(), d, lc, P1i, none, n2, bad, w);
     }
 }
 }  // namespace
@@ -132,10 +134,29 @@ extern "C" int emul_ntt_4step(uint64_t n, uint64_t q, uint64_t *data, int invers
     int a1 = (logn + 1) / 2, a2 = logn - a1;
     std::vector<u64> mod{(u64)q}, psi{hm::find_primitive_root(q, 2 * n)};
     ht::HostTables H;
-    ht::build_host_tables(n, logn, 2, a1, a2, mod, psi, H);
+    ht::build_host_tables(n, logn, 2, a1, a2, mod, psi, H, false);
     int bad = 0;
-    if (H.lazy && !force_strict) run<true>(H, n, a1, a2, (u64 *)data, inverse, &bad);
-    else run<false>(H, n, a1, a2, (u64 *)data, inverse, &bad);
+    if (H.lazy && !force_strict)
+        run<true>(H.lc[0], H.P1.data(), H.P1i.data(), H.W2.data(), H.W2i.data(), H.TT.data(), H.TTi.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u64)0);
+    else
+        run<false>(H.lc[0], H.P1.data(), H.P1i.data(), H.W2.data(), H.W2i.data(), H.TT.data(), H.TTi.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u64)0);
+    return bad;
+}
+// Same with 32-bit words (q < 2^31).  Returns -2 if the table builder does not select the 32-bit path.
+extern "C" int emul_ntt_4step32(uint64_t n, uint64_t q, uint64_t *data, int inverse, int force_strict) {
+    int logn = 0;
+    while (((u64)1 << logn) < n) ++logn;
+    if (logn < 8 || logn > 16) return -1;
+    int a1 = (logn + 1) / 2, a2 = logn - a1;
+    std::vector<u64> mod{(u64)q}, psi{hm::find_primitive_root(q, 2 * n)};
+    ht::HostTables H;
+    ht::build_host_tables(n, logn, 2, a1, a2, mod, psi, H, true);
+    if (!H.w32) return -2;
+    int bad = 0;
+    if (H.lazy && !force_strict)
+        run<true>(H.lc[0], H.P1_32.data(), H.P1i_32.data(), H.W2_32.data(), H.W2i_32.data(), H.TT_32.data(), H.TTi_32.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u32)0);
+    else
+        run<false>(H.lc[0], H.P1_32.data(), H.P1i_32.data(), H.W2_32.data(), H.W2i_32.data(), H.TT_32.data(), H.TTi_32.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u32)0);
     return bad;
 }
 // Internal position of natural slot k (same formula as ntt_pos in kernels.cuh).
@@ -148,18 +169,18 @@ extern "C" uint64_t emul_psi(uint64_t n, uint64_t q) { return hm::find_primitive
 extern "C" uint64_t emul_mulmod(uint64_t a, uint64_t b, uint64_t q) {
     std::vector<u64> mod{(u64)q}, psi{1};
     ht::HostTables H;
-    ht::build_host_tables(1, 0, 1, 0, 0, mod, psi, H);
+    ht::build_host_tables(1, 0, 1, 0, 0, mod, psi, H, false);
     return mulmod(a, b, H.lc[0]);
 }
 extern "C" uint64_t emul_mulmod_add(uint64_t a, uint64_t b, uint64_t c, uint64_t q) {
     std::vector<u64> mod{(u64)q}, psi{1};
     ht::HostTables H;
-    ht::build_host_tables(1, 0, 1, 0, 0, mod, psi, H);
+    ht::build_host_tables(1, 0, 1, 0, 0, mod, psi, H, false);
     return mulmod_add(a, b, c, H.lc[0]);
 }
 extern "C" uint64_t emul_barrett_word(uint64_t a, uint64_t q) {
     std::vector<u64> mod{(u64)q}, psi{1};
     ht::HostTables H;
-    ht::build_host_tables(1, 0, 1, 0, 0, mod, psi, H);
+    ht::build_host_tables(1, 0, 1, 0, 0, mod, psi, H, false);
     return barrett_word(a, H.lc[0]);
 }

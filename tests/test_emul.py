@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def emul(built):
     lib = C.CDLL(os.path.join(HERE, "emul", "libntt_emul.so"))
     lib.emul_ntt_4step.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int]
+    lib.emul_ntt_4step32.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int]
     lib.emul_ntt_pos.argtypes = [C.c_uint32, C.c_int, C.c_int]
     lib.emul_ntt_pos.restype = C.c_uint32
     lib.emul_psi.argtypes = [C.c_uint64, C.c_uint64]
@@ -43,6 +44,27 @@ def test_four_step_matches_oracle(emul, orc, logn, bits, strict):
     assert np.array_equal(d[pos], ref)
     assert emul.emul_ntt_4step(n, q, d.ctypes.data_as(C.POINTER(C.c_uint64)), 1, strict) == 0
     assert np.array_equal(d, x)
+
+
+@pytest.mark.parametrize("logn,bits,strict", [(8, 30, 0), (9, 31, 0), (10, 20, 0), (12, 30, 1), (14, 30, 0), (16, 30, 0), (13, 31, 0)])
+def test_four_step_32bit_words_match_oracle(emul, orc, logn, bits, strict):
+    """The 32-bit word path (all q < 2^31; lazy for q < 2^30, strict for 31-bit primes)."""
+    n = 1 << logn
+    q = orc.generate_primes(bits, 1, n)[0]
+    ob = orc.Basis(n, [q])
+    rng = np.random.default_rng(logn * 100 + bits)
+    x = rng.integers(0, q, n, dtype=np.uint64)
+    x[:3] = [q - 1, 0, 1]
+    ref = ob.to_ntt(x[None, :])[0]
+    d = x.copy()
+    assert emul.emul_ntt_4step32(n, q, d.ctypes.data_as(C.POINTER(C.c_uint64)), 0, strict) == 0
+    a1 = (logn + 1) // 2
+    pos = np.array([emul.emul_ntt_pos(k, a1, logn - a1) for k in range(n)])
+    assert np.array_equal(d[pos], ref)
+    assert emul.emul_ntt_4step32(n, q, d.ctypes.data_as(C.POINTER(C.c_uint64)), 1, strict) == 0
+    assert np.array_equal(d, x)
+    big = orc.generate_primes(40, 1, n)[0]
+    assert emul.emul_ntt_4step32(n, big, d.ctypes.data_as(C.POINTER(C.c_uint64)), 0, 0) == -2  # not selected for q >= 2^31
 
 
 def test_modarith_against_python_integers(emul):

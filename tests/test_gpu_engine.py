@@ -141,6 +141,44 @@ def test_unfused_building_blocks_match_fused_and_oracle(gpu, orc, n, bits, l):
         assert np.array_equal(rot.c0.channels()[1], r0) and np.array_equal(rot.c1.channels()[1], r1), f"unfused={unfused}"
 
 
+@pytest.mark.parametrize("n,bits,l", [(256, 30, 3), (1024, 31, 3), (16384, 30, 8), (4096, 20, 4)])
+def test_word32_and_word64_paths_agree_with_oracle(gpu, orc, n, bits, l):
+    """Moduli below 2^31 take the 32-bit word path by default; forcing the 64-bit code must give the
+    same limbs, and both equal the oracle (31-bit primes run the strict, non-lazy 32-bit butterflies)."""
+    moduli = orc.generate_primes(bits, l, n)
+    ob = orc.Basis(n, moduli)
+    rng = np.random.default_rng(400 + n)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, 2) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    m0, m1 = ob.mul_ciphertexts_gadget(a0[1], a1[1], b0[1], b1[1], ka, kb)
+    q0, q1, _ = ob.rescale_ciphertext(m0, m1)
+    r0, r1 = ob.rotate_ciphertext(a0[0], a1[0], ka, kb, 1)
+    ntt = ob.to_ntt(a0[0])
+    for w32 in (True, False):
+        gpu.set_word32(w32)
+        try:
+            gb = gpu.RnsBasis(n, moduli)
+        finally:
+            gpu.set_word32(True)
+        key = gpu.GadgetKey.upload(gb, ka, kb, rotation=1)
+        cta, ctb = _ct(gpu, gb, a0, a1, 30, 90), _ct(gpu, gb, b0, b1, 30, 90)
+        p = cta.c0.clone()
+        p.to_ntt_domain()
+        assert np.array_equal(p.channels()[0], ntt), f"w32={w32}"
+        p.to_coeff_domain()
+        assert np.array_equal(p.channels(), a0)
+        prod = gpu.CkksEngine.mul_ciphertexts_gadget(cta, ctb, key)
+        assert np.array_equal(prod.c0.channels()[1], m0) and np.array_equal(prod.c1.channels()[1], m1), f"w32={w32}"
+        fused = gpu.CkksEngine.mul_relin_rescale(cta, ctb, key)
+        assert np.array_equal(fused.c0.channels()[1], q0) and np.array_equal(fused.c1.channels()[1], q1), f"w32={w32}"
+        rot = gpu.CkksEngine.rotate_ciphertext(cta, key)
+        assert np.array_equal(rot.c0.channels()[0], r0) and np.array_equal(rot.c1.channels()[0], r1), f"w32={w32}"
+        x = cta.c0.clone()
+        x *= ctb.c1
+        assert np.array_equal(x.channels()[1], ob.mul(a0[1], b1[1]))
+        assert np.array_equal(cta.c0.rescale().channels()[0], ob.rescale(a0[0]))
+
+
 def test_add_encrypt_decrypt_keygen_match_oracle(gpu, orc):
     n, l = 1024, 3
     moduli = orc.generate_primes(40, l, n)

@@ -90,6 +90,7 @@ _sig("ckks_ctx_psi", C.c_uint64, _vp, C.c_size_t)
 _sig("ckks_ctx_reconstruct_centered_coeff", C.c_int, _vp, _u64p, _i64p)
 _sig("ckks_set_ntt_path", C.c_int, C.c_int)
 _sig("ckks_set_unfused", C.c_int, C.c_int)
+_sig("ckks_set_word32", C.c_int, C.c_int)
 _sig("ckks_prof_enable", C.c_int, C.c_int)
 _sig("ckks_prof_collect", C.c_size_t, C.c_char_p, C.c_size_t)
 _sig("ckks_poly_from_device", C.c_int, _vp, C.c_size_t, _u64p, C.c_int, _pp)
@@ -173,6 +174,11 @@ def launch_table() -> dict:
 def set_ntt_path(path: int):
     """0 = automatic, 1 = small single-CTA NTT (N <= 2048), 2 = four-step (N >= 256)."""
     _check(_lib.ckks_set_ntt_path(path))
+
+
+def set_word32(on: bool):
+    """Test hook: allow (default) or forbid the 32-bit word path for contexts created afterwards."""
+    _check(_lib.ckks_set_word32(int(on)))
 
 
 def set_unfused(on: bool):

@@ -24,7 +24,8 @@ static std::atomic<uint64_t> g_launches{0};
 static std::mutex g_mu;
 static std::map<std::string, uint64_t> g_launch_table;
 static int g_ntt_path = 0;
-static int g_force_unfused = 0;  // test hook: run the unfused key-switch building blocks
+static int g_force_unfused = 0;
+static int g_allow_w32 = 1;  // test hook: 0 forces 64-bit words even for small moduli  // test hook: run the unfused key-switch building blocks
 
 static int cuda_fail(cudaError_t e, const char *what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -145,6 +146,10 @@ extern "C" size_t ckks_launch_table(char *buf, size_t cap) {
     }
     return s.size() + 1;
 }
+extern "C" int ckks_set_word32(int on) {
+    g_allow_w32 = on != 0;
+    return CKKS_OK;
+}
 extern "C" int ckks_set_unfused(int on) {
     g_force_unfused = on != 0;
     return CKKS_OK;
@@ -172,7 +177,7 @@ static void destroy_host_pipe(struct HostPipe *p);
 Tables::~Tables() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    void *ptrs[] = {d_lc, d_psi, d_psi_inv, d_ninv, d_P1, d_P1i, d_W2, d_W2i, d_TT, d_TTi, d_TTt, d_qlinv};
+    void *ptrs[] = {d_lc, d_psi, d_psi_inv, d_ninv, d_P1, d_P1i, d_W2, d_W2i, d_TT, d_TTi, d_TTt, d_qlinv, d_qlinv_w == d_qlinv ? nullptr : d_qlinv_w};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     destroy_host_pipe(pipe);
@@ -205,8 +210,9 @@ static tw_t mk_tw(u64 w, u64 q) { return ht::mk_tw(w, q); }
 
 static int build_tables(Tables &T) {
     ht::HostTables H;
-    ht::build_host_tables(T.n, T.logn, T.path, T.a1, T.a2, T.moduli, T.psi, H);
+    ht::build_host_tables(T.n, T.logn, T.path, T.a1, T.a2, T.moduli, T.psi, H, g_allow_w32 != 0);
     T.lazy = H.lazy;
+    T.w32 = H.w32;
     T.digit_reduce = H.digit_reduce;
     T.w2_stride = H.w2_stride;
     TRY(upload_vec(&T.d_lc, H.lc));
@@ -217,13 +223,25 @@ static int build_tables(Tables &T) {
         TRY(upload_vec(&T.d_ninv, H.ninv));
         return CKKS_OK;
     }
-    TRY(upload_vec(&T.d_P1, H.P1));
-    TRY(upload_vec(&T.d_P1i, H.P1i));
-    TRY(upload_vec(&T.d_W2, H.W2));
-    TRY(upload_vec(&T.d_W2i, H.W2i));
-    TRY(upload_vec(&T.d_TT, H.TT));
-    TRY(upload_vec(&T.d_TTi, H.TTi));
-    TRY(upload_vec(&T.d_TTt, H.TTt));
+    if (H.w32) {
+        TRY(upload_vec((tw32_t **)&T.d_P1, H.P1_32));
+        TRY(upload_vec((tw32_t **)&T.d_P1i, H.P1i_32));
+        TRY(upload_vec((tw32_t **)&T.d_W2, H.W2_32));
+        TRY(upload_vec((tw32_t **)&T.d_W2i, H.W2i_32));
+        TRY(upload_vec((tw32_t **)&T.d_TT, H.TT_32));
+        TRY(upload_vec((tw32_t **)&T.d_TTi, H.TTi_32));
+        TRY(upload_vec((tw32_t **)&T.d_TTt, H.TTt_32));
+        TRY(upload_vec((tw32_t **)&T.d_qlinv_w, H.ql32));
+        return CKKS_OK;
+    }
+    TRY(upload_vec((tw_t **)&T.d_P1, H.P1));
+    TRY(upload_vec((tw_t **)&T.d_P1i, H.P1i));
+    TRY(upload_vec((tw_t **)&T.d_W2, H.W2));
+    TRY(upload_vec((tw_t **)&T.d_W2i, H.W2i));
+    TRY(upload_vec((tw_t **)&T.d_TT, H.TT));
+    TRY(upload_vec((tw_t **)&T.d_TTi, H.TTi));
+    TRY(upload_vec((tw_t **)&T.d_TTt, H.TTt));
+    T.d_qlinv_w = T.d_qlinv;
     return CKKS_OK;
 }
 
@@ -351,25 +369,30 @@ static unsigned ew_grid(size_t total) {
     return (unsigned)(g < cap ? (g ? g : 1) : cap);
 }
 
-template <int KIND, int A, bool PRE, bool POST, bool TR>
-static int launch_pass_a(const char *name, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+template <typename WD, int KIND, int A, bool PRE, bool POST, bool TR>
+static int launch_pass_w(const char *name, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
     constexpr int E = 4, C = 16;
-    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(u64);
+    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
     if (lazy)
-        KL(name, (ntt_pass_kernel<KIND, A, E, C, true, PRE, POST, TR><<<grid, block, smem, s>>>(a)));
+        KL(name, (ntt_pass_kernel<WD, KIND, A, E, C, true, PRE, POST, TR><<<grid, block, smem, s>>>(a)));
     else
-        KL(name, (ntt_pass_kernel<KIND, A, E, C, false, PRE, POST, TR><<<grid, block, smem, s>>>(a)));
+        KL(name, (ntt_pass_kernel<WD, KIND, A, E, C, false, PRE, POST, TR><<<grid, block, smem, s>>>(a)));
     return CKKS_OK;
 }
+template <int KIND, int A, bool PRE, bool POST, bool TR>
+static int launch_pass_a(const char *name, bool w32, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+    if (w32) return launch_pass_w<u32, KIND, A, PRE, POST, TR>(name, lazy, grid, s, a);
+    return launch_pass_w<u64, KIND, A, PRE, POST, TR>(name, lazy, grid, s, a);
+}
 template <int KIND, bool PRE, bool POST, bool TR>
-static int launch_pass(const char *name, int A, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+static int launch_pass(const char *name, int A, bool w32, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
     switch (A) {
-        case 4: return launch_pass_a<KIND, 4, PRE, POST, TR>(name, lazy, grid, s, a);
-        case 5: return launch_pass_a<KIND, 5, PRE, POST, TR>(name, lazy, grid, s, a);
-        case 6: return launch_pass_a<KIND, 6, PRE, POST, TR>(name, lazy, grid, s, a);
-        case 7: return launch_pass_a<KIND, 7, PRE, POST, TR>(name, lazy, grid, s, a);
-        case 8: return launch_pass_a<KIND, 8, PRE, POST, TR>(name, lazy, grid, s, a);
+        case 4: return launch_pass_a<KIND, 4, PRE, POST, TR>(name, w32, lazy, grid, s, a);
+        case 5: return launch_pass_a<KIND, 5, PRE, POST, TR>(name, w32, lazy, grid, s, a);
+        case 6: return launch_pass_a<KIND, 6, PRE, POST, TR>(name, w32, lazy, grid, s, a);
+        case 7: return launch_pass_a<KIND, 7, PRE, POST, TR>(name, w32, lazy, grid, s, a);
+        case 8: return launch_pass_a<KIND, 8, PRE, POST, TR>(name, w32, lazy, grid, s, a);
     }
     return CKKS_UNSUPPORTED;
 }
@@ -385,8 +408,14 @@ struct Span {
 static Span whole(size_t nb, size_t L) { return Span{nb, (int)L, 0, (int)L, (int)L, 0}; }
 
 enum { P_FWD1, P_FWD2, P_INV2, P_INV1 };
-static int run_pass(const Tables &T, int which, Span sp, const u64 *src, u64 *dst) {
+// src/dst are u64 words except the intermediate between the two passes of a transform (dst of
+// P_FWD1 / P_INV2, src of P_FWD2 / P_INV1), which holds the transform word type (u32 when T.w32).
+static int run_pass(const Tables &T, int which, Span sp, const void *src_, void *dst_) {
     if (sp.nb == 0 || sp.nl == 0) return CKKS_OK;
+    const size_t wsz = T.w32 ? 4 : 8;
+    const size_t ssz = (which == P_FWD2 || which == P_INV1) ? wsz : 8, dsz = (which == P_FWD1 || which == P_INV2) ? wsz : 8;
+    const char *src = (const char *)src_;
+    char *dst = (char *)dst_;
     const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
     cudaStream_t s = T.stream;
     for (size_t b0 = 0; b0 < sp.nb; b0 += 32768) {
@@ -398,35 +427,35 @@ static int run_pass(const Tables &T, int which, Span sp, const u64 *src, u64 *ds
         a.limb0 = sp.limb0;
         a.dstL = sp.dstL;
         a.dst_limb0 = sp.dst_limb0;
-        a.src = src + b0 * sp.L * T.n;
-        a.dst = dst + b0 * sp.dstL * T.n;
+        a.src = src + b0 * sp.L * T.n * ssz;
+        a.dst = dst + b0 * sp.dstL * T.n * dsz;
         a.elt = nullptr;
         switch (which) {
             case P_FWD1:
                 a.tab = T.d_P1;
                 a.tab_stride = n1;
                 a.ncols = n2;
-                TRY((launch_pass<XF_NEG_FWD, false, false, true>("ntt_fwd_pass1", T.a1, T.lazy, dim3(n2 / 16, sp.nl, (unsigned)nb), s, a)));
+                TRY((launch_pass<XF_NEG_FWD, false, false, true>("ntt_fwd_pass1", T.a1, T.w32, T.lazy, dim3(n2 / 16, sp.nl, (unsigned)nb), s, a)));
                 break;
             case P_FWD2:
                 a.tab = T.d_W2;
                 a.tab_stride = T.w2_stride;
                 a.elt = T.d_TT;
                 a.ncols = n1;
-                TRY((launch_pass<XF_CYC_FWD, true, false, false>("ntt_fwd_pass2", T.a2, T.lazy, dim3(n1 / 16, sp.nl, (unsigned)nb), s, a)));
+                TRY((launch_pass<XF_CYC_FWD, true, false, false>("ntt_fwd_pass2", T.a2, T.w32, T.lazy, dim3(n1 / 16, sp.nl, (unsigned)nb), s, a)));
                 break;
             case P_INV2:
                 a.tab = T.d_W2i;
                 a.tab_stride = T.w2_stride;
                 a.elt = T.d_TTi;
                 a.ncols = n1;
-                TRY((launch_pass<XF_CYC_INV, false, true, true>("ntt_inv_pass2", T.a2, T.lazy, dim3(n1 / 16, sp.nl, (unsigned)nb), s, a)));
+                TRY((launch_pass<XF_CYC_INV, false, true, true>("ntt_inv_pass2", T.a2, T.w32, T.lazy, dim3(n1 / 16, sp.nl, (unsigned)nb), s, a)));
                 break;
             case P_INV1:
                 a.tab = T.d_P1i;
                 a.tab_stride = n1;
                 a.ncols = n2;
-                TRY((launch_pass<XF_NEG_INV, false, false, false>("ntt_inv_pass1", T.a1, T.lazy, dim3(n2 / 16, sp.nl, (unsigned)nb), s, a)));
+                TRY((launch_pass<XF_NEG_INV, false, false, false>("ntt_inv_pass1", T.a1, T.w32, T.lazy, dim3(n2 / 16, sp.nl, (unsigned)nb), s, a)));
                 break;
         }
     }
@@ -982,12 +1011,12 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
 // ---- fused four-step key-switch pipeline -----------------------------------------------------------
 constexpr int KS_E2 = 3, KS_C2 = 16;  // ks_pass2: 8 elements per thread leave room for the 128-bit accumulators
 
-template <int A>
-static int launch_ks1_a(bool lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
+template <typename WD, int A>
+static int launch_ks1_w(bool lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
     constexpr int E = 4, C = 16;
-    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(u64);
+    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
-#define KS1(LZ, RD, DG) KL("ks_pass1", (ks_pass1_kernel<A, E, C, LZ, RD, DG><<<grid, block, smem, s>>>(a)))
+#define KS1(LZ, RD, DG) KL("ks_pass1", (ks_pass1_kernel<WD, A, E, C, LZ, RD, DG><<<grid, block, smem, s>>>(a)))
     if (lazy) {
         if (reduce) { if (diag) KS1(true, true, true); else KS1(true, true, false); }
         else { if (diag) KS1(true, false, true); else KS1(true, false, false); }
@@ -998,15 +1027,20 @@ static int launch_ks1_a(bool lazy, bool reduce, bool diag, dim3 grid, cudaStream
     return CKKS_OK;
 }
 template <int A>
-static int launch_ks2_a(bool lazy, bool mul, dim3 grid, cudaStream_t s, const KsArgs &a) {
+static int launch_ks1_a(bool w32, bool lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
+    if (w32) return launch_ks1_w<u32, A>(lazy, reduce, diag, grid, s, a);
+    return launch_ks1_w<u64, A>(lazy, reduce, diag, grid, s, a);
+}
+template <typename WD, int A>
+static int launch_ks2_w(bool lazy, bool mul, dim3 grid, cudaStream_t s, const KsArgs &a) {
     constexpr int E = KS_E2, C = KS_C2;
-    const size_t smem = ks2_smem_words<A, C>() * sizeof(u64);
+    const size_t smem = ks2_smem_bytes<WD, A, C>();
     const int block = C << (A - E);
 #define KS2(LZ, MU)                                                                                                     \
     do {                                                                                                                \
         if (smem > 48 * 1024)                                                                                           \
-            CU(cudaFuncSetAttribute(ks_pass2_kernel<A, E, C, LZ, MU, MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        KL("ks_pass2", (ks_pass2_kernel<A, E, C, LZ, MU, MU><<<grid, block, smem, s>>>(a)));                             \
+            CU(cudaFuncSetAttribute(ks_pass2_kernel<WD, A, E, C, LZ, MU, MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        KL("ks_pass2", (ks_pass2_kernel<WD, A, E, C, LZ, MU, MU><<<grid, block, smem, s>>>(a)));                         \
     } while (0)
     if (lazy) { if (mul) KS2(true, true); else KS2(true, false); }
     else { if (mul) KS2(false, true); else KS2(false, false); }
@@ -1014,13 +1048,23 @@ static int launch_ks2_a(bool lazy, bool mul, dim3 grid, cudaStream_t s, const Ks
     return CKKS_OK;
 }
 template <int A>
-static int launch_inv1_rescale_a(bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const tw_t *ql) {
+static int launch_ks2_a(bool w32, bool lazy, bool mul, dim3 grid, cudaStream_t s, const KsArgs &a) {
+    if (w32) return launch_ks2_w<u32, A>(lazy, mul, grid, s, a);
+    return launch_ks2_w<u64, A>(lazy, mul, grid, s, a);
+}
+template <typename WD, int A>
+static int launch_inv1_rescale_w(bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const void *ql) {
     constexpr int E = 4, C = 16;
-    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(u64);
+    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
-    if (lazy) KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<A, E, C, true><<<grid, block, smem, s>>>(a, last, ql)));
-    else KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<A, E, C, false><<<grid, block, smem, s>>>(a, last, ql)));
+    if (lazy) KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<WD, A, E, C, true><<<grid, block, smem, s>>>(a, last, ql)));
+    else KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<WD, A, E, C, false><<<grid, block, smem, s>>>(a, last, ql)));
     return CKKS_OK;
+}
+template <int A>
+static int launch_inv1_rescale_a(bool w32, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const void *ql) {
+    if (w32) return launch_inv1_rescale_w<u32, A>(lazy, grid, s, a, last, ql);
+    return launch_inv1_rescale_w<u64, A>(lazy, grid, s, a, last, ql);
 }
 #define DISPATCH_A(Aval, CALL)                   \
     switch (Aval) {                              \
@@ -1071,9 +1115,9 @@ static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, con
     const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
     cudaStream_t s = T.stream;
     dim3 g1(n2 / 16, (unsigned)(L * L), (unsigned)cs);
-    DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.lazy, T.digit_reduce, mul, g1, s, a)));
+    DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.w32, T.lazy, T.digit_reduce, mul, g1, s, a)));
     dim3 g2(n1 / KS_C2, (unsigned)L, (unsigned)cs);
-    DISPATCH_A(T.a2, TRY(launch_ks2_a<AA>(T.lazy, mul, g2, s, a)));
+    DISPATCH_A(T.a2, TRY(launch_ks2_a<AA>(T.w32, T.lazy, mul, g2, s, a)));
     return CKKS_OK;
 }
 
@@ -1140,13 +1184,13 @@ static int fused_mul_relin(const Tables &T, size_t L, size_t batch, const u64 *a
             pa.dstL = (int)L - 1;
             pa.dst_limb0 = 0;
             dim3 g((1u << T.a2) / 16, (unsigned)(L - 1), (unsigned)cs);
-            const tw_t *ql = T.d_qlinv + (L - 1) * T.L;
+            const void *ql = T.w32 ? (const void *)((const tw32_t *)T.d_qlinv_w + (L - 1) * T.L) : (const void *)(T.d_qlinv + (L - 1) * T.L);
             pa.src = TMP;
             pa.dst = d0;
-            DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.lazy, g, T.stream, pa, LAST, ql)));
+            DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, LAST, ql)));
             pa.src = B1;
             pa.dst = d1;
-            DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.lazy, g, T.stream, pa, LAST + cs * n, ql)));
+            DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, LAST + cs * n, ql)));
             return CKKS_OK;
         };
         rc = step();

@@ -17,7 +17,8 @@ struct Tables {
     int logn = 0;
     int path = 0;  // 1 = small single-CTA NTT, 2 = four-step
     int a1 = 0, a2 = 0;  // four-step: N = 2^a1 * 2^a2 (small path: a1 = logn, a2 = 0)
-    bool lazy = true;    // all q < 2^62
+    bool lazy = true;    // all q < 2^62 (u64 words) / all q < 2^30 (u32 words)
+    bool w32 = false;    // all q < 2^31 on the four-step path: 32-bit butterflies, tables and scratch
     bool digit_reduce = true;  // key-switch digits need `% q_j` before the lazy NTT
     size_t L = 0;
     std::vector<u64> moduli, psi;
@@ -25,7 +26,9 @@ struct Tables {
     // small path
     tw_t *d_psi = nullptr, *d_psi_inv = nullptr, *d_ninv = nullptr;
     // four-step
-    tw_t *d_P1 = nullptr, *d_P1i = nullptr, *d_W2 = nullptr, *d_W2i = nullptr, *d_TT = nullptr, *d_TTi = nullptr, *d_TTt = nullptr;
+    // (tw_t entries, or tw32_t when w32)
+    void *d_P1 = nullptr, *d_P1i = nullptr, *d_W2 = nullptr, *d_W2i = nullptr, *d_TT = nullptr, *d_TTi = nullptr, *d_TTt = nullptr;
+    void *d_qlinv_w = nullptr;  // qlinv in the transform word type (tw32_t when w32, else aliases d_qlinv)
     size_t w2_stride = 1;
     // rescale: qlinv[last][i] = q_last^-1 mod q_i (Shoup pair), [L][L]
     tw_t *d_qlinv = nullptr;

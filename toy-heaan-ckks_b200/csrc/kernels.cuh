@@ -1,6 +1,8 @@
 // kernels.cuh -- CUDA kernels (sm_100a) of the RNS-NTT hot path.  Each kernel cites the reference
 // code whose effect it reproduces (paths relative to the reference repository root).
 #pragma once
+#include <type_traits>
+
 #include "ntt_tile.cuh"
 
 // Data layout everywhere: [batch][limb][N] u64, limb-major like the reference's Vec<[u64; N]>
@@ -11,11 +13,11 @@
 // Four-step NTT passes
 // =================================================================================================
 struct PassArgs {
-    const u64 *src;
-    u64 *dst;
+    const void *src;      // u64 words, or the internal word type WD for the second pass of a transform
+    void *dst;            // WD for a transposed (internal) store, u64 otherwise
     const LimbConst *lc;  // [L]
-    const tw_t *tab;      // small per-limb twiddle table, tab_stride entries per limb
-    const tw_t *elt;      // per-element table (N entries per limb), or null
+    const void *tab;      // small per-limb twiddle table (TwOf<WD>), tab_stride entries per limb
+    const void *elt;      // per-element table (N entries per limb), or null
     size_t tab_stride;
     int L;          // limbs per polynomial in src
     unsigned ncols;  // columns (= stride of the transform dimension, in words)
@@ -33,13 +35,22 @@ struct PassArgs {
 //              otherwise store in place dst[idx][col] as canonical representatives.
 // Forward  to_ntt_domain  (poly.rs:136-148, 574-580) = <NEG_FWD,TRANSPOSE> then <CYC_FWD,PREMUL>.
 // Inverse  to_coeff_domain(poly.rs:154-166, 582-591) = <CYC_INV,POSTMUL,TRANSPOSE> then <NEG_INV>.
-template <int KIND, int A, int E, int C, bool LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE>
+// WD = u64 (any q < 2^63) or u32 (all q < 2^31: 32-bit butterflies, 32-bit internal scratch; the words
+// that cross the boundary stay u64).
+template <typename WD, int KIND, int A, int E, int C, bool LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a) {
     typedef TileGeom<A, E> GM;
+    typedef typename TwOf<WD>::type TW;
     constexpr int CP = C + 1;
     constexpr int NT = C * GM::G;
     constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);
-    extern __shared__ u64 sm[];
+    constexpr bool SRC_INTERNAL = (KIND == XF_CYC_FWD || KIND == XF_NEG_INV);
+    typedef typename std::conditional<SRC_INTERNAL, WD, u64>::type SRC_T;
+    typedef typename std::conditional<TRANSPOSE, WD, u64>::type DST_T;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    WD *sm = reinterpret_cast<WD *>(sm_raw);
+    const SRC_T *src = reinterpret_cast<const SRC_T *>(a.src);
+    DST_T *dst = reinterpret_cast<DST_T *>(a.dst);
     const int tid = threadIdx.x;
     const int c = tid % C, g = tid / C;
     const int limb = blockIdx.y + a.limb0;
@@ -47,17 +58,17 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
     const size_t base = ((size_t)blockIdx.z * a.L + limb) * a.N;
     const size_t dbase = ((size_t)blockIdx.z * a.dstL + (limb - a.dst_limb0)) * a.N;
     const LimbConst m = a.lc[limb];
-    const u64 q = m.q, q2 = m.q2;
-    const tw_t *tab = a.tab + (size_t)limb * a.tab_stride;
-    const tw_t *elt = (PREMUL || POSTMUL) ? a.elt + (size_t)limb * a.N : nullptr;
+    const WD q = (WD)m.q, q2 = (WD)m.q2;
+    const TW *tab = reinterpret_cast<const TW *>(a.tab) + (size_t)limb * a.tab_stride;
+    const TW *elt = (PREMUL || POSTMUL) ? reinterpret_cast<const TW *>(a.elt) + (size_t)limb * a.N : nullptr;
 
-    u64 v[1 << E];
+    WD v[1 << E];
     constexpr int lo_in = FWD ? GM::lo(0) : GM::lo(GM::NS - 1);
     constexpr int lo_out = FWD ? GM::lo(GM::NS - 1) : GM::lo(0);
 #pragma unroll
     for (int k = 0; k < (1 << E); ++k) {
         size_t off = (size_t)tile_idx<E>(g, k, lo_in) * a.ncols + c0 + c;
-        u64 x = a.src[base + off];
+        WD x = (WD)src[base + off];
         if (PREMUL) x = mul_tw<LAZY>(x, ldg_tw(elt + off), q);
         v[k] = x;
     }
@@ -74,19 +85,19 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
         if (GM::NS >= 2) __syncthreads();
         tile_put<E, CP>(sm, v, g, c, lo_out);
         __syncthreads();
-        u64 *d = a.dst + dbase + c0 * (size_t)(1 << A);
+        DST_T *d = dst + dbase + c0 * (size_t)(1 << A);
         for (int e = tid; e < (C << A); e += NT) {
             int cc = e >> A, r = e & ((1 << A) - 1);
-            d[e] = sm[r * CP + cc];
+            d[e] = (DST_T)sm[r * CP + cc];
         }
     } else {
 #pragma unroll
         for (int k = 0; k < (1 << E); ++k) {
             size_t off = (size_t)tile_idx<E>(g, k, lo_out) * a.ncols + c0 + c;
-            u64 x = v[k];
+            WD x = v[k];
             if (POSTMUL || !CT_RANGE) x = canon2<LAZY>(x, q);
             else x = canon4<LAZY>(x, q, q2);
-            a.dst[dbase + off] = x;
+            dst[dbase + off] = (DST_T)x;
         }
     }
 }
@@ -361,12 +372,12 @@ __global__ void modmul_peak_kernel(u64 *out, int iters, u64 q, tw_t t) {
 struct KsArgs {
     const u64 *digits;   // [cts][L][N] coefficient domain (d2 or the rotated c1)
     const u64 *dig_ntt;  // [cts][L][N] NTT domain of the same polynomial (digit i == j shortcut)
-    u64 *scratch;        // [cts][L(j)][L(i)][N] transposed pass-1 output
+    void *scratch;       // [cts][L(j)][L(i)][N] transposed pass-1 output, internal word type WD
     const u64 *key_b, *key_a;  // [L(i)][L(j)][N] NTT domain
     const u64 *add0, *add1;    // [cts][L][N] NTT domain addends (d0, d1) or null
-    u64 *out0, *out1;          // [cts][L][N] transposed inverse-pass-2 output
+    void *out0, *out1;         // [cts][L][N] transposed inverse-pass-2 output, internal word type WD
     const LimbConst *lc;
-    const tw_t *P1, *W2, *W2i, *TTt, *TTi;
+    const void *P1, *W2, *W2i, *TTt, *TTi;  // TwOf<WD> tables
     size_t w2_stride;
     int L;
     int a1, a2;
@@ -374,12 +385,14 @@ struct KsArgs {
     size_t N;
 };
 
-template <int A, int E, int C, bool LAZY, bool REDUCE, bool DIAG>
+template <typename WD, int A, int E, int C, bool LAZY, bool REDUCE, bool DIAG>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
     typedef TileGeom<A, E> GM;
+    typedef typename TwOf<WD>::type TW;
     constexpr int CP = C + 1;
     constexpr int NT = C * GM::G;
-    extern __shared__ u64 sm[];
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    WD *sm = reinterpret_cast<WD *>(sm_raw);
     const int L = a.L;
     const int j = blockIdx.y / L, i = blockIdx.y % L;
     if (DIAG && i == j) return;  // ks_pass2 takes the NTT-domain limb itself for this digit
@@ -388,20 +401,20 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
     const size_t c0 = (size_t)blockIdx.x * C;
     const unsigned ncols = 1u << a.a2;
     const LimbConst m = a.lc[j];
-    const u64 q = m.q, q2 = m.q2;
+    const WD q = (WD)m.q, q2 = (WD)m.q2;
     const u64 *src = a.digits + ((size_t)blockIdx.z * L + i) * a.N;
-    u64 *dst = a.scratch + (((size_t)blockIdx.z * L + j) * L + i) * a.N;
-    const tw_t *tab = a.P1 + ((size_t)j << A);
-    u64 v[1 << E];
+    WD *dst = reinterpret_cast<WD *>(a.scratch) + (((size_t)blockIdx.z * L + j) * L + i) * a.N;
+    const TW *tab = reinterpret_cast<const TW *>(a.P1) + ((size_t)j << A);
+    WD v[1 << E];
 #pragma unroll
     for (int k = 0; k < (1 << E); ++k) {
         u64 x = src[(size_t)tile_idx<E>(g, k, GM::lo(0)) * ncols + c0 + c];
         if (REDUCE) x = LAZY ? barrett_word_lazy(x, m) : barrett_word(x, m);
-        v[k] = x;
+        v[k] = (WD)x;
     }
     xf_tile<XF_NEG_FWD, A, E, CP, LAZY>(v, g, c, sm, tab, q, q2);
     {  // four-step twiddle psi^(j2 (2 k1 + 1)), table in this pass's [rho][j2] layout
-        const tw_t *TTt = a.TTt + (size_t)j * a.N;
+        const TW *TTt = reinterpret_cast<const TW *>(a.TTt) + (size_t)j * a.N;
 #pragma unroll
         for (int k = 0; k < (1 << E); ++k)
             v[k] = mul_tw<LAZY>(v[k], ldg_tw(TTt + (size_t)tile_idx<E>(g, k, GM::lo(GM::NS - 1)) * ncols + c0 + c), q);
@@ -409,7 +422,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
     if (GM::NS >= 2) __syncthreads();
     tile_put<E, CP>(sm, v, g, c, GM::lo(GM::NS - 1));
     __syncthreads();
-    u64 *d = dst + c0 * (size_t)(1 << A);
+    WD *d = dst + c0 * (size_t)(1 << A);
     for (int e = tid; e < (C << A); e += NT) {
         int cc = e >> A, r = e & ((1 << A) - 1);
         d[e] = sm[r * CP + cc];
@@ -428,36 +441,62 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// Asynchronous copy of a [2^A][C] word tile (row stride `ncols` words in global memory) into a dense
-// [2^A][C] shared-memory tile, 16 bytes per request (LDGSTS), issued by all NT threads.
-template <int A, int C, int NT>
-__device__ __forceinline__ void stage_tile(u64 *sdst, const u64 *gsrc, unsigned ncols, int tid) {
-    constexpr int CH = C / 2;  // 16-byte chunks per row
+// Asynchronous copy of a [2^A][C] tile of T words (row stride `ncols` words in global memory) into a
+// dense [2^A][C] shared-memory tile, 16 bytes per request (LDGSTS), issued by all NT threads.
+template <typename T, int A, int C, int NT>
+__device__ __forceinline__ void stage_tile(T *sdst, const T *gsrc, unsigned ncols, int tid) {
+    constexpr int PER = 16 / sizeof(T);  // words per 16-byte chunk
+    constexpr int CH = C / PER;          // chunks per row
     for (int e = tid; e < (CH << A); e += NT) {
         int r = e / CH, part = e % CH;
-        cp_async16(sdst + r * C + part * 2, gsrc + (size_t)r * ncols + part * 2);
+        cp_async16(sdst + r * C + part * PER, gsrc + (size_t)r * ncols + part * PER);
     }
 }
 
-// Shared memory of ks_pass2: exchange tile [2^A][C+1], two scratch stages and one key-pair stage
-// of [2^A][C] words each.
-template <int A, int C>
-constexpr size_t ks2_smem_words() {
-    return (size_t)(1 << A) * (C + 1) + 4 * (size_t)(1 << A) * C;
+// Key-switch accumulators: sum_i x_i * k_i kept unreduced.
+//   u64 limbs: 128-bit (lo, hi) registers;  u32 limbs: one 64-bit register (products < 2^62).
+template <typename WD>
+struct KsAcc;
+template <>
+struct KsAcc<u64> {
+    u64 lo, hi;
+    __device__ __forceinline__ void clear() { lo = hi = 0; }
+    __device__ __forceinline__ void mac(u64 x, u64 k) { mac128(lo, hi, x, k); }
+    __device__ __forceinline__ u64 reduce(const LimbConst &m) const { return reduce128(hi, lo, m); }
+    __device__ __forceinline__ void set(u64 r) {
+        lo = r;
+        hi = 0;
+    }
+};
+template <>
+struct KsAcc<u32> {
+    u64 s;
+    __device__ __forceinline__ void clear() { s = 0; }
+    __device__ __forceinline__ void mac(u32 x, u64 k) { s += (u64)x * (u32)k; }
+    __device__ __forceinline__ u32 reduce(const LimbConst &m) const { return (u32)barrett_word(s, m); }
+    __device__ __forceinline__ void set(u32 r) { s = r; }
+};
+
+// Shared memory of ks_pass2 in bytes: two stages of the digit tile (WD), key_b and key_a tiles (u64),
+// exchange tile [2^A][C+1] (WD).
+template <typename WD, int A, int C>
+constexpr size_t ks2_smem_bytes() {
+    return (size_t)(1 << A) * C * (2 * sizeof(WD) + 2 * sizeof(u64)) + (size_t)(1 << A) * (C + 1) * sizeof(WD);
 }
 
-template <int A, int E, int C, bool LAZY, bool ADD, bool DIAG>
+template <typename WD, int A, int E, int C, bool LAZY, bool ADD, bool DIAG>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
     typedef TileGeom<A, E> GM;
+    typedef typename TwOf<WD>::type TW;
     constexpr int CP = C + 1;
     constexpr int NT = C * GM::G;
     constexpr int R = 1 << E;
     constexpr int TILE = (1 << A) * C;
-    extern __shared__ __align__(16) u64 sm_all[];
-    u64 *stS = sm_all;                 // 2 stages of the digit's pass-1 output
-    u64 *stKb = sm_all + 2 * TILE;     // key_b tile of the current digit
-    u64 *stKa = sm_all + 3 * TILE;     // key_a tile
-    u64 *sm = sm_all + 4 * TILE;       // exchange buffer
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    u64 *stKb = reinterpret_cast<u64 *>(sm_raw);  // key_b tile of the current digit
+    u64 *stKa = stKb + TILE;                      // key_a tile
+    WD *stS = reinterpret_cast<WD *>(stKa + TILE);  // 2 stages of the digit's pass-1 output
+    WD *sm = stS + 2 * TILE;                        // exchange buffer
     const int L = a.L;
     const int j = blockIdx.y;
     const int tid = threadIdx.x;
@@ -465,23 +504,25 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
     const size_t c0 = (size_t)blockIdx.x * C;
     const unsigned ncols = 1u << a.a1;  // rho runs along the contiguous dimension
     const LimbConst m = a.lc[j];
-    const u64 q = m.q, q2 = m.q2;
+    const WD q = (WD)m.q, q2 = (WD)m.q2;
     const size_t ct = blockIdx.z;
-    const tw_t *W = a.W2 + (size_t)j * a.w2_stride;
+    const TW *W = reinterpret_cast<const TW *>(a.W2) + (size_t)j * a.w2_stride;
     constexpr int lo_in = GM::lo(0), lo_out = GM::lo(GM::NS - 1);
     const int nd = DIAG ? L - 1 : L;  // digits that need a transform
     auto digit_of = [&](int t) { return (DIAG && t >= j) ? t + 1 : t; };
-    const u64 *scr = a.scratch + (ct * L + j) * (size_t)L * a.N + c0;
+    const WD *scr = reinterpret_cast<const WD *>(a.scratch) + (ct * L + j) * (size_t)L * a.N + c0;
     const u64 *kbase_b = a.key_b + (size_t)j * a.N + c0;
     const u64 *kbase_a = a.key_a + (size_t)j * a.N + c0;
     const size_t kstride = (size_t)L * a.N;
 
-    u64 a0l[R], a0h[R], a1l[R], a1h[R];
+    KsAcc<WD> acc0[R], acc1[R];
 #pragma unroll
-    for (int k = 0; k < R; ++k) a0l[k] = a0h[k] = a1l[k] = a1h[k] = 0;
-
+    for (int k = 0; k < R; ++k) {
+        acc0[k].clear();
+        acc1[k].clear();
+    }
     if (nd > 0) {
-        stage_tile<A, C, NT>(stS, scr + (size_t)digit_of(0) * a.N, ncols, tid);
+        stage_tile<WD, A, C, NT>(stS, scr + (size_t)digit_of(0) * a.N, ncols, tid);
         cp_async_commit();
     }
     if (DIAG) {  // digit i == j: the NTT-domain limb itself
@@ -490,21 +531,21 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             size_t off = (size_t)tile_idx<E>(g, k, lo_out) * ncols;
-            u64 x = src[off];
-            mac128(a0l[k], a0h[k], x, __ldg(kb + off));
-            mac128(a1l[k], a1h[k], x, __ldg(ka + off));
+            WD x = (WD)src[off];
+            acc0[k].mac(x, __ldg(kb + off));
+            acc1[k].mac(x, __ldg(ka + off));
         }
     }
     for (int t = 0; t < nd; ++t) {
         const int i = digit_of(t);
         cp_async_wait_all();
         __syncthreads();  // scratch(t) landed for everyone; MAC(t-1) finished reading the key stage
-        if (t + 1 < nd) stage_tile<A, C, NT>(stS + ((t + 1) & 1) * TILE, scr + (size_t)digit_of(t + 1) * a.N, ncols, tid);
-        stage_tile<A, C, NT>(stKb, kbase_b + (size_t)i * kstride, ncols, tid);
-        stage_tile<A, C, NT>(stKa, kbase_a + (size_t)i * kstride, ncols, tid);
+        if (t + 1 < nd) stage_tile<WD, A, C, NT>(stS + ((t + 1) & 1) * TILE, scr + (size_t)digit_of(t + 1) * a.N, ncols, tid);
+        stage_tile<u64, A, C, NT>(stKb, kbase_b + (size_t)i * kstride, ncols, tid);
+        stage_tile<u64, A, C, NT>(stKa, kbase_a + (size_t)i * kstride, ncols, tid);
         cp_async_commit();
-        u64 v[R];
-        const u64 *S = stS + (t & 1) * TILE;
+        WD v[R];
+        const WD *S = stS + (t & 1) * TILE;
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = S[tile_idx<E>(g, k, lo_in) * C + c];
         xf_tile<XF_CYC_FWD, A, E, CP, LAZY>(v, g, c, sm, W, q, q2);
@@ -513,34 +554,32 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             int so = tile_idx<E>(g, k, lo_out) * C + c;
-            u64 x = canon2<LAZY>(v[k], q);
-            mac128(a0l[k], a0h[k], x, stKb[so]);
-            mac128(a1l[k], a1h[k], x, stKa[so]);
+            WD x = canon2<LAZY>(v[k], q);
+            acc0[k].mac(x, stKb[so]);
+            acc1[k].mac(x, stKa[so]);
         }
         if ((t + 1) % a.reduce_every == 0 && t + 1 < nd) {
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                a0l[k] = reduce128(a0h[k], a0l[k], m);
-                a0h[k] = 0;
-                a1l[k] = reduce128(a1h[k], a1l[k], m);
-                a1h[k] = 0;
+                acc0[k].set(acc0[k].reduce(m));
+                acc1[k].set(acc1[k].reduce(m));
             }
         }
     }
     // epilogue: reduce, add d0 / d1, inverse pass 2 (cyclic DIT + four-step twiddle and 1/N), transposed store
-    const tw_t *Wi = a.W2i + (size_t)j * a.w2_stride;
-    const tw_t *TTi = a.TTi + (size_t)j * a.N;
+    const TW *Wi = reinterpret_cast<const TW *>(a.W2i) + (size_t)j * a.w2_stride;
+    const TW *TTi = reinterpret_cast<const TW *>(a.TTi) + (size_t)j * a.N;
 #pragma unroll
     for (int comp = 0; comp < 2; ++comp) {
-        u64 v[R];
+        WD v[R];
         const u64 *add = comp ? a.add1 : a.add0;
-        u64 *out = (comp ? a.out1 : a.out0) + (ct * L + j) * a.N;
+        WD *out = reinterpret_cast<WD *>(comp ? a.out1 : a.out0) + (ct * L + j) * a.N;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            u64 r = comp ? reduce128(a1h[k], a1l[k], m) : reduce128(a0h[k], a0l[k], m);
+            WD r = comp ? acc1[k].reduce(m) : acc0[k].reduce(m);
             if (ADD) {
                 size_t off = (size_t)tile_idx<E>(g, k, lo_out) * ncols + c0 + c;
-                r = addmod(r, add[(ct * L + j) * a.N + off], q);
+                r = csub((WD)(r + (WD)add[(ct * L + j) * a.N + off]), q);
             }
             v[k] = r;
         }
@@ -554,7 +593,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
         if (GM::NS >= 2) __syncthreads();
         tile_put<E, CP>(sm, v, g, c, lo_in);
         __syncthreads();
-        u64 *d = out + c0 * (size_t)(1 << A);
+        WD *d = out + c0 * (size_t)(1 << A);
         for (int e = tid; e < (C << A); e += NT) {
             int cc = e >> A, r = e & ((1 << A) - 1);
             d[e] = sm[r * CP + cc];
@@ -565,13 +604,17 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
 // Last pass of the inverse transform (negacyclic GS over rho) fused with rescale_into
 // (poly.rs:214-225): limb i < L-1 of the result is (c_i - (c_last % q_i)) * q_last^-1 mod q_i, where
 // c_last is the already finished coefficient-domain last limb.  src: [cts][L][N] transposed
-// inverse-pass-2 output; last: [cts][N] coefficient domain; dst: [cts][L-1][N].
-template <int A, int E, int C, bool LAZY>
+// inverse-pass-2 output (WD); last: [cts][N] coefficient domain (u64); dst: [cts][L-1][N] (u64).
+template <typename WD, int A, int E, int C, bool LAZY>
 __global__ void __launch_bounds__(C *(1 << (A - E))) inv_pass1_rescale_kernel(PassArgs a, const u64 *__restrict__ last,
-                                                                               const tw_t *__restrict__ qlinv) {
+                                                                               const void *__restrict__ qlinv_) {
     typedef TileGeom<A, E> GM;
+    typedef typename TwOf<WD>::type TW;
     constexpr int CP = C + 1;
-    extern __shared__ u64 sm[];
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    WD *sm = reinterpret_cast<WD *>(sm_raw);
+    const WD *src = reinterpret_cast<const WD *>(a.src);
+    u64 *dst = reinterpret_cast<u64 *>(a.dst);
     const int tid = threadIdx.x;
     const int c = tid % C, g = tid / C;
     const int limb = blockIdx.y;  // < L-1
@@ -579,18 +622,19 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) inv_pass1_rescale_kernel(Pa
     const size_t base_in = ((size_t)blockIdx.z * a.L + limb) * a.N;
     const size_t base_out = ((size_t)blockIdx.z * (a.L - 1) + limb) * a.N;
     const LimbConst m = a.lc[limb];
-    const u64 q = m.q, q2 = m.q2;
-    const tw_t *tab = a.tab + (size_t)limb * a.tab_stride;
-    const tw_t qi = ldg_tw(qlinv + limb);
-    u64 v[1 << E];
+    const WD q = (WD)m.q, q2 = (WD)m.q2;
+    const TW *tab = reinterpret_cast<const TW *>(a.tab) + (size_t)limb * a.tab_stride;
+    const TW qi = ldg_tw(reinterpret_cast<const TW *>(qlinv_) + limb);
+    WD v[1 << E];
 #pragma unroll
-    for (int k = 0; k < (1 << E); ++k) v[k] = a.src[base_in + (size_t)tile_idx<E>(g, k, GM::lo(GM::NS - 1)) * a.ncols + c0 + c];
+    for (int k = 0; k < (1 << E); ++k) v[k] = src[base_in + (size_t)tile_idx<E>(g, k, GM::lo(GM::NS - 1)) * a.ncols + c0 + c];
     xf_tile<XF_NEG_INV, A, E, CP, LAZY>(v, g, c, sm, tab, q, q2);
 #pragma unroll
     for (int k = 0; k < (1 << E); ++k) {
         size_t off = (size_t)tile_idx<E>(g, k, GM::lo(0)) * a.ncols + c0 + c;
-        u64 ci = canon2<LAZY>(v[k], q);
-        u64 cl = barrett_word(last[(size_t)blockIdx.z * a.N + off], m);
-        a.dst[base_out + off] = shoup(submod(ci, cl, q), qi, q);
+        WD ci = canon2<LAZY>(v[k], q);
+        WD cl = (WD)barrett_word(last[(size_t)blockIdx.z * a.N + off], m);
+        WD d = ci >= cl ? ci - cl : ci + q - cl;
+        dst[base_out + off] = (u64)shoup(d, qi, q);
     }
 }

@@ -24,12 +24,34 @@ struct ulonglong2 {
     u64 x, y;
 };
 static inline ulonglong2 __ldg(const ulonglong2 *p) { return *p; }
+struct uint2 {
+    unsigned x, y;
+};
+static inline uint2 __ldg(const uint2 *p) { return *p; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline void __syncthreads() {}
 #endif
+
+typedef unsigned int u32;
 
 // A constant w in [0, q) with its Shoup companion ws = floor(w * 2^64 / q).
 struct alignas(16) tw_t {
     u64 w, ws;
+};
+// 32-bit limbs (all q < 2^31): w and ws = floor(w * 2^32 / q).  Words stay u64 in HBM (reference layout);
+// only the arithmetic, the twiddle tables and the internal scratch are 32-bit.
+struct alignas(8) tw32_t {
+    u32 w, ws;
+};
+template <typename W>
+struct TwOf;
+template <>
+struct TwOf<u64> {
+    typedef tw_t type;
+};
+template <>
+struct TwOf<u32> {
+    typedef tw32_t type;
 };
 
 // Per-limb constants (one entry per RNS prime, resident in HBM / L2, read through the RO path).
@@ -43,6 +65,10 @@ struct LimbConst {
 };
 
 __device__ __forceinline__ u64 csub(u64 x, u64 q) { return x >= q ? x - q : x; }
+__device__ __forceinline__ u32 csub(u32 x, u32 q) {
+    u32 y = x - q;  // wraps above x when x < q
+    return y < x ? y : x;
+}
 
 // x * w mod q for any word x: result in [0, 2q)  (q < 2^63).
 __device__ __forceinline__ u64 shoup_lazy(u64 x, tw_t t, u64 q) {
@@ -50,6 +76,12 @@ __device__ __forceinline__ u64 shoup_lazy(u64 x, tw_t t, u64 q) {
     return x * t.w - h * q;
 }
 __device__ __forceinline__ u64 shoup(u64 x, tw_t t, u64 q) { return csub(shoup_lazy(x, t, q), q); }
+// 32-bit: x * w mod q for any 32-bit x: result in [0, 2q)  (q < 2^31).
+__device__ __forceinline__ u32 shoup_lazy(u32 x, tw32_t t, u32 q) {
+    u32 h = __umulhi(x, t.ws);
+    return x * t.w - h * q;
+}
+__device__ __forceinline__ u32 shoup(u32 x, tw32_t t, u32 q) { return csub(shoup_lazy(x, t, q), q); }
 
 // x mod q for any word x: result in [0, 2q).
 __device__ __forceinline__ u64 barrett_word_lazy(u64 x, const LimbConst &m) {
@@ -89,86 +121,93 @@ __device__ __forceinline__ u64 negmod(u64 a, u64 q) { return a ? q - a : 0; }
 // ---- butterflies ---------------------------------------------------------------------------------
 // Cooley-Tukey (decimation in time): (x, y) -> (x + w*y, x - w*y).
 //   LAZY: in/out [0, 4q).  !LAZY: in/out [0, q).
-template <bool LAZY>
-__device__ __forceinline__ void ct_bfly(u64 &x, u64 &y, tw_t t, u64 q, u64 q2) {
+template <bool LAZY, typename W, typename TW>
+__device__ __forceinline__ void ct_bfly(W &x, W &y, TW t, W q, W q2) {
     if (LAZY) {
-        u64 xx = csub(x, q2);
-        u64 v = shoup_lazy(y, t, q);
+        W xx = csub(x, q2);
+        W v = shoup_lazy(y, t, q);
         x = xx + v;
         y = xx - v + q2;
     } else {
-        u64 v = shoup(y, t, q);
-        u64 xx = x;
+        W v = shoup(y, t, q);
+        W xx = x;
         x = csub(xx + v, q);
         y = xx >= v ? xx - v : xx + q - v;
     }
 }
 // Gentleman-Sande (decimation in frequency): (x, y) -> (x + y, (x - y) * w).
 //   LAZY: in/out [0, 2q).  !LAZY: in/out [0, q).
-template <bool LAZY>
-__device__ __forceinline__ void gs_bfly(u64 &x, u64 &y, tw_t t, u64 q, u64 q2) {
+template <bool LAZY, typename W, typename TW>
+__device__ __forceinline__ void gs_bfly(W &x, W &y, TW t, W q, W q2) {
     if (LAZY) {
-        u64 s = csub(x + y, q2);
-        u64 d = x - y + q2;
+        W s = csub(x + y, q2);
+        W d = x - y + q2;
         y = shoup_lazy(d, t, q);
         x = s;
     } else {
-        u64 s = csub(x + y, q);
-        u64 d = x >= y ? x - y : x + q - y;
+        W s = csub(x + y, q);
+        W d = x >= y ? x - y : x + q - y;
         y = shoup(d, t, q);
         x = s;
     }
 }
 // Gentleman-Sande with unit twiddle.
-template <bool LAZY>
-__device__ __forceinline__ void gs_bfly_one(u64 &x, u64 &y, u64 q, u64 q2) {
+template <bool LAZY, typename W>
+__device__ __forceinline__ void gs_bfly_one(W &x, W &y, W q, W q2) {
     if (LAZY) {
-        u64 s = csub(x + y, q2);
-        u64 d = csub(x - y + q2, q2);
+        W s = csub(x + y, q2);
+        W d = csub(x - y + q2, q2);
         x = s;
         y = d;
     } else {
-        u64 s = csub(x + y, q);
-        u64 d = x >= y ? x - y : x + q - y;
+        W s = csub(x + y, q);
+        W d = x >= y ? x - y : x + q - y;
         x = s;
         y = d;
     }
 }
 // Cooley-Tukey with unit twiddle.  LAZY: in [0, 4q) -> out [0, 4q).
-template <bool LAZY>
-__device__ __forceinline__ void ct_bfly_one(u64 &x, u64 &y, u64 q, u64 q2) {
+template <bool LAZY, typename W>
+__device__ __forceinline__ void ct_bfly_one(W &x, W &y, W q, W q2) {
     if (LAZY) {
-        u64 xx = csub(x, q2);
-        u64 v = csub(y, q2);
+        W xx = csub(x, q2);
+        W v = csub(y, q2);
         x = xx + v;
         y = xx - v + q2;
     } else {
-        u64 xx = x, v = y;
+        W xx = x, v = y;
         x = csub(xx + v, q);
         y = xx >= v ? xx - v : xx + q - v;
     }
 }
 
 // Canonicalise a lazy value.
-template <bool LAZY>
-__device__ __forceinline__ u64 canon4(u64 x, u64 q, u64 q2) {  // from the CT range
+template <bool LAZY, typename W>
+__device__ __forceinline__ W canon4(W x, W q, W q2) {  // from the CT range
     if (LAZY) return csub(csub(x, q2), q);
     return x;
 }
-template <bool LAZY>
-__device__ __forceinline__ u64 canon2(u64 x, u64 q) {  // from the GS range
+template <bool LAZY, typename W>
+__device__ __forceinline__ W canon2(W x, W q) {  // from the GS range
     if (LAZY) return csub(x, q);
     return x;
 }
 // x * t into the GS range ([0,2q) lazy / [0,q) strict) from any word.
-template <bool LAZY>
-__device__ __forceinline__ u64 mul_tw(u64 x, tw_t t, u64 q) {
+template <bool LAZY, typename W, typename TW>
+__device__ __forceinline__ W mul_tw(W x, TW t, W q) {
     return LAZY ? shoup_lazy(x, t, q) : shoup(x, t, q);
 }
 
 __device__ __forceinline__ tw_t ldg_tw(const tw_t *p) {
     ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
     tw_t t;
+    t.w = v.x;
+    t.ws = v.y;
+    return t;
+}
+__device__ __forceinline__ tw32_t ldg_tw(const tw32_t *p) {
+    uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+    tw32_t t;
     t.w = v.x;
     t.ws = v.y;
     return t;

@@ -37,8 +37,8 @@ __device__ __forceinline__ int tile_idx(int g, int k, int lo) {
 }
 
 // ---- one register step of each transform (T = step number in forward order) ---------------------
-template <int A, int E, int T, bool LAZY>
-__device__ __forceinline__ void neg_fwd_step(u64 (&v)[1 << E], int g, const tw_t *__restrict__ P, u64 q, u64 q2) {
+template <int A, int E, int T, bool LAZY, typename WD, typename TW>
+__device__ __forceinline__ void neg_fwd_step(WD (&v)[1 << E], int g, const TW *__restrict__ P, WD q, WD q2) {
     constexpr int lo = TileGeom<A, E>::lo(T);
     constexpr int top = TileGeom<A, E>::top(T);
 #pragma unroll
@@ -49,14 +49,14 @@ __device__ __forceinline__ void neg_fwd_step(u64 (&v)[1 << E], int g, const tw_t
 #pragma unroll
         for (int k = 0; k < (1 << E); ++k) {
             if (k & (1 << rb)) continue;
-            tw_t tw = ldg_tw(P + base + (k >> (rb + 1)));
+            TW tw = ldg_tw(P + base + (k >> (rb + 1)));
             ct_bfly<LAZY>(v[k], v[k | (1 << rb)], tw, q, q2);
         }
     }
 }
 
-template <int A, int E, int T, bool LAZY>
-__device__ __forceinline__ void neg_inv_step(u64 (&v)[1 << E], int g, const tw_t *__restrict__ P, u64 q, u64 q2) {
+template <int A, int E, int T, bool LAZY, typename WD, typename TW>
+__device__ __forceinline__ void neg_inv_step(WD (&v)[1 << E], int g, const TW *__restrict__ P, WD q, WD q2) {
     constexpr int lo = TileGeom<A, E>::lo(T);
     constexpr int top = TileGeom<A, E>::top(T);
 #pragma unroll
@@ -67,14 +67,14 @@ __device__ __forceinline__ void neg_inv_step(u64 (&v)[1 << E], int g, const tw_t
 #pragma unroll
         for (int k = 0; k < (1 << E); ++k) {
             if (k & (1 << rb)) continue;
-            tw_t tw = ldg_tw(P + base + (k >> (rb + 1)));
+            TW tw = ldg_tw(P + base + (k >> (rb + 1)));
             gs_bfly<LAZY>(v[k], v[k | (1 << rb)], tw, q, q2);
         }
     }
 }
 
-template <int A, int E, int T, bool LAZY>
-__device__ __forceinline__ void cyc_fwd_step(u64 (&v)[1 << E], int g, const tw_t *__restrict__ W, u64 q, u64 q2) {
+template <int A, int E, int T, bool LAZY, typename WD, typename TW>
+__device__ __forceinline__ void cyc_fwd_step(WD (&v)[1 << E], int g, const TW *__restrict__ W, WD q, WD q2) {
     constexpr int lo = TileGeom<A, E>::lo(T);
     constexpr int top = TileGeom<A, E>::top(T);
     const int glo = g & ((1 << lo) - 1);
@@ -90,15 +90,15 @@ __device__ __forceinline__ void cyc_fwd_step(u64 (&v)[1 << E], int g, const tw_t
                 gs_bfly_one<LAZY>(v[k], v[k | (1 << rb)], q, q2);
             } else {
                 const int e = (((klow << lo) | glo)) << sh;
-                tw_t tw = ldg_tw(W + e);
+                TW tw = ldg_tw(W + e);
                 gs_bfly<LAZY>(v[k], v[k | (1 << rb)], tw, q, q2);
             }
         }
     }
 }
 
-template <int A, int E, int T, bool LAZY>
-__device__ __forceinline__ void cyc_inv_step(u64 (&v)[1 << E], int g, const tw_t *__restrict__ W, u64 q, u64 q2) {
+template <int A, int E, int T, bool LAZY, typename WD, typename TW>
+__device__ __forceinline__ void cyc_inv_step(WD (&v)[1 << E], int g, const TW *__restrict__ W, WD q, WD q2) {
     constexpr int lo = TileGeom<A, E>::lo(T);
     constexpr int top = TileGeom<A, E>::top(T);
     const int glo = g & ((1 << lo) - 1);
@@ -114,7 +114,7 @@ __device__ __forceinline__ void cyc_inv_step(u64 (&v)[1 << E], int g, const tw_t
                 ct_bfly_one<LAZY>(v[k], v[k | (1 << rb)], q, q2);
             } else {
                 const int e = (((klow << lo) | glo)) << sh;
-                tw_t tw = ldg_tw(W + e);
+                TW tw = ldg_tw(W + e);
                 ct_bfly<LAZY>(v[k], v[k | (1 << rb)], tw, q, q2);
             }
         }
@@ -124,21 +124,21 @@ __device__ __forceinline__ void cyc_inv_step(u64 (&v)[1 << E], int g, const tw_t
 // ---- shared-memory exchange between two register windows -----------------------------------------
 // Tile layout in shared memory: [idx][CP] words, CP = C + 1 (the pad keeps both the column-lane
 // accesses here and the row-lane accesses of the transposing store conflict-free).
-template <int E, int CP>
-__device__ __forceinline__ void tile_put(u64 *sm, const u64 (&v)[1 << E], int g, int c, int lo) {
+template <int E, int CP, typename WD>
+__device__ __forceinline__ void tile_put(WD *sm, const WD (&v)[1 << E], int g, int c, int lo) {
 #pragma unroll
     for (int k = 0; k < (1 << E); ++k) sm[tile_idx<E>(g, k, lo) * CP + c] = v[k];
 }
-template <int E, int CP>
-__device__ __forceinline__ void tile_get(const u64 *sm, u64 (&v)[1 << E], int g, int c, int lo) {
+template <int E, int CP, typename WD>
+__device__ __forceinline__ void tile_get(const WD *sm, WD (&v)[1 << E], int g, int c, int lo) {
 #pragma unroll
     for (int k = 0; k < (1 << E); ++k) v[k] = sm[tile_idx<E>(g, k, lo) * CP + c];
 }
 
 enum { XF_NEG_FWD = 0, XF_CYC_FWD = 1, XF_CYC_INV = 2, XF_NEG_INV = 3 };
 
-template <int KIND, int A, int E, int T, bool LAZY>
-__device__ __forceinline__ void xf_step(u64 (&v)[1 << E], int g, const tw_t *__restrict__ tab, u64 q, u64 q2) {
+template <int KIND, int A, int E, int T, bool LAZY, typename WD, typename TW>
+__device__ __forceinline__ void xf_step(WD (&v)[1 << E], int g, const TW *__restrict__ tab, WD q, WD q2) {
     if (KIND == XF_NEG_FWD) neg_fwd_step<A, E, T, LAZY>(v, g, tab, q, q2);
     if (KIND == XF_CYC_FWD) cyc_fwd_step<A, E, T, LAZY>(v, g, tab, q, q2);
     if (KIND == XF_CYC_INV) cyc_inv_step<A, E, T, LAZY>(v, g, tab, q, q2);
@@ -148,9 +148,8 @@ __device__ __forceinline__ void xf_step(u64 (&v)[1 << E], int g, const tw_t *__r
 // Full transform of the tile.  On entry the thread holds the window of the FIRST step (forward
 // kinds: step 0; inverse kinds: step NS-1); on exit it holds the window of the LAST step
 // (forward: NS-1; inverse: 0).  `sm` is the [2^A][CP] exchange buffer (unused if NS == 1).
-template <int KIND, int A, int E, int CP, bool LAZY>
-__device__ __forceinline__ void xf_tile(u64 (&v)[1 << E], int g, int c, u64 *sm, const tw_t *__restrict__ tab, u64 q,
-                                        u64 q2) {
+template <int KIND, int A, int E, int CP, bool LAZY, typename WD, typename TW>
+__device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, const TW *__restrict__ tab, WD q, WD q2) {
     typedef TileGeom<A, E> GM;
     constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);
     static_assert(GM::NS >= 1 && GM::NS <= 3, "1..3 register steps supported");

@@ -11,6 +11,8 @@
 namespace ht {
 struct HostTables {
     bool lazy = true, digit_reduce = true;
+    bool w32 = false;  // all q < 2^31: 32-bit tables are filled instead of the 64-bit four-step ones
+    std::vector<tw32_t> ql32, P1_32, P1i_32, W2_32, W2i_32, TT_32, TTi_32, TTt_32;
     size_t w2_stride = 1;
     std::vector<LimbConst> lc;
     std::vector<tw_t> ql;                   // [L][L] q_last^-1 mod q_i
@@ -23,8 +25,14 @@ inline tw_t mk_tw(u64 w, u64 q) {
     t.ws = hm::shoup_of(w, q);
     return t;
 }
+inline tw32_t mk_tw32(u64 w, u64 q) {
+    tw32_t t;
+    t.w = (u32)w;
+    t.ws = (u32)((w << 32) / q);
+    return t;
+}
 inline void build_host_tables(u64 n, int logn, int path, int a1, int a2, const std::vector<u64> &moduli,
-                              const std::vector<u64> &psis, HostTables &H) {
+                              const std::vector<u64> &psis, HostTables &H, bool allow_w32 = true) {
     const size_t L = moduli.size();
     H.lc.resize(L);
     u64 qmin = ~0ull, qmax = 0;
@@ -42,6 +50,8 @@ inline void build_host_tables(u64 n, int logn, int path, int a1, int a2, const s
         qmin = q < qmin ? q : qmin;
         qmax = q > qmax ? q : qmax;
     }
+    H.w32 = allow_w32 && path == 2 && (qmax >> 31) == 0;
+    if (H.w32) H.lazy = (qmax >> 30) == 0;  // 32-bit Harvey butterflies need 4q < 2^32
     // A digit x < q_i enters the lazy forward transform mod q_j unreduced iff x < 4 q_j.
     H.digit_reduce = !(H.lazy && (qmax >> 2) < qmin);
     H.ql.resize(L * L);
@@ -50,6 +60,10 @@ inline void build_host_tables(u64 n, int logn, int path, int a1, int a2, const s
             u64 qi = moduli[i];
             H.ql[last * L + i] = (i == last) ? mk_tw(0, qi) : mk_tw(hm::inv_mod(moduli[last] % qi, qi), qi);
         }
+    if (H.w32) {
+        H.ql32.resize(L * L);
+        for (size_t k = 0; k < L * L; ++k) H.ql32[k] = mk_tw32(H.ql[k].w, moduli[k % L]);
+    }
     if (path == 1) {
         H.psi.resize(L * n);
         H.psii.resize(L * n);
@@ -116,6 +130,20 @@ inline void build_host_tables(u64 n, int logn, int path, int a1, int a2, const s
                 vi = hm::mul_mod(vi, geni, q);
             }
         }
+    }
+    if (H.w32) {
+        auto narrow = [&](std::vector<tw_t> &src, std::vector<tw32_t> &dst, size_t per_limb) {
+            dst.resize(src.size());
+            for (size_t k = 0; k < src.size(); ++k) dst[k] = mk_tw32(src[k].w, moduli[k / per_limb]);
+            std::vector<tw_t>().swap(src);
+        };
+        narrow(H.P1, H.P1_32, n1);
+        narrow(H.P1i, H.P1i_32, n1);
+        narrow(H.W2, H.W2_32, H.w2_stride);
+        narrow(H.W2i, H.W2i_32, H.w2_stride);
+        narrow(H.TT, H.TT_32, n);
+        narrow(H.TTi, H.TTi_32, n);
+        narrow(H.TTt, H.TTt_32, n);
     }
 }
 }  // namespace ht
