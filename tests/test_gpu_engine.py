@@ -128,17 +128,19 @@ def test_unfused_building_blocks_match_fused_and_oracle(gpu, orc, n, bits, l):
     m0, m1 = ob.mul_ciphertexts_gadget(a0[1], a1[1], b0[1], b1[1], ka, kb)
     q0, q1, _ = ob.rescale_ciphertext(m0, m1)
     r0, r1 = ob.rotate_ciphertext(a0[1], a1[1], ka, kb, 2)
-    for unfused in (False, True):
+    for unfused, tma in ((False, True), (False, False), (True, True)):  # TMA-staged, cp.async-staged, unfused
         gpu.set_unfused(unfused)
+        gpu.set_tma(tma)
         try:
             prod = gpu.CkksEngine.mul_ciphertexts_gadget(cta, ctb, key)
             fused = gpu.CkksEngine.mul_relin_rescale(cta, ctb, key)
             rot = gpu.CkksEngine.rotate_ciphertext(cta, key)
         finally:
             gpu.set_unfused(False)
-        assert np.array_equal(prod.c0.channels()[1], m0) and np.array_equal(prod.c1.channels()[1], m1), f"unfused={unfused}"
-        assert np.array_equal(fused.c0.channels()[1], q0) and np.array_equal(fused.c1.channels()[1], q1), f"unfused={unfused}"
-        assert np.array_equal(rot.c0.channels()[1], r0) and np.array_equal(rot.c1.channels()[1], r1), f"unfused={unfused}"
+            gpu.set_tma(True)
+        assert np.array_equal(prod.c0.channels()[1], m0) and np.array_equal(prod.c1.channels()[1], m1), f"unfused={unfused} tma={tma}"
+        assert np.array_equal(fused.c0.channels()[1], q0) and np.array_equal(fused.c1.channels()[1], q1), f"unfused={unfused} tma={tma}"
+        assert np.array_equal(rot.c0.channels()[1], r0) and np.array_equal(rot.c1.channels()[1], r1), f"unfused={unfused} tma={tma}"
 
 
 @pytest.mark.parametrize("n,bits,l", [(256, 30, 3), (1024, 31, 3), (16384, 30, 8), (4096, 20, 4)])

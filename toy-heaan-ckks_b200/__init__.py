@@ -91,6 +91,7 @@ _sig("ckks_ctx_reconstruct_centered_coeff", C.c_int, _vp, _u64p, _i64p)
 _sig("ckks_set_ntt_path", C.c_int, C.c_int)
 _sig("ckks_set_unfused", C.c_int, C.c_int)
 _sig("ckks_set_word32", C.c_int, C.c_int)
+_sig("ckks_set_tma", C.c_int, C.c_int)
 _sig("ckks_prof_enable", C.c_int, C.c_int)
 _sig("ckks_prof_collect", C.c_size_t, C.c_char_p, C.c_size_t)
 _sig("ckks_poly_from_device", C.c_int, _vp, C.c_size_t, _u64p, C.c_int, _pp)
@@ -179,6 +180,11 @@ def set_ntt_path(path: int):
 def set_word32(on: bool):
     """Test hook: allow (default) or forbid the 32-bit word path for contexts created afterwards."""
     _check(_lib.ckks_set_word32(int(on)))
+
+
+def set_tma(on: bool):
+    """Test hook: TMA (default) or cp.async staging in the fused key-switch kernel."""
+    _check(_lib.ckks_set_tma(int(on)))
 
 
 def set_unfused(on: bool):

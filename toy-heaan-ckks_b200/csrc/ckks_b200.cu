@@ -2,6 +2,7 @@
 // No torch types, no CPU fallback: every compute entry point needs a CUDA device.
 #include "../../include/ckks_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -25,6 +26,7 @@ static std::mutex g_mu;
 static std::map<std::string, uint64_t> g_launch_table;
 static int g_ntt_path = 0;
 static int g_force_unfused = 0;
+static int g_use_tma = 1;    // test hook: 0 stages ks_pass2 tiles with cp.async instead of TMA
 static int g_allow_w32 = 1;  // test hook: 0 forces 64-bit words even for small moduli  // test hook: run the unfused key-switch building blocks
 
 static int cuda_fail(cudaError_t e, const char *what) {
@@ -145,6 +147,10 @@ extern "C" size_t ckks_launch_table(char *buf, size_t cap) {
         buf[n] = 0;
     }
     return s.size() + 1;
+}
+extern "C" int ckks_set_tma(int on) {
+    g_use_tma = on != 0;
+    return CKKS_OK;
 }
 extern "C" int ckks_set_word32(int on) {
     g_allow_w32 = on != 0;
@@ -1031,26 +1037,65 @@ static int launch_ks1_a(bool w32, bool lazy, bool reduce, bool diag, dim3 grid, 
     if (w32) return launch_ks1_w<u32, A>(lazy, reduce, diag, grid, s, a);
     return launch_ks1_w<u64, A>(lazy, reduce, diag, grid, s, a);
 }
+// Rank-3 tensor map (cols, rows, slabs) with a [rows][C] box for the TMA path of ks_pass2.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+static bool make_tile_map(unsigned char *out128, const void *base, size_t elem, size_t cols, size_t rows, size_t slabs, unsigned box_cols) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || slabs == 0) return false;
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap image");
+    CUtensorMap m;
+    cuuint64_t dims[3] = {cols, rows, slabs};
+    cuuint64_t strides[2] = {cols * elem, cols * rows * elem};
+    cuuint32_t box[3] = {box_cols, (cuuint32_t)rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMapDataType dt = elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+    CUresult r = fn(&m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    memcpy(out128, &m, 128);
+    return true;
+}
+
 template <typename WD, int A>
-static int launch_ks2_w(bool lazy, bool mul, dim3 grid, cudaStream_t s, const KsArgs &a) {
+static int launch_ks2_w(bool lazy, bool mul, bool tma, dim3 grid, cudaStream_t s, const KsArgs &a, const KsMaps &maps) {
     constexpr int E = KS_E2, C = KS_C2;
     const size_t smem = ks2_smem_bytes<WD, A, C>();
     const int block = C << (A - E);
-#define KS2(LZ, MU)                                                                                                     \
+#define KS2(LZ, MU, TM)                                                                                                 \
     do {                                                                                                                \
         if (smem > 48 * 1024)                                                                                           \
-            CU(cudaFuncSetAttribute(ks_pass2_kernel<WD, A, E, C, LZ, MU, MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        KL("ks_pass2", (ks_pass2_kernel<WD, A, E, C, LZ, MU, MU><<<grid, block, smem, s>>>(a)));                         \
+            CU(cudaFuncSetAttribute(ks_pass2_kernel<WD, A, E, C, LZ, MU, MU, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        KL(TM ? "ks_pass2_tma" : "ks_pass2", (ks_pass2_kernel<WD, A, E, C, LZ, MU, MU, TM><<<grid, block, smem, s>>>(a, maps)));  \
     } while (0)
-    if (lazy) { if (mul) KS2(true, true); else KS2(true, false); }
-    else { if (mul) KS2(false, true); else KS2(false, false); }
+    if (tma) {
+        if (lazy) { if (mul) KS2(true, true, true); else KS2(true, false, true); }
+        else { if (mul) KS2(false, true, true); else KS2(false, false, true); }
+    } else {
+        if (lazy) { if (mul) KS2(true, true, false); else KS2(true, false, false); }
+        else { if (mul) KS2(false, true, false); else KS2(false, false, false); }
+    }
 #undef KS2
     return CKKS_OK;
 }
 template <int A>
-static int launch_ks2_a(bool w32, bool lazy, bool mul, dim3 grid, cudaStream_t s, const KsArgs &a) {
-    if (w32) return launch_ks2_w<u32, A>(lazy, mul, grid, s, a);
-    return launch_ks2_w<u64, A>(lazy, mul, grid, s, a);
+static int launch_ks2_a(bool w32, bool lazy, bool mul, bool tma, dim3 grid, cudaStream_t s, const KsArgs &a, const KsMaps &maps) {
+    if (w32) return launch_ks2_w<u32, A>(lazy, mul, tma, grid, s, a, maps);
+    return launch_ks2_w<u64, A>(lazy, mul, tma, grid, s, a, maps);
 }
 template <typename WD, int A>
 static int launch_inv1_rescale_w(bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const void *ql) {
@@ -1117,7 +1162,14 @@ static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, con
     dim3 g1(n2 / 16, (unsigned)(L * L), (unsigned)cs);
     DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.w32, T.lazy, T.digit_reduce, mul, g1, s, a)));
     dim3 g2(n1 / KS_C2, (unsigned)L, (unsigned)cs);
-    DISPATCH_A(T.a2, TRY(launch_ks2_a<AA>(T.w32, T.lazy, mul, g2, s, a)));
+    // TMA descriptors: (rho, j2 / gamma, slab) tensors with a [n2][16] box
+    KsMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    bool tma = g_use_tma && n1 >= (unsigned)KS_C2;
+    tma = tma && make_tile_map(maps.scratch, scratch, T.w32 ? 4 : 8, n1, n2, cs * L * L, KS_C2);
+    tma = tma && make_tile_map(maps.key_b, key->b, 8, n1, n2, L * L, KS_C2);
+    tma = tma && make_tile_map(maps.key_a, key->a, 8, n1, n2, L * L, KS_C2);
+    DISPATCH_A(T.a2, TRY(launch_ks2_a<AA>(T.w32, T.lazy, mul, tma, g2, s, a, maps)));
     return CKKS_OK;
 }
 

@@ -441,6 +441,40 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: the Blackwell-native way to stage the tiles ------------
+__device__ __forceinline__ void mbar_init(u64 *bar, unsigned count) {
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(b), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, unsigned bytes) {
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_LOOP_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
+// One [2^A][C] box of a rank-3 tensor (cols, rows, slab) -> dense shared-memory tile; completion is
+// signalled on `bar` by the copy engine (SASS: UTMALDG).
+__device__ __forceinline__ void tma_load_tile(void *sdst, const void *tmap, int col0, int slab, u64 *bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(d),
+        "l"(tmap), "r"(col0), "r"(0), "r"(slab), "r"(b)
+        : "memory");
+}
+
 // Asynchronous copy of a [2^A][C] tile of T words (row stride `ncols` words in global memory) into a
 // dense [2^A][C] shared-memory tile, 16 bytes per request (LDGSTS), issued by all NT threads.
 template <typename T, int A, int C, int NT>
@@ -480,23 +514,29 @@ struct KsAcc<u32> {
 // Shared memory of ks_pass2 in bytes: two stages of the digit tile (WD), key_b and key_a tiles (u64),
 // exchange tile [2^A][C+1] (WD).
 template <typename WD, int A, int C>
-constexpr size_t ks2_smem_bytes() {
-    return (size_t)(1 << A) * C * (2 * sizeof(WD) + 2 * sizeof(u64)) + (size_t)(1 << A) * (C + 1) * sizeof(WD);
+__host__ __device__ constexpr size_t ks2_smem_bytes() {
+    return (size_t)(1 << A) * C * (2 * sizeof(WD) + 2 * sizeof(u64)) + (((size_t)(1 << A) * (C + 1) * sizeof(WD) + 15) / 16) * 16 + 64;
 }
 
-template <typename WD, int A, int E, int C, bool LAZY, bool ADD, bool DIAG>
-__global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
+// TMA = true: the digit tile and the two key tiles are fetched by the copy engine
+// (cp.async.bulk.tensor + mbarrier) from the rank-3 tensor maps; TMA = false: LDGSTS (cp.async).
+struct KsMaps {
+    alignas(64) unsigned char scratch[128], key_b[128], key_a[128];  // CUtensorMap images
+};
+template <typename WD, int A, int E, int C, bool LAZY, bool ADD, bool DIAG, bool TMA>
+__global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a, const __grid_constant__ KsMaps maps) {
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
     constexpr int CP = C + 1;
     constexpr int NT = C * GM::G;
     constexpr int R = 1 << E;
     constexpr int TILE = (1 << A) * C;
-    extern __shared__ __align__(16) unsigned char sm_raw[];
+    extern __shared__ __align__(128) unsigned char sm_raw[];
     u64 *stKb = reinterpret_cast<u64 *>(sm_raw);  // key_b tile of the current digit
     u64 *stKa = stKb + TILE;                      // key_a tile
     WD *stS = reinterpret_cast<WD *>(stKa + TILE);  // 2 stages of the digit's pass-1 output
     WD *sm = stS + 2 * TILE;                        // exchange buffer
+    u64 *bars = reinterpret_cast<u64 *>(sm_raw + ks2_smem_bytes<WD, A, C>() - 64);  // [0,1]: digit stages, [2]: keys
     const int L = a.L;
     const int j = blockIdx.y;
     const int tid = threadIdx.x;
@@ -521,7 +561,20 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
         acc0[k].clear();
         acc1[k].clear();
     }
-    if (nd > 0) {
+    const int slab0 = (int)((ct * L + j) * L);  // scratch slabs of this (ciphertext, target limb)
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(bars + 0, 1);
+            mbar_init(bars + 1, 1);
+            mbar_init(bars + 2, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0 && nd > 0) {
+            mbar_expect_tx(bars + 0, TILE * sizeof(WD));
+            tma_load_tile(stS, maps.scratch, (int)c0, slab0 + digit_of(0), bars + 0);
+        }
+    } else if (nd > 0) {
         stage_tile<WD, A, C, NT>(stS, scr + (size_t)digit_of(0) * a.N, ncols, tid);
         cp_async_commit();
     }
@@ -538,19 +591,37 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a) {
     }
     for (int t = 0; t < nd; ++t) {
         const int i = digit_of(t);
-        cp_async_wait_all();
-        __syncthreads();  // scratch(t) landed for everyone; MAC(t-1) finished reading the key stage
-        if (t + 1 < nd) stage_tile<WD, A, C, NT>(stS + ((t + 1) & 1) * TILE, scr + (size_t)digit_of(t + 1) * a.N, ncols, tid);
-        stage_tile<u64, A, C, NT>(stKb, kbase_b + (size_t)i * kstride, ncols, tid);
-        stage_tile<u64, A, C, NT>(stKa, kbase_a + (size_t)i * kstride, ncols, tid);
-        cp_async_commit();
+        if (TMA) {
+            mbar_wait(bars + (t & 1), (t >> 1) & 1);  // scratch(t) landed
+            __syncthreads();  // MAC(t-1) finished reading the key stage; stage (t+1)&1 is free
+            if (tid == 0) {
+                if (t + 1 < nd) {
+                    mbar_expect_tx(bars + ((t + 1) & 1), TILE * sizeof(WD));
+                    tma_load_tile(stS + ((t + 1) & 1) * TILE, maps.scratch, (int)c0, slab0 + digit_of(t + 1), bars + ((t + 1) & 1));
+                }
+                mbar_expect_tx(bars + 2, 2 * TILE * sizeof(u64));
+                tma_load_tile(stKb, maps.key_b, (int)c0, i * L + j, bars + 2);
+                tma_load_tile(stKa, maps.key_a, (int)c0, i * L + j, bars + 2);
+            }
+        } else {
+            cp_async_wait_all();
+            __syncthreads();  // scratch(t) landed for everyone; MAC(t-1) finished reading the key stage
+            if (t + 1 < nd) stage_tile<WD, A, C, NT>(stS + ((t + 1) & 1) * TILE, scr + (size_t)digit_of(t + 1) * a.N, ncols, tid);
+            stage_tile<u64, A, C, NT>(stKb, kbase_b + (size_t)i * kstride, ncols, tid);
+            stage_tile<u64, A, C, NT>(stKa, kbase_a + (size_t)i * kstride, ncols, tid);
+            cp_async_commit();
+        }
         WD v[R];
         const WD *S = stS + (t & 1) * TILE;
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = S[tile_idx<E>(g, k, lo_in) * C + c];
         xf_tile<XF_CYC_FWD, A, E, CP, LAZY>(v, g, c, sm, W, q, q2);
-        cp_async_wait_all();
-        __syncthreads();  // keys(t) (and scratch(t+1)) landed for everyone
+        if (TMA) {
+            mbar_wait(bars + 2, t & 1);  // keys(t) landed
+        } else {
+            cp_async_wait_all();
+            __syncthreads();  // keys(t) (and scratch(t+1)) landed for everyone
+        }
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             int so = tile_idx<E>(g, k, lo_out) * C + c;
