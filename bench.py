@@ -469,19 +469,38 @@ def run_ntt_sweep(args):
                       "config": {"workload": "NTT/INTT sweep N=2^12..2^16, L in {1,8,24,32}, 30- and 61-bit chains, ~1 GiB of limbs per point (> L2)"}}), flush=True)
 
 
-# algorithmic bytes per launch of each kernel as launched by the batched ct-mult
+# Algorithmic bytes per launch of each kernel as launched by the batched ct-mult.
+# The fused pipeline works on chunks of cs = min(batch, 4 GiB / (L^2 N 8)) ciphertexts (ks_chunk in
+# csrc/ckks_b200.cu); w = 8-byte words (61-bit chain; 4 for the internal scratch of the 32-bit path).
+def _cs(n, l, batch):
+    return max(1, min(batch, (4 << 30) // (l * l * n * 8)))
+
+
+def _ks2(n, l, batch, w=8):
+    cs = _cs(n, l, batch)
+    return cs * l * (l - 1) * n * w + 2 * l * l * n * 8 + cs * l * n * 8 * 3 + 2 * cs * l * n * w
+
+
 KERNEL_BYTES = {
-    "ntt_fwd_pass1": lambda n, l, batch: 8.0 * n * l * batch,
-    "ntt_fwd_pass2": lambda n, l, batch: 8.0 * n * l * batch,
-    "ntt_inv_pass1": lambda n, l, batch: 8.0 * n * l * batch,
-    "ntt_inv_pass2": lambda n, l, batch: 8.0 * n * l * batch,
+    # an NTT pass is half of a limb transform (16 N bytes per transform) -> 8 N per limb per pass
+    "ntt_fwd_pass1": lambda n, l, batch: 8.0 * n * l * _cs(n, l, batch),
+    "ntt_fwd_pass2": lambda n, l, batch: 8.0 * n * l * _cs(n, l, batch),
+    "ntt_inv_pass1": lambda n, l, batch: 8.0 * n * l * _cs(n, l, batch),
+    "ntt_inv_pass2": lambda n, l, batch: 8.0 * n * l * _cs(n, l, batch),
+    "ntt_inv_pass1_rescale": lambda n, l, batch: 8.0 * n * _cs(n, l, batch) * (3 * (l - 1)),
+    # ks_pass1: read each digit limb once (its L-1 re-reads are L2 hits), write the (i, j) scratch slabs
+    "ks_pass1": lambda n, l, batch: 8.0 * n * _cs(n, l, batch) * (l + l * (l - 1)),
+    # ks_pass2: scratch slabs + key once per launch + NTT-domain digit limb + d0/d1 in + two outputs
+    "ks_pass2": lambda n, l, batch: float(_ks2(n, l, batch)),
+    "ks_pass2_tma": lambda n, l, batch: float(_ks2(n, l, batch)),
     "ks_mac": lambda n, l, batch: 8.0 * n * l * batch * 5 + 16.0 * n * l,
     "digit_broadcast": lambda n, l, batch: 8.0 * n * batch * (l + 1),
-    "tensor": lambda n, l, batch: 8.0 * n * l * batch * 7,
+    "tensor": lambda n, l, batch: 8.0 * n * l * _cs(n, l, batch) * 7,
     "rescale": lambda n, l, batch: 8.0 * n * batch * (2 * l - 1),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/)
-TRAFFIC_NCU = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at cfg4, from the
+# committed `ncu --set full` capture (profiles/); None until measured.
+TRAFFIC_NCU = {"ks_pass2_tma": 5264371200 + 438982912}  # profiles/r01_ncu_ks_pass2_traffic_after_grid_reorder.csv (14 ciphertexts per launch)
 
 
 def main():

@@ -1161,7 +1161,7 @@ static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, con
     cudaStream_t s = T.stream;
     dim3 g1(n2 / 16, (unsigned)(L * L), (unsigned)cs);
     DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.w32, T.lazy, T.digit_reduce, mul, g1, s, a)));
-    dim3 g2(n1 / KS_C2, (unsigned)L, (unsigned)cs);
+    dim3 g2((unsigned)cs, n1 / KS_C2, (unsigned)L);
     // TMA descriptors: (rho, j2 / gamma, slab) tensors with a [n2][16] box
     KsMaps maps;
     memset(&maps, 0, sizeof(maps));

@@ -538,14 +538,16 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a, c
     WD *sm = stS + 2 * TILE;                        // exchange buffer
     u64 *bars = reinterpret_cast<u64 *>(sm_raw + ks2_smem_bytes<WD, A, C>() - 64);  // [0,1]: digit stages, [2]: keys
     const int L = a.L;
-    const int j = blockIdx.y;
+    // grid = (ciphertexts, tiles, target limbs): the ciphertext index runs fastest so that the CTAs
+    // resident at the same time share the key tiles of one (target limb, tile) through L2.
+    const int j = blockIdx.z;
     const int tid = threadIdx.x;
     const int c = tid % C, g = tid / C;
-    const size_t c0 = (size_t)blockIdx.x * C;
+    const size_t c0 = (size_t)blockIdx.y * C;
     const unsigned ncols = 1u << a.a1;  // rho runs along the contiguous dimension
     const LimbConst m = a.lc[j];
     const WD q = (WD)m.q, q2 = (WD)m.q2;
-    const size_t ct = blockIdx.z;
+    const size_t ct = blockIdx.x;
     const TW *W = reinterpret_cast<const TW *>(a.W2) + (size_t)j * a.w2_stride;
     constexpr int lo_in = GM::lo(0), lo_out = GM::lo(GM::NS - 1);
     const int nd = DIAG ? L - 1 : L;  // digits that need a transform
