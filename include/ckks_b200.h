@@ -98,6 +98,9 @@ int ckks_set_word32(int on);
 /* Test hook: 1 (default) = ks_pass2 stages its tiles with TMA (cp.async.bulk.tensor + mbarrier);
  * 0 = LDGSTS (cp.async).  Same results. */
 int ckks_set_tma(int on);
+/* Test hook: 1 (default) = 2^12 <= N <= 2^14 transforms run as one kernel with the limb resident in shared
+ * memory; 0 = two passes through global memory.  Same results. */
+int ckks_set_fused_ntt(int on);
 
 /* ---- RnsPoly<N>  (poly.rs) --------------------------------------------------------------------- */
 /* RnsPoly::zero(basis) poly.rs:36-42, for `batch` polynomials (coefficient domain). */

@@ -50,6 +50,27 @@ def test_ntt_matches_oracle(gpu, orc, path, n, bits, l):
     assert np.array_equal(pn.channels(), x)
 
 
+@pytest.mark.parametrize("n,bits,l", [(4096, 30, 3), (4096, 61, 2), (8192, 31, 2), (8192, 40, 3), (16384, 30, 4), (16384, 62, 2), (16384, 63, 2)])
+def test_fused_and_two_pass_transforms_agree(gpu, orc, n, bits, l):
+    """2^12 <= N <= 2^14: the single-kernel transform (limb resident in shared memory) and the two-pass
+    transform produce the oracle's words; round trips are exact."""
+    moduli = orc.generate_primes(bits, l, n)
+    gb, ob = _bases(gpu, orc, n, moduli)
+    rng = np.random.default_rng(n + bits + 7)
+    x = uniform_limbs(rng, moduli, n, 3)
+    ref = ob.to_ntt(x[2])
+    for fused in (True, False):
+        gpu.set_fused_ntt(fused)
+        try:
+            p = gpu.RnsPoly.from_channels(x, gb)
+            p.to_ntt_domain()
+            assert np.array_equal(p.channels()[2], ref), f"fused={fused}"
+            p.to_coeff_domain()
+            assert np.array_equal(p.channels(), x), f"fused={fused}"
+        finally:
+            gpu.set_fused_ntt(True)
+
+
 def test_basis_surface(gpu, orc):
     with pytest.raises(gpu.RnsNttError) as e:
         gpu.RnsBasis(8, [])

@@ -92,6 +92,7 @@ _sig("ckks_set_ntt_path", C.c_int, C.c_int)
 _sig("ckks_set_unfused", C.c_int, C.c_int)
 _sig("ckks_set_word32", C.c_int, C.c_int)
 _sig("ckks_set_tma", C.c_int, C.c_int)
+_sig("ckks_set_fused_ntt", C.c_int, C.c_int)
 _sig("ckks_prof_enable", C.c_int, C.c_int)
 _sig("ckks_prof_collect", C.c_size_t, C.c_char_p, C.c_size_t)
 _sig("ckks_poly_from_device", C.c_int, _vp, C.c_size_t, _u64p, C.c_int, _pp)
@@ -180,6 +181,11 @@ def set_ntt_path(path: int):
 def set_word32(on: bool):
     """Test hook: allow (default) or forbid the 32-bit word path for contexts created afterwards."""
     _check(_lib.ckks_set_word32(int(on)))
+
+
+def set_fused_ntt(on: bool):
+    """Test hook: single-kernel (default) or two-pass transforms for 2^12 <= N <= 2^14."""
+    _check(_lib.ckks_set_fused_ntt(int(on)))
 
 
 def set_tma(on: bool):

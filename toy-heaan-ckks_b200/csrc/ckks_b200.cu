@@ -26,6 +26,7 @@ static std::mutex g_mu;
 static std::map<std::string, uint64_t> g_launch_table;
 static int g_ntt_path = 0;
 static int g_force_unfused = 0;
+static int g_use_fused_ntt = 1;  // test hook: 0 runs 2^12..2^14 transforms as two passes through global memory
 static int g_use_tma = 1;    // test hook: 0 stages ks_pass2 tiles with cp.async instead of TMA
 static int g_allow_w32 = 1;  // test hook: 0 forces 64-bit words even for small moduli  // test hook: run the unfused key-switch building blocks
 
@@ -147,6 +148,10 @@ extern "C" size_t ckks_launch_table(char *buf, size_t cap) {
         buf[n] = 0;
     }
     return s.size() + 1;
+}
+extern "C" int ckks_set_fused_ntt(int on) {
+    g_use_fused_ntt = on != 0;
+    return CKKS_OK;
 }
 extern "C" int ckks_set_tma(int on) {
     g_use_tma = on != 0;
@@ -468,6 +473,40 @@ static int run_pass(const Tables &T, int which, Span sp, const void *src_, void 
     return CKKS_OK;
 }
 
+// Fused single-CTA transform (2^12 <= N <= 2^14): the limb stays in shared memory between the passes.
+template <typename WD, int A1, int A2>
+static int launch_fused_w(const Tables &T, size_t L, size_t batch, u64 *d, bool inverse) {
+    FusedArgs a;
+    a.data = d;
+    a.lc = T.d_lc;
+    a.P1 = inverse ? T.d_P1i : T.d_P1;
+    a.W2 = inverse ? T.d_W2i : T.d_W2;
+    a.TT = inverse ? T.d_TTi : T.d_TTt;
+    a.w2_stride = T.w2_stride;
+    a.L = (int)L;
+    const size_t smem = fused_smem_words<A1, A2>() * sizeof(WD);
+    const int block = (1 << (A1 + A2)) / 16;
+    const unsigned grid = (unsigned)(batch * L);
+#define FUSED(LZ, IV)                                                                                                  \
+    do {                                                                                                               \
+        if (smem > 48 * 1024)                                                                                          \
+            CU(cudaFuncSetAttribute(ntt_fused_kernel<WD, A1, A2, LZ, IV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        KL(IV ? "ntt_fused_inv" : "ntt_fused_fwd", (ntt_fused_kernel<WD, A1, A2, LZ, IV><<<grid, block, smem, T.stream>>>(a)));       \
+    } while (0)
+    if (T.lazy) { if (inverse) FUSED(true, true); else FUSED(true, false); }
+    else { if (inverse) FUSED(false, true); else FUSED(false, false); }
+#undef FUSED
+    return CKKS_OK;
+}
+static int ntt_fused_run(const Tables &T, size_t L, size_t batch, u64 *d, bool inverse) {
+#define FW(A1v, A2v) (T.w32 ? launch_fused_w<u32, A1v, A2v>(T, L, batch, d, inverse) : launch_fused_w<u64, A1v, A2v>(T, L, batch, d, inverse))
+    if (T.a1 == 6 && T.a2 == 6) return FW(6, 6);
+    if (T.a1 == 7 && T.a2 == 6) return FW(7, 6);
+    if (T.a1 == 7 && T.a2 == 7) return FW(7, 7);
+#undef FW
+    return CKKS_UNSUPPORTED;
+}
+
 // Forward / inverse transform of [batch][L][N] words in place (tmp: same size, four-step only).
 static int ntt_run(const Tables &T, size_t L, size_t batch, u64 *d, u64 *tmp, bool inverse) {
     if (batch == 0) return CKKS_OK;
@@ -492,6 +531,13 @@ static int ntt_run(const Tables &T, size_t L, size_t batch, u64 *d, u64 *tmp, bo
         }
         return CKKS_OK;
     }
+    // Measured on B200 (profiles/): with 32-bit words the single-kernel transform wins up to N = 2^14;
+    // with 64-bit words (register- and IMAD-bound) only at N = 2^12.
+    if (g_use_fused_ntt && ((T.w32 && T.logn >= 12 && T.logn <= 14) || (!T.w32 && T.logn == 12)))
+        return ntt_fused_run(T, L, batch, d, inverse);
+    // Two passes through an intermediate of the transform word type.  (Walking the batch in chunks with
+    // the intermediate pinned in L2 by an access-policy window was measured slower on B200 -- the carve-out
+    // and the small launches cost more than the saved HBM round trip -- and is not used.)
     Span sp = whole(batch, L);
     if (!inverse) {
         TRY(run_pass(T, P_FWD1, sp, d, tmp));

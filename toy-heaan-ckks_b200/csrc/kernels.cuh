@@ -711,3 +711,90 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) inv_pass1_rescale_kernel(Pa
         dst[base_out + off] = (u64)shoup(d, qi, q);
     }
 }
+
+// =================================================================================================
+// Fused four-step transform: both passes of to_ntt_domain / to_coeff_domain (poly.rs:136-166) in one
+// CTA per limb, the limb resident in shared memory between the passes, so a limb crosses HBM exactly
+// once in each direction (16 N bytes per transform = the algorithmic figure of SURVEY 8d).
+// N = 2^(A1+A2) <= 2^14; N/16 threads; in place.
+//   forward : load x[j1][j2] (lanes over j2) -> negacyclic pass over j1 -> four-step twiddle ->
+//             transposed hand-off through shared memory -> cyclic pass over j2 (lanes over rho) -> store
+//   inverse : the mirror image.
+// Shared memory: max(N * 17/16, N + max(n1, n2)) words, used first as per-tile exchange regions of the
+// first pass, then as the padded hand-off matrix, then as exchange regions of the second pass.
+// =================================================================================================
+struct FusedArgs {
+    u64 *data;            // [batch][L][N], in place
+    const LimbConst *lc;  // [L]
+    const void *P1, *W2, *TT;  // forward: P1, W2, TTt; inverse: P1i, W2i, TTi  (TwOf<WD>)
+    size_t w2_stride;
+    int L;
+};
+template <int A1, int A2>
+__host__ __device__ constexpr size_t fused_smem_words() {
+    return ((size_t)1 << (A1 + A2)) / 16 * 17 > ((size_t)1 << (A1 + A2)) + ((size_t)1 << A1) + ((size_t)1 << A2)
+               ? ((size_t)1 << (A1 + A2)) / 16 * 17
+               : ((size_t)1 << (A1 + A2)) + ((size_t)1 << A1) + ((size_t)1 << A2);
+}
+
+template <typename WD, int A1, int A2, bool LAZY, bool INV>
+__global__ void __launch_bounds__((1 << (A1 + A2)) / 16) ntt_fused_kernel(FusedArgs a) {
+    constexpr int E = 4, C = 16, CP = 17;
+    typedef typename TwOf<WD>::type TW;
+    typedef TileGeom<A1, E> G1;
+    typedef TileGeom<A2, E> G2;
+    constexpr int N1 = 1 << A1, N2 = 1 << A2;
+    constexpr size_t N = (size_t)N1 * N2;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    WD *sm = reinterpret_cast<WD *>(sm_raw);
+    const int tid = threadIdx.x;
+    const int limb = blockIdx.x % a.L;
+    u64 *d = a.data + (size_t)blockIdx.x * N;
+    const LimbConst m = a.lc[limb];
+    const WD q = (WD)m.q, q2 = (WD)m.q2;
+    const TW *P1 = reinterpret_cast<const TW *>(a.P1) + (size_t)limb * N1;
+    const TW *W2 = reinterpret_cast<const TW *>(a.W2) + (size_t)limb * a.w2_stride;
+    const TW *TT = reinterpret_cast<const TW *>(a.TT) + (size_t)limb * N;
+    // pass over j1 / rho (negacyclic, length n1): tiles over j2
+    const int c1 = tid % C, g1 = (tid / C) % G1::G, t1 = tid / (C * G1::G);
+    // pass over j2 / gamma (cyclic, length n2): tiles over rho
+    const int c2 = tid % C, g2 = (tid / C) % G2::G, t2 = tid / (C * G2::G);
+    WD v[1 << E];
+    if (!INV) {
+        constexpr int lo_in1 = G1::lo(0), lo_out1 = G1::lo(G1::NS - 1), lo_in2 = G2::lo(0), lo_out2 = G2::lo(G2::NS - 1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (WD)d[(size_t)tile_idx<E>(g1, k, lo_in1) * N2 + t1 * C + c1];
+        xf_tile<XF_NEG_FWD, A1, E, CP, LAZY>(v, g1, c1, sm + (size_t)t1 * N1 * CP, P1, q, q2);
+#pragma unroll
+        for (int k = 0; k < 16; ++k)  // four-step twiddle, table in [rho][j2] layout
+            v[k] = mul_tw<LAZY>(v[k], ldg_tw(TT + (size_t)tile_idx<E>(g1, k, lo_out1) * N2 + t1 * C + c1), q);
+        __syncthreads();  // exchange regions are dead
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sm[(size_t)(t1 * C + c1) * (N1 + 1) + tile_idx<E>(g1, k, lo_out1)] = v[k];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = sm[(size_t)tile_idx<E>(g2, k, lo_in2) * (N1 + 1) + t2 * C + c2];
+        __syncthreads();  // hand-off consumed before the second pass reuses the memory
+        xf_tile<XF_CYC_FWD, A2, E, CP, LAZY>(v, g2, c2, sm + (size_t)t2 * N2 * CP, W2, q, q2);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[(size_t)tile_idx<E>(g2, k, lo_out2) * N1 + t2 * C + c2] = (u64)canon2<LAZY>(v[k], q);
+    } else {
+        constexpr int lo_in2 = G2::lo(G2::NS - 1), lo_out2 = G2::lo(0), lo_in1 = G1::lo(G1::NS - 1), lo_out1 = G1::lo(0);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (WD)d[(size_t)tile_idx<E>(g2, k, lo_in2) * N1 + t2 * C + c2];
+        xf_tile<XF_CYC_INV, A2, E, CP, LAZY>(v, g2, c2, sm + (size_t)t2 * N2 * CP, W2, q, q2);
+#pragma unroll
+        for (int k = 0; k < 16; ++k)  // four-step twiddle and 1/N, table in [j2][rho] layout
+            v[k] = mul_tw<LAZY>(v[k], ldg_tw(TT + (size_t)tile_idx<E>(g2, k, lo_out2) * N1 + t2 * C + c2), q);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sm[(size_t)(t2 * C + c2) * (N2 + 1) + tile_idx<E>(g2, k, lo_out2)] = v[k];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = sm[(size_t)tile_idx<E>(g1, k, lo_in1) * (N2 + 1) + t1 * C + c1];
+        __syncthreads();
+        xf_tile<XF_NEG_INV, A1, E, CP, LAZY>(v, g1, c1, sm + (size_t)t1 * N1 * CP, P1, q, q2);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[(size_t)tile_idx<E>(g1, k, lo_out1) * N2 + t1 * C + c1] = (u64)canon2<LAZY>(v[k], q);
+    }
+}
