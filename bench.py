@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # name: (log2 N, L, prime bits, batch per GPU, e2e batch per GPU)
-    "cfg4": (16, 24, 61, 256, 64),    # BASELINE.json configs[3]: the metric's configuration (default)
+    "cfg4": (16, 24, 61, 256, 128),   # BASELINE.json configs[3]: the metric's configuration (default)
     "cfg3": (14, 8, 30, 1024, 256),   # configs[2]: rotation (automorphism + key-switch), see --op
     "cfg2": (12, 3, 40, 4096, 1024),  # configs[1]
     "tiny": (12, 3, 40, 8, 8),
@@ -219,6 +219,8 @@ def run_b200(args):
 
     g.build_cuda()
     ck = importlib.import_module("toy-heaan-ckks_b200")
+    if args.host_chunk_mib:
+        ck._check(ck._lib.ckks_set_host_chunk_mib(args.host_chunk_mib))
     logn, l, bits, batch, e2e_batch = CONFIGS[args.config]
     if args.batch:
         batch = args.batch
@@ -516,6 +518,7 @@ def main():
     ap.add_argument("--no-prof", dest="prof", action="store_false")
     ap.add_argument("--imad", action="store_true", help="also run the integer-pipe microbenchmark")
     ap.add_argument("--op", default="", choices=["", "mul", "rotate"], help="hot-path operation (default: mul; rotate for cfg3)")
+    ap.add_argument("--host-chunk-mib", type=int, default=0, help="pipeline chunk of the host-buffer entry point")
     ap.add_argument("--ntt-sweep", action="store_true", help="BASELINE.json configs[4]: limb-batched NTT/INTT sweep instead of the ct-mult bench")
     args = ap.parse_args()
     if args.ntt_sweep:

@@ -101,6 +101,8 @@ int ckks_set_tma(int on);
 /* Test hook: 1 (default) = 2^12 <= N <= 2^14 transforms run as one kernel with the limb resident in shared
  * memory; 0 = two passes through global memory.  Same results. */
 int ckks_set_fused_ntt(int on);
+/* Tuning knob of the host-buffer entry points: MiB per component and pipeline chunk (default 64). */
+int ckks_set_host_chunk_mib(int mib);
 
 /* ---- RnsPoly<N>  (poly.rs) --------------------------------------------------------------------- */
 /* RnsPoly::zero(basis) poly.rs:36-42, for `batch` polynomials (coefficient domain). */

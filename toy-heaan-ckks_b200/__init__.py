@@ -93,6 +93,7 @@ _sig("ckks_set_unfused", C.c_int, C.c_int)
 _sig("ckks_set_word32", C.c_int, C.c_int)
 _sig("ckks_set_tma", C.c_int, C.c_int)
 _sig("ckks_set_fused_ntt", C.c_int, C.c_int)
+_sig("ckks_set_host_chunk_mib", C.c_int, C.c_int)
 _sig("ckks_prof_enable", C.c_int, C.c_int)
 _sig("ckks_prof_collect", C.c_size_t, C.c_char_p, C.c_size_t)
 _sig("ckks_poly_from_device", C.c_int, _vp, C.c_size_t, _u64p, C.c_int, _pp)

@@ -26,6 +26,7 @@ static std::mutex g_mu;
 static std::map<std::string, uint64_t> g_launch_table;
 static int g_ntt_path = 0;
 static int g_force_unfused = 0;
+static int g_host_chunk_mib = 64;
 static int g_use_fused_ntt = 1;  // test hook: 0 runs 2^12..2^14 transforms as two passes through global memory
 static int g_use_tma = 1;    // test hook: 0 stages ks_pass2 tiles with cp.async instead of TMA
 static int g_allow_w32 = 1;  // test hook: 0 forces 64-bit words even for small moduli  // test hook: run the unfused key-switch building blocks
@@ -148,6 +149,11 @@ extern "C" size_t ckks_launch_table(char *buf, size_t cap) {
         buf[n] = 0;
     }
     return s.size() + 1;
+}
+extern "C" int ckks_set_host_chunk_mib(int mib) {
+    if (mib < 1) return CKKS_BAD_ARGUMENT;
+    g_host_chunk_mib = mib;
+    return CKKS_OK;
 }
 extern "C" int ckks_set_fused_ntt(int on) {
     g_use_fused_ntt = on != 0;
@@ -1600,9 +1606,9 @@ struct HostPipe {
 };
 
 static size_t host_chunk(const Tables &T, size_t L, size_t batch) {
-    // about 128 MiB per component and chunk: small enough to pipeline, large enough to fill the GPU
+    // about g_host_chunk_mib MiB per component and chunk: small enough to pipeline, large enough to fill the GPU
     size_t per = L * T.n * sizeof(u64);
-    size_t c = ((size_t)128 << 20) / per;
+    size_t c = ((size_t)g_host_chunk_mib << 20) / per;
     if (c < 1) c = 1;
     return c < batch ? c : batch;
 }
