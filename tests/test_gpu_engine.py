@@ -300,6 +300,100 @@ def test_rotation_decodes_rotated_slots(gpu, orc, n, ks, tol):
         assert np.max(np.abs(got.real - np.roll(vals, -abs(k)))) < tol
 
 
+def test_rotation_stress_example(gpu, orc):
+    """examples/rotation_stress.rs: N=32, generate_primes(30,3,32), scale 2^58, slots 1..16, one rotation key
+    for offset +1 reused for 800 sequential rotate_ciphertext calls; max error < 1e-3 at every checkpoint
+    (:62-95).  Also checks the final ciphertext limbs against the oracle replaying the same chain."""
+    n, l, sb = 32, 3, 58
+    moduli = orc.generate_primes(30, l, n)
+    P = Party(orc, n, moduli, seed=42, hw=n // 2, sigma=3.2 ** 0.5)
+    gb, ob = gpu.RnsBasis(n, moduli), P.ob
+    ka, kb = P.rotation_key(1)
+    rotk = gpu.GadgetKey.upload(gb, ka, kb, rotation=1)
+    vals = np.arange(1, n // 2 + 1, dtype=np.float64)
+    c0, c1 = P.encrypt(vals, sb)
+    ct = _ct(gpu, gb, c0, c1, sb, 87)
+    s = gpu.RnsPoly.from_channels(P.s, gb)
+    expected, done = vals.copy(), 0
+    for checkpoint in (1, 5, 10, 50, 100, 200, 400, 800):
+        for _ in range(checkpoint - done):
+            ct = gpu.CkksEngine.rotate_ciphertext(ct, rotk)
+            if done < 10:  # replay the first steps on the oracle: limbs stay identical along the chain
+                c0, c1 = ob.rotate_ciphertext(c0, c1, ka, kb, 1)
+                assert np.array_equal(ct.c0.channels()[0], c0) and np.array_equal(ct.c1.channels()[0], c1)
+            done += 1
+        expected = np.roll(vals, -checkpoint)
+        got = orc.decode(n, sb, gpu.CkksEngine.decrypt(ct, s).to_coeffs()[0], n // 2)
+        assert np.max(np.abs(got.real - expected)) < 1e-3, f"after {checkpoint} rotations"
+
+
+def test_horner_chain_example(gpu, orc):
+    """examples/horner_chain.rs (BASELINE configs[3] workload) at N=2048: five x <- x*alpha + beta steps
+    over seven 61-bit primes, scale 2^61, fresh keys per level generated ON THE DEVICE from host samples
+    (public key public_key.rs:111-131, gadget relin key engine.rs:304-332), ending with two primes;
+    max error over all slots <= 1e-5 (horner_chain.rs:306-317)."""
+    n, iters, sb, alpha, beta = 2048, 5, 61, 0.8, 0.1
+    moduli = orc.generate_primes(61, iters + 2, n)
+    rng = np.random.default_rng(42)
+    sigma = 3.2 ** 0.5
+    slots = n // 2
+
+    def ternary():
+        v = np.zeros(n, dtype=np.int64)
+        idx = rng.permutation(n)[: n // 2]
+        v[idx] = rng.choice([-1, 1], size=n // 2)
+        return v
+
+    def gauss(*lead):
+        return np.rint(rng.normal(0, sigma, size=(*lead, n))).astype(np.int64)
+
+    s_coeffs = ternary()
+    basis = gpu.RnsBasis(n, moduli)
+    x0 = np.arange(1, slots + 1) / slots
+    x_ref = x0.copy()
+
+    def level_keys(b, with_rlk=True):
+        """pk = (-(a s) + e, a) and the gadget relin key at basis b, computed by the device kernels."""
+        l = b.channel_count()
+        mods = b.moduli()
+        s = gpu.RnsPoly.from_coeffs(s_coeffs, b)
+        a = gpu.RnsPoly.from_channels(uniform_limbs(rng, mods, n), b)
+        pk_b = a.clone()
+        pk_b *= s
+        pk_b = -pk_b
+        pk_b += gpu.RnsPoly.from_coeffs(gauss(), b)
+        rlk = None
+        if with_rlk:
+            ka = gpu.RnsPoly.from_channels(uniform_limbs(rng, mods, n, l), b)
+            ke = gpu.RnsPoly.from_coeffs(gauss(l), b)
+            s2 = s.clone()
+            s2 *= s
+            kb = gpu.CkksEngine.gadget_key_b(s, s2, ka, ke)
+            rlk = gpu.GadgetKey.from_polys(ka, kb)
+        return s, pk_b, a, rlk
+
+    def encrypt(values, b, pk_b, pk_a, logq):
+        m = gpu.RnsPoly.from_coeffs(orc.encode(n, sb, values), b)
+        u = gpu.RnsPoly.from_coeffs(ternary(), b)
+        return gpu.CkksEngine.encrypt(pk_b, pk_a, u, gpu.RnsPoly.from_coeffs(gauss(), b), gpu.RnsPoly.from_coeffs(gauss(), b), m, sb, logq)
+
+    s_cur, pk_b, pk_a, rlk = level_keys(basis)
+    ct = encrypt(x0, basis, pk_b, pk_a, basis.total_bits())
+    for it in range(1, iters + 1):
+        b = ct.c0.basis()
+        ct_alpha = encrypt(np.full(slots, alpha), b, pk_b, pk_a, ct.logq)
+        ct = gpu.CkksEngine.mul_relin_rescale(ct, ct_alpha, rlk)
+        assert ct.logp == sb and ct.c0.channel_count() == iters + 2 - it
+        b = ct.c0.basis()
+        s_cur, pk_b, pk_a, rlk = level_keys(b, with_rlk=it < iters)
+        ct = gpu.CkksEngine.add_ciphertexts(ct, encrypt(np.full(slots, beta), b, pk_b, pk_a, ct.logq))
+        x_ref = x_ref * alpha + beta
+    assert ct.c0.channel_count() == 2
+    dec = gpu.CkksEngine.decrypt(ct, s_cur)
+    got = orc.decode(n, ct.logp, dec.to_coeffs()[0], slots)
+    assert np.max(np.abs(got.real - x_ref)) <= 1e-5
+
+
 def test_full_size_properties_n65536_l24(gpu, orc):
     """BASELINE configs[3] shape (N=2^16, L=24, 61-bit chain): size-independent properties, since
     one oracle ct-mult at this size costs minutes.
