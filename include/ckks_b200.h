@@ -95,6 +95,9 @@ int ckks_set_unfused(int on);
 /* Test hook: contexts created afterwards with all moduli < 2^31 use 32-bit butterflies, tables and
  * scratch on the four-step path (1, default) or the generic 64-bit code (0).  Same results. */
 int ckks_set_word32(int on);
+/* Test hook: 1 (default) = moduli below 2^61 use the approximate-quotient butterflies (values in [0, 8q));
+ * 0 = Harvey butterflies ([0, 4q)).  Same results. */
+int ckks_set_lazy8(int on);
 /* Test hook: 1 (default) = ks_pass2 stages its tiles with TMA (cp.async.bulk.tensor + mbarrier);
  * 0 = LDGSTS (cp.async).  Same results. */
 int ckks_set_tma(int on);

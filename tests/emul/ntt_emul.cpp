@@ -13,7 +13,7 @@
 namespace {
 constexpr int E = 4, C = 16, CP = C + 1;
 
-template <int KIND, int A, int T, bool LAZY, typename WD, typename TW>
+template <int KIND, int A, int T, int LAZY, typename WD, typename TW>
 void step_all(std::vector<std::array<WD, 16>> &regs, const TW *tab, WD q, WD q2) {
     const int G = TileGeom<A, E>::G;
     for (int g = 0; g < G; ++g)
@@ -37,7 +37,7 @@ void exchange(std::vector<std::array<WD, 16>> &regs, std::vector<WD> &sm, int lo
         }
 }
 
-template <int KIND, int A, bool LAZY, bool PRE, bool POST, bool TR, typename WD, typename TW>
+template <int KIND, int A, int LAZY, bool PRE, bool POST, bool TR, typename WD, typename TW>
 void pass(const u64 *src, u64 *dst, const LimbConst &m, const TW *tab, const TW *elt, unsigned ncols, int *range_bad, WD) {
     typedef TileGeom<A, E> GM;
     constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);
@@ -84,7 +84,8 @@ void pass(const u64 *src, u64 *dst, const LimbConst &m, const TW *tab, const TW 
                     size_t off = (size_t)idx * ncols + c0 + c;
                     WD x = regs[g * C + c][k];
                     // lazy-range audit: CT kinds must stay below 4q, GS kinds below 2q
-                    if (LAZY && (u64)x >= (CT_RANGE ? 4 * (u64)q : 2 * (u64)q)) *range_bad = 1;
+                    if (LAZY == 2 && (u64)x >= (CT_RANGE ? 8 * (u64)q : 4 * (u64)q)) *range_bad = 1;
+                    if (LAZY == 1 && (u64)x >= (CT_RANGE ? 4 * (u64)q : 2 * (u64)q)) *range_bad = 1;
                     if (!LAZY && x >= q) *range_bad = 1;
                     if (POST) x = mul_tw<LAZY>(x, elt[off], q);
                     if (TR) {
@@ -98,7 +99,7 @@ void pass(const u64 *src, u64 *dst, const LimbConst &m, const TW *tab, const TW 
     }
 }
 
-template <int KIND, bool LAZY, bool PRE, bool POST, bool TR, typename WD, typename TW>
+template <int KIND, int LAZY, bool PRE, bool POST, bool TR, typename WD, typename TW>
 void pass_a(int A, const u64 *src, u64 *dst, const LimbConst &m, const TW *tab, const TW *elt, unsigned ncols, int *bad, WD w) {
     switch (A) {
         case 4: pass<KIND, 4, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad, w); break;
@@ -108,7 +109,7 @@ void pass_a(int A, const u64 *src, u64 *dst, const LimbConst &m, const TW *tab, 
         case 8: pass<KIND, 8, LAZY, PRE, POST, TR>(src, dst, m, tab, elt, ncols, bad, w); break;
     }
 }
-template <bool LAZY, typename WD, typename TW>
+template <int LAZY, typename WD, typename TW>
 void run(const LimbConst &lc, const TW *P1, const TW *P1i, const TW *W2, const TW *W2i, const TW *TT, const TW *TTi, u64 n, int a1,
          int a2, u64 *d, int inverse, int *bad, WD w) {
     std::vector<u64> tmp(n);
@@ -134,12 +135,17 @@ extern "C" int emul_ntt_4step(uint64_t n, uint64_t q, uint64_t *data, int invers
     int a1 = (logn + 1) / 2, a2 = logn - a1;
     std::vector<u64> mod{(u64)q}, psi{hm::find_primitive_root(q, 2 * n)};
     ht::HostTables H;
-    ht::build_host_tables(n, logn, 2, a1, a2, mod, psi, H, false);
+    ht::build_host_tables(n, logn, 2, a1, a2, mod, psi, H, false, true);
     int bad = 0;
-    if (H.lazy && !force_strict)
-        run<true>(H.lc[0], H.P1.data(), H.P1i.data(), H.W2.data(), H.W2i.data(), H.TT.data(), H.TTi.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u64)0);
+    // force_strict: 0 = the mode the table builder selects (2 for q < 2^61, 1 for q < 2^62, else 0),
+    // 1 = strict, 2 = Harvey lazy where the modulus allows it
+    int mode = force_strict == 1 ? 0 : (force_strict == 2 ? (H.lazy ? 1 : 0) : H.lazy);
+    if (mode == 2)
+        run<2>(H.lc[0], H.P1.data(), H.P1i.data(), H.W2.data(), H.W2i.data(), H.TT.data(), H.TTi.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u64)0);
+    else if (mode == 1)
+        run<1>(H.lc[0], H.P1.data(), H.P1i.data(), H.W2.data(), H.W2i.data(), H.TT.data(), H.TTi.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u64)0);
     else
-        run<false>(H.lc[0], H.P1.data(), H.P1i.data(), H.W2.data(), H.W2i.data(), H.TT.data(), H.TTi.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u64)0);
+        run<0>(H.lc[0], H.P1.data(), H.P1i.data(), H.W2.data(), H.W2i.data(), H.TT.data(), H.TTi.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u64)0);
     return bad;
 }
 // Same with 32-bit words (q < 2^31).  Returns -2 if the table builder does not select the 32-bit path.
@@ -154,9 +160,9 @@ extern "C" int emul_ntt_4step32(uint64_t n, uint64_t q, uint64_t *data, int inve
     if (!H.w32) return -2;
     int bad = 0;
     if (H.lazy && !force_strict)
-        run<true>(H.lc[0], H.P1_32.data(), H.P1i_32.data(), H.W2_32.data(), H.W2i_32.data(), H.TT_32.data(), H.TTi_32.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u32)0);
+        run<1>(H.lc[0], H.P1_32.data(), H.P1i_32.data(), H.W2_32.data(), H.W2i_32.data(), H.TT_32.data(), H.TTi_32.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u32)0);
     else
-        run<false>(H.lc[0], H.P1_32.data(), H.P1i_32.data(), H.W2_32.data(), H.W2i_32.data(), H.TT_32.data(), H.TTi_32.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u32)0);
+        run<0>(H.lc[0], H.P1_32.data(), H.P1i_32.data(), H.W2_32.data(), H.W2i_32.data(), H.TT_32.data(), H.TTi_32.data(), n, a1, a2, (u64 *)data, inverse, &bad, (u32)0);
     return bad;
 }
 // Internal position of natural slot k (same formula as ntt_pos in kernels.cuh).
@@ -183,4 +189,10 @@ extern "C" uint64_t emul_barrett_word(uint64_t a, uint64_t q) {
     ht::HostTables H;
     ht::build_host_tables(1, 0, 1, 0, 0, mod, psi, H, false);
     return barrett_word(a, H.lc[0]);
+}
+
+// shoup_lazy8 (approximate quotient): value and range for property tests.
+extern "C" uint64_t emul_shoup_lazy8(uint64_t x, uint64_t w, uint64_t q) {
+    tw_t t = ht::mk_tw(w, q);
+    return shoup_lazy8((u64)x, t, (u64)(0 - q));
 }

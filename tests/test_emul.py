@@ -20,14 +20,17 @@ def emul(built):
     lib.emul_ntt_pos.restype = C.c_uint32
     lib.emul_psi.argtypes = [C.c_uint64, C.c_uint64]
     lib.emul_psi.restype = C.c_uint64
-    for name, nargs in (("emul_mulmod", 3), ("emul_mulmod_add", 4), ("emul_barrett_word", 2)):
+    for name, nargs in (("emul_mulmod", 3), ("emul_mulmod_add", 4), ("emul_barrett_word", 2), ("emul_shoup_lazy8", 3)):
         f = getattr(lib, name)
         f.argtypes = [C.c_uint64] * nargs
         f.restype = C.c_uint64
     return lib
 
 
-@pytest.mark.parametrize("logn,bits,strict", [(8, 30, 0), (9, 61, 0), (10, 62, 0), (11, 63, 0), (12, 40, 0), (12, 40, 1), (13, 61, 0), (14, 30, 0), (16, 61, 0)])
+# mode: 0 = what the table builder selects (lazy8 for q < 2^61, Harvey for q < 2^62, strict above),
+#       1 = strict, 2 = Harvey lazy
+@pytest.mark.parametrize("logn,bits,strict", [(8, 30, 0), (9, 61, 0), (9, 61, 2), (10, 62, 0), (11, 63, 0), (12, 40, 0), (12, 40, 1), (12, 40, 2),
+                                                (13, 61, 0), (14, 30, 0), (14, 60, 0), (16, 61, 0), (16, 61, 2)])
 def test_four_step_matches_oracle(emul, orc, logn, bits, strict):
     n = 1 << logn
     q = orc.generate_primes(bits, 1, n)[0]
@@ -77,3 +80,14 @@ def test_modarith_against_python_integers(emul):
             assert emul.emul_mulmod(a, b, q) == (a * b) % q
             assert emul.emul_mulmod_add(a, b, c, q) == (a * b + c) % q
             assert emul.emul_barrett_word(c, q) == c % q
+
+
+def test_approximate_shoup_range_and_value(emul):
+    """shoup_lazy8 (three partial products for the quotient): congruent to x*w and below 4q for any word x."""
+    rnd = random.Random(9)
+    for q in (2305843009211596801, 2305843009132953601, 1152921504606584833, 1099511592961, 1073741441):
+        edge = [0, 1, q - 1, q, 2 * q, 2**64 - 1, 2**63, 2**32 - 1, 2**32]
+        for x in edge + [rnd.randrange(2**64) for _ in range(400)]:
+            for w in (1, q - 1, rnd.randrange(q)):
+                r = emul.emul_shoup_lazy8(x, w, q)
+                assert r % q == (x * w) % q and r < 4 * q

@@ -181,6 +181,38 @@ def test_word32_and_word64_paths_agree_with_oracle(gpu, orc, n, bits, l):
         assert np.array_equal(cta.c0.rescale().channels()[0], ob.rescale(a0[0]))
 
 
+@pytest.mark.parametrize("n,bits,l", [(256, 61, 3), (4096, 40, 3), (65536, 60, 2)])
+def test_lazy8_and_harvey_butterflies_agree_with_oracle(gpu, orc, n, bits, l):
+    """Moduli below 2^61 take the approximate-quotient butterflies ([0, 8q) lazy range) by default; the
+    Harvey [0, 4q) butterflies must give the same limbs, and both equal the oracle."""
+    moduli = orc.generate_primes(bits, l, n)
+    ob = orc.Basis(n, moduli)
+    rng = np.random.default_rng(500 + n)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, 1) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    m0, m1 = ob.mul_ciphertexts_gadget(a0[0], a1[0], b0[0], b1[0], ka, kb)
+    q0, q1, _ = ob.rescale_ciphertext(m0, m1)
+    r0, r1 = ob.rotate_ciphertext(a0[0], a1[0], ka, kb, 1)
+    ntt = ob.to_ntt(a0[0])
+    for lazy8 in (True, False):
+        gpu.set_lazy8(lazy8)
+        try:
+            gb = gpu.RnsBasis(n, moduli)
+        finally:
+            gpu.set_lazy8(True)
+        key = gpu.GadgetKey.upload(gb, ka, kb, rotation=1)
+        cta, ctb = _ct(gpu, gb, a0, a1, 30, 90), _ct(gpu, gb, b0, b1, 30, 90)
+        p = cta.c0.clone()
+        p.to_ntt_domain()
+        assert np.array_equal(p.channels()[0], ntt), f"lazy8={lazy8}"
+        p.to_coeff_domain()
+        assert np.array_equal(p.channels(), a0)
+        fused = gpu.CkksEngine.mul_relin_rescale(cta, ctb, key)
+        assert np.array_equal(fused.c0.channels()[0], q0) and np.array_equal(fused.c1.channels()[0], q1), f"lazy8={lazy8}"
+        rot = gpu.CkksEngine.rotate_ciphertext(cta, key)
+        assert np.array_equal(rot.c0.channels()[0], r0) and np.array_equal(rot.c1.channels()[0], r1), f"lazy8={lazy8}"
+
+
 def test_add_encrypt_decrypt_keygen_match_oracle(gpu, orc):
     n, l = 1024, 3
     moduli = orc.generate_primes(40, l, n)

@@ -91,6 +91,7 @@ _sig("ckks_ctx_reconstruct_centered_coeff", C.c_int, _vp, _u64p, _i64p)
 _sig("ckks_set_ntt_path", C.c_int, C.c_int)
 _sig("ckks_set_unfused", C.c_int, C.c_int)
 _sig("ckks_set_word32", C.c_int, C.c_int)
+_sig("ckks_set_lazy8", C.c_int, C.c_int)
 _sig("ckks_set_tma", C.c_int, C.c_int)
 _sig("ckks_set_fused_ntt", C.c_int, C.c_int)
 _sig("ckks_set_host_chunk_mib", C.c_int, C.c_int)
@@ -187,6 +188,11 @@ def set_word32(on: bool):
 def set_fused_ntt(on: bool):
     """Test hook: single-kernel (default) or two-pass transforms for 2^12 <= N <= 2^14."""
     _check(_lib.ckks_set_fused_ntt(int(on)))
+
+
+def set_lazy8(on: bool):
+    """Test hook: approximate-quotient butterflies (default, q < 2^61) or Harvey butterflies."""
+    _check(_lib.ckks_set_lazy8(int(on)))
 
 
 def set_tma(on: bool):

@@ -29,6 +29,7 @@ static int g_force_unfused = 0;
 static int g_host_chunk_mib = 64;
 static int g_use_fused_ntt = 1;  // test hook: 0 runs 2^12..2^14 transforms as two passes through global memory
 static int g_use_tma = 1;    // test hook: 0 stages ks_pass2 tiles with cp.async instead of TMA
+static int g_allow_lazy8 = 1;  // test hook: 0 keeps Harvey [0,4q) butterflies even when q < 2^61
 static int g_allow_w32 = 1;  // test hook: 0 forces 64-bit words even for small moduli  // test hook: run the unfused key-switch building blocks
 
 static int cuda_fail(cudaError_t e, const char *what) {
@@ -163,6 +164,10 @@ extern "C" int ckks_set_tma(int on) {
     g_use_tma = on != 0;
     return CKKS_OK;
 }
+extern "C" int ckks_set_lazy8(int on) {
+    g_allow_lazy8 = on != 0;
+    return CKKS_OK;
+}
 extern "C" int ckks_set_word32(int on) {
     g_allow_w32 = on != 0;
     return CKKS_OK;
@@ -227,7 +232,7 @@ static tw_t mk_tw(u64 w, u64 q) { return ht::mk_tw(w, q); }
 
 static int build_tables(Tables &T) {
     ht::HostTables H;
-    ht::build_host_tables(T.n, T.logn, T.path, T.a1, T.a2, T.moduli, T.psi, H, g_allow_w32 != 0);
+    ht::build_host_tables(T.n, T.logn, T.path, T.a1, T.a2, T.moduli, T.psi, H, g_allow_w32 != 0, g_allow_lazy8 != 0);
     T.lazy = H.lazy;
     T.w32 = H.w32;
     T.digit_reduce = H.digit_reduce;
@@ -386,24 +391,31 @@ static unsigned ew_grid(size_t total) {
     return (unsigned)(g < cap ? (g ? g : 1) : cap);
 }
 
+// Dispatch on the lazy mode (0 strict, 1 Harvey, 2 lazy8); 32-bit words never use mode 2.
+#define LZ_SWITCH(WDT, lazy, M)                                  \
+    do {                                                         \
+        if ((lazy) == 2 && sizeof(WDT) == 8) { M(2); }           \
+        else if (lazy) { M(1); }                                 \
+        else { M(0); }                                           \
+    } while (0)
+
 template <typename WD, int KIND, int A, bool PRE, bool POST, bool TR>
-static int launch_pass_w(const char *name, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+static int launch_pass_w(const char *name, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
     constexpr int E = 4, C = 16;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
-    if (lazy)
-        KL(name, (ntt_pass_kernel<WD, KIND, A, E, C, true, PRE, POST, TR><<<grid, block, smem, s>>>(a)));
-    else
-        KL(name, (ntt_pass_kernel<WD, KIND, A, E, C, false, PRE, POST, TR><<<grid, block, smem, s>>>(a)));
+#define M(LZ) KL(name, (ntt_pass_kernel<WD, KIND, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), PRE, POST, TR><<<grid, block, smem, s>>>(a)))
+    LZ_SWITCH(WD, lazy, M);
+#undef M
     return CKKS_OK;
 }
 template <int KIND, int A, bool PRE, bool POST, bool TR>
-static int launch_pass_a(const char *name, bool w32, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+static int launch_pass_a(const char *name, bool w32, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
     if (w32) return launch_pass_w<u32, KIND, A, PRE, POST, TR>(name, lazy, grid, s, a);
     return launch_pass_w<u64, KIND, A, PRE, POST, TR>(name, lazy, grid, s, a);
 }
 template <int KIND, bool PRE, bool POST, bool TR>
-static int launch_pass(const char *name, int A, bool w32, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+static int launch_pass(const char *name, int A, bool w32, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
     switch (A) {
         case 4: return launch_pass_a<KIND, 4, PRE, POST, TR>(name, w32, lazy, grid, s, a);
         case 5: return launch_pass_a<KIND, 5, PRE, POST, TR>(name, w32, lazy, grid, s, a);
@@ -499,8 +511,14 @@ static int launch_fused_w(const Tables &T, size_t L, size_t batch, u64 *d, bool 
             CU(cudaFuncSetAttribute(ntt_fused_kernel<WD, A1, A2, LZ, IV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         KL(IV ? "ntt_fused_inv" : "ntt_fused_fwd", (ntt_fused_kernel<WD, A1, A2, LZ, IV><<<grid, block, smem, T.stream>>>(a)));       \
     } while (0)
-    if (T.lazy) { if (inverse) FUSED(true, true); else FUSED(true, false); }
-    else { if (inverse) FUSED(false, true); else FUSED(false, false); }
+#define M(LZ)                                                           \
+    do {                                                                \
+        constexpr int LZZ = sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0);        \
+        if (inverse) FUSED(LZZ, true);                                  \
+        else FUSED(LZZ, false);                                         \
+    } while (0)
+    LZ_SWITCH(WD, T.lazy, M);
+#undef M
 #undef FUSED
     return CKKS_OK;
 }
@@ -529,11 +547,11 @@ static int ntt_run(const Tables &T, size_t L, size_t batch, u64 *d, u64 *tmp, bo
         size_t smem = T.n * sizeof(u64);
         unsigned grid = (unsigned)(batch * L);
         if (!inverse) {
-            if (T.lazy) KL("ntt_small_fwd", (ntt_small_kernel<false, true><<<grid, block, smem, s>>>(a)));
-            else KL("ntt_small_fwd", (ntt_small_kernel<false, false><<<grid, block, smem, s>>>(a)));
+            if (T.lazy) KL("ntt_small_fwd", (ntt_small_kernel<false, 1><<<grid, block, smem, s>>>(a)));
+            else KL("ntt_small_fwd", (ntt_small_kernel<false, 0><<<grid, block, smem, s>>>(a)));
         } else {
-            if (T.lazy) KL("ntt_small_inv", (ntt_small_kernel<true, true><<<grid, block, smem, s>>>(a)));
-            else KL("ntt_small_inv", (ntt_small_kernel<true, false><<<grid, block, smem, s>>>(a)));
+            if (T.lazy) KL("ntt_small_inv", (ntt_small_kernel<true, 1><<<grid, block, smem, s>>>(a)));
+            else KL("ntt_small_inv", (ntt_small_kernel<true, 0><<<grid, block, smem, s>>>(a)));
         }
         return CKKS_OK;
     }
@@ -1070,22 +1088,26 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
 constexpr int KS_E2 = 3, KS_C2 = 16;  // ks_pass2: 8 elements per thread leave room for the 128-bit accumulators
 
 template <typename WD, int A>
-static int launch_ks1_w(bool lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
+static int launch_ks1_w(int lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
     constexpr int E = 4, C = 16;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
 #define KS1(LZ, RD, DG) KL("ks_pass1", (ks_pass1_kernel<WD, A, E, C, LZ, RD, DG><<<grid, block, smem, s>>>(a)))
-    if (lazy) {
-        if (reduce) { if (diag) KS1(true, true, true); else KS1(true, true, false); }
-        else { if (diag) KS1(true, false, true); else KS1(true, false, false); }
+    if (lazy == 2 && sizeof(WD) == 8) {
+        constexpr int LZ2 = sizeof(WD) == 8 ? 2 : 1;
+        if (reduce) { if (diag) KS1(LZ2, true, true); else KS1(LZ2, true, false); }
+        else { if (diag) KS1(LZ2, false, true); else KS1(LZ2, false, false); }
+    } else if (lazy) {
+        if (reduce) { if (diag) KS1(1, true, true); else KS1(1, true, false); }
+        else { if (diag) KS1(1, false, true); else KS1(1, false, false); }
     } else {
-        if (diag) KS1(false, true, true); else KS1(false, true, false);
+        if (diag) KS1(0, true, true); else KS1(0, true, false);
     }
 #undef KS1
     return CKKS_OK;
 }
 template <int A>
-static int launch_ks1_a(bool w32, bool lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
+static int launch_ks1_a(bool w32, int lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
     if (w32) return launch_ks1_w<u32, A>(lazy, reduce, diag, grid, s, a);
     return launch_ks1_w<u64, A>(lazy, reduce, diag, grid, s, a);
 }
@@ -1124,7 +1146,7 @@ static bool make_tile_map(unsigned char *out128, const void *base, size_t elem, 
 }
 
 template <typename WD, int A>
-static int launch_ks2_w(bool lazy, bool mul, bool tma, dim3 grid, cudaStream_t s, const KsArgs &a, const KsMaps &maps) {
+static int launch_ks2_w(int lazy, bool mul, bool tma, dim3 grid, cudaStream_t s, const KsArgs &a, const KsMaps &maps) {
     constexpr int E = KS_E2, C = KS_C2;
     const size_t smem = ks2_smem_bytes<WD, A, C>();
     const int block = C << (A - E);
@@ -1134,32 +1156,34 @@ static int launch_ks2_w(bool lazy, bool mul, bool tma, dim3 grid, cudaStream_t s
             CU(cudaFuncSetAttribute(ks_pass2_kernel<WD, A, E, C, LZ, MU, MU, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         KL(TM ? "ks_pass2_tma" : "ks_pass2", (ks_pass2_kernel<WD, A, E, C, LZ, MU, MU, TM><<<grid, block, smem, s>>>(a, maps)));  \
     } while (0)
-    if (tma) {
-        if (lazy) { if (mul) KS2(true, true, true); else KS2(true, false, true); }
-        else { if (mul) KS2(false, true, true); else KS2(false, false, true); }
-    } else {
-        if (lazy) { if (mul) KS2(true, true, false); else KS2(true, false, false); }
-        else { if (mul) KS2(false, true, false); else KS2(false, false, false); }
-    }
+#define M(LZ)                                                           \
+    do {                                                                \
+        constexpr int LZZ = sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0);        \
+        if (tma) { if (mul) KS2(LZZ, true, true); else KS2(LZZ, false, true); } \
+        else { if (mul) KS2(LZZ, true, false); else KS2(LZZ, false, false); }   \
+    } while (0)
+    LZ_SWITCH(WD, lazy, M);
+#undef M
 #undef KS2
     return CKKS_OK;
 }
 template <int A>
-static int launch_ks2_a(bool w32, bool lazy, bool mul, bool tma, dim3 grid, cudaStream_t s, const KsArgs &a, const KsMaps &maps) {
+static int launch_ks2_a(bool w32, int lazy, bool mul, bool tma, dim3 grid, cudaStream_t s, const KsArgs &a, const KsMaps &maps) {
     if (w32) return launch_ks2_w<u32, A>(lazy, mul, tma, grid, s, a, maps);
     return launch_ks2_w<u64, A>(lazy, mul, tma, grid, s, a, maps);
 }
 template <typename WD, int A>
-static int launch_inv1_rescale_w(bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const void *ql) {
+static int launch_inv1_rescale_w(int lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const void *ql) {
     constexpr int E = 4, C = 16;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
-    if (lazy) KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<WD, A, E, C, true><<<grid, block, smem, s>>>(a, last, ql)));
-    else KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<WD, A, E, C, false><<<grid, block, smem, s>>>(a, last, ql)));
+#define M(LZ) KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<WD, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0))><<<grid, block, smem, s>>>(a, last, ql)))
+    LZ_SWITCH(WD, lazy, M);
+#undef M
     return CKKS_OK;
 }
 template <int A>
-static int launch_inv1_rescale_a(bool w32, bool lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const void *ql) {
+static int launch_inv1_rescale_a(bool w32, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const void *ql) {
     if (w32) return launch_inv1_rescale_w<u32, A>(lazy, grid, s, a, last, ql);
     return launch_inv1_rescale_w<u64, A>(lazy, grid, s, a, last, ql);
 }

@@ -17,7 +17,7 @@ struct Tables {
     int logn = 0;
     int path = 0;  // 1 = small single-CTA NTT, 2 = four-step
     int a1 = 0, a2 = 0;  // four-step: N = 2^a1 * 2^a2 (small path: a1 = logn, a2 = 0)
-    bool lazy = true;    // all q < 2^62 (u64 words) / all q < 2^30 (u32 words)
+    int lazy = 1;        // 0 strict; 1 Harvey lazy (q < 2^62, or < 2^30 with u32 words); 2 lazy8 (u64 words, q < 2^61)
     bool w32 = false;    // all q < 2^31 on the four-step path: 32-bit butterflies, tables and scratch
     bool digit_reduce = true;  // key-switch digits need `% q_j` before the lazy NTT
     size_t L = 0;

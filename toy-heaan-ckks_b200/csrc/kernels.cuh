@@ -37,7 +37,7 @@ struct PassArgs {
 // Inverse  to_coeff_domain(poly.rs:154-166, 582-591) = <CYC_INV,POSTMUL,TRANSPOSE> then <NEG_INV>.
 // WD = u64 (any q < 2^63) or u32 (all q < 2^31: 32-bit butterflies, 32-bit internal scratch; the words
 // that cross the boundary stay u64).
-template <typename WD, int KIND, int A, int E, int C, bool LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE>
+template <typename WD, int KIND, int A, int E, int C, int LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a) {
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
@@ -116,7 +116,7 @@ struct SmallArgs {
     int logn;
 };
 
-template <bool INVERSE, bool LAZY>
+template <bool INVERSE, int LAZY>
 __global__ void ntt_small_kernel(SmallArgs a) {
     extern __shared__ u64 sm[];
     const int n = 1 << a.logn;
@@ -385,7 +385,7 @@ struct KsArgs {
     size_t N;
 };
 
-template <typename WD, int A, int E, int C, bool LAZY, bool REDUCE, bool DIAG>
+template <typename WD, int A, int E, int C, int LAZY, bool REDUCE, bool DIAG>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
@@ -523,7 +523,7 @@ __host__ __device__ constexpr size_t ks2_smem_bytes() {
 struct KsMaps {
     alignas(64) unsigned char scratch[128], key_b[128], key_a[128];  // CUtensorMap images
 };
-template <typename WD, int A, int E, int C, bool LAZY, bool ADD, bool DIAG, bool TMA>
+template <typename WD, int A, int E, int C, int LAZY, bool ADD, bool DIAG, bool TMA>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a, const __grid_constant__ KsMaps maps) {
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a, c
 // (poly.rs:214-225): limb i < L-1 of the result is (c_i - (c_last % q_i)) * q_last^-1 mod q_i, where
 // c_last is the already finished coefficient-domain last limb.  src: [cts][L][N] transposed
 // inverse-pass-2 output (WD); last: [cts][N] coefficient domain (u64); dst: [cts][L-1][N] (u64).
-template <typename WD, int A, int E, int C, bool LAZY>
+template <typename WD, int A, int E, int C, int LAZY>
 __global__ void __launch_bounds__(C *(1 << (A - E))) inv_pass1_rescale_kernel(PassArgs a, const u64 *__restrict__ last,
                                                                                const void *__restrict__ qlinv_) {
     typedef TileGeom<A, E> GM;
@@ -737,7 +737,7 @@ __host__ __device__ constexpr size_t fused_smem_words() {
                : ((size_t)1 << (A1 + A2)) + ((size_t)1 << A1) + ((size_t)1 << A2);
 }
 
-template <typename WD, int A1, int A2, bool LAZY, bool INV>
+template <typename WD, int A1, int A2, int LAZY, bool INV>
 __global__ void __launch_bounds__((1 << (A1 + A2)) / 16) ntt_fused_kernel(FusedArgs a) {
     constexpr int E = 4, C = 16, CP = 17;
     typedef typename TwOf<WD>::type TW;

@@ -37,7 +37,7 @@ __device__ __forceinline__ int tile_idx(int g, int k, int lo) {
 }
 
 // ---- one register step of each transform (T = step number in forward order) ---------------------
-template <int A, int E, int T, bool LAZY, typename WD, typename TW>
+template <int A, int E, int T, int LAZY, typename WD, typename TW>
 __device__ __forceinline__ void neg_fwd_step(WD (&v)[1 << E], int g, const TW *__restrict__ P, WD q, WD q2) {
     constexpr int lo = TileGeom<A, E>::lo(T);
     constexpr int top = TileGeom<A, E>::top(T);
@@ -55,7 +55,7 @@ __device__ __forceinline__ void neg_fwd_step(WD (&v)[1 << E], int g, const TW *_
     }
 }
 
-template <int A, int E, int T, bool LAZY, typename WD, typename TW>
+template <int A, int E, int T, int LAZY, typename WD, typename TW>
 __device__ __forceinline__ void neg_inv_step(WD (&v)[1 << E], int g, const TW *__restrict__ P, WD q, WD q2) {
     constexpr int lo = TileGeom<A, E>::lo(T);
     constexpr int top = TileGeom<A, E>::top(T);
@@ -73,7 +73,7 @@ __device__ __forceinline__ void neg_inv_step(WD (&v)[1 << E], int g, const TW *_
     }
 }
 
-template <int A, int E, int T, bool LAZY, typename WD, typename TW>
+template <int A, int E, int T, int LAZY, typename WD, typename TW>
 __device__ __forceinline__ void cyc_fwd_step(WD (&v)[1 << E], int g, const TW *__restrict__ W, WD q, WD q2) {
     constexpr int lo = TileGeom<A, E>::lo(T);
     constexpr int top = TileGeom<A, E>::top(T);
@@ -97,7 +97,7 @@ __device__ __forceinline__ void cyc_fwd_step(WD (&v)[1 << E], int g, const TW *_
     }
 }
 
-template <int A, int E, int T, bool LAZY, typename WD, typename TW>
+template <int A, int E, int T, int LAZY, typename WD, typename TW>
 __device__ __forceinline__ void cyc_inv_step(WD (&v)[1 << E], int g, const TW *__restrict__ W, WD q, WD q2) {
     constexpr int lo = TileGeom<A, E>::lo(T);
     constexpr int top = TileGeom<A, E>::top(T);
@@ -137,7 +137,7 @@ __device__ __forceinline__ void tile_get(const WD *sm, WD (&v)[1 << E], int g, i
 
 enum { XF_NEG_FWD = 0, XF_CYC_FWD = 1, XF_CYC_INV = 2, XF_NEG_INV = 3 };
 
-template <int KIND, int A, int E, int T, bool LAZY, typename WD, typename TW>
+template <int KIND, int A, int E, int T, int LAZY, typename WD, typename TW>
 __device__ __forceinline__ void xf_step(WD (&v)[1 << E], int g, const TW *__restrict__ tab, WD q, WD q2) {
     if (KIND == XF_NEG_FWD) neg_fwd_step<A, E, T, LAZY>(v, g, tab, q, q2);
     if (KIND == XF_CYC_FWD) cyc_fwd_step<A, E, T, LAZY>(v, g, tab, q, q2);
@@ -148,7 +148,7 @@ __device__ __forceinline__ void xf_step(WD (&v)[1 << E], int g, const TW *__rest
 // Full transform of the tile.  On entry the thread holds the window of the FIRST step (forward
 // kinds: step 0; inverse kinds: step NS-1); on exit it holds the window of the LAST step
 // (forward: NS-1; inverse: 0).  `sm` is the [2^A][CP] exchange buffer (unused if NS == 1).
-template <int KIND, int A, int E, int CP, bool LAZY, typename WD, typename TW>
+template <int KIND, int A, int E, int CP, int LAZY, typename WD, typename TW>
 __device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, const TW *__restrict__ tab, WD q, WD q2) {
     typedef TileGeom<A, E> GM;
     constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);

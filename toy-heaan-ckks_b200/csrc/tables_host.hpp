@@ -10,7 +10,8 @@
 
 namespace ht {
 struct HostTables {
-    bool lazy = true, digit_reduce = true;
+    int lazy = 1;  // 0 strict, 1 Harvey lazy, 2 lazy8 (approximate Shoup quotient; 64-bit words, q < 2^61)
+    bool digit_reduce = true;
     bool w32 = false;  // all q < 2^31: 32-bit tables are filled instead of the 64-bit four-step ones
     std::vector<tw32_t> ql32, P1_32, P1i_32, W2_32, W2i_32, TT_32, TTi_32, TTt_32;
     size_t w2_stride = 1;
@@ -32,11 +33,11 @@ inline tw32_t mk_tw32(u64 w, u64 q) {
     return t;
 }
 inline void build_host_tables(u64 n, int logn, int path, int a1, int a2, const std::vector<u64> &moduli,
-                              const std::vector<u64> &psis, HostTables &H, bool allow_w32 = true) {
+                              const std::vector<u64> &psis, HostTables &H, bool allow_w32 = true, bool allow_lazy8 = true) {
     const size_t L = moduli.size();
     H.lc.resize(L);
     u64 qmin = ~0ull, qmax = 0;
-    H.lazy = true;
+    H.lazy = 1;
     for (size_t j = 0; j < L; ++j) {
         u64 q = moduli[j];
         LimbConst &m = H.lc[j];
@@ -46,12 +47,12 @@ inline void build_host_tables(u64 n, int logn, int path, int a1, int a2, const s
         m.bar = (u64)((((hm::u128)1) << 64) / q);
         m.c64 = (u64)((((hm::u128)1) << 64) % q);
         m.c64s = hm::shoup_of(m.c64, q);
-        if (q >> 62) H.lazy = false;
         qmin = q < qmin ? q : qmin;
         qmax = q > qmax ? q : qmax;
     }
+    H.lazy = (qmax >> 61) == 0 ? (allow_lazy8 && path == 2 ? 2 : 1) : ((qmax >> 62) == 0 ? 1 : 0);
     H.w32 = allow_w32 && path == 2 && (qmax >> 31) == 0;
-    if (H.w32) H.lazy = (qmax >> 30) == 0;  // 32-bit Harvey butterflies need 4q < 2^32
+    if (H.w32) H.lazy = (qmax >> 30) == 0 ? 1 : 0;  // 32-bit Harvey butterflies need 4q < 2^32
     // A digit x < q_i enters the lazy forward transform mod q_j unreduced iff x < 4 q_j.
     H.digit_reduce = !(H.lazy && (qmax >> 2) < qmin);
     H.ql.resize(L * L);
