@@ -143,7 +143,7 @@ def test_unfused_building_blocks_match_fused_and_oracle(gpu, orc, n, bits, l):
         assert np.array_equal(rot.c0.channels()[1], r0) and np.array_equal(rot.c1.channels()[1], r1), f"unfused={unfused} tma={tma}"
 
 
-@pytest.mark.parametrize("n,bits,l", [(256, 30, 3), (1024, 31, 3), (16384, 30, 8), (4096, 20, 4)])
+@pytest.mark.parametrize("n,bits,l", [(256, 30, 3), (1024, 31, 3), (16384, 30, 8), (4096, 20, 4), (256, 30, 20), (512, 31, 7)])
 def test_word32_and_word64_paths_agree_with_oracle(gpu, orc, n, bits, l):
     """Moduli below 2^31 take the 32-bit word path by default; forcing the 64-bit code must give the
     same limbs, and both equal the oracle (31-bit primes run the strict, non-lazy 32-bit butterflies)."""

@@ -1200,9 +1200,12 @@ static int launch_inv1_rescale_a(bool w32, int lazy, dim3 grid, cudaStream_t s, 
 static int reduce_every_for(const Tables &T, size_t L) {
     u64 qmax = 0;
     for (size_t i = 0; i < L; ++i) qmax = T.moduli[i] > qmax ? T.moduli[i] : qmax;
+    // products are x * k with k < q and x < q (x < 2q in lazy8 mode, where ks_pass2 reduces only once)
     hm::u128 sq = (hm::u128)(qmax - 1) * (qmax - 1);
     hm::u128 lim = ~(hm::u128)0;
-    hm::u128 t = lim / sq;  // t products of (q-1)^2 fit 128 bits
+    if (T.w32) lim = ~(u64)0;  // 32-bit words accumulate in one 64-bit register
+    if (T.lazy == 2) lim /= 2;
+    hm::u128 t = lim / sq;  // t products fit the accumulator
     if (t > 1) t -= 1;      // one slot for the carried-in residue
     return t > 1000000 ? 1000000 : (int)t;
 }

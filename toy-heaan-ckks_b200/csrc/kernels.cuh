@@ -627,7 +627,8 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a, c
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             int so = tile_idx<E>(g, k, lo_out) * C + c;
-            WD x = canon2<LAZY>(v[k], q);
+            // lazy8: one conditional subtraction ([0,4q) -> [0,2q)) is enough for the 128-bit accumulators
+            WD x = (LAZY == 2) ? csub(v[k], q2) : canon2<LAZY>(v[k], q);
             acc0[k].mac(x, stKb[so]);
             acc1[k].mac(x, stKa[so]);
         }

@@ -68,6 +68,8 @@ struct LimbConst {
     u64 pad[3];
 };
 
+// (a compare + predicated-subtract form in PTX was measured: marginally faster in the plain passes,
+// 7 % slower in ks_pass2, so the compiler's compare/select form stays)
 __device__ __forceinline__ u64 csub(u64 x, u64 q) { return x >= q ? x - q : x; }
 __device__ __forceinline__ u32 csub(u32 x, u32 q) {
     u32 y = x - q;  // wraps above x when x < q
