@@ -211,6 +211,13 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    try:  # run (and first-touch the pinned staging buffers) on the CPUs/NUMA node closest to this GPU
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         import torch.distributed as dist
 

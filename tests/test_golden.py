@@ -77,3 +77,38 @@ def test_gpu_reproduces_golden(gpu):
     assert np.array_equal(xn.channels()[0], A(g["ntt_x"]))
     x *= y
     assert np.array_equal(x.channels()[0], A(g["mul"]))
+
+
+def test_limb_dump_round_trip_and_replay_bundle(tmp_path, orc):
+    """The limb dump format round-trips, rejects corruption and non-reduced words, and the
+    replay bundle written from the oracle is self-consistent."""
+    import importlib.util
+    import subprocess
+    import sys
+
+    root = os.path.dirname(HERE)
+    spec = importlib.util.spec_from_file_location("limbdump", os.path.join(root, "toy-heaan-ckks_b200", "limbdump.py"))
+    ld = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ld)
+    g = G["engine_n16"]
+    a0 = A(g["a0"])
+    hdr = ld.write(str(tmp_path / "x"), a0, g["moduli"], note="t")
+    back, h2 = ld.read(str(tmp_path / "x"))
+    assert np.array_equal(back[0], a0) and h2 == hdr and hdr["limbs"] == 4 and hdr["degree"] == 16
+    with pytest.raises(ValueError):
+        bad = a0.copy()
+        bad[0, 0] = g["moduli"][0]
+        ld.write(str(tmp_path / "y"), bad, g["moduli"])
+    with open(str(tmp_path / "x.u64"), "r+b") as f:
+        f.write(b"\x01")
+    with pytest.raises(ValueError):
+        ld.read(str(tmp_path / "x"))
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "make_replay_bundle.py"), str(tmp_path / "bundle"), "oracle"],
+                          stdout=subprocess.DEVNULL)
+    r0, h = ld.read(str(tmp_path / "bundle" / "cfg1_n16" / "mul_rescale_c0"))
+    assert h["limbs"] == 3 and h["moduli"] == orc.generate_primes(31, 4, 16)[:3]
+    b = orc.Basis(16, orc.generate_primes(31, 4, 16))
+    rd = lambda n: ld.read(str(tmp_path / "bundle" / "cfg1_n16" / n))[0]
+    m0, m1 = b.mul_ciphertexts_gadget(rd("ct1_c0")[0], rd("ct1_c1")[0], rd("ct2_c0")[0], rd("ct2_c1")[0], rd("key_a"), rd("key_b"))
+    q0, _, _ = b.rescale_ciphertext(m0, m1)
+    assert np.array_equal(q0, r0[0])
