@@ -399,9 +399,16 @@ static unsigned ew_grid(size_t total) {
         else { M(0); }                                           \
     } while (0)
 
+// Column tile of the plain passes: 8 for 64-bit words (more, smaller CTAs hide each other's barriers on the
+// IMAD-bound path), 16 for 32-bit words (HBM-bound: wider coalesced segments).
+template <typename WD>
+constexpr int pass_c() {
+    return sizeof(WD) == 8 ? 8 : 16;
+}
 template <typename WD, int KIND, int A, bool PRE, bool POST, bool TR>
 static int launch_pass_w(const char *name, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
-    constexpr int E = 4, C = 16;
+    constexpr int E = 4, C = pass_c<WD>();
+    grid.x = a.ncols / C;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
 #define M(LZ) KL(name, (ntt_pass_kernel<WD, KIND, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), PRE, POST, TR><<<grid, block, smem, s>>>(a)))
@@ -1085,11 +1092,12 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
 }
 
 // ---- fused four-step key-switch pipeline -----------------------------------------------------------
-constexpr int KS_E2 = 3, KS_C2 = 16;  // ks_pass2: 8 elements per thread leave room for the 128-bit accumulators
+constexpr int KS_E2 = 3, KS_C2 = 4;  // ks_pass2: 8 elements per thread leave room for the 128-bit accumulators
 
+constexpr int KS_C1 = 8;
 template <typename WD, int A>
 static int launch_ks1_w(int lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
-    constexpr int E = 4, C = 16;
+    constexpr int E = 4, C = KS_C1;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
 #define KS1(LZ, RD, DG) KL("ks_pass1", (ks_pass1_kernel<WD, A, E, C, LZ, RD, DG><<<grid, block, smem, s>>>(a)))
@@ -1174,7 +1182,8 @@ static int launch_ks2_a(bool w32, int lazy, bool mul, bool tma, dim3 grid, cudaS
 }
 template <typename WD, int A>
 static int launch_inv1_rescale_w(int lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const void *ql) {
-    constexpr int E = 4, C = 16;
+    constexpr int E = 4, C = pass_c<WD>();
+    grid.x = a.ncols / C;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
 #define M(LZ) KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<WD, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0))><<<grid, block, smem, s>>>(a, last, ql)))
@@ -1238,7 +1247,7 @@ static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, con
     a.N = T.n;
     const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
     cudaStream_t s = T.stream;
-    dim3 g1(n2 / 16, (unsigned)(L * L), (unsigned)cs);
+    dim3 g1(n2 / KS_C1, (unsigned)(L * L), (unsigned)cs);
     DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.w32, T.lazy, T.digit_reduce, mul, g1, s, a)));
     dim3 g2((unsigned)cs, n1 / KS_C2, (unsigned)L);
     // TMA descriptors: (rho, j2 / gamma, slab) tensors with a [n2][16] box

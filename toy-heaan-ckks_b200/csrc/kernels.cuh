@@ -524,7 +524,7 @@ struct KsMaps {
     alignas(64) unsigned char scratch[128], key_b[128], key_a[128];  // CUtensorMap images
 };
 template <typename WD, int A, int E, int C, int LAZY, bool ADD, bool DIAG, bool TMA>
-__global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass2_kernel(KsArgs a, const __grid_constant__ KsMaps maps) {
+__global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 : 1))) ks_pass2_kernel(KsArgs a, const __grid_constant__ KsMaps maps) {
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
     constexpr int CP = C + 1;
