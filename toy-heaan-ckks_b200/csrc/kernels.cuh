@@ -429,10 +429,35 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
     }
 }
 
+// (hi:lo) += x * k for x, k < 2^63: four 32x32 products (the two cross terms cannot overflow a word when
+// both high halves are below 2^31) and one 128-bit carry chain.
 __device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 x, u64 k) {
-    u64 pl = x * k, ph = __umul64hi(x, k);
-    lo += pl;
-    hi += ph + (lo < pl ? 1ull : 0ull);
+#ifdef __CUDA_ARCH__
+    u32 x0, x1, k0, k1, a0, a1, a2, a3, b0, b1, m0, m1, d0, d1;
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(x0), "=r"(x1) : "l"(x));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(k0), "=r"(k1) : "l"(k));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(a0), "=r"(a1) : "l"(lo));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(a2), "=r"(a3) : "l"(hi));
+    u64 p00, mid, p11;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p00) : "r"(x0), "r"(k0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(mid) : "r"(x0), "r"(k1));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(mid) : "r"(x1), "r"(k0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p11) : "r"(x1), "r"(k1));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(b0), "=r"(b1) : "l"(p00));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(m0), "=r"(m1) : "l"(mid));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(d0), "=r"(d1) : "l"(p11));
+    asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %6;\n\taddc.u32 %3, %3, %7;"
+        : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3)
+        : "r"(b0), "r"(b1), "r"(d0), "r"(d1));
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+r"(a1), "+r"(a2), "+r"(a3) : "r"(m0), "r"(m1));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(lo) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(hi) : "r"(a2), "r"(a3));
+#else
+    unsigned __int128 acc = ((unsigned __int128)hi << 64) | lo;
+    acc += (unsigned __int128)x * k;
+    lo = (u64)acc;
+    hi = (u64)(acc >> 64);
+#endif
 }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
