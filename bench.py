@@ -309,9 +309,17 @@ def run_b200(args):
     value = world * batch / (ms_per_step * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------
-    wi, wo = (e2e_batch, l, n), (e2e_batch, l - 1 if op == "mul" else l, n)
-    hin = [ck.PinnedBuffer(wi) for _ in range(4)]
-    hout = [ck.PinnedBuffer(wo) for _ in range(2)]
+    while True:  # page-locked staging buffers; halve the e2e batch if the host cannot pin that much
+        wi, wo = (e2e_batch, l, n), (e2e_batch, l - 1 if op == "mul" else l, n)
+        try:
+            hin = [ck.PinnedBuffer(wi) for _ in range(4)]
+            hout = [ck.PinnedBuffer(wo) for _ in range(2)]
+            break
+        except ck.RnsNttError:
+            hin = hout = None
+            if e2e_batch <= 1:
+                raise
+            e2e_batch //= 2
     e2e_polys = [uni_poly(e2e_batch) for _ in range(4)]
     for hb, p in zip(hin, e2e_polys):  # host copies of the e2e inputs (outside the timed region)
         ck._check(ck._lib.ckks_poly_download(p._h, ck._ptr(hb.array)))

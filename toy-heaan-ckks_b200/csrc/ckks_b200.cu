@@ -57,11 +57,13 @@ struct ProfRec {
     const char *name;
     cudaEvent_t e0, e1;
 };
-static bool g_prof = false;
+static std::atomic<bool> g_prof{false};
+static std::mutex g_prof_mu;  // guards the two vectors below
 static std::vector<ProfRec> g_prof_recs;
 static std::vector<cudaEvent_t> g_prof_pool;
 static cudaEvent_t prof_event() {
     cudaEvent_t e;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     if (!g_prof_pool.empty()) {
         e = g_prof_pool.back();
         g_prof_pool.pop_back();
@@ -74,7 +76,7 @@ struct ProfScope {
     ProfRec r;
     cudaStream_t s;
     bool on;
-    ProfScope(const char *name, cudaStream_t st) : s(st), on(g_prof && g_prof_recs.size() < 400000) {
+    ProfScope(const char *name, cudaStream_t st) : s(st), on(g_prof.load(std::memory_order_relaxed)) {
         if (on) {
             r.name = name;
             r.e0 = prof_event();
@@ -85,11 +87,16 @@ struct ProfScope {
     ~ProfScope() {
         if (on) {
             cudaEventRecord(r.e1, s);
-            g_prof_recs.push_back(r);
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            if (g_prof_recs.size() < 400000) g_prof_recs.push_back(r);
+            else {
+                g_prof_pool.push_back(r.e0);
+                g_prof_pool.push_back(r.e1);
+            }
         }
     }
 };
-static cudaStream_t g_cur_stream = nullptr;  // stream of the context whose call is running
+static thread_local cudaStream_t g_cur_stream = nullptr;  // stream of the context whose call is running on this thread
 #define KL(name, ...)                                            \
     do {                                                         \
         count_launch(name);                                      \
@@ -1075,10 +1082,9 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
                                 u64 *acc1) {
     EwArgs e = ew_args(T, L, batch);
     if (!e.total) return CKKS_OK;
-    u64 *alpha, *tmp = nullptr;
-    TRY(dev_alloc(T, e.total, &alpha));
-    if (T.path == 2) TRY(dev_alloc(T, e.total, &tmp));
-    int rc = CKKS_OK;
+    u64 *alpha = nullptr, *tmp = nullptr;
+    int rc = dev_alloc(T, e.total, &alpha);
+    if (rc == CKKS_OK && T.path == 2) rc = dev_alloc(T, e.total, &tmp);
     for (size_t i = 0; i < L && rc == CKKS_OK; ++i) {
         KLV("digit_broadcast", (digit_broadcast_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, digits, alpha, (int)i)));
         rc = ntt_run(T, L, batch, alpha, tmp, false);
@@ -1810,6 +1816,7 @@ extern "C" int ckks_prof_enable(int on) {
 }
 extern "C" size_t ckks_prof_collect(char *buf, size_t cap) {
     std::map<std::string, std::pair<uint64_t, double>> agg;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto &r : g_prof_recs) {
         cudaEventSynchronize(r.e1);
         float ms = 0;
