@@ -184,6 +184,15 @@ int ckks_ct_encrypt(const ckks_poly *pk_b, const ckks_poly *pk_a, const ckks_pol
 /* decrypt engine.rs:114-128: c1*s + c0 (s has batch 1 or `batch`). */
 int ckks_ct_decrypt(const ckks_poly *c0, const ckks_poly *c1, const ckks_poly *s, ckks_poly **out);
 
+/* ---- CkksEncoder<N> (ckks_encoder.rs:65-156) on the device: O(N log N) instead of the reference's O(N^2) --- */
+/* encode_complex: values [batch][nvals] complex (re, im interleaved), nvals <= N/2 (CKKS_SHORT_INPUT otherwise,
+ * the reference asserts); scaled by 2^scale_bits, conjugate-symmetric slots, inverse canonical embedding, rounding
+ * (f64::round), from_coeffs.  f64 summation order differs from the reference: tolerance-checked, not bit-exact. */
+int ckks_encode(ckks_ctx *ctx, uint32_t scale_bits, size_t batch, const double *values, size_t nvals, ckks_poly **out);
+/* decode_complex: centred CRT (Q < 2^128 as in the reference), canonical embedding, first `nslots` slots divided
+ * by 2^scale_bits; out [batch][nslots] complex. */
+int ckks_decode(const ckks_poly *p, uint32_t scale_bits, size_t nslots, double *out);
+
 /* ---- host-buffer entry points (what a reference-side caller with `Vec<[u64;N]>` data uses) ------ */
 /* mul_ciphertexts_gadget + rescale_ciphertext on `batch` ciphertext pairs held in HOST memory in
  * the reference layout ([batch][L][N] per component; outputs [batch][L-1][N]).  Copies are chunked

@@ -130,6 +130,8 @@ _sig("ckks_ct_mul_relin_rescale", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _pp, _p
 _sig("ckks_ct_rotate", C.c_int, _vp, _vp, _vp, C.c_int32, _pp, _pp)
 _sig("ckks_ct_encrypt", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _pp, _pp)
 _sig("ckks_ct_decrypt", C.c_int, _vp, _vp, _vp, _pp)
+_sig("ckks_encode", C.c_int, _vp, C.c_uint32, C.c_size_t, C.POINTER(C.c_double), C.c_size_t, _pp)
+_sig("ckks_decode", C.c_int, _vp, C.c_uint32, C.c_size_t, C.POINTER(C.c_double))
 _sig("ckks_ct_mul_relin_rescale_host", C.c_int, _vp, _vp, _vp, C.c_size_t, _u64p, _u64p, _u64p, _u64p, _u64p, _u64p)
 _sig("ckks_ct_rotate_host", C.c_int, _vp, _vp, C.c_int32, C.c_size_t, _u64p, _u64p, _u64p, _u64p)
 _sig("ckks_host_alloc", C.c_int, C.c_size_t, _pp)
@@ -525,6 +527,48 @@ class CkksEngine:
         h = _vp()
         _check(_lib.ckks_gen_gadget_key_b(s._h, target._h, a._h, e._h, C.byref(h)))
         return RnsPoly(h, s.basis())
+
+
+class Plaintext:
+    """`Plaintext` (types.rs:4-20): (poly, scale_bits, slots)."""
+
+    def __init__(self, poly: RnsPoly, scale_bits: int, slots: int):
+        self.poly, self.scale_bits, self.slots = poly, scale_bits, slots
+
+
+class CkksEncoder:
+    """`CkksEncoder<N>` (ckks_encoder.rs:32-157) evaluated on the device in O(N log N)."""
+
+    def __init__(self, degree: int, scale_bits: int):
+        if degree & (degree - 1) or scale_bits <= 0:
+            raise RnsNttError(31, "CkksEncoder: DEGREE must be a power of two and scale_bits positive")
+        self.degree, self.scale_bits = degree, scale_bits
+
+    def scale_factor(self) -> float:
+        return 2.0 ** self.scale_bits
+
+    def max_slots(self) -> int:
+        return self.degree // 2
+
+    def encode_complex(self, values, basis: RnsBasis) -> Plaintext:
+        v = np.ascontiguousarray(values, dtype=np.complex128)
+        if v.ndim == 1:
+            v = v[None, :]
+        flat = np.ascontiguousarray(v.view(np.float64))
+        h = _vp()
+        _check(_lib.ckks_encode(basis._h, self.scale_bits, v.shape[0], flat.ctypes.data_as(C.POINTER(C.c_double)), v.shape[1], C.byref(h)))
+        return Plaintext(RnsPoly(h, basis), self.scale_bits, v.shape[1])
+
+    def encode(self, values, basis: RnsBasis) -> Plaintext:
+        return self.encode_complex(np.asarray(values, dtype=np.float64).astype(np.complex128), basis)
+
+    def decode_complex(self, pt: Plaintext) -> np.ndarray:
+        out = np.zeros((pt.poly.batch(), pt.slots), dtype=np.complex128)
+        _check(_lib.ckks_decode(pt.poly._h, pt.scale_bits, pt.slots, out.view(np.float64).ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def decode(self, pt: Plaintext) -> np.ndarray:
+        return self.decode_complex(pt).real
 
 
 # ── host-buffer entry points ─────────────────────────────────────────────────────────────────────

@@ -15,6 +15,7 @@
 #include "context.hpp"
 #include "host_math.hpp"
 #include "tables_host.hpp"
+#include "encoder.cuh"
 #include "kernels.cuh"
 
 // -------------------------------------------------------------------------------------------------
@@ -1880,4 +1881,105 @@ extern "C" int ckks_poly_device_ptr(ckks_poly *p, uint64_t **out) {
     if (!ok_poly(p) || !out) return CKKS_BAD_HANDLE;
     *out = (uint64_t *)p->d;
     return CKKS_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// CkksEncoder on the device (ckks_encoder.rs:65-156, special_fft.rs:194-242): O(N log N), f64
+// -------------------------------------------------------------------------------------------------
+static int fft_run(const Tables &T, cplx *buf, size_t batch, double sign) {
+    const size_t work = batch * (T.n / 2);
+    for (int lh = 0; lh < T.logn; ++lh)
+        KL("encoder_fft_stage", (fft_stage_kernel<<<(unsigned)((work + 255) / 256), 256, 0, T.stream>>>(buf, T.logn, lh, sign, batch)));
+    return CKKS_OK;
+}
+static int pow5_table(const Tables &T, unsigned **out) {
+    std::vector<unsigned> h(T.n / 2 ? T.n / 2 : 1);
+    u64 v = 1;
+    for (size_t i = 0; i < h.size(); ++i) {
+        h[i] = (unsigned)v;
+        v = (v * 5) % (2 * T.n);
+    }
+    CU(cudaMallocAsync((void **)out, h.size() * sizeof(unsigned), T.stream));
+    CU(cudaMemcpyAsync(*out, h.data(), h.size() * sizeof(unsigned), cudaMemcpyHostToDevice, T.stream));
+    CU(cudaStreamSynchronize(T.stream));  // `h` goes out of scope
+    return CKKS_OK;
+}
+extern "C" int ckks_encode(ckks_ctx *ctx, uint32_t scale_bits, size_t batch, const double *values, size_t nvals, ckks_poly **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    const Tables &T = *ctx->T;
+    if (T.n < 2 || scale_bits == 0) return CKKS_BAD_ARGUMENT;  // ckks_encoder.rs:38-45
+    if (nvals > T.n / 2) return CKKS_SHORT_INPUT;                // ckks_encoder.rs:70-75: more values than slots
+    if (!values && batch && nvals) return CKKS_BAD_ARGUMENT;
+    CU(cudaSetDevice(T.device));
+    TRY(poly_new(ctx, batch, false, out));
+    if (!batch) return CKKS_OK;
+    cplx *dv = nullptr, *buf = nullptr;
+    long long *dc = nullptr;
+    unsigned *p5 = nullptr;
+    auto body = [&]() -> int {
+        TRY(pow5_table(T, &p5));
+        CU(cudaMallocAsync((void **)&dv, (batch * nvals + 1) * sizeof(cplx), T.stream));
+        CU(cudaMallocAsync((void **)&buf, batch * T.n * sizeof(cplx), T.stream));
+        CU(cudaMallocAsync((void **)&dc, batch * T.n * sizeof(long long), T.stream));
+        if (nvals) CU(cudaMemcpyAsync(dv, values, batch * nvals * sizeof(cplx), cudaMemcpyHostToDevice, T.stream));
+        const size_t half = batch * (T.n / 2);
+        KL("encoder_scatter", (enc_scatter_kernel<<<(unsigned)((half + 255) / 256), 256, 0, T.stream>>>(dv, nvals, ldexp(1.0, (int)scale_bits), p5, buf,
+                                                                                                         T.logn, batch)));
+        TRY(fft_run(T, buf, batch, +1.0));
+        const size_t tot = batch * T.n;
+        KL("encoder_finish", (enc_finish_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, T.stream>>>(buf, dc, T.logn, batch)));
+        EwArgs a = ew_args(T, ctx->L, batch);
+        KL("from_coeffs", (from_coeffs_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, dc, T.n, (*out)->d)));
+        CU(cudaStreamSynchronize(T.stream));  // `values` may be pageable and reused by the caller
+        return CKKS_OK;
+    };
+    int rc = body();
+    dev_free(T, dv);
+    dev_free(T, buf);
+    dev_free(T, dc);
+    dev_free(T, p5);
+    if (rc != CKKS_OK) {
+        ckks_poly_free(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+extern "C" int ckks_decode(const ckks_poly *p, uint32_t scale_bits, size_t nslots, double *out) {
+    if (!ok_poly(p)) return CKKS_BAD_HANDLE;
+    const Tables &T = *p->ctx->T;
+    if (T.n < 2 || nslots > T.n / 2) return CKKS_BAD_ARGUMENT;
+    if (!p->batch || !nslots) return CKKS_OK;
+    if (!out) return CKKS_BAD_ARGUMENT;
+    CU(cudaSetDevice(T.device));
+    // centred CRT exactly as the reference (basis.rs:158-180, Q < 2^128), then the transform on the device
+    std::vector<int64_t> co(p->batch * T.n);
+    TRY(ckks_poly_to_coeffs(p, co.data()));
+    cplx *buf = nullptr, *dout = nullptr;
+    long long *dc = nullptr;
+    unsigned *p5 = nullptr;
+    const size_t batch = p->batch;
+    auto body = [&]() -> int {
+        TRY(pow5_table(T, &p5));
+        CU(cudaMallocAsync((void **)&buf, batch * T.n * sizeof(cplx), T.stream));
+        CU(cudaMallocAsync((void **)&dc, batch * T.n * sizeof(long long), T.stream));
+        CU(cudaMallocAsync((void **)&dout, batch * nslots * sizeof(cplx), T.stream));
+        CU(cudaMemcpyAsync(dc, co.data(), batch * T.n * sizeof(long long), cudaMemcpyHostToDevice, T.stream));
+        const size_t tot = batch * T.n;
+        KL("decoder_twist", (dec_twist_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, T.stream>>>(dc, buf, T.logn, batch)));
+        TRY(fft_run(T, buf, batch, -1.0));
+        const size_t ns = batch * nslots;
+        KL("decoder_gather", (dec_gather_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, T.stream>>>(buf, p5, ldexp(1.0, -(int)scale_bits), dout, nslots,
+                                                                                                     T.logn, batch)));
+        CU(cudaMemcpyAsync(out, dout, ns * sizeof(cplx), cudaMemcpyDeviceToHost, T.stream));
+        CU(cudaStreamSynchronize(T.stream));
+        return CKKS_OK;
+    };
+    int rc = body();
+    dev_free(T, buf);
+    dev_free(T, dc);
+    dev_free(T, dout);
+    dev_free(T, p5);
+    return rc;
 }
