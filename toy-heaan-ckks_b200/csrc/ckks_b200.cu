@@ -572,7 +572,8 @@ static int ntt_run(const Tables &T, size_t L, size_t batch, u64 *d, u64 *tmp, bo
     }
     // Measured on B200 (profiles/): with 32-bit words the single-kernel transform wins up to N = 2^14;
     // with 64-bit words (register- and IMAD-bound) only at N = 2^12.
-    if (g_use_fused_ntt && ((T.w32 && T.logn >= 12 && T.logn <= 14) || (!T.w32 && T.logn == 12)))
+    // (at N = 2^14 the 1024-thread fused kernel wins forward, 3.73 vs 3.36 TB/s, and loses inverse, 3.21 vs 3.63)
+    if (g_use_fused_ntt && ((T.w32 && T.logn >= 12 && (T.logn <= 13 || (T.logn == 14 && !inverse))) || (!T.w32 && T.logn == 12)))
         return ntt_fused_run(T, L, batch, d, inverse);
     // Two passes through an intermediate of the transform word type.  (Walking the batch in chunks with
     // the intermediate pinned in L2 by an access-policy window was measured slower on B200 -- the carve-out
