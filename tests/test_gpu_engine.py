@@ -332,6 +332,27 @@ def test_rotation_decodes_rotated_slots(gpu, orc, n, ks, tol):
         assert np.max(np.abs(got.real - np.roll(vals, -abs(k)))) < tol
 
 
+def test_large_batch_small_degree(gpu, orc):
+    """70 000 ciphertext pairs at N=256, L=2: more than one grid-dimension chunk (65 535) in every kernel;
+    spot-checked against the oracle and against a batch-1 run of the same inputs."""
+    n, l, batch = 256, 2, 70000
+    moduli = orc.generate_primes(30, l, n)
+    gb, ob = gpu.RnsBasis(n, moduli), orc.Basis(n, moduli)
+    rng = np.random.default_rng(77)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    key = gpu.GadgetKey.upload(gb, ka, kb, rotation=1)
+    out = gpu.CkksEngine.mul_relin_rescale(_ct(gpu, gb, a0, a1, 30, 60), _ct(gpu, gb, b0, b1, 30, 60), key)
+    g0, g1 = out.c0.channels(), out.c1.channels()
+    rot = gpu.CkksEngine.rotate_ciphertext(_ct(gpu, gb, a0, a1, 30, 60), key)
+    h0 = rot.c0.channels()
+    for i in (0, 32767, 32768, 65535, 65536, batch - 1):
+        m0, m1 = ob.mul_ciphertexts_gadget(a0[i], a1[i], b0[i], b1[i], ka, kb)
+        r0, r1, _ = ob.rescale_ciphertext(m0, m1)
+        assert np.array_equal(g0[i], r0) and np.array_equal(g1[i], r1), i
+        assert np.array_equal(h0[i], ob.rotate_ciphertext(a0[i], a1[i], ka, kb, 1)[0]), i
+
+
 def test_rotation_stress_example(gpu, orc):
     """examples/rotation_stress.rs: N=32, generate_primes(30,3,32), scale 2^58, slots 1..16, one rotation key
     for offset +1 reused for 800 sequential rotate_ciphertext calls; max error < 1e-3 at every checkpoint

@@ -1273,6 +1273,7 @@ static size_t ks_chunk(const Tables &T, size_t L, size_t batch) {
     size_t per = L * L * T.n * sizeof(u64);
     size_t c = ((size_t)4 << 30) / per;
     if (c < 1) c = 1;
+    if (c > 32768) c = 32768;  // the ciphertext index is a grid dimension (y/z limit 65535)
     return c < batch ? c : batch;
 }
 
