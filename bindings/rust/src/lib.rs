@@ -20,6 +20,7 @@ use rand_distr::{Distribution, Normal};
 use toy_heaan_ckks::math::{ternary_coefficients, uniform_coefficients};
 use toy_heaan_ckks::rings::backends::rns_ntt::RnsNttError;
 use toy_heaan_ckks::rings::traits::{PolyAutomorphism, PolyRing, PolySampler};
+// (PolyAutomorphism is not re-exported from `rings`, only from `rings::traits`: src/rings/mod.rs:6)
 
 pub mod ffi {
     #[repr(C)]
@@ -78,12 +79,13 @@ pub mod ffi {
 /// Status codes 1..6 are `RnsNttError` one to one (errors.rs:3-22); everything else is a bug or a CUDA failure.
 fn to_err(rc: i32, n: usize) -> RnsNttError {
     match rc {
-        1 => RnsNttError::InvalidDegree(n),
+        // variant payloads (errors.rs:5-21) that only the host knows are filled by the callers below
+        1 => RnsNttError::InvalidDegree { degree: n },
         2 => RnsNttError::EmptyBasis,
         3 => RnsNttError::NonNttFriendlyModulus { modulus: 0, degree: n },
-        4 => RnsNttError::InvalidModDrop { requested: 0, available: 0 },
-        5 => RnsNttError::ChannelCountMismatch { expected: 0, found: 0 },
-        6 => RnsNttError::NonReducedCoefficient { channel: 0, value: 0, modulus: 0 },
+        4 => RnsNttError::InvalidModDrop { drop_count: 0, channel_count: 0 },
+        5 => RnsNttError::ChannelCountMismatch { expected: 0, actual: 0 },
+        6 => RnsNttError::NonReducedCoefficient { coefficient: 0, modulus: 0 },
         other => panic!("ckks_b200: {}", unsafe { std::ffi::CStr::from_ptr(ffi::ckks_status_str(other)) }.to_string_lossy()),
     }
 }
@@ -107,6 +109,10 @@ impl<const N: usize> RnsBasis<N> {
     pub fn new(moduli: Vec<u64>) -> Result<Self, RnsNttError> {
         let mut ctx = ptr::null_mut();
         let rc = unsafe { ffi::ckks_ctx_create(N as u64, moduli.as_ptr(), moduli.len(), 0, &mut ctx) };
+        if rc == 3 {
+            let bad = moduli.iter().copied().find(|&q| !toy_heaan_ckks::math::is_ntt_friendly_prime(q, N as u64)).unwrap_or(0);
+            return Err(RnsNttError::NonNttFriendlyModulus { modulus: bad, degree: N });
+        }
         if rc != 0 {
             return Err(to_err(rc, N));
         }
@@ -121,6 +127,9 @@ impl<const N: usize> RnsBasis<N> {
     pub fn drop_last(&self, drop_count: usize) -> Result<Self, RnsNttError> {
         let mut ctx = ptr::null_mut();
         let rc = unsafe { ffi::ckks_ctx_drop_last(self.ctx.as_ptr(), drop_count, &mut ctx) };
+        if rc == 4 {
+            return Err(RnsNttError::InvalidModDrop { drop_count, channel_count: self.moduli.len() });
+        }
         if rc != 0 {
             return Err(to_err(rc, N));
         }
