@@ -332,6 +332,29 @@ def test_rotation_decodes_rotated_slots(gpu, orc, n, ks, tol):
         assert np.max(np.abs(got.real - np.roll(vals, -abs(k)))) < tol
 
 
+@pytest.mark.parametrize("n,bits", [(16, 31), (256, 40), (4096, 61)])
+def test_single_limb_basis(gpu, orc, n, bits):
+    """L = 1: the gadget has a single digit (its own NTT-domain limb); multiplication and rotation still equal the
+    oracle, rescale is refused like the reference (poly.rs:191-197)."""
+    moduli = orc.generate_primes(bits, 1, n)
+    gb, ob = gpu.RnsBasis(n, moduli), orc.Basis(n, moduli)
+    rng = np.random.default_rng(n)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, 2) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, 1), uniform_limbs(rng, moduli, n, 1)
+    key = gpu.GadgetKey.upload(gb, ka, kb, rotation=2)
+    cta, ctb = _ct(gpu, gb, a0, a1, 20, 30), _ct(gpu, gb, b0, b1, 20, 30)
+    prod = gpu.CkksEngine.mul_ciphertexts_gadget(cta, ctb, key)
+    rot = gpu.CkksEngine.rotate_ciphertext(cta, key)
+    for i in range(2):
+        m0, m1 = ob.mul_ciphertexts_gadget(a0[i], a1[i], b0[i], b1[i], ka, kb)
+        assert np.array_equal(prod.c0.channels()[i], m0) and np.array_equal(prod.c1.channels()[i], m1)
+        r0, r1 = ob.rotate_ciphertext(a0[i], a1[i], ka, kb, 2)
+        assert np.array_equal(rot.c0.channels()[i], r0) and np.array_equal(rot.c1.channels()[i], r1)
+    with pytest.raises(gpu.RnsNttError) as e:
+        gpu.CkksEngine.rescale_ciphertext(prod)
+    assert e.value.kind == "InvalidModDrop"
+
+
 def test_large_batch_small_degree(gpu, orc):
     """70 000 ciphertext pairs at N=256, L=2: more than one grid-dimension chunk (65 535) in every kernel;
     spot-checked against the oracle and against a batch-1 run of the same inputs."""
