@@ -421,6 +421,168 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+class _DevBuf:
+    """A library-owned device buffer seen by torch (for the NCCL variant of the limb-sharded mode)."""
+
+    def __init__(self, ptr: int, words: int):
+        self.__cuda_array_interface__ = {"shape": (words,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+def run_limb_sharded(args):
+    """Optional limb-sharded mode: ONE batch whose limbs are spread over the GPUs (limb j on
+    GPU j mod N), strong scaling.  --comm peer: digits all-gathered / dropped limb broadcast by stores into
+    peer HBM from the producing kernels + flag barrier (one library call per step);  --comm nccl: the same
+    phases with torch.distributed all_gather_into_tensor / broadcast on the exchange buffers."""
+    import numpy as np
+    import torch
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+
+    g.build_cuda()
+    ck = importlib.import_module("toy-heaan-ckks_b200")
+    logn, l, bits, batch, _ = CONFIGS[args.config]
+    if args.batch:
+        batch = args.batch
+    n = 1 << logn
+    moduli = ck.generate_primes(bits, l, n)
+    sh = ck.LimbShard(n, moduli, rank, world, device=local, chunk=args.ls_chunk)
+    kid = sh.drop_last()
+    basis = sh.local_basis()
+    stream = torch.cuda.current_stream()
+    basis.set_stream(stream.cuda_stream)
+    if world > 1:
+        sh.connect_process_group()
+    dev = torch.device("cuda", local)
+    own = sh.owned()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)  # every rank holds limbs of the SAME ciphertexts; the values are synthetic anyway
+    qt = torch.tensor([moduli[j] for j in own], dtype=torch.int64, device=dev)[:, None]
+
+    def uni_poly(b):
+        t = torch.randint(0, 1 << 62, (b, len(own), n), dtype=torch.int64, device=dev, generator=gen) % qt
+        h = ck._vp()
+        ck._check(ck._lib.ckks_poly_from_device(basis._h, b, ck.C.cast(t.data_ptr(), ck._u64p), 0, ck.C.byref(h)))
+        p = ck.RnsPoly(h, basis)
+        del t
+        return p
+
+    rng = np.random.default_rng(7 + rank)
+    qn = np.array([moduli[j] for j in own], dtype=np.uint64)[None, :, None]
+    ka = rng.integers(0, 1 << 62, size=(l, len(own), n), dtype=np.uint64) % qn
+    kb = rng.integers(0, 1 << 62, size=(l, len(own), n), dtype=np.uint64) % qn
+    key = sh.upload_key(ka, kb)
+    del ka, kb
+    cta = ck.Ciphertext(uni_poly(batch), uni_poly(batch), bits, bits * l)
+    ctb = ck.Ciphertext(uni_poly(batch), uni_poly(batch), bits, bits * l)
+    torch.cuda.empty_cache()
+    chunk = sh.chunk()
+    if args.comm == "nccl" and world > 1:
+        gp, gw, lp, lw = sh.buffers()
+        gt = torch.as_tensor(_DevBuf(gp, gw), device=dev).view(l, chunk * n)
+        lt = torch.as_tensor(_DevBuf(lp, lw), device=dev)
+        owner = (l - 1) % world
+
+    def step():
+        if args.comm == "peer" or world == 1:
+            return sh.mul_relin_rescale(cta, ctb, key, kid)
+        out = ck.Ciphertext(ck.RnsPoly.zero(kid.local_basis(), batch), ck.RnsPoly.zero(kid.local_basis(), batch), 0, 0)
+        for s0 in range(0, batch, chunk):
+            cs = min(chunk, batch - s0)
+            sh.mul_phase(0, s0, cs, cta, ctb, key, kid, out, False)
+            for k0 in range(0, l, world):  # slots k0..k0+world-1 are owned by ranks 0..world-1
+                if k0 + world <= l:
+                    dist.all_gather_into_tensor(gt[k0 : k0 + world].view(-1), gt[k0 + rank])
+                else:
+                    for i in range(k0, l):
+                        dist.broadcast(gt[i], src=i % world)
+            sh.mul_phase(1, s0, cs, cta, ctb, key, kid, out, False)
+            dist.broadcast(lt, src=owner)
+            sh.mul_phase(2, s0, cs, cta, ctb, key, kid, out, False)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sh.check()
+    sampler = ClockSampler(local)
+    ck._lib.ckks_prof_enable(1 if args.prof else 0)
+    launches0 = ck.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    sh.check()
+    launches = ck.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ck._lib.ckks_prof_enable(0)
+    prof = {}
+    if args.prof:
+        buf = ck.C.create_string_buffer(1 << 20)
+        ck._lib.ckks_prof_collect(buf, len(buf))
+        for ln in buf.value.decode().splitlines():
+            name, rest = ln.split("=")
+            cnt, kms = rest.split(",")
+            prof[name] = (int(cnt), float(kms))
+    ms_per_step = ms / args.steps
+    value = batch / (ms_per_step * 1e-3)
+    tot = sum(m for _, m in prof.values()) or 1.0
+    line = {
+        "metric": "ct-mults/sec (mul+relin+rescale)",
+        "value": value,
+        "unit": "ct-mult/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "u64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"{args.config}: N=2^{logn}, L={l}, {bits}-bit primes, ONE batch of {batch} ciphertext pairs, limbs spread over "
+            f"{world} GPU(s), mul_ciphertexts_gadget+rescale_ciphertext",
+            "parallelism": f"limb-sharded x{world} (limb j on GPU j mod {world}); exchange: "
+            + ("stores into peer HBM from the producing kernels + flag barrier" if args.comm == "peer" else "NCCL all-gather / broadcast between the phases"),
+            "chunk": chunk,
+            "exchange_bytes_per_ct_per_gpu": (len(own) * (world - 1) * n * 8) + (2 * (world - 1) * n * 8 if rank == (l - 1) % world else 0),
+            "key_bytes_per_gpu": 2 * l * len(own) * n * 8,
+        },
+        "clocks": clocks,
+        "gpu_launches": launches,
+        "kernels": {k: {"launches": c, "ms": round(m, 3), "share": round(m / tot, 4)} for k, (c, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    del cta, ctb, key
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ntt_sweep(args):
     """BASELINE.json configs[4]: standalone limb-batched NTT / INTT, N = 2^12..2^16, L in {1, 8, 24, 32},
     30-bit and 61-bit chains; batch sized to ~1 GiB of limbs.  transforms/s and achieved GB/s
@@ -535,8 +697,13 @@ def main():
     ap.add_argument("--op", default="", choices=["", "mul", "rotate"], help="hot-path operation (default: mul; rotate for cfg3)")
     ap.add_argument("--host-chunk-mib", type=int, default=0, help="pipeline chunk of the host-buffer entry point")
     ap.add_argument("--ntt-sweep", action="store_true", help="BASELINE.json configs[4]: limb-batched NTT/INTT sweep instead of the ct-mult bench")
+    ap.add_argument("--limb-sharded", action="store_true", help="optional limb-sharded mode (one batch, limbs spread over the GPUs)")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="limb-sharded exchange: fused peer stores or NCCL collectives")
+    ap.add_argument("--ls-chunk", type=int, default=0, help="limb-sharded: ciphertexts per pass (0 = automatic)")
     args = ap.parse_args()
-    if args.ntt_sweep:
+    if args.limb_sharded:
+        run_limb_sharded(args)
+    elif args.ntt_sweep:
         run_ntt_sweep(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -206,6 +206,62 @@ int ckks_ct_rotate_host(ckks_ctx *ctx, const ckks_ksk *rotk, int32_t k, size_t b
 int ckks_host_alloc(size_t bytes, void **out);
 int ckks_host_free(void *p);
 
+/* ---- optional limb-sharded mode (north_star "limb-sharded mode at N=2^16 / L>=24") ------
+ * Replaces nothing in the reference (it is single-threaded and single-device); it is the multi-GPU form
+ * of mul_ciphertexts_gadget engine.rs:473-539 + rescale_ciphertext engine.rs:263-282 for ONE batch whose
+ * limbs are spread over the GPUs of a box: limb j of the basis lives on GPU (j mod world); local limb jl of
+ * rank r is basis limb r + world*jl.  Each GPU keeps 1/world of every ciphertext and of the gadget key.
+ * The all-gather of the digits and the broadcast of the dropped limb are plain stores into peer HBM
+ * issued by the kernels that produce those words, ordered by a flag barrier in peer memory; every
+ * GPU of the group makes the same calls on its own share.  Output words equal the reference's. */
+typedef struct ckks_lshard ckks_lshard;
+/* moduli: the WHOLE basis (validated like RnsBasis::new basis.rs:97-106).  chunk: ciphertexts per pass
+ * (0 = as many as 4 GiB of key-switch scratch allow).  CKKS_UNSUPPORTED if l < world or N < 256. */
+int ckks_lshard_create(uint64_t n, const uint64_t *moduli, size_t l, int rank, int world, int device,
+                       size_t chunk, ckks_lshard **out);
+int ckks_lshard_destroy(ckks_lshard *s);
+/* The level below (RnsBasis::drop_last basis.rs:122-134 for the whole basis): the owner of the dropped
+ * limb loses one local limb; exchange buffers are shared with the parent. */
+int ckks_lshard_drop_last(ckks_lshard *s, ckks_lshard **child);
+/* Context over the limbs held here: build / read this GPU's share of a polynomial with the ckks_poly_* calls. */
+ckks_ctx *ckks_lshard_local_ctx(ckks_lshard *s);
+size_t ckks_lshard_channel_count(const ckks_lshard *s); /* limbs of the whole basis at this level */
+size_t ckks_lshard_chunk(const ckks_lshard *s);
+/* One process per GPU: export this rank's buffer handle (ckks_lshard_ipc_size() bytes), move the
+ * handles of all ranks with any host-side all-gather, import them in rank order. */
+size_t ckks_lshard_ipc_size(void);
+int ckks_lshard_ipc_export(ckks_lshard *s, void *blob);
+int ckks_lshard_ipc_import(ckks_lshard *s, const void *blobs);
+/* All ranks in one process (several GPUs with peer access, or several ranks on one GPU). */
+int ckks_lshard_connect_local(ckks_lshard **shards, int world);
+/* Key slice: a, b host [digit i < L][own limb jl][N] = rows of RnsGadgetRelinKey (engine.rs:225-253)
+ * restricted to this GPU's limbs, coefficient domain; transformed once. */
+int ckks_lshard_ksk_upload(ckks_lshard *s, const uint64_t *a, const uint64_t *b, ckks_ksk **out);
+/* mul_ciphertexts_gadget on this GPU's limbs of a batch; with child != NULL followed by
+ * rescale_ciphertext into the child's level.  Inputs / outputs: polynomials of the local contexts,
+ * coefficient domain.  Enqueues everything, exchanges included, without synchronising the host. */
+int ckks_lshard_ct_mul_relin_rescale(ckks_lshard *s, const ckks_poly *a0, const ckks_poly *a1,
+                                     const ckks_poly *b0, const ckks_poly *b1, const ckks_ksk *rlk,
+                                     ckks_lshard *child, ckks_poly **o0, ckks_poly **o1);
+/* The same in three phases (0: limb-local up to the digits, 1: key-switch, 2: rescale epilogue) over the
+ * ciphertexts [s0, s0+cs), cs <= chunk, for a caller that runs the two exchanges itself on the exported
+ * buffers (peer_stores = 0: e.g. NCCL all-gather / broadcast through torch.distributed) or that wants to
+ * place the barriers (peer_stores = 1).  o0/o1: preallocated on the output level's local context. */
+int ckks_lshard_mul_phase(ckks_lshard *s, int phase, size_t s0, size_t cs, const ckks_poly *a0,
+                          const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1,
+                          const ckks_ksk *rlk, ckks_lshard *child, ckks_poly *o0, ckks_poly *o1,
+                          int peer_stores);
+int ckks_lshard_barrier(ckks_lshard *s);
+/* Barrier by stream events for a group living in one process and driven phase by phase in lockstep. */
+int ckks_lshard_barrier_local(ckks_lshard **shards, int world);
+/* gather: [L of the top level][chunk][N] (digit limb i of chunk ciphertext c at (i*chunk + c)*N words);
+ * last: [2][chunk][N] (finished last limb of c0 and c1). */
+int ckks_lshard_buffers(ckks_lshard *s, uint64_t **gather, size_t *gather_words, uint64_t **last,
+                        size_t *last_words);
+/* Synchronise and report a barrier that gave up waiting for a peer (CKKS_NCCL_ERROR). */
+int ckks_lshard_check(ckks_lshard *s);
+int ckks_lshard_set_timeout_ms(ckks_lshard *s, uint64_t ms);
+
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* Kernel launches issued by this library since process start (bench.py's gpu_launches). */
 uint64_t ckks_launch_count(void);

@@ -139,6 +139,24 @@ _sig("ckks_host_free", C.c_int, _vp)
 _sig("ckks_launch_count", C.c_uint64)
 _sig("ckks_launch_table", C.c_size_t, C.c_char_p, C.c_size_t)
 _sig("ckks_bench_modmul_peak", C.c_double, C.c_int, C.c_int)
+_sig("ckks_lshard_create", C.c_int, C.c_uint64, _u64p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_size_t, _pp)
+_sig("ckks_lshard_destroy", C.c_int, _vp)
+_sig("ckks_lshard_drop_last", C.c_int, _vp, _pp)
+_sig("ckks_lshard_local_ctx", _vp, _vp)
+_sig("ckks_lshard_channel_count", C.c_size_t, _vp)
+_sig("ckks_lshard_chunk", C.c_size_t, _vp)
+_sig("ckks_lshard_ipc_size", C.c_size_t)
+_sig("ckks_lshard_ipc_export", C.c_int, _vp, _vp)
+_sig("ckks_lshard_ipc_import", C.c_int, _vp, _vp)
+_sig("ckks_lshard_connect_local", C.c_int, _pp, C.c_int)
+_sig("ckks_lshard_ksk_upload", C.c_int, _vp, _u64p, _u64p, _pp)
+_sig("ckks_lshard_ct_mul_relin_rescale", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pp, _pp)
+_sig("ckks_lshard_mul_phase", C.c_int, _vp, C.c_int, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int)
+_sig("ckks_lshard_barrier", C.c_int, _vp)
+_sig("ckks_lshard_barrier_local", C.c_int, _pp, C.c_int)
+_sig("ckks_lshard_buffers", C.c_int, _vp, C.POINTER(_u64p), C.POINTER(C.c_size_t), C.POINTER(_u64p), C.POINTER(C.c_size_t))
+_sig("ckks_lshard_check", C.c_int, _vp)
+_sig("ckks_lshard_set_timeout_ms", C.c_int, _vp, C.c_uint64)
 
 # Every symbol include/ckks_b200.h declares (tests/test_abi.py checks the header against this list).
 ABI_SYMBOLS = sorted(n for n in dir(_lib) if n.startswith("ckks_")) or []
@@ -233,7 +251,8 @@ def generate_primes(bit_size: int, count: int, degree: int) -> list:
 class RnsBasis:
     """`Arc<RnsBasis<N>>` (basis.rs:91-181) with its device tables."""
 
-    def __init__(self, degree: int, moduli, device: int = 0, _handle=None):
+    def __init__(self, degree: int, moduli, device: int = 0, _handle=None, _owned: bool = True):
+        self._owned = _owned  # False: a handle borrowed from a LimbShard
         if _handle is not None:
             self._h = _handle
         else:
@@ -251,7 +270,8 @@ class RnsBasis:
     def __del__(self):
         try:
             if getattr(self, "_h", None):
-                _lib.ckks_ctx_destroy(self._h)
+                if self._owned:
+                    _lib.ckks_ctx_destroy(self._h)
                 self._h = None
         except Exception:
             pass
@@ -603,3 +623,169 @@ def mul_relin_rescale_host(basis: RnsBasis, child: RnsBasis, rlk: GadgetKey, a0,
 
 def rotate_host(basis: RnsBasis, rotk: GadgetKey, c0, c1, o0, o1):
     _check(_lib.ckks_ct_rotate_host(basis._h, rotk._h, rotk.rotation, c0.shape[0], _ptr(c0), _ptr(c1), _ptr(o0), _ptr(o1)))
+
+
+# ── optional limb-sharded mode ────────────────────────────────────────────────────
+def owned_limbs(channel_count: int, rank: int, world: int) -> list:
+    """Basis limbs GPU `rank` of `world` holds: j with j mod world == rank (balanced under drop_last)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return list(range(rank, channel_count, world))
+
+
+class LimbShard:
+    """One GPU's share of a limb-sharded batch: every ciphertext's limbs j = rank (mod world) and the
+    matching slices of the gadget keys.  `mul_relin_rescale` is mul_ciphertexts_gadget + rescale_ciphertext
+    (engine.rs:473-539, 263-282); the digits are all-gathered and the dropped limb broadcast by stores into
+    peer HBM from the producing kernels.  Every rank of the group makes the same calls."""
+
+    def __init__(self, degree: int, moduli, rank: int, world: int, device: int = 0, chunk: int = 0, _handle=None, _parent=None,
+                 _moduli=None):
+        self.rank, self.world, self.device, self.degree = rank, world, device, degree
+        self._parent = _parent  # children share the parent's exchange buffers: keep it alive
+        if _handle is not None:
+            self._h, self._moduli = _handle, list(_moduli)
+        else:
+            m = _u64(list(moduli))
+            h = _vp()
+            _check(_lib.ckks_lshard_create(degree, _ptr(m) if len(m) else None, len(m), rank, world, device, chunk, C.byref(h)))
+            self._h, self._moduli = h, [int(x) for x in m]
+        self._basis = RnsBasis(0, [], device, _handle=_vp(_lib.ckks_lshard_local_ctx(self._h)), _owned=False)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._basis._h = None
+                _lib.ckks_lshard_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def moduli(self) -> list:
+        """The whole basis at this level."""
+        return list(self._moduli)
+
+    def channel_count(self) -> int:
+        return int(_lib.ckks_lshard_channel_count(self._h))
+
+    def owned(self) -> list:
+        return owned_limbs(self.channel_count(), self.rank, self.world)
+
+    def local_basis(self) -> RnsBasis:
+        return self._basis
+
+    def chunk(self) -> int:
+        return int(_lib.ckks_lshard_chunk(self._h))
+
+    def drop_last(self) -> "LimbShard":
+        h = _vp()
+        _check(_lib.ckks_lshard_drop_last(self._h, C.byref(h)))
+        return LimbShard(self.degree, None, self.rank, self.world, self.device, _handle=h, _parent=self, _moduli=self._moduli[:-1])
+
+    # wiring -------------------------------------------------------------------------------------
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(int(_lib.ckks_lshard_ipc_size()))
+        _check(_lib.ckks_lshard_ipc_export(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles):
+        """handles: every rank's `ipc_handle()` in rank order (one process per GPU)."""
+        blob = b"".join(handles)
+        if len(blob) != self.world * int(_lib.ckks_lshard_ipc_size()):
+            raise RnsNttError(31, "connect: need one handle per rank")
+        _check(_lib.ckks_lshard_ipc_import(self._h, C.create_string_buffer(blob, len(blob))))
+
+    def connect_process_group(self, group=None):
+        """Exchange the handles over torch.distributed (plumbing only) and connect."""
+        import torch.distributed as dist
+
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.ipc_handle(), group=group)
+        self.connect(handles)
+
+    @staticmethod
+    def connect_local(shards):
+        """All ranks live in this process (several GPUs, or several ranks on one GPU)."""
+        arr = (C.c_void_p * len(shards))(*[s._h for s in shards])
+        _check(_lib.ckks_lshard_connect_local(arr, len(shards)))
+
+    # data ---------------------------------------------------------------------------------------
+    def scatter(self, channels, is_ntt_domain: bool = False) -> RnsPoly:
+        """This GPU's limbs of host polynomials [batch, L, N] (reference layout) -> device."""
+        ch = _u64(channels)
+        if ch.ndim == 2:
+            ch = ch[None]
+        if ch.shape[1] != self.channel_count():
+            raise RnsNttError(5)
+        return RnsPoly.from_channels(np.ascontiguousarray(ch[:, self.rank :: self.world]), self._basis, is_ntt_domain)
+
+    def upload_key(self, a, b, rotation: int = 0) -> GadgetKey:
+        """a, b: the whole gadget key [L, L, N] (digit, limb, N) or already this GPU's slice [L, L_own, N]."""
+        a, b = _u64(a), _u64(b)
+        l, own, n = self.channel_count(), len(self.owned()), self.degree
+        if a.shape == (l, l, n):
+            a, b = a[:, self.rank :: self.world], b[:, self.rank :: self.world]
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        if a.shape != (l, own, n) or b.shape != (l, own, n):
+            raise RnsNttError(5, "gadget key slice must be [L, L_own, N]")
+        h = _vp()
+        _check(_lib.ckks_lshard_ksk_upload(self._h, _ptr(a), _ptr(b), C.byref(h)))
+        return GadgetKey(h, self._basis, rotation)
+
+    # operations ---------------------------------------------------------------------------------
+    def mul_relin_rescale(self, a: Ciphertext, b: Ciphertext, rlk: GadgetKey, child: "LimbShard | None" = None) -> Ciphertext:
+        """mul_ciphertexts_gadget, then rescale_ciphertext into `child`'s level when given."""
+        if a.logq != b.logq:  # engine.rs:478
+            raise RnsNttError(23)
+        h0, h1 = _vp(), _vp()
+        _check(_lib.ckks_lshard_ct_mul_relin_rescale(self._h, a.c0._h, a.c1._h, b.c0._h, b.c1._h, rlk._h, child._h if child else None,
+                                                     C.byref(h0), C.byref(h1)))
+        bs = child._basis if child else self._basis
+        bits = self._moduli[-1].bit_length() if child else 0
+        return Ciphertext(RnsPoly(h0, bs), RnsPoly(h1, bs), a.logp + b.logp - bits, a.logq - bits)
+
+    def mul_phase(self, phase: int, s0: int, cs: int, a: Ciphertext, b: Ciphertext, rlk: GadgetKey, child, out: Ciphertext,
+                  peer_stores: bool):
+        _check(_lib.ckks_lshard_mul_phase(self._h, phase, s0, cs, a.c0._h, a.c1._h, b.c0._h, b.c1._h, rlk._h,
+                                          child._h if child else None, out.c0._h, out.c1._h, int(peer_stores)))
+
+    def barrier(self):
+        _check(_lib.ckks_lshard_barrier(self._h))
+
+    @staticmethod
+    def group_mul_relin_rescale(shards, a, b, keys, kids=None):
+        """A whole group living in this process, driven in lockstep: per chunk, phase A on every rank, barrier,
+        phase B, barrier, phase C.  a, b, keys (and kids) are per-rank lists; returns the per-rank results."""
+        world = len(shards)
+        arr = (C.c_void_p * world)(*[s._h for s in shards])
+        batch = a[0].c0.batch()
+        outs = []
+        for r, s in enumerate(shards):
+            if a[r].logq != b[r].logq:  # engine.rs:478
+                raise RnsNttError(23)
+            bs = kids[r]._basis if kids else s._basis
+            bits = s._moduli[-1].bit_length() if kids else 0
+            outs.append(Ciphertext(RnsPoly.zero(bs, batch), RnsPoly.zero(bs, batch), a[r].logp + b[r].logp - bits, a[r].logq - bits))
+        step = shards[0].chunk()
+        for s0 in range(0, batch, step):
+            cs = min(step, batch - s0)
+            for phase in range(3):
+                for r, s in enumerate(shards):
+                    s.mul_phase(phase, s0, cs, a[r], b[r], keys[r], kids[r] if kids else None, outs[r], True)
+                if phase < 2:
+                    _check(_lib.ckks_lshard_barrier_local(arr, world))
+        return outs
+
+    def buffers(self):
+        """(gather_ptr, gather_words, last_ptr, last_words): device pointers of the exchange buffers."""
+        g, l = _u64p(), _u64p()
+        gw, lw = C.c_size_t(0), C.c_size_t(0)
+        _check(_lib.ckks_lshard_buffers(self._h, C.byref(g), C.byref(gw), C.byref(l), C.byref(lw)))
+        return C.cast(g, C.c_void_p).value, int(gw.value), C.cast(l, C.c_void_p).value, int(lw.value)
+
+    def check(self):
+        """Synchronise; raises if a barrier gave up waiting for a peer."""
+        _check(_lib.ckks_lshard_check(self._h))
+
+    def set_timeout_ms(self, ms: int):
+        _check(_lib.ckks_lshard_set_timeout_ms(self._h, ms))

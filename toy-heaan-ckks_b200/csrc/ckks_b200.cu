@@ -220,7 +220,8 @@ static bool ok_ctx(const ckks_ctx *c) {
     return true;
 }
 static bool ok_poly(const ckks_poly *p) { return p && p->magic == MAGIC_POLY && ok_ctx(p->ctx); }
-static bool ok_ksk(const ckks_ksk *k) { return k && k->magic == MAGIC_KSK && ok_ctx(k->ctx); }
+static bool ok_ksk(const ckks_ksk *k) { return k && k->magic == MAGIC_KSK && ok_ctx(k->ctx) && k->digits == k->ctx->L; }
+static bool ok_ksk_slice(const ckks_ksk *k) { return k && k->magic == MAGIC_KSK && ok_ctx(k->ctx); }
 static void ctx_ref(ckks_ctx *c) { c->refs.fetch_add(1); }
 static void ctx_unref(ckks_ctx *c) {
     if (c->refs.fetch_sub(1) == 1) {
@@ -465,6 +466,7 @@ static int run_pass(const Tables &T, int which, Span sp, const void *src_, void 
     for (size_t b0 = 0; b0 < sp.nb; b0 += 32768) {
         size_t nb = sp.nb - b0 < 32768 ? sp.nb - b0 : 32768;
         PassArgs a;
+        memset(&a, 0, sizeof(a));
         a.lc = T.d_lc;
         a.L = sp.L;
         a.N = T.n;
@@ -959,9 +961,10 @@ extern "C" int ckks_poly_to_coeffs(const ckks_poly *p, int64_t *out) {
 // -------------------------------------------------------------------------------------------------
 // gadget keys
 // -------------------------------------------------------------------------------------------------
-static int ksk_new(ckks_ctx *ctx, ckks_ksk **out) {
+static int ksk_new(ckks_ctx *ctx, ckks_ksk **out, size_t digits = 0) {
     const Tables &T = *ctx->T;
-    size_t words = ctx->L * ctx->L * T.n;
+    if (!digits) digits = ctx->L;
+    size_t words = digits * ctx->L * T.n;
     u64 *a, *b;
     TRY(dev_alloc(T, words, &a));
     TRY(dev_alloc(T, words, &b));
@@ -971,11 +974,12 @@ static int ksk_new(ckks_ctx *ctx, ckks_ksk **out) {
     ctx_ref(ctx);
     k->a = a;
     k->b = b;
+    k->digits = digits;
     *out = k;
     return CKKS_OK;
 }
 extern "C" int ckks_ksk_free(ckks_ksk *k) {
-    if (!ok_ksk(k)) return CKKS_BAD_HANDLE;
+    if (!ok_ksk_slice(k)) return CKKS_BAD_HANDLE;
     cudaSetDevice(k->ctx->T->device);
     dev_free(*k->ctx->T, k->a);
     dev_free(*k->ctx->T, k->b);
@@ -1229,8 +1233,16 @@ static int reduce_every_for(const Tables &T, size_t L) {
 
 // Key-switch of `cs` polynomials: digits (coefficient domain) [+ dig_ntt] -> transposed inverse-pass-2
 // outputs out0t/out1t (finish with P_INV1).  mul: add d0/d1 and use the NTT-domain limb for i == j.
-static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, const u64 *dig_ntt, const ckks_ksk *key,
-                    const u64 *add0, const u64 *add1, u64 *scratch, u64 *out0t, u64 *out1t, bool mul) {
+// `sh` describes where the target limbs held here sit in the whole basis: everything (0, 1, L digits) on the
+// batch-sharded path, one GPU's share (rank, world, all digits) in limb-sharded mode.
+struct KsShard {
+    size_t Ld;        // digits (limbs of the whole basis)
+    int joff, jstep;  // basis index of local limb j = joff + jstep * j
+    size_t dig_ct_stride, dig_limb_stride;  // layout of `digits` in words
+    bool reduce;      // digits need `% q_j` before entering the lazy transform
+};
+static int ks_fused_ex(const Tables &T, size_t L, const KsShard &sh, size_t cs, const u64 *digits, const u64 *dig_ntt,
+                       const ckks_ksk *key, const u64 *add0, const u64 *add1, u64 *scratch, u64 *out0t, u64 *out1t, bool mul) {
     KsArgs a;
     a.digits = digits;
     a.dig_ntt = dig_ntt;
@@ -1249,24 +1261,35 @@ static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, con
     a.TTi = T.d_TTi;
     a.w2_stride = T.w2_stride;
     a.L = (int)L;
+    a.Ld = (int)sh.Ld;
+    a.joff = sh.joff;
+    a.jstep = sh.jstep;
+    a.dig_ct_stride = sh.dig_ct_stride;
+    a.dig_limb_stride = sh.dig_limb_stride;
     a.a1 = T.a1;
     a.a2 = T.a2;
     a.reduce_every = reduce_every_for(T, L);
     a.N = T.n;
+    const size_t Ld = sh.Ld;
     const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
     cudaStream_t s = T.stream;
-    dim3 g1(n2 / KS_C1, (unsigned)(L * L), (unsigned)cs);
-    DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.w32, T.lazy, T.digit_reduce, mul, g1, s, a)));
+    dim3 g1(n2 / KS_C1, (unsigned)(L * Ld), (unsigned)cs);
+    DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.w32, T.lazy, sh.reduce, mul, g1, s, a)));
     dim3 g2((unsigned)cs, n1 / KS_C2, (unsigned)L);
     // TMA descriptors: (rho, j2 / gamma, slab) tensors with a [n2][16] box
     KsMaps maps;
     memset(&maps, 0, sizeof(maps));
     bool tma = g_use_tma && n1 >= (unsigned)KS_C2;
-    tma = tma && make_tile_map(maps.scratch, scratch, T.w32 ? 4 : 8, n1, n2, cs * L * L, KS_C2);
-    tma = tma && make_tile_map(maps.key_b, key->b, 8, n1, n2, L * L, KS_C2);
-    tma = tma && make_tile_map(maps.key_a, key->a, 8, n1, n2, L * L, KS_C2);
+    tma = tma && make_tile_map(maps.scratch, scratch, T.w32 ? 4 : 8, n1, n2, cs * L * Ld, KS_C2);
+    tma = tma && make_tile_map(maps.key_b, key->b, 8, n1, n2, Ld * L, KS_C2);
+    tma = tma && make_tile_map(maps.key_a, key->a, 8, n1, n2, Ld * L, KS_C2);
     DISPATCH_A(T.a2, TRY(launch_ks2_a<AA>(T.w32, T.lazy, mul, tma, g2, s, a, maps)));
     return CKKS_OK;
+}
+static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, const u64 *dig_ntt, const ckks_ksk *key,
+                    const u64 *add0, const u64 *add1, u64 *scratch, u64 *out0t, u64 *out1t, bool mul) {
+    KsShard sh{L, 0, 1, L * T.n, T.n, T.digit_reduce};
+    return ks_fused_ex(T, L, sh, cs, digits, dig_ntt, key, add0, add1, scratch, out0t, out1t, mul);
 }
 
 static size_t ks_chunk(const Tables &T, size_t L, size_t batch) {
@@ -1322,6 +1345,7 @@ static int fused_mul_relin(const Tables &T, size_t L, size_t batch, const u64 *a
             TRY(run_pass(T, P_INV1, last, TMP, LAST));
             TRY(run_pass(T, P_INV1, last, B1, LAST + cs * n));
             PassArgs pa;
+            memset(&pa, 0, sizeof(pa));
             pa.lc = T.d_lc;
             pa.tab = T.d_P1i;
             pa.tab_stride = (size_t)1 << T.a1;
@@ -1985,3 +2009,5 @@ extern "C" int ckks_decode(const ckks_poly *p, uint32_t scale_bits, size_t nslot
     dev_free(T, p5);
     return rc;
 }
+
+#include "limb_shard.inl"

@@ -58,6 +58,7 @@ struct ckks_ksk {
     uint32_t magic;
     ckks_ctx *ctx;
     u64 *a, *b;  // [digit][limb][N], NTT domain, device-internal order
+    size_t digits;  // == ctx->L, except for a limb-sharded key slice (all digits x this GPU's limbs)
 };
 
-enum : uint32_t { MAGIC_CTX = 0x434b4358u, MAGIC_POLY = 0x434b504cu, MAGIC_KSK = 0x434b4b53u };
+enum : uint32_t { MAGIC_CTX = 0x434b4358u, MAGIC_POLY = 0x434b504cu, MAGIC_KSK = 0x434b4b53u, MAGIC_LSHARD = 0x434b4c53u };

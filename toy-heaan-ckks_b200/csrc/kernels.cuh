@@ -25,6 +25,12 @@ struct PassArgs {
     int limb0;      // first limb handled (blockIdx.y counts from here)
     int dstL;       // limbs per polynomial in dst
     int dst_limb0;  // dst limb index = limb - dst_limb0
+    // MULTI stores (limb-sharded mode): the finished coefficient-domain limb is written into the gather
+    // buffers of `npeer` GPUs (own + NVLink peers) at slot (m_off + m_step * limb), layout [slot][m_cs][N].
+    u64 *peer[8];
+    int npeer;
+    int m_off, m_step;
+    size_t m_cs;
 };
 
 // One pass: a 2^A-point transform along the strided dimension of a [2^A][ncols] limb, for a tile of
@@ -37,7 +43,7 @@ struct PassArgs {
 // Inverse  to_coeff_domain(poly.rs:154-166, 582-591) = <CYC_INV,POSTMUL,TRANSPOSE> then <NEG_INV>.
 // WD = u64 (any q < 2^63) or u32 (all q < 2^31: 32-bit butterflies, 32-bit internal scratch; the words
 // that cross the boundary stay u64).
-template <typename WD, int KIND, int A, int E, int C, int LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE>
+template <typename WD, int KIND, int A, int E, int C, int LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE, bool MULTI = false>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a) {
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
@@ -97,7 +103,13 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
             WD x = v[k];
             if (POSTMUL || !CT_RANGE) x = canon2<LAZY>(x, q);
             else x = canon4<LAZY>(x, q, q2);
-            dst[dbase + off] = (DST_T)x;
+            if (MULTI) {
+                // all-gather fused into the producing pass: plain stores into own and peer HBM
+                const size_t mo = ((size_t)(a.m_off + a.m_step * limb) * a.m_cs + blockIdx.z) * a.N + off;
+                for (int p = 0; p < a.npeer; ++p) a.peer[p][mo] = (u64)x;
+            } else {
+                dst[dbase + off] = (DST_T)x;
+            }
         }
     }
 }
@@ -379,7 +391,10 @@ struct KsArgs {
     const LimbConst *lc;
     const void *P1, *W2, *W2i, *TTt, *TTi;  // TwOf<WD> tables
     size_t w2_stride;
-    int L;
+    int L;   // target limbs held here (all of them, or this GPU's share in limb-sharded mode)
+    int Ld;  // digits = limbs of the whole basis (== L unless limb-sharded)
+    int joff, jstep;  // basis index of local target limb j: joff + jstep * j  (0, 1 unless limb-sharded)
+    size_t dig_ct_stride, dig_limb_stride;  // words between ciphertexts / digits in `digits`
     int a1, a2;
     int reduce_every;  // digits between 128-bit accumulator reductions
     size_t N;
@@ -393,17 +408,17 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
     constexpr int NT = C * GM::G;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     WD *sm = reinterpret_cast<WD *>(sm_raw);
-    const int L = a.L;
-    const int j = blockIdx.y / L, i = blockIdx.y % L;
-    if (DIAG && i == j) return;  // ks_pass2 takes the NTT-domain limb itself for this digit
+    const int L = a.L, Ld = a.Ld;
+    const int j = blockIdx.y / Ld, i = blockIdx.y % Ld;
+    if (DIAG && i == a.joff + a.jstep * j) return;  // ks_pass2 takes the NTT-domain limb itself for this digit
     const int tid = threadIdx.x;
     const int c = tid % C, g = tid / C;
     const size_t c0 = (size_t)blockIdx.x * C;
     const unsigned ncols = 1u << a.a2;
     const LimbConst m = a.lc[j];
     const WD q = (WD)m.q, q2 = (WD)m.q2;
-    const u64 *src = a.digits + ((size_t)blockIdx.z * L + i) * a.N;
-    WD *dst = reinterpret_cast<WD *>(a.scratch) + (((size_t)blockIdx.z * L + j) * L + i) * a.N;
+    const u64 *src = a.digits + (size_t)blockIdx.z * a.dig_ct_stride + (size_t)i * a.dig_limb_stride;
+    WD *dst = reinterpret_cast<WD *>(a.scratch) + (((size_t)blockIdx.z * L + j) * Ld + i) * a.N;
     const TW *tab = reinterpret_cast<const TW *>(a.P1) + ((size_t)j << A);
     WD v[1 << E];
 #pragma unroll
@@ -575,9 +590,10 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
     const size_t ct = blockIdx.x;
     const TW *W = reinterpret_cast<const TW *>(a.W2) + (size_t)j * a.w2_stride;
     constexpr int lo_in = GM::lo(0), lo_out = GM::lo(GM::NS - 1);
-    const int nd = DIAG ? L - 1 : L;  // digits that need a transform
-    auto digit_of = [&](int t) { return (DIAG && t >= j) ? t + 1 : t; };
-    const WD *scr = reinterpret_cast<const WD *>(a.scratch) + (ct * L + j) * (size_t)L * a.N + c0;
+    const int Ld = a.Ld, jg = a.joff + a.jstep * j;  // jg: index of this target limb in the whole basis
+    const int nd = DIAG ? Ld - 1 : Ld;  // digits that need a transform
+    auto digit_of = [&](int t) { return (DIAG && t >= jg) ? t + 1 : t; };
+    const WD *scr = reinterpret_cast<const WD *>(a.scratch) + (ct * L + j) * (size_t)Ld * a.N + c0;
     const u64 *kbase_b = a.key_b + (size_t)j * a.N + c0;
     const u64 *kbase_a = a.key_a + (size_t)j * a.N + c0;
     const size_t kstride = (size_t)L * a.N;
@@ -588,7 +604,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
         acc0[k].clear();
         acc1[k].clear();
     }
-    const int slab0 = (int)((ct * L + j) * L);  // scratch slabs of this (ciphertext, target limb)
+    const int slab0 = (int)((ct * L + j) * Ld);  // scratch slabs of this (ciphertext, target limb)
     if (TMA) {
         if (tid == 0) {
             mbar_init(bars + 0, 1);
@@ -607,7 +623,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
     }
     if (DIAG) {  // digit i == j: the NTT-domain limb itself
         const u64 *src = a.dig_ntt + (ct * L + j) * a.N + c0 + c;
-        const u64 *kb = kbase_b + (size_t)j * kstride + c, *ka = kbase_a + (size_t)j * kstride + c;
+        const u64 *kb = kbase_b + (size_t)jg * kstride + c, *ka = kbase_a + (size_t)jg * kstride + c;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             size_t off = (size_t)tile_idx<E>(g, k, lo_out) * ncols;
@@ -716,10 +732,10 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) inv_pass1_rescale_kernel(Pa
     u64 *dst = reinterpret_cast<u64 *>(a.dst);
     const int tid = threadIdx.x;
     const int c = tid % C, g = tid / C;
-    const int limb = blockIdx.y;  // < L-1
+    const int limb = blockIdx.y;  // < dstL
     const size_t c0 = (size_t)blockIdx.x * C;
     const size_t base_in = ((size_t)blockIdx.z * a.L + limb) * a.N;
-    const size_t base_out = ((size_t)blockIdx.z * (a.L - 1) + limb) * a.N;
+    const size_t base_out = ((size_t)blockIdx.z * a.dstL + limb) * a.N;
     const LimbConst m = a.lc[limb];
     const WD q = (WD)m.q, q2 = (WD)m.q2;
     const TW *tab = reinterpret_cast<const TW *>(a.tab) + (size_t)limb * a.tab_stride;
@@ -736,6 +752,44 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) inv_pass1_rescale_kernel(Pa
         WD d = ci >= cl ? ci - cl : ci + q - cl;
         dst[base_out + off] = (u64)shoup(d, qi, q);
     }
+}
+
+// =================================================================================================
+// Limb-sharded mode (optional): barrier between the GPUs that hold the limbs of one batch.
+// Launched on the stream right after the kernel whose peer stores must be visible: thread t publishes
+// this rank's epoch in GPU t's flag word (release, system scope) and then waits for GPU t's epoch in
+// its own flag array (acquire).  A wall-clock limit turns a lost peer into an error word instead of
+// a hung device.
+// =================================================================================================
+struct BarArgs {
+    unsigned *peer_flags[8];  // flag arrays of every GPU (own included), [world] words each
+    unsigned *my_flags;
+    unsigned *err;
+    int rank, world;
+    unsigned epoch;
+    unsigned long long timeout_ns;
+};
+__global__ void lshard_barrier_kernel(BarArgs a) {
+#ifdef __CUDA_ARCH__
+    const int t = threadIdx.x;
+    if (t >= a.world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[t] + a.rank), "r"(a.epoch) : "memory");
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.my_flags + t) : "memory");
+        if ((int)(v - a.epoch) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > a.timeout_ns) {
+            atomicExch(a.err, a.epoch);
+            break;
+        }
+        __nanosleep(200);
+    }
+#endif
 }
 
 // =================================================================================================

@@ -1,0 +1,549 @@
+// limb_shard.inl -- optional limb-sharded mode of the gadget ct-mult (north_star: "an optional
+// limb-sharded mode at N=2^16 / L>=24, where key-switching all-gathers the decomposed digits").
+// Included at the end of ckks_b200.cu (uses its launch helpers).
+//
+// Ownership: limb j of the basis lives on GPU (j mod G); the local limb jl of rank r is limb r + G*jl, so
+// the share stays balanced while rescale drops limbs from the end.  Every GPU holds, for every ciphertext
+// of the batch, only its own limbs, and of the gadget key only the slices [digit i][own limb j] (1/G).
+//
+// Per chunk of ciphertexts (engine.rs:473-539 + :263-282, same minimal exact schedule as fused_mul_relin):
+//   phase A (limb-local)  4 forward transforms per own limb, tensor, inverse transform of d2 whose LAST PASS
+//                         STORES EVERY FINISHED DIGIT LIMB INTO THE GATHER BUFFER OF ALL G GPUs (plain
+//                         stores over NVLink into peer HBM: the all-gather is fused into the producing kernel)
+//   barrier               flag words in peer memory (lshard_barrier_kernel), no host involvement
+//   phase B               ks_pass1/ks_pass2 over all L digits for the own target limbs, first inverse pass;
+//                         the owner of the last limb finishes it and stores it into every GPU's `last` buffer
+//                         (the broadcast rescale needs, fused the same way)
+//   barrier
+//   phase C               last inverse pass fused with rescale_into (poly.rs:214-225) for the own limbs
+// With `peer_stores = 0` the stores go to the own buffers only and the caller runs the collectives itself
+// (torch.distributed / NCCL all-gather and broadcast on the exported buffers) between the phases.
+//
+// Results are the reference's words: the schedule is the batch-sharded one restricted to the own limbs.
+
+struct LsSym {  // symmetric buffers of one rank: one cudaMalloc block (one IPC handle), shared by all levels
+    int device = 0, rank = 0, world = 1;
+    size_t n = 0, cs_max = 0, Lg0 = 0, Ll0 = 0;
+    unsigned char *block = nullptr;
+    size_t off_last = 0, off_flags = 0, block_bytes = 0;
+    u64 *gather_p[8] = {nullptr}, *last_p[8] = {nullptr};
+    unsigned *flags_p[8] = {nullptr};
+    void *ipc_base[8] = {nullptr};
+    bool connected = false;
+    unsigned epoch = 0;
+    cudaEvent_t ev = nullptr;  // in-process groups: barrier by events (ckks_lshard_barrier_local)
+    unsigned long long timeout_ns = 20ull * 1000000000ull;
+    u64 *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr, *TMP = nullptr, *SCR = nullptr;
+    u64 *gather() const { return reinterpret_cast<u64 *>(block); }
+    u64 *last() const { return reinterpret_cast<u64 *>(block + off_last); }
+    unsigned *flags() const { return reinterpret_cast<unsigned *>(block + off_flags); }  // [8] epochs, [8] = error word
+    ~LsSym() {
+        cudaSetDevice(device);
+        if (ev) cudaEventDestroy(ev);
+        for (int p = 0; p < 8; ++p)
+            if (ipc_base[p]) cudaIpcCloseMemHandle(ipc_base[p]);
+        if (block) cudaFree(block);
+        for (u64 *b : {A0, A1, B0, B1, TMP, SCR})
+            if (b) cudaFree(b);
+    }
+};
+struct ckks_lshard {
+    uint32_t magic;
+    int rank, world;
+    size_t Lg;  // limbs of the whole basis at this level
+    size_t Ll;  // limbs held here
+    std::vector<u64> moduli_g;  // whole basis at the top level
+    ckks_ctx *local;            // context over the own limbs (local limb jl = basis limb rank + world*jl)
+    std::shared_ptr<LsSym> sym;
+    void *d_qlinv_last;  // [Ll] (q_{Lg-1})^-1 mod own q (Shoup pairs in the transform word type)
+    bool digit_reduce;
+};
+static bool ok_lshard(const ckks_lshard *s) { return s && s->magic == MAGIC_LSHARD && ok_ctx(s->local) && s->sym; }
+static size_t ls_count(size_t Lg, int rank, int world) { return Lg > (size_t)rank ? (Lg - rank + world - 1) / world : 0; }
+
+// Level-specific tables: q_last^-1 mod every own modulus, and whether foreign digits fit the lazy input range.
+static int ls_level_tables(ckks_lshard *s) {
+    const Tables &T = *s->local->T;
+    const u64 qlast = s->moduli_g[s->Lg - 1];
+    u64 qmax = 0, qmin = ~0ull;
+    for (size_t i = 0; i < s->Lg; ++i) qmax = s->moduli_g[i] > qmax ? s->moduli_g[i] : qmax;
+    for (size_t jl = 0; jl < s->Ll; ++jl) qmin = T.moduli[jl] < qmin ? T.moduli[jl] : qmin;
+    // a digit x < q_i enters the lazy transform mod q_j unreduced iff x < 4 q_j (and fits the word type)
+    s->digit_reduce = !(T.lazy && (qmax >> 2) < qmin && (!T.w32 || (qmax >> 31) == 0));
+    s->d_qlinv_last = nullptr;
+    if (s->Ll == 0) return CKKS_OK;
+    if (T.w32) {
+        std::vector<tw32_t> h(s->Ll);
+        for (size_t jl = 0; jl < s->Ll; ++jl) {
+            u64 q = T.moduli[jl];
+            h[jl] = (q == qlast) ? ht::mk_tw32(0, q) : ht::mk_tw32(hm::inv_mod(qlast % q, q), q);
+        }
+        TRY(upload_vec((tw32_t **)&s->d_qlinv_last, h));
+    } else {
+        std::vector<tw_t> h(s->Ll);
+        for (size_t jl = 0; jl < s->Ll; ++jl) {
+            u64 q = T.moduli[jl];
+            h[jl] = (q == qlast) ? mk_tw(0, q) : mk_tw(hm::inv_mod(qlast % q, q), q);
+        }
+        TRY(upload_vec((tw_t **)&s->d_qlinv_last, h));
+    }
+    return CKKS_OK;
+}
+
+extern "C" int ckks_lshard_create(uint64_t n, const uint64_t *moduli, size_t l, int rank, int world, int device, size_t chunk,
+                                  ckks_lshard **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (l == 0) return CKKS_EMPTY_BASIS;
+    if (!moduli || world < 1 || world > 8 || rank < 0 || rank >= world) return CKKS_BAD_ARGUMENT;
+    if (l < (size_t)world) {
+        g_err = "limb-sharded mode needs at least one limb per GPU";
+        return CKKS_UNSUPPORTED;
+    }
+    std::vector<u64> own;
+    for (size_t j = rank; j < l; j += world) own.push_back(moduli[j]);
+    // validate the WHOLE basis like RnsBasis::new before building the own share
+    if (n == 0 || (n & (n - 1)) != 0) return CKKS_INVALID_DEGREE;
+    for (size_t i = 0; i < l; ++i)
+        if (!hm::is_ntt_friendly_prime(moduli[i], n)) return CKKS_NON_NTT_FRIENDLY_MODULUS;
+    ckks_ctx *local = nullptr;
+    TRY(ckks_ctx_create(n, reinterpret_cast<const uint64_t *>(own.data()), own.size(), device, &local));
+    if (local->T->path != 2) {
+        ckks_ctx_destroy(local);
+        g_err = "limb-sharded mode is built on the four-step path (N >= 256)";
+        return CKKS_UNSUPPORTED;
+    }
+    auto sym = std::make_shared<LsSym>();
+    sym->device = device;
+    sym->rank = rank;
+    sym->world = world;
+    sym->n = n;
+    sym->Lg0 = l;
+    sym->Ll0 = own.size();
+    size_t per = ls_count(l, 0, world) * l * n * sizeof(u64);  // scratch per ciphertext on the fullest rank
+    size_t cs = ((size_t)4 << 30) / per;
+    if (cs < 1) cs = 1;
+    if (cs > 32768) cs = 32768;
+    if (chunk && chunk < cs) cs = chunk;
+    sym->cs_max = cs;
+    const size_t gather_bytes = l * cs * n * 8, last_bytes = 2 * cs * n * 8;
+    sym->off_last = gather_bytes;
+    sym->off_flags = gather_bytes + last_bytes;
+    sym->block_bytes = sym->off_flags + 256;
+    ckks_lshard *s = new ckks_lshard();
+    s->magic = MAGIC_LSHARD;
+    s->rank = rank;
+    s->world = world;
+    s->Lg = l;
+    s->Ll = own.size();
+    s->moduli_g.assign(moduli, moduli + l);
+    s->local = local;
+    s->sym = sym;
+    s->d_qlinv_last = nullptr;
+    auto body = [&]() -> int {
+        CU(cudaSetDevice(device));
+        CU(cudaMalloc((void **)&sym->block, sym->block_bytes));  // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+        CU(cudaMemset(sym->block + sym->off_flags, 0, 256));
+        const size_t W = cs * sym->Ll0 * n * 8;
+        for (u64 **b : {&sym->A0, &sym->A1, &sym->B0, &sym->B1, &sym->TMP}) CU(cudaMalloc((void **)b, W));
+        CU(cudaMalloc((void **)&sym->SCR, W * l));
+        CU(cudaDeviceSynchronize());
+        sym->gather_p[rank] = sym->gather();
+        sym->last_p[rank] = sym->last();
+        sym->flags_p[rank] = sym->flags();
+        if (world == 1) sym->connected = true;
+        return ls_level_tables(s);
+    };
+    int rc = body();
+    if (rc != CKKS_OK) {
+        s->magic = 0;
+        delete s;
+        ckks_ctx_destroy(local);
+        return rc;
+    }
+    *out = s;
+    return CKKS_OK;
+}
+extern "C" int ckks_lshard_destroy(ckks_lshard *s) {
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    cudaSetDevice(s->sym->device);
+    cudaStreamSynchronize(s->local->T->stream);
+    if (s->d_qlinv_last) cudaFree(s->d_qlinv_last);
+    ckks_ctx_destroy(s->local);
+    s->magic = 0;
+    delete s;
+    return CKKS_OK;
+}
+// The level below (rescale_ciphertext drops the last limb of the basis, engine.rs:263-282): its owner loses
+// one local limb, everyone else keeps theirs; buffers are shared with the parent.
+extern "C" int ckks_lshard_drop_last(ckks_lshard *s, ckks_lshard **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    if (s->Lg < 2) return CKKS_INVALID_MOD_DROP;
+    if (s->Lg - 1 < (size_t)s->world) {
+        g_err = "limb-sharded mode needs at least one limb per GPU";
+        return CKKS_UNSUPPORTED;
+    }
+    const bool owner = (int)((s->Lg - 1) % s->world) == s->rank;
+    ckks_ctx *local = nullptr;
+    TRY(ckks_ctx_drop_last(s->local, owner ? 1 : 0, &local));
+    ckks_lshard *c = new ckks_lshard();
+    c->magic = MAGIC_LSHARD;
+    c->rank = s->rank;
+    c->world = s->world;
+    c->Lg = s->Lg - 1;
+    c->Ll = local->L;
+    c->moduli_g = s->moduli_g;
+    c->local = local;
+    c->sym = s->sym;
+    c->d_qlinv_last = nullptr;
+    CU(cudaSetDevice(s->sym->device));
+    int rc = ls_level_tables(c);
+    if (rc != CKKS_OK) {
+        ckks_lshard_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return CKKS_OK;
+}
+extern "C" ckks_ctx *ckks_lshard_local_ctx(ckks_lshard *s) { return ok_lshard(s) ? s->local : nullptr; }
+extern "C" size_t ckks_lshard_channel_count(const ckks_lshard *s) { return ok_lshard(s) ? s->Lg : 0; }
+extern "C" size_t ckks_lshard_chunk(const ckks_lshard *s) { return ok_lshard(s) ? s->sym->cs_max : 0; }
+extern "C" int ckks_lshard_set_timeout_ms(ckks_lshard *s, uint64_t ms) {
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    s->sym->timeout_ns = ms * 1000000ull;
+    return CKKS_OK;
+}
+// Device pointers of the exchange buffers, for a caller that runs the collectives itself (peer_stores = 0):
+// gather [Lg0][chunk][N] (digit limb i of chunk ciphertext c at (i*chunk + c)*N), last [2][chunk][N].
+extern "C" int ckks_lshard_buffers(ckks_lshard *s, uint64_t **gather, size_t *gather_words, uint64_t **last, size_t *last_words) {
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    const LsSym &y = *s->sym;
+    if (gather) *gather = reinterpret_cast<uint64_t *>(y.gather());
+    if (gather_words) *gather_words = y.Lg0 * y.cs_max * y.n;
+    if (last) *last = reinterpret_cast<uint64_t *>(y.last());
+    if (last_words) *last_words = 2 * y.cs_max * y.n;
+    return CKKS_OK;
+}
+
+// ---- wiring the GPUs together ------------------------------------------------------------------------
+extern "C" size_t ckks_lshard_ipc_size(void) { return sizeof(cudaIpcMemHandle_t); }
+extern "C" int ckks_lshard_ipc_export(ckks_lshard *s, void *blob) {
+    if (!ok_lshard(s) || !blob) return CKKS_BAD_HANDLE;
+    CU(cudaSetDevice(s->sym->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->sym->block));
+    memcpy(blob, &h, sizeof(h));
+    return CKKS_OK;
+}
+// blobs: world handles in rank order (one process per GPU; the caller moves them, e.g. all_gather_object).
+extern "C" int ckks_lshard_ipc_import(ckks_lshard *s, const void *blobs) {
+    if (!ok_lshard(s) || !blobs) return CKKS_BAD_HANDLE;
+    LsSym &y = *s->sym;
+    CU(cudaSetDevice(y.device));
+    for (int p = 0; p < y.world; ++p) {
+        if (p == y.rank || y.ipc_base[p]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char *)blobs + (size_t)p * sizeof(h), sizeof(h));
+        void *base = nullptr;
+        CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        y.ipc_base[p] = base;
+        y.gather_p[p] = reinterpret_cast<u64 *>(base);
+        y.last_p[p] = reinterpret_cast<u64 *>((unsigned char *)base + y.off_last);
+        y.flags_p[p] = reinterpret_cast<unsigned *>((unsigned char *)base + y.off_flags);
+    }
+    y.connected = true;
+    return CKKS_OK;
+}
+// All ranks in ONE process (several GPUs, or several ranks on one GPU for tests): direct pointers.
+extern "C" int ckks_lshard_connect_local(ckks_lshard **shards, int world) {
+    if (!shards || world < 1 || world > 8) return CKKS_BAD_ARGUMENT;
+    for (int r = 0; r < world; ++r)
+        if (!ok_lshard(shards[r]) || shards[r]->world != world || shards[r]->rank != r) return CKKS_BAD_HANDLE;
+    for (int r = 0; r < world; ++r) {
+        LsSym &y = *shards[r]->sym;
+        if (y.block_bytes != shards[0]->sym->block_bytes) return CKKS_BATCH_MISMATCH;  // different chunk / basis
+        CU(cudaSetDevice(y.device));
+        for (int p = 0; p < world; ++p) {
+            LsSym &z = *shards[p]->sym;
+            if (z.device != y.device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, y.device, z.device));
+                if (!can) {
+                    g_err = "no peer access between the GPUs of a limb-sharded group";
+                    return CKKS_CUDA_ERROR;
+                }
+                cudaError_t e = cudaDeviceEnablePeerAccess(z.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+                cudaGetLastError();
+            }
+            y.gather_p[p] = z.gather();
+            y.last_p[p] = z.last();
+            y.flags_p[p] = z.flags();
+        }
+        y.connected = true;
+    }
+    return CKKS_OK;
+}
+
+// ---- key slices --------------------------------------------------------------------------------------
+// a, b: host, [digit i = 0..Lg)[own limb jl][N], coefficient domain (the rows of the reference's
+// RnsGadgetRelinKey, engine.rs:225-253, restricted to this GPU's limbs); transformed once.
+extern "C" int ckks_lshard_ksk_upload(ckks_lshard *s, const uint64_t *a, const uint64_t *b, ckks_ksk **out) {
+    if (!out) return CKKS_BAD_ARGUMENT;
+    *out = nullptr;
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    if (!a || !b) return CKKS_BAD_ARGUMENT;
+    const Tables &T = *s->local->T;
+    CU(cudaSetDevice(T.device));
+    ckks_ksk *k;
+    TRY(ksk_new(s->local, &k, s->Lg));
+    const size_t words = s->Lg * s->Ll * T.n;
+    int rc = CKKS_OK;
+    if (cudaMemcpyAsync(k->a, a, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess ||
+        cudaMemcpyAsync(k->b, b, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "ksk h2d");
+    if (rc == CKKS_OK) rc = ntt_inplace(T, s->Ll, s->Lg, k->a, false);
+    if (rc == CKKS_OK) rc = ntt_inplace(T, s->Ll, s->Lg, k->b, false);
+    if (rc == CKKS_OK && cudaStreamSynchronize(T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ksk sync");
+    if (rc != CKKS_OK) {
+        ckks_ksk_free(k);
+        return rc;
+    }
+    *out = k;
+    return CKKS_OK;
+}
+
+// ---- the three phases --------------------------------------------------------------------------------
+// Last inverse pass (negacyclic GS over rho, canonical coefficient-domain words) with the result stored
+// into `npeer` buffers at slot (m_off + m_step*limb), layout [slot][m_cs][N].
+template <typename WD, int A>
+static int launch_inv1_multi_w(int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+    constexpr int E = 4, C = pass_c<WD>();
+    grid.x = a.ncols / C;
+    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
+    const int block = C << (A - E);
+#define M(LZ) \
+    KL("ntt_inv_pass1_allgather", (ntt_pass_kernel<WD, XF_NEG_INV, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), false, false, false, true><<<grid, block, smem, s>>>(a)))
+    LZ_SWITCH(WD, lazy, M);
+#undef M
+    return CKKS_OK;
+}
+template <int A>
+static int launch_inv1_multi_a(bool w32, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+    if (w32) return launch_inv1_multi_w<u32, A>(lazy, grid, s, a);
+    return launch_inv1_multi_w<u64, A>(lazy, grid, s, a);
+}
+static int ls_inv1_multi(const Tables &T, size_t cs, int L, int limb0, int nl, const void *src, u64 *const *peers, int npeer, int m_off,
+                         int m_step, size_t m_cs) {
+    if (!cs || !nl) return CKKS_OK;
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    a.lc = T.d_lc;
+    a.L = L;
+    a.N = T.n;
+    a.limb0 = limb0;
+    a.src = src;
+    a.tab = T.d_P1i;
+    a.tab_stride = (size_t)1 << T.a1;
+    a.ncols = 1u << T.a2;
+    a.npeer = npeer;
+    for (int p = 0; p < npeer; ++p) a.peer[p] = peers[p];
+    a.m_off = m_off;
+    a.m_step = m_step;
+    a.m_cs = m_cs;
+    dim3 g(1, (unsigned)nl, (unsigned)cs);
+    DISPATCH_A(T.a1, TRY(launch_inv1_multi_a<AA>(T.w32, T.lazy, g, T.stream, a)));
+    return CKKS_OK;
+}
+static int ls_barrier(ckks_lshard *s) {
+    LsSym &y = *s->sym;
+    if (y.world == 1) return CKKS_OK;
+    BarArgs b;
+    memset(&b, 0, sizeof(b));
+    for (int p = 0; p < y.world; ++p) b.peer_flags[p] = y.flags_p[p];
+    b.my_flags = y.flags();
+    b.err = y.flags() + 8;
+    b.rank = y.rank;
+    b.world = y.world;
+    b.epoch = ++y.epoch;
+    b.timeout_ns = y.timeout_ns;
+    KL("lshard_barrier", (lshard_barrier_kernel<<<1, 32, 0, s->local->T->stream>>>(b)));
+    return CKKS_OK;
+}
+// Synchronise the stream and report a barrier that timed out (a peer that never arrived).
+extern "C" int ckks_lshard_check(ckks_lshard *s) {
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    LsSym &y = *s->sym;
+    CU(cudaSetDevice(y.device));
+    unsigned e = 0;
+    CU(cudaMemcpyAsync(&e, y.flags() + 8, sizeof(e), cudaMemcpyDeviceToHost, s->local->T->stream));
+    CU(cudaStreamSynchronize(s->local->T->stream));
+    if (e) {
+        g_err = "limb-sharded barrier " + std::to_string(e) + " timed out waiting for a peer GPU";
+        return CKKS_NCCL_ERROR;
+    }
+    return CKKS_OK;
+}
+
+static int ls_check_inputs(ckks_lshard *s, const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1,
+                           const ckks_ksk *rlk, ckks_lshard *child, const ckks_poly *o0, const ckks_poly *o1) {
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    TRY(check_ct(a0, a1));
+    TRY(check_ct(b0, b1));
+    TRY(check_pair(a0, b0, false));
+    if (!same_basis(a0->ctx, s->local)) return CKKS_BASIS_MISMATCH;
+    if (a0->ntt) return CKKS_DOMAIN_MISMATCH;
+    if (!ok_ksk_slice(rlk) || rlk->digits != s->Lg) return CKKS_BAD_HANDLE;
+    if (!same_basis(rlk->ctx, s->local)) return CKKS_BASIS_MISMATCH;
+    if (child) {
+        if (!ok_lshard(child) || child->sym.get() != s->sym.get() || child->Lg + 1 != s->Lg) return CKKS_BASIS_MISMATCH;
+    }
+    TRY(check_ct(o0, o1));
+    if (!same_basis(o0->ctx, child ? child->local : s->local)) return CKKS_BASIS_MISMATCH;
+    if (o0->batch != a0->batch) return CKKS_BATCH_MISMATCH;
+    return CKKS_OK;
+}
+
+// One phase (0 = A, 1 = B, 2 = C) of mul_ciphertexts_gadget [+ rescale_ciphertext when `child`] for the
+// ciphertexts [s0, s0 + cs) of the batch, cs <= ckks_lshard_chunk().  o0/o1: polynomials of the child's (or
+// this level's) local context with the same batch as the inputs.
+extern "C" int ckks_lshard_mul_phase(ckks_lshard *s, int phase, size_t s0, size_t cs, const ckks_poly *a0, const ckks_poly *a1,
+                                     const ckks_poly *b0, const ckks_poly *b1, const ckks_ksk *rlk, ckks_lshard *child, ckks_poly *o0,
+                                     ckks_poly *o1, int peer_stores) {
+    TRY(ls_check_inputs(s, a0, a1, b0, b1, rlk, child, o0, o1));
+    LsSym &y = *s->sym;
+    if (cs == 0) return CKKS_OK;
+    if (cs > y.cs_max || s0 + cs > a0->batch) return CKKS_BAD_ARGUMENT;
+    if (peer_stores && !y.connected) {
+        g_err = "limb-sharded group is not connected (ckks_lshard_ipc_import / ckks_lshard_connect_local)";
+        return CKKS_BAD_ARGUMENT;
+    }
+    const Tables &T = *s->local->T;
+    CU(cudaSetDevice(T.device));
+    g_cur_stream = T.stream;
+    const size_t n = T.n, Ll = s->Ll, Lg = s->Lg;
+    const size_t off = s0 * Ll * n;
+    const bool rescale = child != nullptr;
+    const int owner = (int)((Lg - 1) % s->world);
+    u64 *self_g[1] = {y.gather()}, *self_l0[1] = {y.last()}, *self_l1[1] = {y.last() + y.cs_max * n};
+    const int np = peer_stores ? y.world : 1;
+    Span sp = whole(cs, Ll);
+    if (phase == 0) {
+        const u64 *in[4] = {a0->d + off, a1->d + off, b0->d + off, b1->d + off};
+        u64 *nt[4] = {y.A0, y.A1, y.B0, y.B1};
+        for (int t = 0; t < 4; ++t) {
+            TRY(run_pass(T, P_FWD1, sp, in[t], y.TMP));
+            TRY(run_pass(T, P_FWD2, sp, y.TMP, nt[t]));
+        }
+        EwArgs e = ew_args(T, Ll, cs);
+        KL("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, y.A0, y.A1, y.B0, y.B1, y.A0, y.A1, y.B0)));  // d0,d1,d2
+        TRY(run_pass(T, P_INV2, sp, y.B0, y.TMP));
+        // digits: coefficient-domain limbs of d2 (engine.rs:493,507), stored where every GPU will read them
+        TRY(ls_inv1_multi(T, cs, (int)Ll, 0, (int)Ll, y.TMP, peer_stores ? y.gather_p : self_g, np, s->rank, s->world, y.cs_max));
+        return CKKS_OK;
+    }
+    if (phase == 1) {
+        KsShard ks{Lg, s->rank, s->world, n, y.cs_max * n, s->digit_reduce};
+        TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(), y.B0, rlk, y.A0, y.A1, y.SCR, y.TMP, y.B1, true));
+        if (!rescale) {
+            const size_t ooff = s0 * Ll * n;
+            TRY(run_pass(T, P_INV1, sp, y.TMP, o0->d + ooff));
+            TRY(run_pass(T, P_INV1, sp, y.B1, o1->d + ooff));
+            return CKKS_OK;
+        }
+        if (s->rank == owner) {  // the limb rescale drops: finish it and hand it to everyone
+            u64 *l1[8];
+            for (int p = 0; p < y.world; ++p) l1[p] = y.last_p[p] ? y.last_p[p] + y.cs_max * n : nullptr;
+            TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, y.TMP, peer_stores ? y.last_p : self_l0, np, 0, 0, y.cs_max));
+            TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, y.B1, peer_stores ? l1 : self_l1, np, 0, 0, y.cs_max));
+        }
+        return CKKS_OK;
+    }
+    if (phase == 2) {
+        if (!rescale) return CKKS_OK;
+        const size_t outL = child->Ll;
+        if (outL == 0) return CKKS_OK;
+        PassArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.lc = T.d_lc;
+        pa.tab = T.d_P1i;
+        pa.tab_stride = (size_t)1 << T.a1;
+        pa.L = (int)Ll;
+        pa.ncols = 1u << T.a2;
+        pa.N = n;
+        pa.dstL = (int)outL;
+        dim3 g(1, (unsigned)outL, (unsigned)cs);
+        const size_t ooff = s0 * outL * n;
+        pa.src = y.TMP;
+        pa.dst = o0->d + ooff;
+        DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, y.last(), s->d_qlinv_last)));
+        pa.src = y.B1;
+        pa.dst = o1->d + ooff;
+        DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, y.last() + y.cs_max * n, s->d_qlinv_last)));
+        return CKKS_OK;
+    }
+    return CKKS_BAD_ARGUMENT;
+}
+extern "C" int ckks_lshard_barrier(ckks_lshard *s) {
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    if (!s->sym->connected) return CKKS_BAD_ARGUMENT;
+    CU(cudaSetDevice(s->sym->device));
+    g_cur_stream = s->local->T->stream;
+    return ls_barrier(s);
+}
+
+// Barrier for a group whose ranks all live in this process and are driven in lockstep by one host thread
+// (phase by phase): an event per stream, every stream waits for every other one.  Unlike the flag barrier
+// no kernel spins, so ranks may even share one GPU (tests) without depending on how the hardware
+// interleaves their streams.
+extern "C" int ckks_lshard_barrier_local(ckks_lshard **shards, int world) {
+    if (!shards || world < 1 || world > 8) return CKKS_BAD_ARGUMENT;
+    for (int r = 0; r < world; ++r)
+        if (!ok_lshard(shards[r]) || shards[r]->world != world || shards[r]->rank != r) return CKKS_BAD_HANDLE;
+    for (int r = 0; r < world; ++r) {
+        LsSym &y = *shards[r]->sym;
+        CU(cudaSetDevice(y.device));
+        if (!y.ev) CU(cudaEventCreateWithFlags(&y.ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(y.ev, shards[r]->local->T->stream));
+    }
+    for (int r = 0; r < world; ++r) {
+        CU(cudaSetDevice(shards[r]->sym->device));
+        for (int p = 0; p < world; ++p)
+            if (p != r) CU(cudaStreamWaitEvent(shards[r]->local->T->stream, shards[p]->sym->ev, 0));
+    }
+    return CKKS_OK;
+}
+
+// mul_ciphertexts_gadget (+ rescale_ciphertext into `child`'s level when child != NULL) on this GPU's limbs
+// of a batch, all phases and both cross-GPU exchanges enqueued on the stream without host synchronisation.
+// Every GPU of the group must make the same call on its own share.
+extern "C" int ckks_lshard_ct_mul_relin_rescale(ckks_lshard *s, const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0,
+                                                const ckks_poly *b1, const ckks_ksk *rlk, ckks_lshard *child, ckks_poly **o0,
+                                                ckks_poly **o1) {
+    if (!o0 || !o1) return CKKS_BAD_ARGUMENT;
+    *o0 = *o1 = nullptr;
+    if (!ok_lshard(s) || (child && !ok_lshard(child))) return CKKS_BAD_HANDLE;
+    if (!ok_poly(a0)) return CKKS_BAD_HANDLE;
+    ckks_poly *r0 = nullptr, *r1 = nullptr;
+    ckks_ctx *octx = child ? child->local : s->local;
+    int rc = poly_new(octx, a0->batch, false, &r0);
+    if (rc == CKKS_OK) rc = poly_new(octx, a0->batch, false, &r1);
+    const size_t cs_max = s->sym->cs_max;
+    for (size_t s0 = 0; rc == CKKS_OK && s0 < a0->batch; s0 += cs_max) {
+        const size_t cs = a0->batch - s0 < cs_max ? a0->batch - s0 : cs_max;
+        rc = ckks_lshard_mul_phase(s, 0, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1);
+        if (rc == CKKS_OK) rc = ls_barrier(s);  // every digit of this chunk is in every gather buffer
+        if (rc == CKKS_OK) rc = ckks_lshard_mul_phase(s, 1, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1);
+        if (rc == CKKS_OK) rc = ls_barrier(s);  // the dropped limb is everywhere; gather buffers are free again
+        if (rc == CKKS_OK) rc = ckks_lshard_mul_phase(s, 2, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1);
+    }
+    if (rc != CKKS_OK) {
+        free2(r0, r1);
+        return rc;
+    }
+    *o0 = r0;
+    *o1 = r1;
+    return CKKS_OK;
+}
