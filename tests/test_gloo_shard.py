@@ -93,3 +93,98 @@ def test_two_ranks_gloo():
     assert ok and sizes == [2, 2]
     assert ms == 11.0  # max over ranks, not rank 0's own 10.0
     assert abs(rate - 2 * 2 / 11e-3) < 1e-6
+
+
+def _limb_worker(rank, world, port, q):
+    """The limb-sharded protocol (toy-heaan-ckks_b200/csrc/limb_shard.inl) replayed with the oracle's
+    per-limb arithmetic and gloo collectives: limb j on rank j mod world, all-gather of the digits of d2,
+    key-switch on the own target limbs with the own key slices, broadcast of the dropped limb, rescale."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ck = importlib.import_module("toy-heaan-ckks_b200")
+        import oracle as orc
+
+        n, l = 64, 5
+        moduli = orc.generate_primes(40, l, n)
+        own = ck.owned_limbs(l, rank, world)
+        assert own == list(range(rank, l, world))
+        own_q = [moduli[j] for j in own]
+        ob = orc.Basis(n, own_q)
+        rng = np.random.default_rng(2024)  # the same global data on every rank
+        qq = np.array(moduli, dtype=np.uint64)
+        a0, a1, b0, b1 = ((rng.integers(0, 1 << 63, size=(l, n), dtype=np.uint64) % qq[:, None]) for _ in range(4))
+        ka, kb = ((rng.integers(0, 1 << 63, size=(l, l, n), dtype=np.uint64) % qq[None, :, None]) for _ in range(2))
+        mine = lambda x: np.ascontiguousarray(x[rank::world])
+        # phase A (limb-local): tensor product in the coefficient domain
+        d0 = ob.mul(mine(a0), mine(b0))
+        d1 = ob.add(ob.mul(mine(a0), mine(b1)), ob.mul(mine(a1), mine(b0)))
+        d2 = ob.mul(mine(a1), mine(b1))
+        # all-gather of the digits: slot i <- limb i of d2 from rank i mod world
+        gather = torch.zeros((l, n), dtype=torch.int64)
+        for i in range(l):
+            t = torch.from_numpy(d2[i // world].astype(np.int64)) if i % world == rank else torch.zeros(n, dtype=torch.int64)
+            dist.broadcast(t, src=i % world)
+            gather[i] = t
+        digits = gather.numpy().astype(np.uint64)
+        # phase B: key-switch on the own target limbs with the own key slices [digit][own limb]
+        oq = np.array(own_q, dtype=np.uint64)[:, None]
+        c0, c1 = d0, d1
+        for i in range(l):
+            alpha = (digits[i][None, :] % oq).astype(np.uint64)  # engine.rs:507-516
+            c0 = ob.add(c0, ob.mul(alpha, np.ascontiguousarray(kb[i, rank::world])))
+            c1 = ob.add(c1, ob.mul(alpha, np.ascontiguousarray(ka[i, rank::world])))
+        # broadcast of the limb rescale drops, then poly.rs:214-225 on the own limbs
+        owner = (l - 1) % world
+        last = torch.zeros((2, n), dtype=torch.int64)
+        if rank == owner:
+            last = torch.from_numpy(np.stack([c0[-1], c1[-1]]).astype(np.int64))
+        dist.broadcast(last, src=owner)
+        last = last.numpy().astype(np.uint64)
+        keep = [jl for jl, j in enumerate(own) if j != l - 1]
+        ql = moduli[-1]
+        res = []
+        for comp, c in enumerate((c0, c1)):
+            rows = []
+            for jl in keep:
+                qj = own_q[jl]
+                inv = pow(ql % qj, -1, qj)
+                rows.append(np.array([((int(x) - int(y) % qj) * inv) % qj for x, y in zip(c[jl], last[comp])], dtype=np.uint64))
+            res.append(np.stack(rows))
+        full = orc.Basis(n, moduli)
+        m0, m1 = full.mul_ciphertexts_gadget(a0, a1, b0, b1, ka, kb)
+        r0, r1, _ = full.rescale_ciphertext(m0, m1)
+        kept = [j for j in own if j != l - 1]
+        ok = bool(np.array_equal(res[0], r0[kept]) and np.array_equal(res[1], r1[kept]))
+        oks = [None] * world
+        dist.all_gather_object(oks, ok)
+        if rank == 0:
+            q.put(oks)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_limb_sharded_protocol_two_ranks_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_limb_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == [True, True]
+
+
+def test_owned_limbs_partition_and_stay_balanced():
+    ck = importlib.import_module("toy-heaan-ckks_b200")
+    for l in range(1, 33):
+        for world in (1, 2, 3, 4, 8):
+            parts = [ck.owned_limbs(l, r, world) for r in range(world)]
+            assert sorted(j for p in parts for j in p) == list(range(l))
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= 1  # also after every drop_last, since it is the same rule at l-1

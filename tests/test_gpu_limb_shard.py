@@ -42,10 +42,10 @@ def _group(gpu, n, moduli, world, chunk):
 
 @pytest.mark.parametrize("n,bits,l,world,batch,chunk", [
     (1024, 40, 4, 2, 3, 2),     # two chunks, the second one ragged
-    (4096, 61, 5, 3, 2, 0),     # lazy8 butterflies; ownership 2/2/1
+    (4096, 61, 5, 3, 2, 8),     # lazy8 butterflies; ownership 2/2/1
     (16384, 30, 6, 4, 2, 1),    # 32-bit word path; ownership 2/2/1/1
-    (256, 62, 2, 2, 2, 0),      # one limb per rank, Harvey butterflies
-    (2048, 63, 3, 1, 2, 0),     # a group of one (no peers): strict arithmetic
+    (256, 62, 2, 2, 2, 8),      # one limb per rank, Harvey butterflies
+    (2048, 63, 3, 1, 2, 8),     # a group of one (no peers): strict arithmetic
 ])
 def test_limb_sharded_mul_relin_rescale_matches_oracle(gpu, orc, n, bits, l, world, batch, chunk):
     moduli = orc.generate_primes(bits, l, n)
@@ -99,7 +99,7 @@ def test_limb_sharded_chain_two_levels(gpu, orc):
     moduli = orc.generate_primes(40, l, n)
     rng = np.random.default_rng(4242)
     x0, x1, y0, y1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
-    level = _group(gpu, n, moduli, world, 0)
+    level = _group(gpu, n, moduli, world, 4)
     cx = [_ct(gpu, s, x0, x1) for s in level]
     cy = [_ct(gpu, s, y0, y1) for s in level]
     hx0, hx1, hy0, hy1 = x0, x1, y0, y1
@@ -142,7 +142,7 @@ def test_limb_sharded_phases_with_caller_run_collectives(gpu, orc):
     rng = np.random.default_rng(31337)
     a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
     ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
-    shards = [gpu.LimbShard(n, moduli, r, world) for r in range(world)]  # never connected
+    shards = [gpu.LimbShard(n, moduli, r, world, chunk=4) for r in range(world)]  # never connected
     kids = [s.drop_last() for s in shards]
     keys = [s.upload_key(ka, kb) for s in shards]
     cta = [_ct(gpu, s, a0, a1) for s in shards]
@@ -162,6 +162,7 @@ def test_limb_sharded_phases_with_caller_run_collectives(gpu, orc):
         for r in range(world):
             if r != i % world:
                 assert rt.cudaMemcpy(bufs[r][0] + i * slot_bytes, src, slot_bytes, 3) == 0
+    assert rt.cudaDeviceSynchronize() == 0  # device-to-device cudaMemcpy does not block the host
     for r, s in enumerate(shards):
         s.mul_phase(1, 0, batch, cta[r], ctb[r], keys[r], kids[r], outs[r], False)
         s.check()
@@ -169,6 +170,7 @@ def test_limb_sharded_phases_with_caller_run_collectives(gpu, orc):
     for r in range(world):  # "broadcast" of the dropped limb
         if r != owner:
             assert rt.cudaMemcpy(bufs[r][2], bufs[owner][2], bufs[owner][3] * 8, 3) == 0
+    assert rt.cudaDeviceSynchronize() == 0
     for r, s in enumerate(shards):
         s.mul_phase(2, 0, batch, cta[r], ctb[r], keys[r], kids[r], outs[r], False)
         s.check()
@@ -195,14 +197,14 @@ def test_limb_sharded_argument_checks(gpu, orc):
     with pytest.raises(gpu.RnsNttError) as e:
         gpu.LimbShard(n, [moduli[0], 19], 0, 2)  # the whole basis is validated, not only the own share
     assert e.value.kind == "NonNttFriendlyModulus"
-    s = gpu.LimbShard(n, moduli, 1, 2)
+    s = gpu.LimbShard(n, moduli, 1, 2, chunk=2)
     assert s.owned() == [1] and s.local_basis().moduli() == [moduli[1]] and s.channel_count() == 3
     rng = np.random.default_rng(1)
     wrong = gpu.RnsBasis(n, moduli)
     full = gpu.RnsPoly.from_channels(uniform_limbs(rng, moduli, n, 1), wrong)
     key = s.upload_key(uniform_limbs(rng, moduli, n, 3), uniform_limbs(rng, moduli, n, 3))
     ct = gpu.Ciphertext(full, full, 0, 0)
-    peer = gpu.LimbShard(n, moduli, 0, 2)
+    peer = gpu.LimbShard(n, moduli, 0, 2, chunk=2)
     gpu.LimbShard.connect_local([peer, s])
     with pytest.raises(gpu.RnsNttError) as e:
         s.mul_relin_rescale(ct, ct, key)  # polynomials of the whole basis, not of the share
@@ -235,7 +237,7 @@ def _ipc_worker(rank, world, port, q):
         rng = np.random.default_rng(555)  # the same global batch on every rank
         a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
         ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
-        sh = ck.LimbShard(n, moduli, rank, world, device=0)
+        sh = ck.LimbShard(n, moduli, rank, world, device=0, chunk=4)
         sh.set_timeout_ms(60000)
         sh.connect_process_group()
         kid = sh.drop_last()

@@ -123,7 +123,7 @@ extern "C" int ckks_lshard_create(uint64_t n, const uint64_t *moduli, size_t l, 
     size_t per = ls_count(l, 0, world) * l * n * sizeof(u64);  // scratch per ciphertext on the fullest rank
     size_t cs = ((size_t)4 << 30) / per;
     if (cs < 1) cs = 1;
-    if (cs > 32768) cs = 32768;
+    if (cs > 1024) cs = 1024;  // small rings: bound the exchange buffers rather than fill 4 GiB
     if (chunk && chunk < cs) cs = chunk;
     sym->cs_max = cs;
     const size_t gather_bytes = l * cs * n * 8, last_bytes = 2 * cs * n * 8;
