@@ -251,6 +251,14 @@ int ckks_lshard_mul_phase(ckks_lshard *s, int phase, size_t s0, size_t cs, const
                           const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1,
                           const ckks_ksk *rlk, ckks_lshard *child, ckks_poly *o0, ckks_poly *o1,
                           int peer_stores);
+/* rotate_ciphertext engine.rs:412-463 on this GPU's limbs (rotate_slots is limb-local; the rotated c1 is the
+ * digit polynomial, pushed to every GPU); rotk: a key slice from ckks_lshard_ksk_upload. */
+int ckks_lshard_ct_rotate(ckks_lshard *s, const ckks_poly *c0, const ckks_poly *c1, const ckks_ksk *rotk,
+                          int32_t k, ckks_poly **o0, ckks_poly **o1);
+/* The gadget key-switch of a coefficient-domain polynomial (engine.rs:429-452) in two phases (0: digits to
+ * every GPU's gather buffer, 1: ks0/ks1 = sum_i alpha_i * key_b[i] / key_a[i] on the own limbs). */
+int ckks_lshard_ks_phase(ckks_lshard *s, int phase, size_t s0, size_t cs, const ckks_poly *digits,
+                         const ckks_ksk *key, ckks_poly *ks0, ckks_poly *ks1, int peer_stores);
 int ckks_lshard_barrier(ckks_lshard *s);
 /* Barrier by stream events for a group living in one process and driven phase by phase in lockstep. */
 int ckks_lshard_barrier_local(ckks_lshard **shards, int world);

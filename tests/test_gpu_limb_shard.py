@@ -129,6 +129,29 @@ def test_limb_sharded_chain_two_levels(gpu, orc):
         level = kids
 
 
+@pytest.mark.parametrize("n,bits,l,world,rots", [(1024, 30, 4, 2, [1, -3]), (4096, 61, 5, 3, [5]), (16384, 30, 8, 4, [64])])
+def test_limb_sharded_rotate_matches_oracle(gpu, orc, n, bits, l, world, rots):
+    """rotate_ciphertext (engine.rs:412-463): automorphism limb-local, rotated c1 pushed to every rank, key-switch."""
+    moduli = orc.generate_primes(bits, l, n)
+    ob = orc.Basis(n, moduli)
+    rng = np.random.default_rng(77 + n)
+    batch = 3
+    c0, c1 = uniform_limbs(rng, moduli, n, batch), uniform_limbs(rng, moduli, n, batch)
+    shards = _group(gpu, n, moduli, world, 2)  # two chunks
+    cts = [_ct(gpu, s, c0, c1) for s in shards]
+    for k in rots:
+        ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+        keys = [s.upload_key(ka, kb, rotation=k) for s in shards]
+        outs = gpu.LimbShard.group_rotate(shards, cts, keys)
+        for s in shards:
+            s.check()
+        g0 = _assemble([o.c0.channels() for o in outs], world, l)
+        g1 = _assemble([o.c1.channels() for o in outs], world, l)
+        for i in range(batch):
+            e0, e1 = ob.rotate_ciphertext(c0[i], c1[i], ka, kb, k)
+            assert np.array_equal(g0[i], e0) and np.array_equal(g1[i], e1), f"rotation {k}"
+
+
 def test_limb_sharded_phases_with_caller_run_collectives(gpu, orc):
     """peer_stores = 0: the kernels fill only the rank's own slots; the caller moves the digits and the
     dropped limb itself (here: device-to-device copies standing in for NCCL all-gather / broadcast)."""
@@ -254,6 +277,12 @@ def _ipc_worker(rank, world, port, q):
                 m0, m1 = ob.mul_ciphertexts_gadget(a0[i], a1[i], b0[i], b1[i], ka, kb)
                 o0, o1, _ = ob.rescale_ciphertext(m0, m1)
                 ok &= bool(np.array_equal(g0[i], o0[rank::world]) and np.array_equal(g1[i], o1[rank::world]))
+        ra, rb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+        rot = sh.rotate_ciphertext(cta, sh.upload_key(ra, rb, rotation=3))
+        sh.check()
+        for i in range(batch):
+            e0, e1 = ob.rotate_ciphertext(a0[i], a1[i], ra, rb, 3)
+            ok &= bool(np.array_equal(rot.c0.channels()[i], e0[rank::world]) and np.array_equal(rot.c1.channels()[i], e1[rank::world]))
         dist.barrier()
         q.put((rank, ok))
     finally:

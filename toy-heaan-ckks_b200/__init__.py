@@ -153,6 +153,8 @@ _sig("ckks_lshard_ksk_upload", C.c_int, _vp, _u64p, _u64p, _pp)
 _sig("ckks_lshard_ct_mul_relin_rescale", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pp, _pp)
 _sig("ckks_lshard_mul_phase", C.c_int, _vp, C.c_int, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int)
 _sig("ckks_lshard_barrier", C.c_int, _vp)
+_sig("ckks_lshard_ct_rotate", C.c_int, _vp, _vp, _vp, _vp, C.c_int32, _pp, _pp)
+_sig("ckks_lshard_ks_phase", C.c_int, _vp, C.c_int, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, C.c_int)
 _sig("ckks_lshard_barrier_local", C.c_int, _pp, C.c_int)
 _sig("ckks_lshard_buffers", C.c_int, _vp, C.POINTER(_u64p), C.POINTER(C.c_size_t), C.POINTER(_u64p), C.POINTER(C.c_size_t))
 _sig("ckks_lshard_check", C.c_int, _vp)
@@ -743,6 +745,35 @@ class LimbShard:
         bs = child._basis if child else self._basis
         bits = self._moduli[-1].bit_length() if child else 0
         return Ciphertext(RnsPoly(h0, bs), RnsPoly(h1, bs), a.logp + b.logp - bits, a.logq - bits)
+
+    def rotate_ciphertext(self, ct: Ciphertext, rotk: GadgetKey) -> Ciphertext:
+        """rotate_ciphertext (engine.rs:412-463) by the key's `rotation`."""
+        h0, h1 = _vp(), _vp()
+        _check(_lib.ckks_lshard_ct_rotate(self._h, ct.c0._h, ct.c1._h, rotk._h, rotk.rotation, C.byref(h0), C.byref(h1)))
+        return Ciphertext(RnsPoly(h0, self._basis), RnsPoly(h1, self._basis), ct.logp, ct.logq)
+
+    @staticmethod
+    def group_rotate(shards, cts, keys):
+        """rotate_ciphertext for a group living in this process, driven in lockstep (see group_mul_relin_rescale)."""
+        world = len(shards)
+        arr = (C.c_void_p * world)(*[s._h for s in shards])
+        batch = cts[0].c0.batch()
+        r0 = [ct.c0.rotate_slots(keys[r].rotation) for r, ct in enumerate(cts)]
+        r1 = [ct.c1.rotate_slots(keys[r].rotation) for r, ct in enumerate(cts)]
+        k0 = [RnsPoly.zero(s._basis, batch) for s in shards]
+        k1 = [RnsPoly.zero(s._basis, batch) for s in shards]
+        step = shards[0].chunk()
+        for s0 in range(0, batch, step):
+            cs = min(step, batch - s0)
+            for phase in range(2):
+                for r, s in enumerate(shards):
+                    _check(_lib.ckks_lshard_ks_phase(s._h, phase, s0, cs, r1[r]._h, keys[r]._h, k0[r]._h, k1[r]._h, 1))
+                _check(_lib.ckks_lshard_barrier_local(arr, world))
+        outs = []
+        for r, ct in enumerate(cts):
+            r0[r] += k0[r]
+            outs.append(Ciphertext(r0[r], k1[r], ct.logp, ct.logq))
+        return outs
 
     def mul_phase(self, phase: int, s0: int, cs: int, a: Ciphertext, b: Ciphertext, rlk: GadgetKey, child, out: Ciphertext,
                   peer_stores: bool):

@@ -754,6 +754,30 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) inv_pass1_rescale_kernel(Pa
     }
 }
 
+// Coefficient-domain limbs that already exist (the rotated c1 of rotate_ciphertext, engine.rs:429) pushed
+// into the gather buffers of every GPU: src [cs][L][N] -> slot (m_off + m_step*limb) of [slot][m_cs][N],
+// 16 bytes per store.
+struct PushArgs {
+    const u64 *src;
+    u64 *peer[8];
+    int npeer;
+    int m_off, m_step;
+    size_t m_cs;
+    int L;
+    int logn;
+    size_t total2;  // cs * L * N / 2
+};
+__global__ void lshard_push_kernel(PushArgs a) {
+    const size_t half = (size_t)1 << (a.logn - 1);
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.total2; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t k2 = t & (half - 1), row = t >> (a.logn - 1);
+        const size_t ct = row / a.L, limb = row % a.L;
+        const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(a.src)[t];
+        const size_t dst = (((size_t)(a.m_off + a.m_step * (int)limb) * a.m_cs + ct) << (a.logn - 1)) + k2;
+        for (int p = 0; p < a.npeer; ++p) reinterpret_cast<ulonglong2 *>(a.peer[p])[dst] = v;
+    }
+}
+
 // =================================================================================================
 // Limb-sharded mode (optional): barrier between the GPUs that hold the limbs of one batch.
 // Launched on the stream right after the kernel whose peer stores must be visible: thread t publishes

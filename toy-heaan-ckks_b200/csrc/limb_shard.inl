@@ -494,6 +494,89 @@ extern "C" int ckks_lshard_barrier(ckks_lshard *s) {
     return ls_barrier(s);
 }
 
+// ---- gadget key-switch of a coefficient-domain polynomial (rotate_ciphertext, engine.rs:429-452) ------
+// phase 0: this GPU's limbs of `digits` (ciphertexts [s0, s0+cs)) go to every GPU's gather buffer;
+// phase 1: ks0/ks1[s0..] = sum_i alpha_i * key_b[i] / key_a[i] on the own limbs, coefficient domain.
+extern "C" int ckks_lshard_ks_phase(ckks_lshard *s, int phase, size_t s0, size_t cs, const ckks_poly *digits, const ckks_ksk *key,
+                                    ckks_poly *ks0, ckks_poly *ks1, int peer_stores) {
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    if (!ok_poly(digits) || !ok_poly(ks0) || !ok_poly(ks1)) return CKKS_BAD_HANDLE;
+    if (!same_basis(digits->ctx, s->local) || !same_basis(ks0->ctx, s->local) || !same_basis(ks1->ctx, s->local)) return CKKS_BASIS_MISMATCH;
+    if (digits->ntt) return CKKS_DOMAIN_MISMATCH;
+    if (!ok_ksk_slice(key) || key->digits != s->Lg || !same_basis(key->ctx, s->local)) return CKKS_BAD_HANDLE;
+    if (ks0->batch != digits->batch || ks1->batch != digits->batch) return CKKS_BATCH_MISMATCH;
+    LsSym &y = *s->sym;
+    if (cs == 0) return CKKS_OK;
+    if (cs > y.cs_max || s0 + cs > digits->batch) return CKKS_BAD_ARGUMENT;
+    if (peer_stores && !y.connected) {
+        g_err = "limb-sharded group is not connected (ckks_lshard_ipc_import / ckks_lshard_connect_local)";
+        return CKKS_BAD_ARGUMENT;
+    }
+    const Tables &T = *s->local->T;
+    CU(cudaSetDevice(T.device));
+    g_cur_stream = T.stream;
+    const size_t n = T.n, Ll = s->Ll, off = s0 * Ll * n;
+    if (phase == 0) {
+        PushArgs a;
+        memset(&a, 0, sizeof(a));
+        a.src = digits->d + off;
+        a.npeer = peer_stores ? y.world : 1;
+        for (int p = 0; p < a.npeer; ++p) a.peer[p] = peer_stores ? y.gather_p[p] : y.gather();
+        a.m_off = s->rank;
+        a.m_step = s->world;
+        a.m_cs = y.cs_max;
+        a.L = (int)Ll;
+        a.logn = T.logn;
+        a.total2 = cs * Ll * n / 2;
+        KL("lshard_push", (lshard_push_kernel<<<ew_grid(a.total2), 256, 0, T.stream>>>(a)));
+        return CKKS_OK;
+    }
+    if (phase == 1) {
+        KsShard ks{s->Lg, s->rank, s->world, n, y.cs_max * n, s->digit_reduce};
+        TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(), nullptr, key, nullptr, nullptr, y.SCR, y.TMP, y.B1, false));
+        Span sp = whole(cs, Ll);
+        TRY(run_pass(T, P_INV1, sp, y.TMP, ks0->d + off));
+        TRY(run_pass(T, P_INV1, sp, y.B1, ks1->d + off));
+        ks0->ntt = ks1->ntt = false;
+        return CKKS_OK;
+    }
+    return CKKS_BAD_ARGUMENT;
+}
+// rotate_ciphertext (engine.rs:412-463) on this GPU's limbs: rotate_slots(k) of c0 and c1 is limb-local; the
+// rotated c1 is the digit polynomial every GPU needs.  Same calling rules as ckks_lshard_ct_mul_relin_rescale.
+extern "C" int ckks_lshard_ct_rotate(ckks_lshard *s, const ckks_poly *c0, const ckks_poly *c1, const ckks_ksk *rotk, int32_t k,
+                                     ckks_poly **o0, ckks_poly **o1) {
+    if (!o0 || !o1) return CKKS_BAD_ARGUMENT;
+    *o0 = *o1 = nullptr;
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    TRY(check_ct(c0, c1));
+    if (!same_basis(c0->ctx, s->local)) return CKKS_BASIS_MISMATCH;
+    ckks_poly *r0 = nullptr, *r1 = nullptr, *k0 = nullptr, *k1 = nullptr;
+    int rc = ckks_poly_rotate_slots(c0, k, &r0);  // engine.rs:417-419
+    if (rc == CKKS_OK) rc = ckks_poly_rotate_slots(c1, k, &r1);
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(r0);
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(r1);
+    if (rc == CKKS_OK) rc = poly_new(s->local, c0->batch, false, &k0);
+    if (rc == CKKS_OK) rc = poly_new(s->local, c0->batch, false, &k1);
+    const size_t cs_max = s->sym->cs_max;
+    for (size_t s0 = 0; rc == CKKS_OK && s0 < c0->batch; s0 += cs_max) {
+        const size_t cs = c0->batch - s0 < cs_max ? c0->batch - s0 : cs_max;
+        rc = ckks_lshard_ks_phase(s, 0, s0, cs, r1, rotk, k0, k1, 1);
+        if (rc == CKKS_OK) rc = ls_barrier(s);
+        if (rc == CKKS_OK) rc = ckks_lshard_ks_phase(s, 1, s0, cs, r1, rotk, k0, k1, 1);
+        if (rc == CKKS_OK) rc = ls_barrier(s);  // gather buffers are free again
+    }
+    if (rc == CKKS_OK) rc = ckks_poly_add_assign(r0, k0);  // engine.rs:454-455
+    free2(r1, k0);
+    if (rc != CKKS_OK) {
+        free2(r0, k1);
+        return rc;
+    }
+    *o0 = r0;
+    *o1 = k1;
+    return CKKS_OK;
+}
+
 // Barrier for a group whose ranks all live in this process and are driven in lockstep by one host thread
 // (phase by phase): an event per stream, every stream waits for every other one.  Unlike the flag barrier
 // no kernel spins, so ranks may even share one GPU (tests) without depending on how the hardware
