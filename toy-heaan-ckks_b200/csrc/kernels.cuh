@@ -28,7 +28,7 @@ struct PassArgs {
     // MULTI stores (limb-sharded mode): the finished coefficient-domain limb is written into the gather
     // buffers of `npeer` GPUs (own + NVLink peers) at slot (m_off + m_step * limb), layout [slot][m_cs][N].
     u64 *peer[8];
-    int npeer;
+    int npeer, m_first;
     int m_off, m_step;
     size_t m_cs;
 };
@@ -105,8 +105,13 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
             else x = canon4<LAZY>(x, q, q2);
             if (MULTI) {
                 // all-gather fused into the producing pass: plain stores into own and peer HBM
+                // (each GPU starts with a different peer so that no destination is hit by everyone at once)
                 const size_t mo = ((size_t)(a.m_off + a.m_step * limb) * a.m_cs + blockIdx.z) * a.N + off;
-                for (int p = 0; p < a.npeer; ++p) a.peer[p][mo] = (u64)x;
+                for (int t = 0; t < a.npeer; ++t) {
+                    int p = a.m_first + t;
+                    if (p >= a.npeer) p -= a.npeer;
+                    a.peer[p][mo] = (u64)x;
+                }
             } else {
                 dst[dbase + off] = (DST_T)x;
             }
@@ -760,7 +765,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) inv_pass1_rescale_kernel(Pa
 struct PushArgs {
     const u64 *src;
     u64 *peer[8];
-    int npeer;
+    int npeer, m_first;
     int m_off, m_step;
     size_t m_cs;
     int L;
@@ -774,7 +779,11 @@ __global__ void lshard_push_kernel(PushArgs a) {
         const size_t ct = row / a.L, limb = row % a.L;
         const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(a.src)[t];
         const size_t dst = (((size_t)(a.m_off + a.m_step * (int)limb) * a.m_cs + ct) << (a.logn - 1)) + k2;
-        for (int p = 0; p < a.npeer; ++p) reinterpret_cast<ulonglong2 *>(a.peer[p])[dst] = v;
+        for (int t2 = 0; t2 < a.npeer; ++t2) {
+            int p = a.m_first + t2;
+            if (p >= a.npeer) p -= a.npeer;
+            reinterpret_cast<ulonglong2 *>(a.peer[p])[dst] = v;
+        }
     }
 }
 

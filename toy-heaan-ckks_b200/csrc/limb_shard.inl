@@ -320,7 +320,7 @@ extern "C" int ckks_lshard_ksk_upload(ckks_lshard *s, const uint64_t *a, const u
 // into `npeer` buffers at slot (m_off + m_step*limb), layout [slot][m_cs][N].
 template <typename WD, int A>
 static int launch_inv1_multi_w(int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
-    constexpr int E = 4, C = pass_c<WD>();
+    constexpr int E = 4, C = 16;  // 16 columns: 128-byte segments for the stores that cross NVLink
     grid.x = a.ncols / C;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
@@ -335,8 +335,8 @@ static int launch_inv1_multi_a(bool w32, int lazy, dim3 grid, cudaStream_t s, co
     if (w32) return launch_inv1_multi_w<u32, A>(lazy, grid, s, a);
     return launch_inv1_multi_w<u64, A>(lazy, grid, s, a);
 }
-static int ls_inv1_multi(const Tables &T, size_t cs, int L, int limb0, int nl, const void *src, u64 *const *peers, int npeer, int m_off,
-                         int m_step, size_t m_cs) {
+static int ls_inv1_multi(const Tables &T, size_t cs, int L, int limb0, int nl, const void *src, u64 *const *peers, int npeer, int first,
+                         int m_off, int m_step, size_t m_cs) {
     if (!cs || !nl) return CKKS_OK;
     PassArgs a;
     memset(&a, 0, sizeof(a));
@@ -349,6 +349,7 @@ static int ls_inv1_multi(const Tables &T, size_t cs, int L, int limb0, int nl, c
     a.tab_stride = (size_t)1 << T.a1;
     a.ncols = 1u << T.a2;
     a.npeer = npeer;
+    a.m_first = npeer > 1 ? first % npeer : 0;
     for (int p = 0; p < npeer; ++p) a.peer[p] = peers[p];
     a.m_off = m_off;
     a.m_step = m_step;
@@ -441,7 +442,7 @@ extern "C" int ckks_lshard_mul_phase(ckks_lshard *s, int phase, size_t s0, size_
         KL("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, y.A0, y.A1, y.B0, y.B1, y.A0, y.A1, y.B0)));  // d0,d1,d2
         TRY(run_pass(T, P_INV2, sp, y.B0, y.TMP));
         // digits: coefficient-domain limbs of d2 (engine.rs:493,507), stored where every GPU will read them
-        TRY(ls_inv1_multi(T, cs, (int)Ll, 0, (int)Ll, y.TMP, peer_stores ? y.gather_p : self_g, np, s->rank, s->world, y.cs_max));
+        TRY(ls_inv1_multi(T, cs, (int)Ll, 0, (int)Ll, y.TMP, peer_stores ? y.gather_p : self_g, np, s->rank + 1, s->rank, s->world, y.cs_max));
         return CKKS_OK;
     }
     if (phase == 1) {
@@ -456,8 +457,8 @@ extern "C" int ckks_lshard_mul_phase(ckks_lshard *s, int phase, size_t s0, size_
         if (s->rank == owner) {  // the limb rescale drops: finish it and hand it to everyone
             u64 *l1[8];
             for (int p = 0; p < y.world; ++p) l1[p] = y.last_p[p] ? y.last_p[p] + y.cs_max * n : nullptr;
-            TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, y.TMP, peer_stores ? y.last_p : self_l0, np, 0, 0, y.cs_max));
-            TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, y.B1, peer_stores ? l1 : self_l1, np, 0, 0, y.cs_max));
+            TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, y.TMP, peer_stores ? y.last_p : self_l0, np, s->rank + 1, 0, 0, y.cs_max));
+            TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, y.B1, peer_stores ? l1 : self_l1, np, s->rank + 1, 0, 0, y.cs_max));
         }
         return CKKS_OK;
     }
@@ -521,6 +522,7 @@ extern "C" int ckks_lshard_ks_phase(ckks_lshard *s, int phase, size_t s0, size_t
         memset(&a, 0, sizeof(a));
         a.src = digits->d + off;
         a.npeer = peer_stores ? y.world : 1;
+        a.m_first = a.npeer > 1 ? (s->rank + 1) % a.npeer : 0;
         for (int p = 0; p < a.npeer; ++p) a.peer[p] = peer_stores ? y.gather_p[p] : y.gather();
         a.m_off = s->rank;
         a.m_step = s->world;
