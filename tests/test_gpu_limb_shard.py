@@ -45,7 +45,7 @@ def _group(gpu, n, moduli, world, chunk):
     (4096, 61, 5, 3, 2, 8),     # lazy8 butterflies; ownership 2/2/1
     (16384, 30, 6, 4, 2, 1),    # 32-bit word path; ownership 2/2/1/1
     (256, 62, 2, 2, 2, 8),      # one limb per rank, Harvey butterflies
-    (2048, 63, 3, 1, 2, 8),     # a group of one (no peers): strict arithmetic
+    (2048, 63, 3, 1, 5, 2),     # a group of one (no peers): strict arithmetic; three chunks through the pipeline
 ])
 def test_limb_sharded_mul_relin_rescale_matches_oracle(gpu, orc, n, bits, l, world, batch, chunk):
     moduli = orc.generate_primes(bits, l, n)
@@ -83,6 +83,10 @@ def test_limb_sharded_mul_relin_rescale_matches_oracle(gpu, orc, n, bits, l, wor
         o0, o1, dropped = ob.rescale_ciphertext(exp[i][0], exp[i][1])
         assert np.array_equal(r0[i], o0) and np.array_equal(r1[i], o1), "rescale_ciphertext limbs differ"
         assert res[0].logp == 60 - dropped and res[0].logq == 90 - dropped
+    if world == 1:  # the one-call entry point (chunk pipeline over two streams; no peers to wait for)
+        one = shards[0].mul_relin_rescale(cta[0], ctb[0], keys[0], kids[0])
+        shards[0].check()
+        assert np.array_equal(one.c0.channels(), r0) and np.array_equal(one.c1.channels(), r1)
     # and the unsharded device path agrees word for word
     gb = gpu.RnsBasis(n, moduli)
     full = gpu.CkksEngine.mul_relin_rescale(

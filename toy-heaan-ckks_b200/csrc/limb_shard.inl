@@ -16,35 +16,52 @@
 //                         (the broadcast rescale needs, fused the same way)
 //   barrier
 //   phase C               last inverse pass fused with rescale_into (poly.rs:214-225) for the own limbs
+// The one-call entry point software-pipelines the chunks over two streams and two buffer sets: phase A of
+// chunk k+1 (NVLink-bound in its last kernel) runs on an auxiliary stream while phases B/C of chunk k
+// (integer-pipe bound) run on the context's stream, so the exchange hides behind the key-switch.
 // With `peer_stores = 0` the stores go to the own buffers only and the caller runs the collectives itself
 // (torch.distributed / NCCL all-gather and broadcast on the exported buffers) between the phases.
 //
 // Results are the reference's words: the schedule is the batch-sharded one restricted to the own limbs.
 
+struct LsSet {  // one of the two buffer sets the chunk pipeline alternates between
+    u64 *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr, *TMP = nullptr;
+    size_t off_gather = 0, off_last = 0;  // byte offsets in the symmetric block
+};
 struct LsSym {  // symmetric buffers of one rank: one cudaMalloc block (one IPC handle), shared by all levels
     int device = 0, rank = 0, world = 1;
     size_t n = 0, cs_max = 0, Lg0 = 0, Ll0 = 0;
-    unsigned char *block = nullptr;
-    size_t off_last = 0, off_flags = 0, block_bytes = 0;
-    u64 *gather_p[8] = {nullptr}, *last_p[8] = {nullptr};
-    unsigned *flags_p[8] = {nullptr};
+    unsigned char *block = nullptr;  // gather[0] | gather[1] | last[0] | last[1] | flags
+    size_t off_flags = 0, block_bytes = 0;
+    unsigned char *base_p[8] = {nullptr};  // block of every rank (own included)
     void *ipc_base[8] = {nullptr};
     bool connected = false;
-    unsigned epoch = 0;
-    cudaEvent_t ev = nullptr;  // in-process groups: barrier by events (ckks_lshard_barrier_local)
+    unsigned epochA = 0, epochB = 0;  // flag words [0..8) / [16..24): barriers on the auxiliary / main stream
+    cudaEvent_t ev = nullptr;         // in-process groups: barrier by events (ckks_lshard_barrier_local)
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
     unsigned long long timeout_ns = 20ull * 1000000000ull;
-    u64 *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr, *TMP = nullptr, *SCR = nullptr;
-    u64 *gather() const { return reinterpret_cast<u64 *>(block); }
-    u64 *last() const { return reinterpret_cast<u64 *>(block + off_last); }
-    unsigned *flags() const { return reinterpret_cast<unsigned *>(block + off_flags); }  // [8] epochs, [8] = error word
+    LsSet set[2];
+    u64 *SCR = nullptr;
+    u64 *gather(int k = 0) const { return reinterpret_cast<u64 *>(block + set[k].off_gather); }
+    u64 *last(int k = 0) const { return reinterpret_cast<u64 *>(block + set[k].off_last); }
+    u64 *gather_of(int p, int k) const { return reinterpret_cast<u64 *>(base_p[p] + set[k].off_gather); }
+    u64 *last_of(int p, int k) const { return reinterpret_cast<u64 *>(base_p[p] + set[k].off_last); }
+    unsigned *flags() const { return reinterpret_cast<unsigned *>(block + off_flags); }  // [8] = error word
+    unsigned *flags_of(int p) const { return reinterpret_cast<unsigned *>(base_p[p] + off_flags); }
     ~LsSym() {
         cudaSetDevice(device);
         if (ev) cudaEventDestroy(ev);
+        for (cudaEvent_t e : {ev_start, ev_a[0], ev_a[1], ev_c[0], ev_c[1]})
+            if (e) cudaEventDestroy(e);
+        if (aux) cudaStreamDestroy(aux);
         for (int p = 0; p < 8; ++p)
             if (ipc_base[p]) cudaIpcCloseMemHandle(ipc_base[p]);
         if (block) cudaFree(block);
-        for (u64 *b : {A0, A1, B0, B1, TMP, SCR})
-            if (b) cudaFree(b);
+        for (int k = 0; k < 2; ++k)
+            for (u64 *b : {set[k].A0, set[k].A1, set[k].B0, set[k].B1, set[k].TMP})
+                if (b) cudaFree(b);
+        if (SCR) cudaFree(SCR);
     }
 };
 struct ckks_lshard {
@@ -127,8 +144,11 @@ extern "C" int ckks_lshard_create(uint64_t n, const uint64_t *moduli, size_t l, 
     if (chunk && chunk < cs) cs = chunk;
     sym->cs_max = cs;
     const size_t gather_bytes = l * cs * n * 8, last_bytes = 2 * cs * n * 8;
-    sym->off_last = gather_bytes;
-    sym->off_flags = gather_bytes + last_bytes;
+    sym->set[0].off_gather = 0;
+    sym->set[1].off_gather = gather_bytes;
+    sym->set[0].off_last = 2 * gather_bytes;
+    sym->set[1].off_last = 2 * gather_bytes + last_bytes;
+    sym->off_flags = 2 * gather_bytes + 2 * last_bytes;
     sym->block_bytes = sym->off_flags + 256;
     ckks_lshard *s = new ckks_lshard();
     s->magic = MAGIC_LSHARD;
@@ -145,12 +165,14 @@ extern "C" int ckks_lshard_create(uint64_t n, const uint64_t *moduli, size_t l, 
         CU(cudaMalloc((void **)&sym->block, sym->block_bytes));  // plain cudaMalloc: exportable with cudaIpcGetMemHandle
         CU(cudaMemset(sym->block + sym->off_flags, 0, 256));
         const size_t W = cs * sym->Ll0 * n * 8;
-        for (u64 **b : {&sym->A0, &sym->A1, &sym->B0, &sym->B1, &sym->TMP}) CU(cudaMalloc((void **)b, W));
+        for (int k = 0; k < 2; ++k)
+            for (u64 **b : {&sym->set[k].A0, &sym->set[k].A1, &sym->set[k].B0, &sym->set[k].B1, &sym->set[k].TMP}) CU(cudaMalloc((void **)b, W));
         CU(cudaMalloc((void **)&sym->SCR, W * l));
+        CU(cudaStreamCreateWithFlags(&sym->aux, cudaStreamNonBlocking));
+        for (cudaEvent_t *e : {&sym->ev_start, &sym->ev_a[0], &sym->ev_a[1], &sym->ev_c[0], &sym->ev_c[1]})
+            CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         CU(cudaDeviceSynchronize());
-        sym->gather_p[rank] = sym->gather();
-        sym->last_p[rank] = sym->last();
-        sym->flags_p[rank] = sym->flags();
+        sym->base_p[rank] = sym->block;
         if (world == 1) sym->connected = true;
         return ls_level_tables(s);
     };
@@ -220,9 +242,9 @@ extern "C" int ckks_lshard_set_timeout_ms(ckks_lshard *s, uint64_t ms) {
 extern "C" int ckks_lshard_buffers(ckks_lshard *s, uint64_t **gather, size_t *gather_words, uint64_t **last, size_t *last_words) {
     if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
     const LsSym &y = *s->sym;
-    if (gather) *gather = reinterpret_cast<uint64_t *>(y.gather());
+    if (gather) *gather = reinterpret_cast<uint64_t *>(y.gather(0));
     if (gather_words) *gather_words = y.Lg0 * y.cs_max * y.n;
-    if (last) *last = reinterpret_cast<uint64_t *>(y.last());
+    if (last) *last = reinterpret_cast<uint64_t *>(y.last(0));
     if (last_words) *last_words = 2 * y.cs_max * y.n;
     return CKKS_OK;
 }
@@ -249,9 +271,7 @@ extern "C" int ckks_lshard_ipc_import(ckks_lshard *s, const void *blobs) {
         void *base = nullptr;
         CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
         y.ipc_base[p] = base;
-        y.gather_p[p] = reinterpret_cast<u64 *>(base);
-        y.last_p[p] = reinterpret_cast<u64 *>((unsigned char *)base + y.off_last);
-        y.flags_p[p] = reinterpret_cast<unsigned *>((unsigned char *)base + y.off_flags);
+        y.base_p[p] = reinterpret_cast<unsigned char *>(base);
     }
     y.connected = true;
     return CKKS_OK;
@@ -278,9 +298,7 @@ extern "C" int ckks_lshard_connect_local(ckks_lshard **shards, int world) {
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
                 cudaGetLastError();
             }
-            y.gather_p[p] = z.gather();
-            y.last_p[p] = z.last();
-            y.flags_p[p] = z.flags();
+            y.base_p[p] = z.block;
         }
         y.connected = true;
     }
@@ -358,19 +376,23 @@ static int ls_inv1_multi(const Tables &T, size_t cs, int L, int limb0, int nl, c
     DISPATCH_A(T.a1, TRY(launch_inv1_multi_a<AA>(T.w32, T.lazy, g, T.stream, a)));
     return CKKS_OK;
 }
-static int ls_barrier(ckks_lshard *s) {
+// which = 0: flag words [0,8) (auxiliary-stream sequence of the chunk pipeline); 1: words [16,24) (main stream).
+// Each sequence is issued in the same order on every rank, so one monotonic epoch per sequence suffices.
+static int ls_barrier(ckks_lshard *s, int which, cudaStream_t st) {
     LsSym &y = *s->sym;
     if (y.world == 1) return CKKS_OK;
     BarArgs b;
     memset(&b, 0, sizeof(b));
-    for (int p = 0; p < y.world; ++p) b.peer_flags[p] = y.flags_p[p];
-    b.my_flags = y.flags();
+    const int fo = which ? 16 : 0;
+    for (int p = 0; p < y.world; ++p) b.peer_flags[p] = y.flags_of(p) + fo;
+    b.my_flags = y.flags() + fo;
     b.err = y.flags() + 8;
     b.rank = y.rank;
     b.world = y.world;
-    b.epoch = ++y.epoch;
+    b.epoch = which ? ++y.epochB : ++y.epochA;
     b.timeout_ns = y.timeout_ns;
-    KL("lshard_barrier", (lshard_barrier_kernel<<<1, 32, 0, s->local->T->stream>>>(b)));
+    g_cur_stream = st;
+    KL("lshard_barrier", (lshard_barrier_kernel<<<1, 32, 0, st>>>(b)));
     return CKKS_OK;
 }
 // Synchronise the stream and report a barrier that timed out (a peer that never arrived).
@@ -408,13 +430,12 @@ static int ls_check_inputs(ckks_lshard *s, const ckks_poly *a0, const ckks_poly 
 }
 
 // One phase (0 = A, 1 = B, 2 = C) of mul_ciphertexts_gadget [+ rescale_ciphertext when `child`] for the
-// ciphertexts [s0, s0 + cs) of the batch, cs <= ckks_lshard_chunk().  o0/o1: polynomials of the child's (or
-// this level's) local context with the same batch as the inputs.
-extern "C" int ckks_lshard_mul_phase(ckks_lshard *s, int phase, size_t s0, size_t cs, const ckks_poly *a0, const ckks_poly *a1,
-                                     const ckks_poly *b0, const ckks_poly *b1, const ckks_ksk *rlk, ckks_lshard *child, ckks_poly *o0,
-                                     ckks_poly *o1, int peer_stores) {
-    TRY(ls_check_inputs(s, a0, a1, b0, b1, rlk, child, o0, o1));
+// ciphertexts [s0, s0 + cs) of the batch on buffer set `k`, enqueued on the context's current stream.
+static int ls_mul_phase(ckks_lshard *s, int k, int phase, size_t s0, size_t cs, const ckks_poly *a0, const ckks_poly *a1,
+                        const ckks_poly *b0, const ckks_poly *b1, const ckks_ksk *rlk, ckks_lshard *child, ckks_poly *o0, ckks_poly *o1,
+                        int peer_stores) {
     LsSym &y = *s->sym;
+    const LsSet &w = y.set[k];
     if (cs == 0) return CKKS_OK;
     if (cs > y.cs_max || s0 + cs > a0->batch) return CKKS_BAD_ARGUMENT;
     if (peer_stores && !y.connected) {
@@ -428,37 +449,40 @@ extern "C" int ckks_lshard_mul_phase(ckks_lshard *s, int phase, size_t s0, size_
     const size_t off = s0 * Ll * n;
     const bool rescale = child != nullptr;
     const int owner = (int)((Lg - 1) % s->world);
-    u64 *self_g[1] = {y.gather()}, *self_l0[1] = {y.last()}, *self_l1[1] = {y.last() + y.cs_max * n};
     const int np = peer_stores ? y.world : 1;
+    u64 *pg[8], *pl0[8], *pl1[8];  // where the digits / the two components of the dropped limb go
+    for (int p = 0; p < np; ++p) {
+        pg[p] = peer_stores ? y.gather_of(p, k) : y.gather(k);
+        pl0[p] = peer_stores ? y.last_of(p, k) : y.last(k);
+        pl1[p] = pl0[p] + y.cs_max * n;
+    }
     Span sp = whole(cs, Ll);
     if (phase == 0) {
         const u64 *in[4] = {a0->d + off, a1->d + off, b0->d + off, b1->d + off};
-        u64 *nt[4] = {y.A0, y.A1, y.B0, y.B1};
+        u64 *nt[4] = {w.A0, w.A1, w.B0, w.B1};
         for (int t = 0; t < 4; ++t) {
-            TRY(run_pass(T, P_FWD1, sp, in[t], y.TMP));
-            TRY(run_pass(T, P_FWD2, sp, y.TMP, nt[t]));
+            TRY(run_pass(T, P_FWD1, sp, in[t], w.TMP));
+            TRY(run_pass(T, P_FWD2, sp, w.TMP, nt[t]));
         }
         EwArgs e = ew_args(T, Ll, cs);
-        KL("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, y.A0, y.A1, y.B0, y.B1, y.A0, y.A1, y.B0)));  // d0,d1,d2
-        TRY(run_pass(T, P_INV2, sp, y.B0, y.TMP));
+        KL("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, w.A0, w.A1, w.B0, w.B1, w.A0, w.A1, w.B0)));  // d0,d1,d2
+        TRY(run_pass(T, P_INV2, sp, w.B0, w.TMP));
         // digits: coefficient-domain limbs of d2 (engine.rs:493,507), stored where every GPU will read them
-        TRY(ls_inv1_multi(T, cs, (int)Ll, 0, (int)Ll, y.TMP, peer_stores ? y.gather_p : self_g, np, s->rank + 1, s->rank, s->world, y.cs_max));
+        TRY(ls_inv1_multi(T, cs, (int)Ll, 0, (int)Ll, w.TMP, pg, np, s->rank + 1, s->rank, s->world, y.cs_max));
         return CKKS_OK;
     }
     if (phase == 1) {
         KsShard ks{Lg, s->rank, s->world, n, y.cs_max * n, s->digit_reduce};
-        TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(), y.B0, rlk, y.A0, y.A1, y.SCR, y.TMP, y.B1, true));
+        TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(k), w.B0, rlk, w.A0, w.A1, y.SCR, w.TMP, w.B1, true));
         if (!rescale) {
             const size_t ooff = s0 * Ll * n;
-            TRY(run_pass(T, P_INV1, sp, y.TMP, o0->d + ooff));
-            TRY(run_pass(T, P_INV1, sp, y.B1, o1->d + ooff));
+            TRY(run_pass(T, P_INV1, sp, w.TMP, o0->d + ooff));
+            TRY(run_pass(T, P_INV1, sp, w.B1, o1->d + ooff));
             return CKKS_OK;
         }
         if (s->rank == owner) {  // the limb rescale drops: finish it and hand it to everyone
-            u64 *l1[8];
-            for (int p = 0; p < y.world; ++p) l1[p] = y.last_p[p] ? y.last_p[p] + y.cs_max * n : nullptr;
-            TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, y.TMP, peer_stores ? y.last_p : self_l0, np, s->rank + 1, 0, 0, y.cs_max));
-            TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, y.B1, peer_stores ? l1 : self_l1, np, s->rank + 1, 0, 0, y.cs_max));
+            TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, w.TMP, pl0, np, s->rank + 1, 0, 0, y.cs_max));
+            TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, w.B1, pl1, np, s->rank + 1, 0, 0, y.cs_max));
         }
         return CKKS_OK;
     }
@@ -477,22 +501,29 @@ extern "C" int ckks_lshard_mul_phase(ckks_lshard *s, int phase, size_t s0, size_
         pa.dstL = (int)outL;
         dim3 g(1, (unsigned)outL, (unsigned)cs);
         const size_t ooff = s0 * outL * n;
-        pa.src = y.TMP;
+        pa.src = w.TMP;
         pa.dst = o0->d + ooff;
-        DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, y.last(), s->d_qlinv_last)));
-        pa.src = y.B1;
+        DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, y.last(k), s->d_qlinv_last)));
+        pa.src = w.B1;
         pa.dst = o1->d + ooff;
-        DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, y.last() + y.cs_max * n, s->d_qlinv_last)));
+        DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, y.last(k) + y.cs_max * n, s->d_qlinv_last)));
         return CKKS_OK;
     }
     return CKKS_BAD_ARGUMENT;
+}
+// The public phase call: buffer set 0, the context's stream; cs <= ckks_lshard_chunk().  o0/o1: polynomials of
+// the child's (or this level's) local context with the same batch as the inputs.
+extern "C" int ckks_lshard_mul_phase(ckks_lshard *s, int phase, size_t s0, size_t cs, const ckks_poly *a0, const ckks_poly *a1,
+                                     const ckks_poly *b0, const ckks_poly *b1, const ckks_ksk *rlk, ckks_lshard *child, ckks_poly *o0,
+                                     ckks_poly *o1, int peer_stores) {
+    TRY(ls_check_inputs(s, a0, a1, b0, b1, rlk, child, o0, o1));
+    return ls_mul_phase(s, 0, phase, s0, cs, a0, a1, b0, b1, rlk, child, o0, o1, peer_stores);
 }
 extern "C" int ckks_lshard_barrier(ckks_lshard *s) {
     if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
     if (!s->sym->connected) return CKKS_BAD_ARGUMENT;
     CU(cudaSetDevice(s->sym->device));
-    g_cur_stream = s->local->T->stream;
-    return ls_barrier(s);
+    return ls_barrier(s, 1, s->local->T->stream);
 }
 
 // ---- gadget key-switch of a coefficient-domain polynomial (rotate_ciphertext, engine.rs:429-452) ------
@@ -523,7 +554,7 @@ extern "C" int ckks_lshard_ks_phase(ckks_lshard *s, int phase, size_t s0, size_t
         a.src = digits->d + off;
         a.npeer = peer_stores ? y.world : 1;
         a.m_first = a.npeer > 1 ? (s->rank + 1) % a.npeer : 0;
-        for (int p = 0; p < a.npeer; ++p) a.peer[p] = peer_stores ? y.gather_p[p] : y.gather();
+        for (int p = 0; p < a.npeer; ++p) a.peer[p] = peer_stores ? y.gather_of(p, 0) : y.gather(0);
         a.m_off = s->rank;
         a.m_step = s->world;
         a.m_cs = y.cs_max;
@@ -535,10 +566,10 @@ extern "C" int ckks_lshard_ks_phase(ckks_lshard *s, int phase, size_t s0, size_t
     }
     if (phase == 1) {
         KsShard ks{s->Lg, s->rank, s->world, n, y.cs_max * n, s->digit_reduce};
-        TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(), nullptr, key, nullptr, nullptr, y.SCR, y.TMP, y.B1, false));
+        TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(0), nullptr, key, nullptr, nullptr, y.SCR, y.set[0].TMP, y.set[0].B1, false));
         Span sp = whole(cs, Ll);
-        TRY(run_pass(T, P_INV1, sp, y.TMP, ks0->d + off));
-        TRY(run_pass(T, P_INV1, sp, y.B1, ks1->d + off));
+        TRY(run_pass(T, P_INV1, sp, y.set[0].TMP, ks0->d + off));
+        TRY(run_pass(T, P_INV1, sp, y.set[0].B1, ks1->d + off));
         ks0->ntt = ks1->ntt = false;
         return CKKS_OK;
     }
@@ -564,9 +595,9 @@ extern "C" int ckks_lshard_ct_rotate(ckks_lshard *s, const ckks_poly *c0, const 
     for (size_t s0 = 0; rc == CKKS_OK && s0 < c0->batch; s0 += cs_max) {
         const size_t cs = c0->batch - s0 < cs_max ? c0->batch - s0 : cs_max;
         rc = ckks_lshard_ks_phase(s, 0, s0, cs, r1, rotk, k0, k1, 1);
-        if (rc == CKKS_OK) rc = ls_barrier(s);
+        if (rc == CKKS_OK) rc = ls_barrier(s, 1, s->local->T->stream);
         if (rc == CKKS_OK) rc = ckks_lshard_ks_phase(s, 1, s0, cs, r1, rotk, k0, k1, 1);
-        if (rc == CKKS_OK) rc = ls_barrier(s);  // gather buffers are free again
+        if (rc == CKKS_OK) rc = ls_barrier(s, 1, s->local->T->stream);  // gather buffers are free again
     }
     if (rc == CKKS_OK) rc = ckks_poly_add_assign(r0, k0);  // engine.rs:454-455
     free2(r1, k0);
@@ -601,6 +632,57 @@ extern "C" int ckks_lshard_barrier_local(ckks_lshard **shards, int world) {
     return CKKS_OK;
 }
 
+// Chunk pipeline of the one-call entry point.  Stream `aux`: phase A of chunk k+1 on buffer set (k+1)%2 and the
+// barrier that says "every digit of that chunk is in every gather buffer".  Context stream: phases B, barrier
+// ("the dropped limb is everywhere; this set's gather buffer may be overwritten"), C of chunk k.  Events order
+// the two streams; the two barrier sequences use separate flag words.
+//   set reuse: A(k+2) waits for C(k) locally; a peer's A(k+2) stores come after that peer passed the main-stream
+//   barrier of chunk k, which this GPU signals only after its phase B(k) has read the gather buffer.
+static int ls_mul_pipeline(ckks_lshard *s, const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1,
+                           const ckks_ksk *rlk, ckks_lshard *child, ckks_poly *r0, ckks_poly *r1) {
+    LsSym &y = *s->sym;
+    Tables &T = *s->local->T;
+    CU(cudaSetDevice(T.device));
+    const cudaStream_t main = T.stream, aux = y.aux;
+    const size_t batch = a0->batch, cs_max = y.cs_max;
+    const size_t K = (batch + cs_max - 1) / cs_max;
+    if (K == 0) return CKKS_OK;
+    auto span = [&](size_t k, size_t &s0, size_t &cs) {
+        s0 = k * cs_max;
+        cs = batch - s0 < cs_max ? batch - s0 : cs_max;
+    };
+    // phase A of chunk k on the auxiliary stream (the launch helpers take the stream from the tables)
+    auto phase_a = [&](size_t k) -> int {
+        size_t s0, cs;
+        span(k, s0, cs);
+        T.stream = aux;
+        int rc = ls_mul_phase(s, (int)(k & 1), 0, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1);
+        T.stream = main;
+        if (rc == CKKS_OK) rc = ls_barrier(s, 0, aux);
+        if (rc != CKKS_OK) return rc;
+        CU(cudaEventRecord(y.ev_a[k & 1], aux));
+        return CKKS_OK;
+    };
+    CU(cudaEventRecord(y.ev_start, main));  // inputs and earlier work on the context's stream
+    CU(cudaStreamWaitEvent(aux, y.ev_start, 0));
+    TRY(phase_a(0));
+    for (size_t k = 0; k < K; ++k) {
+        if (k + 1 < K) {
+            if (k >= 1) CU(cudaStreamWaitEvent(aux, y.ev_c[(k + 1) & 1], 0));  // C(k-1) released that buffer set
+            TRY(phase_a(k + 1));
+        }
+        size_t s0, cs;
+        span(k, s0, cs);
+        CU(cudaStreamWaitEvent(main, y.ev_a[k & 1], 0));
+        TRY(ls_mul_phase(s, (int)(k & 1), 1, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1));
+        TRY(ls_barrier(s, 1, main));
+        TRY(ls_mul_phase(s, (int)(k & 1), 2, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1));
+        CU(cudaEventRecord(y.ev_c[k & 1], main));
+    }
+    g_cur_stream = main;
+    return CKKS_OK;
+}
+
 // mul_ciphertexts_gadget (+ rescale_ciphertext into `child`'s level when child != NULL) on this GPU's limbs
 // of a batch, all phases and both cross-GPU exchanges enqueued on the stream without host synchronisation.
 // Every GPU of the group must make the same call on its own share.
@@ -615,15 +697,8 @@ extern "C" int ckks_lshard_ct_mul_relin_rescale(ckks_lshard *s, const ckks_poly 
     ckks_ctx *octx = child ? child->local : s->local;
     int rc = poly_new(octx, a0->batch, false, &r0);
     if (rc == CKKS_OK) rc = poly_new(octx, a0->batch, false, &r1);
-    const size_t cs_max = s->sym->cs_max;
-    for (size_t s0 = 0; rc == CKKS_OK && s0 < a0->batch; s0 += cs_max) {
-        const size_t cs = a0->batch - s0 < cs_max ? a0->batch - s0 : cs_max;
-        rc = ckks_lshard_mul_phase(s, 0, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1);
-        if (rc == CKKS_OK) rc = ls_barrier(s);  // every digit of this chunk is in every gather buffer
-        if (rc == CKKS_OK) rc = ckks_lshard_mul_phase(s, 1, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1);
-        if (rc == CKKS_OK) rc = ls_barrier(s);  // the dropped limb is everywhere; gather buffers are free again
-        if (rc == CKKS_OK) rc = ckks_lshard_mul_phase(s, 2, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1);
-    }
+    if (rc == CKKS_OK) rc = ls_check_inputs(s, a0, a1, b0, b1, rlk, child, r0, r1);
+    if (rc == CKKS_OK) rc = ls_mul_pipeline(s, a0, a1, b0, b1, rlk, child, r0, r1);
     if (rc != CKKS_OK) {
         free2(r0, r1);
         return rc;
