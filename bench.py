@@ -456,6 +456,8 @@ def run_limb_sharded(args):
     moduli = ck.generate_primes(bits, l, n)
     sh = ck.LimbShard(n, moduli, rank, world, device=local, chunk=args.ls_chunk)
     kid = sh.drop_last()
+    if args.comm == "ce":
+        sh.set_exchange(1)
     basis = sh.local_basis()
     stream = torch.cuda.current_stream()
     basis.set_stream(stream.cuda_stream)
@@ -492,7 +494,7 @@ def run_limb_sharded(args):
         owner = (l - 1) % world
 
     def step():
-        if args.comm == "peer" or world == 1:
+        if args.comm != "nccl" or world == 1:
             return sh.mul_relin_rescale(cta, ctb, key, kid)
         out = ck.Ciphertext(ck.RnsPoly.zero(kid.local_basis(), batch), ck.RnsPoly.zero(kid.local_basis(), batch), 0, 0)
         for s0 in range(0, batch, chunk):
@@ -566,7 +568,8 @@ def run_limb_sharded(args):
             "workload": f"{args.config}: N=2^{logn}, L={l}, {bits}-bit primes, ONE batch of {batch} ciphertext pairs, limbs spread over "
             f"{world} GPU(s), mul_ciphertexts_gadget+rescale_ciphertext",
             "parallelism": f"limb-sharded x{world} (limb j on GPU j mod {world}); exchange: "
-            + ("stores into peer HBM from the producing kernels + flag barrier" if args.comm == "peer" else "NCCL all-gather / broadcast between the phases"),
+            + {"peer": "stores into peer HBM from the producing kernels + flag barrier", "ce": "digits pushed by the copy engines, dropped limb by peer stores, flag barrier",
+               "nccl": "NCCL all-gather / broadcast between the phases"}[args.comm],
             "chunk": chunk,
             "exchange_bytes_per_ct_per_gpu": (len(own) * (world - 1) * n * 8) + (2 * (world - 1) * n * 8 if rank == (l - 1) % world else 0),
             "key_bytes_per_gpu": 2 * l * len(own) * n * 8,
@@ -698,7 +701,8 @@ def main():
     ap.add_argument("--host-chunk-mib", type=int, default=0, help="pipeline chunk of the host-buffer entry point")
     ap.add_argument("--ntt-sweep", action="store_true", help="BASELINE.json configs[4]: limb-batched NTT/INTT sweep instead of the ct-mult bench")
     ap.add_argument("--limb-sharded", action="store_true", help="optional limb-sharded mode (one batch, limbs spread over the GPUs)")
-    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="limb-sharded exchange: fused peer stores or NCCL collectives")
+    ap.add_argument("--comm", default="peer", choices=["peer", "ce", "nccl"],
+                    help="limb-sharded exchange: stores into peer HBM from the producing kernels, copy engines for the digits, or NCCL collectives")
     ap.add_argument("--ls-chunk", type=int, default=0, help="limb-sharded: ciphertexts per pass (0 = automatic)")
     args = ap.parse_args()
     if args.limb_sharded:

@@ -269,6 +269,10 @@ int ckks_lshard_buffers(ckks_lshard *s, uint64_t **gather, size_t *gather_words,
 /* Synchronise and report a barrier that gave up waiting for a peer (CKKS_NCCL_ERROR). */
 int ckks_lshard_check(ckks_lshard *s);
 int ckks_lshard_set_timeout_ms(ckks_lshard *s, uint64_t ms);
+/* How the digits travel in the one-call entry points: 0 (default) = stores into peer HBM from the producing
+ * kernel; 1 = that kernel stores locally and copy engines push the limbs to the peers (no SM held while
+ * NVLink is busy: the better choice when a batch spans several chunks and the exchange hides behind compute). */
+int ckks_lshard_set_exchange(ckks_lshard *s, int mode);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* Kernel launches issued by this library since process start (bench.py's gpu_launches). */

@@ -123,6 +123,13 @@ def main():
                 if not (np.array_equal(g0, e0[:, rank::world]) and np.array_equal(g1, e1[:, rank::world])):
                     print(f"rank {rank}: MISMATCH peer-store exchange N={n} L={lv} rep={rep}", flush=True)
                     sys.exit(1)
+            level.set_exchange(1)  # digits by the copy engines
+            outc = level.mul_relin_rescale(ca, cb, key, kid)
+            level.check()
+            level.set_exchange(0)
+            if not (np.array_equal(outc.c0.channels(), e0[:, rank::world]) and np.array_equal(outc.c1.channels(), e1[:, rank::world])):
+                print(f"rank {rank}: MISMATCH copy-engine exchange N={n} L={lv}", flush=True)
+                sys.exit(1)
             outn = nccl_step(ck, dist, torch, level, kid, ca, cb, key, batch, dev)
             level.check()
             if not (np.array_equal(outn.c0.channels(), e0[:, rank::world]) and np.array_equal(outn.c1.channels(), e1[:, rank::world])):

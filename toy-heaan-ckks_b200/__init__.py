@@ -159,6 +159,7 @@ _sig("ckks_lshard_barrier_local", C.c_int, _pp, C.c_int)
 _sig("ckks_lshard_buffers", C.c_int, _vp, C.POINTER(_u64p), C.POINTER(C.c_size_t), C.POINTER(_u64p), C.POINTER(C.c_size_t))
 _sig("ckks_lshard_check", C.c_int, _vp)
 _sig("ckks_lshard_set_timeout_ms", C.c_int, _vp, C.c_uint64)
+_sig("ckks_lshard_set_exchange", C.c_int, _vp, C.c_int)
 
 # Every symbol include/ckks_b200.h declares (tests/test_abi.py checks the header against this list).
 ABI_SYMBOLS = sorted(n for n in dir(_lib) if n.startswith("ckks_")) or []
@@ -817,6 +818,10 @@ class LimbShard:
     def check(self):
         """Synchronise; raises if a barrier gave up waiting for a peer."""
         _check(_lib.ckks_lshard_check(self._h))
+
+    def set_exchange(self, mode: int):
+        """0: digits stored into peer HBM by the producing kernel; 1: pushed by the copy engines."""
+        _check(_lib.ckks_lshard_set_exchange(self._h, mode))
 
     def set_timeout_ms(self, ms: int):
         _check(_lib.ckks_lshard_set_timeout_ms(self._h, ms))

@@ -41,6 +41,10 @@ struct LsSym {  // symmetric buffers of one rank: one cudaMalloc block (one IPC 
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
     unsigned long long timeout_ns = 20ull * 1000000000ull;
+    // how the digits reach the peers in the pipelined entry point: 0 = stores from the producing kernel,
+    // 1 = copy engines (cudaMemcpyAsync over the peer mappings: no SM is held while NVLink is busy, so the
+    // exchange of chunk k+1 really runs under the key-switch of chunk k)
+    int exchange = 0;
     LsSet set[2];
     u64 *SCR = nullptr;
     u64 *gather(int k = 0) const { return reinterpret_cast<u64 *>(block + set[k].off_gather); }
@@ -232,6 +236,12 @@ extern "C" int ckks_lshard_drop_last(ckks_lshard *s, ckks_lshard **out) {
 extern "C" ckks_ctx *ckks_lshard_local_ctx(ckks_lshard *s) { return ok_lshard(s) ? s->local : nullptr; }
 extern "C" size_t ckks_lshard_channel_count(const ckks_lshard *s) { return ok_lshard(s) ? s->Lg : 0; }
 extern "C" size_t ckks_lshard_chunk(const ckks_lshard *s) { return ok_lshard(s) ? s->sym->cs_max : 0; }
+extern "C" int ckks_lshard_set_exchange(ckks_lshard *s, int mode) {
+    if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
+    if (mode != 0 && mode != 1) return CKKS_BAD_ARGUMENT;
+    s->sym->exchange = mode;
+    return CKKS_OK;
+}
 extern "C" int ckks_lshard_set_timeout_ms(ckks_lshard *s, uint64_t ms) {
     if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
     s->sym->timeout_ns = ms * 1000000ull;
@@ -468,6 +478,18 @@ static int ls_mul_phase(ckks_lshard *s, int k, int phase, size_t s0, size_t cs, 
         KL("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, w.A0, w.A1, w.B0, w.B1, w.A0, w.A1, w.B0)));  // d0,d1,d2
         TRY(run_pass(T, P_INV2, sp, w.B0, w.TMP));
         // digits: coefficient-domain limbs of d2 (engine.rs:493,507), stored where every GPU will read them
+        if (peer_stores && y.exchange == 1 && y.world > 1) {
+            u64 *self[1] = {y.gather(k)};
+            TRY(ls_inv1_multi(T, cs, (int)Ll, 0, (int)Ll, w.TMP, self, 1, 0, s->rank, s->world, y.cs_max));
+            for (int t = 1; t < y.world; ++t) {
+                const int p = (s->rank + t) % y.world;
+                for (size_t jl = 0; jl < Ll; ++jl) {
+                    const size_t slot = ((size_t)s->rank + (size_t)s->world * jl) * y.cs_max * n;
+                    CU(cudaMemcpyAsync(y.gather_of(p, k) + slot, y.gather(k) + slot, cs * n * sizeof(u64), cudaMemcpyDefault, T.stream));
+                }
+            }
+            return CKKS_OK;
+        }
         TRY(ls_inv1_multi(T, cs, (int)Ll, 0, (int)Ll, w.TMP, pg, np, s->rank + 1, s->rank, s->world, y.cs_max));
         return CKKS_OK;
     }
