@@ -961,6 +961,7 @@ extern "C" int ckks_poly_to_coeffs(const ckks_poly *p, int64_t *out) {
 // -------------------------------------------------------------------------------------------------
 // gadget keys
 // -------------------------------------------------------------------------------------------------
+constexpr int KS_E2 = 3, KS_C2 = 4;  // ks_pass2: 8 elements per thread leave room for the 128-bit accumulators
 static int ksk_new(ckks_ctx *ctx, ckks_ksk **out, size_t digits = 0) {
     const Tables &T = *ctx->T;
     if (!digits) digits = ctx->L;
@@ -975,6 +976,7 @@ static int ksk_new(ckks_ctx *ctx, ckks_ksk **out, size_t digits = 0) {
     k->a = a;
     k->b = b;
     k->digits = digits;
+    k->perm_e = -1;
     *out = k;
     return CKKS_OK;
 }
@@ -987,6 +989,22 @@ extern "C" int ckks_ksk_free(ckks_ksk *k) {
     k->magic = 0;
     delete k;
     ctx_unref(c);
+    return CKKS_OK;
+}
+// Four-step path: store the transformed key with the rows of every limb in ks_pass2's order (perm_row).
+static int ksk_finalize(const Tables &T, ckks_ksk *k) {
+    if (T.path != 2 || T.a2 <= KS_E2) return CKKS_OK;
+    const size_t words = k->digits * k->ctx->L * T.n;
+    if (!words) return CKKS_OK;
+    u64 *tmp = nullptr;
+    TRY(dev_alloc(T, words, &tmp));
+    for (u64 *p : {k->a, k->b}) {
+        KLV("key_permute", (key_permute_kernel<<<ew_grid(words), 256, 0, T.stream>>>(p, tmp, words, T.logn, T.a1, T.a2, KS_E2)));
+        cudaMemcpyAsync(p, tmp, words * 8, cudaMemcpyDeviceToDevice, T.stream);
+    }
+    dev_free(T, tmp);
+    if (cudaPeekAtLastError() != cudaSuccess) return cuda_fail(cudaGetLastError(), "key_permute");
+    k->perm_e = KS_E2;
     return CKKS_OK;
 }
 extern "C" int ckks_ksk_upload(ckks_ctx *ctx, const uint64_t *a, const uint64_t *b, ckks_ksk **out) {
@@ -1005,6 +1023,7 @@ extern "C" int ckks_ksk_upload(ckks_ctx *ctx, const uint64_t *a, const uint64_t 
         rc = cuda_fail(cudaGetLastError(), "ksk h2d");
     if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, false);
     if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, false);
+    if (rc == CKKS_OK) rc = ksk_finalize(T, k);
     if (rc == CKKS_OK && cudaStreamSynchronize(T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ksk sync");
     if (rc != CKKS_OK) {
         ckks_ksk_free(k);
@@ -1030,6 +1049,7 @@ extern "C" int ckks_ksk_from_polys(const ckks_poly *a, const ckks_poly *b, ckks_
     int rc = CKKS_OK;
     if (!a->ntt) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, false);
     if (rc == CKKS_OK && !b->ntt) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, false);
+    if (rc == CKKS_OK) rc = ksk_finalize(T, k);
     if (rc != CKKS_OK) {
         ckks_ksk_free(k);
         return rc;
@@ -1095,7 +1115,7 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
         KLV("digit_broadcast", (digit_broadcast_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, digits, alpha, (int)i)));
         rc = ntt_run(T, L, batch, alpha, tmp, false);
         if (rc != CKKS_OK) break;
-        KLV("ks_mac", (ks_mac_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, alpha, key->b + i * e.poly, key->a + i * e.poly, acc0, acc1)));
+        KLV("ks_mac", (ks_mac_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, alpha, key->b + i * e.poly, key->a + i * e.poly, acc0, acc1, T.a1, T.a2, key->perm_e)));
         if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "keyswitch");
     }
     dev_free(T, alpha);
@@ -1104,8 +1124,6 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
 }
 
 // ---- fused four-step key-switch pipeline -----------------------------------------------------------
-constexpr int KS_E2 = 3, KS_C2 = 4;  // ks_pass2: 8 elements per thread leave room for the 128-bit accumulators
-
 constexpr int KS_C1 = 8;
 template <typename WD, int A>
 static int launch_ks1_w(int lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
@@ -1243,6 +1261,10 @@ struct KsShard {
 };
 static int ks_fused_ex(const Tables &T, size_t L, const KsShard &sh, size_t cs, const u64 *digits, const u64 *dig_ntt,
                        const ckks_ksk *key, const u64 *add0, const u64 *add1, u64 *scratch, u64 *out0t, u64 *out1t, bool mul) {
+    if (key->perm_e != KS_E2) {
+        g_err = "gadget key is not in the fused key-switch layout";
+        return CKKS_BAD_HANDLE;
+    }
     KsArgs a;
     a.digits = digits;
     a.dig_ntt = dig_ntt;

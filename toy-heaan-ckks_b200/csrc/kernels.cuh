@@ -341,12 +341,32 @@ __global__ void digit_broadcast_kernel(EwArgs a, const u64 *__restrict__ src, u6
         out[i] = (limb == digit) ? v : barrett_word(v, a.lc[limb]);
     }
 }
-// acc0 += x * kb, acc1 += x * ka (all NTT domain); kb/ka: one digit's key polynomial [L][N].
+// Row permutation of the resident gadget keys on the four-step path: within every limb ([2^a2 rows][2^a1]
+// words, internal NTT order) row (g * 2^pe + k) moves to row (k * 2^(a2-pe) + g), pe = ks_pass2's register
+// window.  perm_row() maps a logical row to where it is stored; pe < 0: not permuted.
+__host__ __device__ __forceinline__ size_t perm_row(size_t row, int a2, int pe) {
+    if (pe < 0 || a2 <= pe) return row;
+    return ((row & (((size_t)1 << pe) - 1)) << (a2 - pe)) | (row >> pe);
+}
+__global__ void key_permute_kernel(const u64 *__restrict__ src, u64 *__restrict__ dst, size_t total, int logn, int a1, int a2, int pe) {
+    const size_t n = (size_t)1 << logn;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t k = i & (n - 1), row = k >> a1, col = k & (((size_t)1 << a1) - 1);
+        dst[i - k + (perm_row(row, a2, pe) << a1) + col] = src[i];
+    }
+}
+// acc0 += x * kb, acc1 += x * ka (all NTT domain); kb/ka: one digit's key polynomial [L][N] (rows permuted
+// when pe >= 0).
 __global__ void ks_mac_kernel(EwArgs a, const u64 *__restrict__ x, const u64 *__restrict__ kb,
-                              const u64 *__restrict__ ka, u64 *__restrict__ acc0, u64 *__restrict__ acc1) {
+                              const u64 *__restrict__ ka, u64 *__restrict__ acc0, u64 *__restrict__ acc1, int a1, int a2, int pe) {
+    const size_t n = (size_t)1 << a.logn;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
         const LimbConst &m = a.lc[ew_limb(a, i)];
         size_t r = i % a.poly;
+        if (pe >= 0) {
+            const size_t k = r & (n - 1);
+            r = r - k + (perm_row(k >> a1, a2, pe) << a1) + (k & (((size_t)1 << a1) - 1));
+        }
         u64 xx = x[i];
         acc0[i] = mulmod_add(xx, __ldg(kb + r), acc0[i], m);
         acc1[i] = mulmod_add(xx, __ldg(ka + r), acc1[i], m);
@@ -576,6 +596,9 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
     constexpr int NT = C * GM::G;
     constexpr int R = 1 << E;
     constexpr int TILE = (1 << A) * C;
+    // exchange tile: dense rows, XOR-swizzled over the rows one 128-byte wavefront covers (ntt_tile.cuh)
+    constexpr int SWZ = (128 / (int)(sizeof(WD) * C)) > 0 ? (128 / (int)(sizeof(WD) * C)) : 1;
+    static_assert(GM::lo(GM::NS - 1) == 0, "the key tiles are addressed through the last register window");
     extern __shared__ __align__(128) unsigned char sm_raw[];
     u64 *stKb = reinterpret_cast<u64 *>(sm_raw);  // key_b tile of the current digit
     u64 *stKa = stKb + TILE;                      // key_a tile
@@ -626,15 +649,19 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
         stage_tile<WD, A, C, NT>(stS, scr + (size_t)digit_of(0) * a.N, ncols, tid);
         cp_async_commit();
     }
+    // Key rows are stored permuted, row (g * 2^E + k) of a limb at (k * G + g) (key_permute_kernel): the dense
+    // tile the copy engine delivers is then [k][g][c] and the lanes of a wavefront (consecutive g, fixed k)
+    // read consecutive words instead of rows 2^E apart.
     if (DIAG) {  // digit i == j: the NTT-domain limb itself
         const u64 *src = a.dig_ntt + (ct * L + j) * a.N + c0 + c;
         const u64 *kb = kbase_b + (size_t)jg * kstride + c, *ka = kbase_a + (size_t)jg * kstride + c;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             size_t off = (size_t)tile_idx<E>(g, k, lo_out) * ncols;
+            size_t koff = (size_t)(k * GM::G + g) * ncols;
             WD x = (WD)src[off];
-            acc0[k].mac(x, __ldg(kb + off));
-            acc1[k].mac(x, __ldg(ka + off));
+            acc0[k].mac(x, __ldg(kb + koff));
+            acc1[k].mac(x, __ldg(ka + koff));
         }
     }
     for (int t = 0; t < nd; ++t) {
@@ -663,7 +690,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
         const WD *S = stS + (t & 1) * TILE;
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = S[tile_idx<E>(g, k, lo_in) * C + c];
-        xf_tile<XF_CYC_FWD, A, E, CP, LAZY>(v, g, c, sm, W, q, q2);
+        xf_tile<XF_CYC_FWD, A, E, CP, LAZY, SWZ>(v, g, c, sm, W, q, q2);
         if (TMA) {
             mbar_wait(bars + 2, t & 1);  // keys(t) landed
         } else {
@@ -672,7 +699,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
         }
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            int so = tile_idx<E>(g, k, lo_out) * C + c;
+            const int so = (k * GM::G + g) * C + c;
             // lazy8: one conditional subtraction ([0,4q) -> [0,2q)) is enough for the 128-bit accumulators
             WD x = (LAZY == 2) ? csub(v[k], q2) : canon2<LAZY>(v[k], q);
             acc0[k].mac(x, stKb[so]);
@@ -704,19 +731,19 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
             v[k] = r;
         }
         __syncthreads();
-        xf_tile<XF_CYC_INV, A, E, CP, LAZY>(v, g, c, sm, Wi, q, q2);
+        xf_tile<XF_CYC_INV, A, E, CP, LAZY, SWZ>(v, g, c, sm, Wi, q, q2);
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             size_t off = (size_t)tile_idx<E>(g, k, lo_in) * ncols + c0 + c;
             v[k] = mul_tw<LAZY>(v[k], ldg_tw(TTi + off), q);
         }
         if (GM::NS >= 2) __syncthreads();
-        tile_put<E, CP>(sm, v, g, c, lo_in);
+        tile_put<E, CP, SWZ>(sm, v, g, c, lo_in);
         __syncthreads();
         WD *d = out + c0 * (size_t)(1 << A);
         for (int e = tid; e < (C << A); e += NT) {
             int cc = e >> A, r = e & ((1 << A) - 1);
-            d[e] = sm[r * CP + cc];
+            d[e] = sm[tile_addr<E, CP, SWZ>(r, cc)];
         }
     }
 }

@@ -334,6 +334,7 @@ extern "C" int ckks_lshard_ksk_upload(ckks_lshard *s, const uint64_t *a, const u
         rc = cuda_fail(cudaGetLastError(), "ksk h2d");
     if (rc == CKKS_OK) rc = ntt_inplace(T, s->Ll, s->Lg, k->a, false);
     if (rc == CKKS_OK) rc = ntt_inplace(T, s->Ll, s->Lg, k->b, false);
+    if (rc == CKKS_OK) rc = ksk_finalize(T, k);
     if (rc == CKKS_OK && cudaStreamSynchronize(T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ksk sync");
     if (rc != CKKS_OK) {
         ckks_ksk_free(k);
