@@ -91,3 +91,49 @@ def test_approximate_shoup_range_and_value(emul):
             for w in (1, q - 1, rnd.randrange(q)):
                 r = emul.emul_shoup_lazy8(x, w, q)
                 assert r % q == (x * w) % q and r < 4 * q
+
+
+def _wavefronts(addrs_bytes, size):
+    """Shared-memory wavefronts of one warp-wide access: 32 banks of 4 bytes; 64-bit accesses go half a warp at a time."""
+    groups = [addrs_bytes] if size == 4 else [addrs_bytes[:16], addrs_bytes[16:]]
+    total = 0
+    for grp in groups:
+        banks = {}
+        for a in grp:
+            for w in range(size // 4):
+                banks.setdefault((a // 4 + w) % 32, set()).add(a // 4 + w)
+        total += max(len(v) for v in banks.values())
+    return total
+
+
+@pytest.mark.parametrize("size,e,c_cols", [(8, 3, 4), (4, 3, 4), (8, 4, 8), (4, 4, 8), (4, 4, 16), (8, 4, 16), (8, 3, 8)])
+def test_tile_layout_is_conflict_free(emul, size, e, c_cols):
+    """The exchange layout of csrc/ntt_tile.cuh (tile_addr): a dense bijection, and every access pattern the
+    kernels make -- each register window of every transform size, and the transposing store's row-lane read --
+    costs the minimum number of shared-memory wavefronts (1 per warp for u32, 2 for u64).  Shapes: ks_pass2 (E=3,
+    C=4), ks_pass1 / 64-bit passes (E=4, C=8), 32-bit passes and the fused transform (E=4, C=16)."""
+    emul.emul_tile_addr.argtypes = [C.c_int] * 5
+    ideal = size // 4
+    for a in range(e + 2, 9):  # rows per tile 2^a; smaller tiles have fewer than 32 threads
+        rows = 1 << a
+        addr = [[emul.emul_tile_addr(e, c_cols, size, r, c) for c in range(c_cols)] for r in range(rows)]
+        flat = sorted(x for row in addr for x in row)
+        assert flat == list(range(rows * c_cols)), "tile_addr must be a bijection onto the dense tile"
+        groups = 1 << (a - e)
+        nthreads = c_cols * groups
+        if nthreads < 32:
+            continue
+        ns = (a + e - 1) // e
+        for lo in sorted({max(a - (t + 1) * e, 0) for t in range(ns)}):
+            for w0 in range(0, nthreads, 32):
+                for k in range(1 << e):
+                    lanes = []
+                    for tid in range(w0, w0 + 32):
+                        c, g = tid % c_cols, tid // c_cols
+                        r = ((g >> lo) << (lo + e)) | (k << lo) | (g & ((1 << lo) - 1))
+                        lanes.append(addr[r][c] * size)
+                    assert _wavefronts(lanes, size) == ideal, (a, lo, w0, k)
+        if rows >= 32:
+            for e0 in range(0, c_cols << a, 32):  # transposed read: lane = consecutive rows of one column
+                lanes = [addr[x & (rows - 1)][x >> a] * size for x in range(e0, e0 + 32)]
+                assert _wavefronts(lanes, size) == ideal, (a, "transposed", e0)
