@@ -196,16 +196,14 @@ extern "C" uint64_t emul_shoup_lazy8(uint64_t x, uint64_t w, uint64_t q) {
     tw_t t = ht::mk_tw(w, q);
     return shoup_lazy8((u64)x, t, (u64)(0 - q));
 }
-// Shared-memory tile layout (ntt_tile.cuh tile_addr) for the bank-conflict check of tests/test_emul.py:
-// word index of (row r, column c) for window size E, C columns and 4- or 8-byte words; -1 = not instantiated.
-template <typename WD>
-static int tile_addr_dispatch(int e, int c_cols, int r, int c) {
-    if (e == 3 && c_cols == 4) return tile_addr<3, 5, WD>(r, c);
-    if (e == 3 && c_cols == 8) return tile_addr<3, 9, WD>(r, c);
-    if (e == 4 && c_cols == 8) return tile_addr<4, 9, WD>(r, c);
-    if (e == 4 && c_cols == 16) return tile_addr<4, 17, WD>(r, c);
+// Shared-memory tile layouts (ntt_tile.cuh tile_addr) for the bank-conflict check of tests/test_emul.py: word
+// index of (row r, column c) in ks_pass2's tile shape (E = 3, C = 4); swz = rows per 128-byte wavefront for the
+// XOR-swizzled dense layout of its digit loop, 0 for the padded layout.
+extern "C" int emul_tile_addr(int swz, int r, int c) {
+    switch (swz) {
+        case 0: return tile_addr<3, 5, 0>(r, c);
+        case 4: return tile_addr<3, 5, 4>(r, c);  // u64 words
+        case 8: return tile_addr<3, 5, 8>(r, c);  // u32 words
+    }
     return -1;
-}
-extern "C" int emul_tile_addr(int e, int c_cols, int word_bytes, int r, int c) {
-    return word_bytes == 4 ? tile_addr_dispatch<u32>(e, c_cols, r, c) : tile_addr_dispatch<u64>(e, c_cols, r, c);
 }

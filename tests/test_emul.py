@@ -106,34 +106,37 @@ def _wavefronts(addrs_bytes, size):
     return total
 
 
-@pytest.mark.parametrize("size,e,c_cols", [(8, 3, 4), (4, 3, 4), (8, 4, 8), (4, 4, 8), (4, 4, 16), (8, 4, 16), (8, 3, 8)])
-def test_tile_layout_is_conflict_free(emul, size, e, c_cols):
-    """The exchange layout of csrc/ntt_tile.cuh (tile_addr): a dense bijection, and every access pattern the
-    kernels make -- each register window of every transform size, and the transposing store's row-lane read --
-    costs the minimum number of shared-memory wavefronts (1 per warp for u32, 2 for u64).  Shapes: ks_pass2 (E=3,
-    C=4), ks_pass1 / 64-bit passes (E=4, C=8), 32-bit passes and the fused transform (E=4, C=16)."""
-    emul.emul_tile_addr.argtypes = [C.c_int] * 5
-    ideal = size // 4
-    for a in range(e + 2, 9):  # rows per tile 2^a; smaller tiles have fewer than 32 threads
+@pytest.mark.parametrize("size", [8, 4])
+def test_ks_pass2_exchange_layout_is_conflict_free(emul, size):
+    """The XOR-swizzled exchange tile of ks_pass2's digit loop (csrc/ntt_tile.cuh tile_addr, E = 3, C = 4): a
+    bijection onto the dense tile, and every register-window access of every transform size costs the minimum
+    number of shared-memory wavefronts (1 per warp for u32, 2 for u64), where the padded layout needs twice as
+    many (ncu: 2.4x / 3.3x excess wavefronts before the change).  The padded layout stays conflict-free for the
+    transposing store's row-lane read, which is why the epilogue keeps it."""
+    emul.emul_tile_addr.argtypes = [C.c_int] * 3
+    e, c_cols, ideal = 3, 4, size // 4
+    swz = 128 // (size * c_cols)
+    for a in range(6, 9):
         rows = 1 << a
-        addr = [[emul.emul_tile_addr(e, c_cols, size, r, c) for c in range(c_cols)] for r in range(rows)]
-        flat = sorted(x for row in addr for x in row)
-        assert flat == list(range(rows * c_cols)), "tile_addr must be a bijection onto the dense tile"
-        groups = 1 << (a - e)
-        nthreads = c_cols * groups
-        if nthreads < 32:
-            continue
+        addr = [[emul.emul_tile_addr(swz, r, c) for c in range(c_cols)] for r in range(rows)]
+        pad = [[emul.emul_tile_addr(0, r, c) for c in range(c_cols)] for r in range(rows)]
+        assert sorted(x for row in addr for x in row) == list(range(rows * c_cols))
+        assert len({x for row in pad for x in row}) == rows * c_cols and max(max(r) for r in pad) < rows * (c_cols + 1)
+        nthreads = c_cols << (a - e)
         ns = (a + e - 1) // e
+        worse = 0
         for lo in sorted({max(a - (t + 1) * e, 0) for t in range(ns)}):
             for w0 in range(0, nthreads, 32):
                 for k in range(1 << e):
-                    lanes = []
+                    lanes, lanes_pad = [], []
                     for tid in range(w0, w0 + 32):
                         c, g = tid % c_cols, tid // c_cols
                         r = ((g >> lo) << (lo + e)) | (k << lo) | (g & ((1 << lo) - 1))
                         lanes.append(addr[r][c] * size)
+                        lanes_pad.append(pad[r][c] * size)
                     assert _wavefronts(lanes, size) == ideal, (a, lo, w0, k)
-        if rows >= 32:
-            for e0 in range(0, c_cols << a, 32):  # transposed read: lane = consecutive rows of one column
-                lanes = [addr[x & (rows - 1)][x >> a] * size for x in range(e0, e0 + 32)]
-                assert _wavefronts(lanes, size) == ideal, (a, "transposed", e0)
+                    worse += _wavefronts(lanes_pad, size) > ideal
+        assert worse > 0  # the padded layout does conflict on these accesses
+        for e0 in range(0, c_cols << a, 32):  # transposed read on the padded layout: lane = consecutive rows of one column
+            lanes = [pad[x & (rows - 1)][x >> a] * size for x in range(e0, e0 + 32)]
+            assert _wavefronts(lanes, size) == ideal, (a, "transposed", e0)

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
         DST_T *d = dst + dbase + c0 * (size_t)(1 << A);
         for (int e = tid; e < (C << A); e += NT) {
             int cc = e >> A, r = e & ((1 << A) - 1);
-            d[e] = (DST_T)sm[tile_addr<E, CP, WD>(r, cc)];
+            d[e] = (DST_T)sm[r * CP + cc];
         }
     } else {
 #pragma unroll
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
     WD *d = dst + c0 * (size_t)(1 << A);
     for (int e = tid; e < (C << A); e += NT) {
         int cc = e >> A, r = e & ((1 << A) - 1);
-        d[e] = sm[tile_addr<E, CP, WD>(r, cc)];
+        d[e] = sm[r * CP + cc];
     }
 }
 
@@ -596,6 +596,9 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
     constexpr int NT = C * GM::G;
     constexpr int R = 1 << E;
     constexpr int TILE = (1 << A) * C;
+    // exchange tile of the digit loop: dense rows, XOR-swizzled over the rows one 128-byte wavefront covers
+    // (ntt_tile.cuh); the epilogue keeps the padded layout, whose transposed read is conflict-free
+    constexpr int SWZ = (128 / (int)(sizeof(WD) * C)) > 0 ? (128 / (int)(sizeof(WD) * C)) : 1;
     static_assert(GM::lo(GM::NS - 1) == 0, "the key tiles are addressed through the last register window");
     extern __shared__ __align__(128) unsigned char sm_raw[];
     u64 *stKb = reinterpret_cast<u64 *>(sm_raw);  // key_b tile of the current digit
@@ -688,7 +691,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
         const WD *S = stS + (t & 1) * TILE;
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = S[tile_idx<E>(g, k, lo_in) * C + c];
-        xf_tile<XF_CYC_FWD, A, E, CP, LAZY>(v, g, c, sm, W, q, q2);
+        xf_tile<XF_CYC_FWD, A, E, CP, LAZY, SWZ>(v, g, c, sm, W, q, q2);
         if (TMA) {
             mbar_wait(bars + 2, t & 1);  // keys(t) landed
         } else {
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
         WD *d = out + c0 * (size_t)(1 << A);
         for (int e = tid; e < (C << A); e += NT) {
             int cc = e >> A, r = e & ((1 << A) - 1);
-            d[e] = sm[tile_addr<E, CP, WD>(r, cc)];
+            d[e] = sm[r * CP + cc];
         }
     }
 }

@@ -122,33 +122,32 @@ __device__ __forceinline__ void cyc_inv_step(WD (&v)[1 << E], int g, const TW *_
 }
 
 // ---- shared-memory exchange between two register windows -----------------------------------------
-// Tile layout in shared memory: dense rows of C = CP - 1 words, no padding, addressed through
-//     r' = r ^ ((r >> E) & (R - 1)),   addr(r, c) = r' * C + ((c + (r' >> log2 R)) & (C - 1)),
-// R = rows one 128-byte wavefront covers (128 B / (C words)).
-//   * A register window makes the lanes of a wavefront address either R consecutive rows, rows 2^E apart, or a
-//     mix of both; the XOR swizzle sends all of these to R distinct rows-within-a-line, i.e. disjoint bank groups.
-//   * The transposing store reads consecutive rows of ONE column per lane; rotating the columns of every line
-//     by the line index spreads those over all banks too.
-// Every tile_put / tile_get / transposed read is conflict-free for u32 and u64 words, C = 4, 8, 16 and both
-// window sizes (checked exhaustively by tests/test_emul.py::test_tile_layout_is_conflict_free; ncu before:
-// 2.4x (u64) to 3.3x (u32) excess shared-memory wavefronts in ks_pass2 with the former [idx][C+1] padding).
-template <int E, int CP, typename WD>
+// Two tile layouts in shared memory:
+//   SWZ == 0: [idx][CP] words, CP = C + 1: the pad keeps the row-lane accesses of the transposing store
+//             conflict-free (kernels that end with one);
+//   SWZ == R: dense rows of C = CP - 1 words with the row index XOR-swizzled over R = 128 B / (C words) rows,
+//             r' = r ^ ((r >> E) & (R - 1)).  A wavefront (128 B) covers R rows of one register window; the
+//             windows address either R consecutive rows or rows 2^E apart (or a mix of both), and the XOR
+//             sends all of these to R distinct bank groups: every tile_put / tile_get is conflict-free (the
+//             digit loop of ks_pass2; measured with ncu: 2.4x (u64) / 3.3x (u32) excess wavefronts before).
+//             The index is no longer affine in the register number, so it costs ALU instructions instead of
+//             LDS/STS immediates: a win only where shared memory is the limiter (32-bit words); applying it
+//             to every kernel, with a column rotation that also fixes the transposed read, was measured
+//             slower on the 64-bit path (ks_pass1 +21 %) and is not used.
+template <int E, int CP, int SWZ>
 __host__ __device__ __forceinline__ int tile_addr(int r, int c) {
-    constexpr int C = CP - 1;
-    constexpr int R = (128 / (int)(sizeof(WD) * C)) > 1 ? (128 / (int)(sizeof(WD) * C)) : 1;
-    constexpr int LGR = R >= 16 ? 4 : (R >= 8 ? 3 : (R >= 4 ? 2 : (R >= 2 ? 1 : 0)));
-    const int rp = r ^ ((r >> E) & (R - 1));
-    return rp * C + ((c + (rp >> LGR)) & (C - 1));
+    if (SWZ) return ((r ^ ((r >> E) & (SWZ - 1))) * (CP - 1)) + c;
+    return r * CP + c;
 }
-template <int E, int CP, typename WD>
+template <int E, int CP, int SWZ = 0, typename WD>
 __device__ __forceinline__ void tile_put(WD *sm, const WD (&v)[1 << E], int g, int c, int lo) {
 #pragma unroll
-    for (int k = 0; k < (1 << E); ++k) sm[tile_addr<E, CP, WD>(tile_idx<E>(g, k, lo), c)] = v[k];
+    for (int k = 0; k < (1 << E); ++k) sm[tile_addr<E, CP, SWZ>(tile_idx<E>(g, k, lo), c)] = v[k];
 }
-template <int E, int CP, typename WD>
+template <int E, int CP, int SWZ = 0, typename WD>
 __device__ __forceinline__ void tile_get(const WD *sm, WD (&v)[1 << E], int g, int c, int lo) {
 #pragma unroll
-    for (int k = 0; k < (1 << E); ++k) v[k] = sm[tile_addr<E, CP, WD>(tile_idx<E>(g, k, lo), c)];
+    for (int k = 0; k < (1 << E); ++k) v[k] = sm[tile_addr<E, CP, SWZ>(tile_idx<E>(g, k, lo), c)];
 }
 
 enum { XF_NEG_FWD = 0, XF_CYC_FWD = 1, XF_CYC_INV = 2, XF_NEG_INV = 3 };
@@ -164,7 +163,7 @@ __device__ __forceinline__ void xf_step(WD (&v)[1 << E], int g, const TW *__rest
 // Full transform of the tile.  On entry the thread holds the window of the FIRST step (forward
 // kinds: step 0; inverse kinds: step NS-1); on exit it holds the window of the LAST step
 // (forward: NS-1; inverse: 0).  `sm` is the [2^A][CP] exchange buffer (unused if NS == 1).
-template <int KIND, int A, int E, int CP, int LAZY, typename WD, typename TW>
+template <int KIND, int A, int E, int CP, int LAZY, int SWZ = 0, typename WD, typename TW>
 __device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, const TW *__restrict__ tab, WD q, WD q2) {
     typedef TileGeom<A, E> GM;
     constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);
@@ -172,31 +171,31 @@ __device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, c
     if (FWD) {
         xf_step<KIND, A, E, 0, LAZY>(v, g, tab, q, q2);
         if (GM::NS >= 2) {
-            tile_put<E, CP>(sm, v, g, c, GM::lo(0));
+            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(0));
             __syncthreads();
-            tile_get<E, CP>(sm, v, g, c, GM::lo(1));
+            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(1));
             xf_step<KIND, A, E, (GM::NS >= 2 ? 1 : 0), LAZY>(v, g, tab, q, q2);
         }
         if (GM::NS >= 3) {
             __syncthreads();
-            tile_put<E, CP>(sm, v, g, c, GM::lo(1));
+            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(1));
             __syncthreads();
-            tile_get<E, CP>(sm, v, g, c, GM::lo(2));
+            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(2));
             xf_step<KIND, A, E, (GM::NS >= 3 ? 2 : 0), LAZY>(v, g, tab, q, q2);
         }
     } else {
         xf_step<KIND, A, E, GM::NS - 1, LAZY>(v, g, tab, q, q2);
         if (GM::NS >= 2) {
-            tile_put<E, CP>(sm, v, g, c, GM::lo(GM::NS - 1));
+            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(GM::NS - 1));
             __syncthreads();
-            tile_get<E, CP>(sm, v, g, c, GM::lo(GM::NS - 2));
+            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(GM::NS - 2));
             xf_step<KIND, A, E, (GM::NS >= 2 ? GM::NS - 2 : 0), LAZY>(v, g, tab, q, q2);
         }
         if (GM::NS >= 3) {
             __syncthreads();
-            tile_put<E, CP>(sm, v, g, c, GM::lo(1));
+            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(1));
             __syncthreads();
-            tile_get<E, CP>(sm, v, g, c, GM::lo(0));
+            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(0));
             xf_step<KIND, A, E, 0, LAZY>(v, g, tab, q, q2);
         }
     }
