@@ -197,13 +197,6 @@ extern "C" uint64_t emul_shoup_lazy8(uint64_t x, uint64_t w, uint64_t q) {
     return shoup_lazy8((u64)x, t, (u64)(0 - q));
 }
 // Shared-memory tile layouts (ntt_tile.cuh tile_addr) for the bank-conflict check of tests/test_emul.py: word
-// index of (row r, column c) in ks_pass2's tile shape (E = 3, C = 4); swz = rows per 128-byte wavefront for the
-// XOR-swizzled dense layout of its digit loop, 0 for the padded layout.
-extern "C" int emul_tile_addr(int swz, int r, int c) {
-    switch (swz) {
-        case 0: return tile_addr<3, 5, 0>(r, c);
-        case 4: return tile_addr<3, 5, 4>(r, c);  // u64 words
-        case 8: return tile_addr<3, 5, 8>(r, c);  // u32 words
-    }
-    return -1;
-}
+// index of (row r, column c) in ks_pass2's tile shape (E = 3, C = 4); swz = 1 for the bit-weighted layout of its
+// digit loop, 0 for the padded layout.
+extern "C" int emul_tile_addr(int swz, int r, int c) { return swz ? tile_addr<3, 5, 1>(r, c) : tile_addr<3, 5, 0>(r, c); }

@@ -108,19 +108,20 @@ def _wavefronts(addrs_bytes, size):
 
 @pytest.mark.parametrize("size", [8, 4])
 def test_ks_pass2_exchange_layout_is_conflict_free(emul, size):
-    """The XOR-swizzled exchange tile of ks_pass2's digit loop (csrc/ntt_tile.cuh tile_addr, E = 3, C = 4): a
-    bijection onto the dense tile, and every register-window access of every transform size costs the minimum
+    """The bit-weighted exchange tile of ks_pass2's digit loop (csrc/ntt_tile.cuh tile_addr, E = 3, C = 4): injective
+    within the [2^A][C+1] allocation, and every register-window access of every transform size costs the minimum
     number of shared-memory wavefronts (1 per warp for u32, 2 for u64), where the padded layout needs twice as
     many (ncu: 2.4x / 3.3x excess wavefronts before the change).  The padded layout stays conflict-free for the
     transposing store's row-lane read, which is why the epilogue keeps it."""
     emul.emul_tile_addr.argtypes = [C.c_int] * 3
     e, c_cols, ideal = 3, 4, size // 4
-    swz = 128 // (size * c_cols)
+    swz = 1
     for a in range(6, 9):
         rows = 1 << a
         addr = [[emul.emul_tile_addr(swz, r, c) for c in range(c_cols)] for r in range(rows)]
         pad = [[emul.emul_tile_addr(0, r, c) for c in range(c_cols)] for r in range(rows)]
-        assert sorted(x for row in addr for x in row) == list(range(rows * c_cols))
+        flat = [x for row in addr for x in row]
+        assert len(set(flat)) == rows * c_cols and 0 <= min(flat) and max(flat) < rows * (c_cols + 1)
         assert len({x for row in pad for x in row}) == rows * c_cols and max(max(r) for r in pad) < rows * (c_cols + 1)
         nthreads = c_cols << (a - e)
         ns = (a + e - 1) // e

@@ -596,9 +596,9 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 :
     constexpr int NT = C * GM::G;
     constexpr int R = 1 << E;
     constexpr int TILE = (1 << A) * C;
-    // exchange tile of the digit loop: dense rows, XOR-swizzled over the rows one 128-byte wavefront covers
-    // (ntt_tile.cuh); the epilogue keeps the padded layout, whose transposed read is conflict-free
-    constexpr int SWZ = (128 / (int)(sizeof(WD) * C)) > 0 ? (128 / (int)(sizeof(WD) * C)) : 1;
+    // exchange tile of the digit loop: bit-weighted conflict-free layout (ntt_tile.cuh); the epilogue keeps the
+    // padded layout, whose transposed read is conflict-free
+    constexpr int SWZ = (E == 3 && C == 4) ? 1 : 0;
     static_assert(GM::lo(GM::NS - 1) == 0, "the key tiles are addressed through the last register window");
     extern __shared__ __align__(128) unsigned char sm_raw[];
     u64 *stKb = reinterpret_cast<u64 *>(sm_raw);  // key_b tile of the current digit

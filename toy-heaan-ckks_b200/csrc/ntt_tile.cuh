@@ -124,30 +124,49 @@ __device__ __forceinline__ void cyc_inv_step(WD (&v)[1 << E], int g, const TW *_
 // ---- shared-memory exchange between two register windows -----------------------------------------
 // Two tile layouts in shared memory:
 //   SWZ == 0: [idx][CP] words, CP = C + 1: the pad keeps the row-lane accesses of the transposing store
-//             conflict-free (kernels that end with one);
-//   SWZ == R: dense rows of C = CP - 1 words with the row index XOR-swizzled over R = 128 B / (C words) rows,
-//             r' = r ^ ((r >> E) & (R - 1)).  A wavefront (128 B) covers R rows of one register window; the
-//             windows address either R consecutive rows or rows 2^E apart (or a mix of both), and the XOR
-//             sends all of these to R distinct bank groups: every tile_put / tile_get is conflict-free (the
-//             digit loop of ks_pass2; measured with ncu: 2.4x (u64) / 3.3x (u32) excess wavefronts before).
-//             The index is no longer affine in the register number, so it costs ALU instructions instead of
-//             LDS/STS immediates: a win only where shared memory is the limiter (32-bit words); applying it
-//             to every kernel, with a column rotation that also fixes the transposed read, was measured
-//             slower on the 64-bit path (ks_pass1 +21 %) and is not used.
+//             conflict-free (kernels that end with one); the register windows pay up to 2x wavefronts.
+//   SWZ != 0: bit-weighted rows for ks_pass2's tile shape (E = 3, C = 4): addr(r, c) = sum_b w_b * bit_b(r) + c
+//             with w = {4, 8, 16, 36, 72, 144, 288, 576}.  A wavefront covers 4 (u64) or 8 (u32) thread groups
+//             of one register window, whose rows differ in bits {0,1,2}, {3,4,5} or {0,4,5}/{0,1,5} of r; the
+//             weights of each such set are {4, 8, 16} modulo the 32 banks, so every tile_put / tile_get is
+//             conflict-free for both word sizes, and the tile still fits the [2^A][C+1] allocation.  Because the
+//             address is a SUM over the bits of r, the thread part (g) is computed once per window and the
+//             register part (k, a compile-time constant after unrolling) folds into the LDS/STS immediate:
+//             no extra instructions.  (An XOR swizzle is conflict-free too but is not affine in k; applied to
+//             every kernel, with a column rotation for the transposed read, it was measured SLOWER on the
+//             64-bit path -- ks_pass1 +21 % -- because these kernels are issue-bound, not shared-memory-bound.)
+//             ncu before: 2.4x (u64) / 3.3x (u32) excess shared-memory wavefronts in ks_pass2.
+__host__ __device__ constexpr int tile_waddr(int r) {
+    return 4 * (r & 1) + 8 * ((r >> 1) & 1) + 16 * ((r >> 2) & 1) + 36 * ((r >> 3) & 1) + 72 * ((r >> 4) & 1) + 144 * ((r >> 5) & 1) +
+           288 * ((r >> 6) & 1) + 576 * ((r >> 7) & 1);
+}
 template <int E, int CP, int SWZ>
 __host__ __device__ __forceinline__ int tile_addr(int r, int c) {
-    if (SWZ) return ((r ^ ((r >> E) & (SWZ - 1))) * (CP - 1)) + c;
+    static_assert(SWZ == 0 || (E == 3 && CP == 5), "the bit-weighted layout is built for E = 3, C = 4");
+    if (SWZ) return tile_waddr(r) + c;
     return r * CP + c;
 }
 template <int E, int CP, int SWZ = 0, typename WD>
 __device__ __forceinline__ void tile_put(WD *sm, const WD (&v)[1 << E], int g, int c, int lo) {
+    if (SWZ) {
+        const int base = tile_waddr(tile_idx<E>(g, 0, lo)) + c;  // thread part; the k part below is a constant
 #pragma unroll
-    for (int k = 0; k < (1 << E); ++k) sm[tile_addr<E, CP, SWZ>(tile_idx<E>(g, k, lo), c)] = v[k];
+        for (int k = 0; k < (1 << E); ++k) sm[base + tile_waddr(k << lo)] = v[k];
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << E); ++k) sm[tile_idx<E>(g, k, lo) * CP + c] = v[k];
 }
 template <int E, int CP, int SWZ = 0, typename WD>
 __device__ __forceinline__ void tile_get(const WD *sm, WD (&v)[1 << E], int g, int c, int lo) {
+    if (SWZ) {
+        const int base = tile_waddr(tile_idx<E>(g, 0, lo)) + c;
 #pragma unroll
-    for (int k = 0; k < (1 << E); ++k) v[k] = sm[tile_addr<E, CP, SWZ>(tile_idx<E>(g, k, lo), c)];
+        for (int k = 0; k < (1 << E); ++k) v[k] = sm[base + tile_waddr(k << lo)];
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << E); ++k) v[k] = sm[tile_idx<E>(g, k, lo) * CP + c];
 }
 
 enum { XF_NEG_FWD = 0, XF_CYC_FWD = 1, XF_CYC_INV = 2, XF_NEG_INV = 3 };
