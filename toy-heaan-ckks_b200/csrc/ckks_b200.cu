@@ -1124,10 +1124,16 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
 }
 
 // ---- fused four-step key-switch pipeline -----------------------------------------------------------
-constexpr int KS_C1 = 8;
+// ks_pass1 column tile: 8 for 64-bit words (integer-pipe bound: more, smaller CTAs), 16 for 32-bit words (its
+// u64 digit loads and the per-element twiddles are L1-bound there: 128-byte row segments instead of 64)
+template <typename WD>
+constexpr int ks_c1() {
+    return sizeof(WD) == 8 ? 8 : 16;
+}
 template <typename WD, int A>
 static int launch_ks1_w(int lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
-    constexpr int E = 4, C = KS_C1;
+    constexpr int E = 4, C = ks_c1<WD>();
+    grid.x /= C;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
 #define KS1(LZ, RD, DG) KL("ks_pass1", (ks_pass1_kernel<WD, A, E, C, LZ, RD, DG><<<grid, block, smem, s>>>(a)))
@@ -1295,7 +1301,7 @@ static int ks_fused_ex(const Tables &T, size_t L, const KsShard &sh, size_t cs, 
     const size_t Ld = sh.Ld;
     const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
     cudaStream_t s = T.stream;
-    dim3 g1(n2 / KS_C1, (unsigned)(L * Ld), (unsigned)cs);
+    dim3 g1(n2, (unsigned)(L * Ld), (unsigned)cs);  // x: columns; the launcher divides by its column tile
     DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.w32, T.lazy, sh.reduce, mul, g1, s, a)));
     dim3 g2((unsigned)cs, n1 / KS_C2, (unsigned)L);
     // TMA descriptors: (rho, j2 / gamma, slab) tensors with a [n2][16] box
