@@ -403,7 +403,8 @@ def run_b200(args):
             "peak": hbm_peak,
             "unit": "GB/s",
             "frac": (ach / hbm_peak if ach else None),
-            "traffic": TRAFFIC_NCU.get(name),
+            # the ncu capture was taken at cfg4 with 14 ciphertexts per launch (the default chunk): null elsewhere
+            "traffic": TRAFFIC_NCU.get(name) if (args.config == "cfg4" and op == "mul" and batch >= 14) else None,
             "peak_kind": peak_kind,
             "share_of_step": ms / tot,
             "avg_launch_ms": ms / cnt,

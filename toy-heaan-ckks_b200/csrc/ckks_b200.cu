@@ -1429,6 +1429,72 @@ static int fused_keyswitch(const Tables &T, size_t L, size_t batch, const u64 *c
     return rc;
 }
 
+// Last inverse pass with automorphism(rot_src) added on the fly (ntt_pass_kernel<..., ADDROT>).
+template <typename WD, int A>
+static int launch_inv1_addrot_w(int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+    constexpr int E = 4, C = pass_c<WD>();
+    grid.x = a.ncols / C;
+    const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
+    const int block = C << (A - E);
+#define M(LZ) \
+    KL("ntt_inv_pass1_addrot", (ntt_pass_kernel<WD, XF_NEG_INV, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), false, false, false, false, true><<<grid, block, smem, s>>>(a)))
+    LZ_SWITCH(WD, lazy, M);
+#undef M
+    return CKKS_OK;
+}
+template <int A>
+static int launch_inv1_addrot_a(bool w32, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
+    if (w32) return launch_inv1_addrot_w<u32, A>(lazy, grid, s, a);
+    return launch_inv1_addrot_w<u64, A>(lazy, grid, s, a);
+}
+
+// rotate_ciphertext (engine.rs:412-463) on coefficient-domain device inputs, four-step path, net Galois exponent
+// `e` (odd).  Only the rotated c1 is materialised (it is the digit polynomial); automorphism(c0) is gathered
+// inside the last inverse pass of ks0, so c0 is read once and nothing else of the c0 path touches HBM.
+static int fused_rotate(const Tables &T, size_t L, size_t batch, const u64 *c0, const u64 *c1, u64 e, const ckks_ksk *key, u64 *o0,
+                        u64 *o1) {
+    if (!batch) return CKKS_OK;
+    const size_t n = T.n, cs_max = ks_chunk(T, L, batch);
+    const u64 einv = inv_mod_pow2(e, 2 * n);
+    u64 *D = nullptr, *T0 = nullptr, *T1 = nullptr, *SCR = nullptr;
+    int rc = dev_alloc(T, cs_max * L * n, &D);
+    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * n, &T0);
+    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * n, &T1);
+    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * L * n, &SCR);
+    for (size_t s0 = 0; s0 < batch && rc == CKKS_OK; s0 += cs_max) {
+        const size_t cs = batch - s0 < cs_max ? batch - s0 : cs_max;
+        const size_t off = s0 * L * n;
+        auto step = [&]() -> int {
+            EwArgs ea = ew_args(T, L, cs);
+            KL("automorphism", (automorphism_kernel<<<ew_grid(ea.total), 256, 0, T.stream>>>(ea, c1 + off, D, e, einv)));
+            TRY(ks_fused(T, L, cs, D, nullptr, key, nullptr, nullptr, SCR, T0, T1, false));
+            TRY(run_pass(T, P_INV1, whole(cs, L), T1, o1 + off));
+            PassArgs a;
+            memset(&a, 0, sizeof(a));
+            a.lc = T.d_lc;
+            a.L = (int)L;
+            a.N = n;
+            a.dstL = (int)L;
+            a.src = T0;
+            a.dst = o0 + off;
+            a.tab = T.d_P1i;
+            a.tab_stride = (size_t)1 << T.a1;
+            a.ncols = 1u << T.a2;
+            a.rot_src = c0 + off;
+            a.rot_einv = einv;
+            dim3 g(1, (unsigned)L, (unsigned)cs);
+            DISPATCH_A(T.a1, TRY(launch_inv1_addrot_a<AA>(T.w32, T.lazy, g, T.stream, a)));
+            return CKKS_OK;
+        };
+        rc = step();
+    }
+    dev_free(T, D);
+    dev_free(T, T0);
+    dev_free(T, T1);
+    dev_free(T, SCR);
+    return rc;
+}
+
 static int check_ct(const ckks_poly *c0, const ckks_poly *c1) {
     if (!ok_poly(c0) || !ok_poly(c1)) return CKKS_BAD_HANDLE;
     if (!same_basis(c0->ctx, c1->ctx)) return CKKS_BASIS_MISMATCH;
@@ -1589,6 +1655,23 @@ extern "C" int ckks_ct_rotate(const ckks_poly *c0, const ckks_poly *c1, const ck
     const Tables &T = *c0->ctx->T;
     const size_t L = c0->ctx->L, batch = c0->batch;
     CU(cudaSetDevice(T.device));
+    if (T.path == 2 && !g_force_unfused && !c0->ntt) {
+        // net exponent of rotate_slots (poly.rs:546-569): 5^|k|, times 2N-1 for k < 0 (two odd automorphisms compose)
+        const u64 two_n = 2 * T.n;
+        u64 e = rot_exponent(T.n, k);
+        if (k < 0) e = (e * (two_n - 1)) % two_n;
+        ckks_poly *f0 = nullptr, *f1 = nullptr;
+        int frc = poly_new(c0->ctx, batch, false, &f0);
+        if (frc == CKKS_OK) frc = poly_new(c0->ctx, batch, false, &f1);
+        if (frc == CKKS_OK) frc = fused_rotate(T, L, batch, c0->d, c1->d, e, rotk, f0->d, f1->d);
+        if (frc != CKKS_OK) {
+            free2(f0, f1);
+            return frc;
+        }
+        *o0 = f0;
+        *o1 = f1;
+        return CKKS_OK;
+    }
     ckks_poly *r0 = nullptr, *r1 = nullptr, *k0 = nullptr, *k1 = nullptr;
     int rc = ckks_poly_rotate_slots(c0, k, &r0);  // engine.rs:417-419
     if (rc == CKKS_OK) rc = ckks_poly_rotate_slots(c1, k, &r1);
@@ -1758,11 +1841,6 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
     }
     HostPipe &hp = *TM.pipe;
     const u64 e1 = rot >= 0 ? rot_exponent(n, rot) : (rot_exponent(n, rot) * (2 * n - 1)) % (2 * n);
-    u64 *rot0 = nullptr, *rot1 = nullptr;
-    if (rc == CKKS_OK && kind == 1) {
-        rc = dev_alloc(T, chunk * wi, &rot0);
-        if (rc == CKKS_OK) rc = dev_alloc(T, chunk * wi, &rot1);
-    }
     size_t c = 0;
     for (size_t s = 0; s < batch && rc == CKKS_OK; s += chunk, ++c) {
         const size_t nb = batch - s < chunk ? batch - s : chunk;
@@ -1777,13 +1855,9 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
             if (kind == 0) {
                 TRY(fused_mul_relin(T, L, nb, hp.in[b][0], hp.in[b][1], hp.in[b][2], hp.in[b][3], key, true, hp.out[b][0], hp.out[b][1]));
             } else {
-                // rotate_ciphertext (engine.rs:412-463): signed permutation of both components, key-switch of c1
-                EwArgs ea = ew_args(T, L, nb);
-                const u64 einv = inv_mod_pow2(e1, 2 * n);
-                KL("automorphism", (automorphism_kernel<<<ew_grid(ea.total), 256, 0, T.stream>>>(ea, hp.in[b][0], rot0, e1, einv)));
-                KL("automorphism", (automorphism_kernel<<<ew_grid(ea.total), 256, 0, T.stream>>>(ea, hp.in[b][1], rot1, e1, einv)));
-                TRY(fused_keyswitch(T, L, nb, rot1, key, hp.out[b][0], hp.out[b][1]));
-                KL("ew_add", (ew_binary_kernel<EW_ADD><<<ew_grid(ea.total), 256, 0, T.stream>>>(ea, hp.out[b][0], rot0, ea.poly)));
+                // rotate_ciphertext (engine.rs:412-463): key-switch of the rotated c1, automorphism(c0) gathered in
+                // the last inverse pass
+                TRY(fused_rotate(T, L, nb, hp.in[b][0], hp.in[b][1], e1, key, hp.out[b][0], hp.out[b][1]));
             }
             CU(cudaEventRecord(hp.comp_done[b], T.stream));
             CU(cudaStreamWaitEvent(hp.s_out, hp.comp_done[b], 0));
@@ -1797,8 +1871,6 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
     cudaStreamSynchronize(hp.s_in);
     if (cudaStreamSynchronize(T.stream) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
     if (cudaStreamSynchronize(hp.s_out) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
-    dev_free(T, rot0);
-    dev_free(T, rot1);
     if (rc != CKKS_OK) {  // do not keep a pipeline whose events may be in an unknown state
         destroy_host_pipe(TM.pipe);
         TM.pipe = nullptr;

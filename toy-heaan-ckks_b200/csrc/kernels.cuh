@@ -31,6 +31,10 @@ struct PassArgs {
     int npeer, m_first;
     int m_off, m_step;
     size_t m_cs;
+    // ADDROT (rotate_ciphertext, engine.rs:417-419 + :454): the finished coefficient-domain word at position p gets
+    // automorphism(rot_src)[p] added, gathered on the fly: +-rot_src[p * rot_einv mod 2N] (poly.rs:515-538).
+    const u64 *rot_src;  // [batch][L][N] coefficient domain
+    u64 rot_einv;        // inverse of the (odd) Galois exponent modulo 2N
 };
 
 // One pass: a 2^A-point transform along the strided dimension of a [2^A][ncols] limb, for a tile of
@@ -43,7 +47,7 @@ struct PassArgs {
 // Inverse  to_coeff_domain(poly.rs:154-166, 582-591) = <CYC_INV,POSTMUL,TRANSPOSE> then <NEG_INV>.
 // WD = u64 (any q < 2^63) or u32 (all q < 2^31: 32-bit butterflies, 32-bit internal scratch; the words
 // that cross the boundary stay u64).
-template <typename WD, int KIND, int A, int E, int C, int LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE, bool MULTI = false>
+template <typename WD, int KIND, int A, int E, int C, int LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE, bool MULTI = false, bool ADDROT = false>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a) {
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
@@ -103,6 +107,14 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
             WD x = v[k];
             if (POSTMUL || !CT_RANGE) x = canon2<LAZY>(x, q);
             else x = canon4<LAZY>(x, q, q2);
+            if (ADDROT) {
+                u64 sidx = ((u64)off * a.rot_einv) & (2 * a.N - 1);
+                const bool neg = sidx >= a.N;  // then the source coefficient lands on p + N: negated
+                if (neg) sidx -= a.N;
+                WD y = (WD)a.rot_src[base + sidx];
+                if (neg && y) y = q - y;
+                x = csub((WD)(x + y), q);
+            }
             if (MULTI) {
                 // all-gather fused into the producing pass: plain stores into own and peer HBM
                 // (each GPU starts with a different peer so that no destination is hit by everyone at once)
