@@ -600,8 +600,14 @@ __host__ __device__ constexpr size_t ks2_smem_bytes() {
 struct KsMaps {
     alignas(64) unsigned char scratch[128], key_b[128], key_a[128];  // CUtensorMap images
 };
+// Resident CTAs per SM the compiler must leave room for: 64-bit words need 128 registers (128-bit accumulators);
+// 32-bit words need about 80, so three times as many CTAs fit and hide the barriers of the digit loop.
+template <typename WD, int NT, int C>
+__host__ __device__ constexpr int ks2_min_ctas() {
+    return sizeof(WD) == 8 ? (C <= 4 ? 4 : (C <= 8 ? 2 : 1)) : (768 / NT > 16 ? 16 : (768 / NT < 1 ? 1 : 768 / NT));
+}
 template <typename WD, int A, int E, int C, int LAZY, bool ADD, bool DIAG, bool TMA>
-__global__ void __launch_bounds__(C *(1 << (A - E)), (C <= 4 ? 4 : (C <= 8 ? 2 : 1))) ks_pass2_kernel(KsArgs a, const __grid_constant__ KsMaps maps) {
+__global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (A - E)), C>()) ks_pass2_kernel(KsArgs a, const __grid_constant__ KsMaps maps) {
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
     constexpr int CP = C + 1;
