@@ -977,6 +977,7 @@ static int ksk_new(ckks_ctx *ctx, ckks_ksk **out, size_t digits = 0) {
     k->b = b;
     k->digits = digits;
     k->perm_e = -1;
+    k->k32 = false;
     *out = k;
     return CKKS_OK;
 }
@@ -991,7 +992,8 @@ extern "C" int ckks_ksk_free(ckks_ksk *k) {
     ctx_unref(c);
     return CKKS_OK;
 }
-// Four-step path: store the transformed key with the rows of every limb in ks_pass2's order (perm_row).
+// Four-step path: store the transformed key with the rows of every limb in ks_pass2's order (perm_row) and in
+// the transform word type (u32 words on the 32-bit path: the key is the largest stream ks_pass2 stages).
 static int ksk_finalize(const Tables &T, ckks_ksk *k) {
     if (T.path != 2 || T.a2 <= KS_E2) return CKKS_OK;
     const size_t words = k->digits * k->ctx->L * T.n;
@@ -999,12 +1001,18 @@ static int ksk_finalize(const Tables &T, ckks_ksk *k) {
     u64 *tmp = nullptr;
     TRY(dev_alloc(T, words, &tmp));
     for (u64 *p : {k->a, k->b}) {
-        KLV("key_permute", (key_permute_kernel<<<ew_grid(words), 256, 0, T.stream>>>(p, tmp, words, T.logn, T.a1, T.a2, KS_E2)));
-        cudaMemcpyAsync(p, tmp, words * 8, cudaMemcpyDeviceToDevice, T.stream);
+        if (T.w32) {
+            KLV("key_permute", (key_permute_kernel<u32><<<ew_grid(words), 256, 0, T.stream>>>(p, reinterpret_cast<u32 *>(tmp), words, T.logn, T.a1, T.a2, KS_E2)));
+            cudaMemcpyAsync(p, tmp, words * 4, cudaMemcpyDeviceToDevice, T.stream);
+        } else {
+            KLV("key_permute", (key_permute_kernel<u64><<<ew_grid(words), 256, 0, T.stream>>>(p, tmp, words, T.logn, T.a1, T.a2, KS_E2)));
+            cudaMemcpyAsync(p, tmp, words * 8, cudaMemcpyDeviceToDevice, T.stream);
+        }
     }
     dev_free(T, tmp);
     if (cudaPeekAtLastError() != cudaSuccess) return cuda_fail(cudaGetLastError(), "key_permute");
     k->perm_e = KS_E2;
+    k->k32 = T.w32;
     return CKKS_OK;
 }
 extern "C" int ckks_ksk_upload(ckks_ctx *ctx, const uint64_t *a, const uint64_t *b, ckks_ksk **out) {
@@ -1115,7 +1123,9 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
         KLV("digit_broadcast", (digit_broadcast_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, digits, alpha, (int)i)));
         rc = ntt_run(T, L, batch, alpha, tmp, false);
         if (rc != CKKS_OK) break;
-        KLV("ks_mac", (ks_mac_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, alpha, key->b + i * e.poly, key->a + i * e.poly, acc0, acc1, T.a1, T.a2, key->perm_e)));
+        KLV("ks_mac", (ks_mac_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, alpha, key->k32 ? (const void *)((const u32 *)key->b + i * e.poly) : (const void *)(key->b + i * e.poly),
+                                                                                   key->k32 ? (const void *)((const u32 *)key->a + i * e.poly) : (const void *)(key->a + i * e.poly), acc0, acc1, T.a1,
+                                                                                   T.a2, key->perm_e, key->k32 ? 1 : 0)));
         if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "keyswitch");
     }
     dev_free(T, alpha);
@@ -1267,7 +1277,7 @@ struct KsShard {
 };
 static int ks_fused_ex(const Tables &T, size_t L, const KsShard &sh, size_t cs, const u64 *digits, const u64 *dig_ntt,
                        const ckks_ksk *key, const u64 *add0, const u64 *add1, u64 *scratch, u64 *out0t, u64 *out1t, bool mul) {
-    if (key->perm_e != KS_E2) {
+    if (key->perm_e != KS_E2 || key->k32 != T.w32) {
         g_err = "gadget key is not in the fused key-switch layout";
         return CKKS_BAD_HANDLE;
     }
@@ -1309,8 +1319,8 @@ static int ks_fused_ex(const Tables &T, size_t L, const KsShard &sh, size_t cs, 
     memset(&maps, 0, sizeof(maps));
     bool tma = g_use_tma && n1 >= (unsigned)KS_C2;
     tma = tma && make_tile_map(maps.scratch, scratch, T.w32 ? 4 : 8, n1, n2, cs * L * Ld, KS_C2);
-    tma = tma && make_tile_map(maps.key_b, key->b, 8, n1, n2, Ld * L, KS_C2);
-    tma = tma && make_tile_map(maps.key_a, key->a, 8, n1, n2, Ld * L, KS_C2);
+    tma = tma && make_tile_map(maps.key_b, key->b, T.w32 ? 4 : 8, n1, n2, Ld * L, KS_C2);
+    tma = tma && make_tile_map(maps.key_a, key->a, T.w32 ? 4 : 8, n1, n2, Ld * L, KS_C2);
     DISPATCH_A(T.a2, TRY(launch_ks2_a<AA>(T.w32, T.lazy, mul, tma, g2, s, a, maps)));
     return CKKS_OK;
 }

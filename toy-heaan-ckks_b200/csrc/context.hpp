@@ -60,6 +60,7 @@ struct ckks_ksk {
     u64 *a, *b;  // [digit][limb][N], NTT domain, device-internal order
     size_t digits;  // == ctx->L, except for a limb-sharded key slice (all digits x this GPU's limbs)
     int perm_e;     // >= 0: rows of every limb stored permuted for ks_pass2 (kernels.cuh perm_row), -1: natural
+    bool k32;       // words are u32 (32-bit word path: half the key bytes in HBM, L2 and shared memory)
 };
 
 enum : uint32_t { MAGIC_CTX = 0x434b4358u, MAGIC_POLY = 0x434b504cu, MAGIC_KSK = 0x434b4b53u, MAGIC_LSHARD = 0x434b4c53u };

@@ -360,17 +360,18 @@ __host__ __device__ __forceinline__ size_t perm_row(size_t row, int a2, int pe) 
     if (pe < 0 || a2 <= pe) return row;
     return ((row & (((size_t)1 << pe) - 1)) << (a2 - pe)) | (row >> pe);
 }
-__global__ void key_permute_kernel(const u64 *__restrict__ src, u64 *__restrict__ dst, size_t total, int logn, int a1, int a2, int pe) {
+template <typename KT>
+__global__ void key_permute_kernel(const u64 *__restrict__ src, KT *__restrict__ dst, size_t total, int logn, int a1, int a2, int pe) {
     const size_t n = (size_t)1 << logn;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t k = i & (n - 1), row = k >> a1, col = k & (((size_t)1 << a1) - 1);
-        dst[i - k + (perm_row(row, a2, pe) << a1) + col] = src[i];
+        dst[i - k + (perm_row(row, a2, pe) << a1) + col] = (KT)src[i];
     }
 }
 // acc0 += x * kb, acc1 += x * ka (all NTT domain); kb/ka: one digit's key polynomial [L][N] (rows permuted
 // when pe >= 0).
-__global__ void ks_mac_kernel(EwArgs a, const u64 *__restrict__ x, const u64 *__restrict__ kb,
-                              const u64 *__restrict__ ka, u64 *__restrict__ acc0, u64 *__restrict__ acc1, int a1, int a2, int pe) {
+__global__ void ks_mac_kernel(EwArgs a, const u64 *__restrict__ x, const void *__restrict__ kb_, const void *__restrict__ ka_,
+                              u64 *__restrict__ acc0, u64 *__restrict__ acc1, int a1, int a2, int pe, int k32) {
     const size_t n = (size_t)1 << a.logn;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
         const LimbConst &m = a.lc[ew_limb(a, i)];
@@ -380,8 +381,10 @@ __global__ void ks_mac_kernel(EwArgs a, const u64 *__restrict__ x, const u64 *__
             r = r - k + (perm_row(k >> a1, a2, pe) << a1) + (k & (((size_t)1 << a1) - 1));
         }
         u64 xx = x[i];
-        acc0[i] = mulmod_add(xx, __ldg(kb + r), acc0[i], m);
-        acc1[i] = mulmod_add(xx, __ldg(ka + r), acc1[i], m);
+        const u64 kbv = k32 ? (u64)__ldg(reinterpret_cast<const u32 *>(kb_) + r) : __ldg(reinterpret_cast<const u64 *>(kb_) + r);
+        const u64 kav = k32 ? (u64)__ldg(reinterpret_cast<const u32 *>(ka_) + r) : __ldg(reinterpret_cast<const u64 *>(ka_) + r);
+        acc0[i] = mulmod_add(xx, kbv, acc0[i], m);
+        acc1[i] = mulmod_add(xx, kav, acc1[i], m);
     }
 }
 
@@ -422,7 +425,7 @@ struct KsArgs {
     const u64 *digits;   // [cts][L][N] coefficient domain (d2 or the rotated c1)
     const u64 *dig_ntt;  // [cts][L][N] NTT domain of the same polynomial (digit i == j shortcut)
     void *scratch;       // [cts][L(j)][L(i)][N] transposed pass-1 output, internal word type WD
-    const u64 *key_b, *key_a;  // [L(i)][L(j)][N] NTT domain
+    const void *key_b, *key_a;  // [L(i)][L(j)][N] NTT domain, words of the transform type (u32 on the 32-bit path)
     const u64 *add0, *add1;    // [cts][L][N] NTT domain addends (d0, d1) or null
     void *out0, *out1;         // [cts][L][N] transposed inverse-pass-2 output, internal word type WD
     const LimbConst *lc;
@@ -583,16 +586,16 @@ template <>
 struct KsAcc<u32> {
     u64 s;
     __device__ __forceinline__ void clear() { s = 0; }
-    __device__ __forceinline__ void mac(u32 x, u64 k) { s += (u64)x * (u32)k; }
+    __device__ __forceinline__ void mac(u32 x, u32 k) { s += (u64)x * k; }
     __device__ __forceinline__ u32 reduce(const LimbConst &m) const { return (u32)barrett_word(s, m); }
     __device__ __forceinline__ void set(u32 r) { s = r; }
 };
 
-// Shared memory of ks_pass2 in bytes: two stages of the digit tile (WD), key_b and key_a tiles (u64),
+// Shared memory of ks_pass2 in bytes: two stages of the digit tile (WD), key_b and key_a tiles (WD),
 // exchange tile [2^A][C+1] (WD).
 template <typename WD, int A, int C>
 __host__ __device__ constexpr size_t ks2_smem_bytes() {
-    return (size_t)(1 << A) * C * (2 * sizeof(WD) + 2 * sizeof(u64)) + (((size_t)(1 << A) * (C + 1) * sizeof(WD) + 15) / 16) * 16 + 64;
+    return (size_t)(1 << A) * C * (2 * sizeof(WD) + 2 * sizeof(WD)) + (((size_t)(1 << A) * (C + 1) * sizeof(WD) + 15) / 16) * 16 + 64;
 }
 
 // TMA = true: the digit tile and the two key tiles are fetched by the copy engine
@@ -619,8 +622,9 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
     constexpr int SWZ = (E == 3 && C == 4) ? 1 : 0;
     static_assert(GM::lo(GM::NS - 1) == 0, "the key tiles are addressed through the last register window");
     extern __shared__ __align__(128) unsigned char sm_raw[];
-    u64 *stKb = reinterpret_cast<u64 *>(sm_raw);  // key_b tile of the current digit
-    u64 *stKa = stKb + TILE;                      // key_a tile
+    // (the resident key holds words of the transform type: u32 on the 32-bit path, see ksk_finalize)
+    WD *stKb = reinterpret_cast<WD *>(sm_raw);  // key_b tile of the current digit
+    WD *stKa = stKb + TILE;                     // key_a tile
     WD *stS = reinterpret_cast<WD *>(stKa + TILE);  // 2 stages of the digit's pass-1 output
     WD *sm = stS + 2 * TILE;                        // exchange buffer
     u64 *bars = reinterpret_cast<u64 *>(sm_raw + ks2_smem_bytes<WD, A, C>() - 64);  // [0,1]: digit stages, [2]: keys
@@ -641,8 +645,8 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
     const int nd = DIAG ? Ld - 1 : Ld;  // digits that need a transform
     auto digit_of = [&](int t) { return (DIAG && t >= jg) ? t + 1 : t; };
     const WD *scr = reinterpret_cast<const WD *>(a.scratch) + (ct * L + j) * (size_t)Ld * a.N + c0;
-    const u64 *kbase_b = a.key_b + (size_t)j * a.N + c0;
-    const u64 *kbase_a = a.key_a + (size_t)j * a.N + c0;
+    const WD *kbase_b = reinterpret_cast<const WD *>(a.key_b) + (size_t)j * a.N + c0;
+    const WD *kbase_a = reinterpret_cast<const WD *>(a.key_a) + (size_t)j * a.N + c0;
     const size_t kstride = (size_t)L * a.N;
 
     KsAcc<WD> acc0[R], acc1[R];
@@ -673,7 +677,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
     // read consecutive words instead of rows 2^E apart.
     if (DIAG) {  // digit i == j: the NTT-domain limb itself
         const u64 *src = a.dig_ntt + (ct * L + j) * a.N + c0 + c;
-        const u64 *kb = kbase_b + (size_t)jg * kstride + c, *ka = kbase_a + (size_t)jg * kstride + c;
+        const WD *kb = kbase_b + (size_t)jg * kstride + c, *ka = kbase_a + (size_t)jg * kstride + c;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             size_t off = (size_t)tile_idx<E>(g, k, lo_out) * ncols;
@@ -693,7 +697,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
                     mbar_expect_tx(bars + ((t + 1) & 1), TILE * sizeof(WD));
                     tma_load_tile(stS + ((t + 1) & 1) * TILE, maps.scratch, (int)c0, slab0 + digit_of(t + 1), bars + ((t + 1) & 1));
                 }
-                mbar_expect_tx(bars + 2, 2 * TILE * sizeof(u64));
+                mbar_expect_tx(bars + 2, 2 * TILE * sizeof(WD));
                 tma_load_tile(stKb, maps.key_b, (int)c0, i * L + j, bars + 2);
                 tma_load_tile(stKa, maps.key_a, (int)c0, i * L + j, bars + 2);
             }
@@ -701,8 +705,8 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
             cp_async_wait_all();
             __syncthreads();  // scratch(t) landed for everyone; MAC(t-1) finished reading the key stage
             if (t + 1 < nd) stage_tile<WD, A, C, NT>(stS + ((t + 1) & 1) * TILE, scr + (size_t)digit_of(t + 1) * a.N, ncols, tid);
-            stage_tile<u64, A, C, NT>(stKb, kbase_b + (size_t)i * kstride, ncols, tid);
-            stage_tile<u64, A, C, NT>(stKa, kbase_a + (size_t)i * kstride, ncols, tid);
+            stage_tile<WD, A, C, NT>(stKb, kbase_b + (size_t)i * kstride, ncols, tid);
+            stage_tile<WD, A, C, NT>(stKa, kbase_a + (size_t)i * kstride, ncols, tid);
             cp_async_commit();
         }
         WD v[R];
