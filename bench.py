@@ -683,7 +683,7 @@ KERNEL_BYTES = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at cfg4, from the
 # committed `ncu --set full` capture (profiles/); None until measured.
-TRAFFIC_NCU = {"ks_pass2_tma": 5243547000 + 471124000}  # profiles/r01_ncu_full_ks_kernels_final.json (14 ciphertexts per launch)
+TRAFFIC_NCU = {"ks_pass2_tma": 5229823000 + 370285000}  # profiles/r01_ncu_full_ks_kernels_final.json (14 ciphertexts per launch)
 
 
 def main():
