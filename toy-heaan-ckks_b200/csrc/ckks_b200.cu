@@ -1276,7 +1276,10 @@ struct KsShard {
     bool reduce;      // digits need `% q_j` before entering the lazy transform
 };
 static int ks_fused_ex(const Tables &T, size_t L, const KsShard &sh, size_t cs, const u64 *digits, const u64 *dig_ntt,
-                       const ckks_ksk *key, const u64 *add0, const u64 *add1, u64 *scratch, u64 *out0t, u64 *out1t, bool mul) {
+                       const ckks_ksk *key, const u64 *add0, const u64 *add1, u64 *scratch, u64 *out0t, u64 *out1t, bool mul,
+                       size_t j0 = 0, size_t nj = ~(size_t)0) {
+    if (nj == ~(size_t)0) nj = L - j0;  // target limbs j0 .. j0+nj-1 (all of them by default)
+    if (nj == 0) return CKKS_OK;
     if (key->perm_e != KS_E2 || key->k32 != T.w32) {
         g_err = "gadget key is not in the fused key-switch layout";
         return CKKS_BAD_HANDLE;
@@ -1302,6 +1305,7 @@ static int ks_fused_ex(const Tables &T, size_t L, const KsShard &sh, size_t cs, 
     a.Ld = (int)sh.Ld;
     a.joff = sh.joff;
     a.jstep = sh.jstep;
+    a.j0 = (int)j0;
     a.dig_ct_stride = sh.dig_ct_stride;
     a.dig_limb_stride = sh.dig_limb_stride;
     a.a1 = T.a1;
@@ -1311,9 +1315,9 @@ static int ks_fused_ex(const Tables &T, size_t L, const KsShard &sh, size_t cs, 
     const size_t Ld = sh.Ld;
     const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
     cudaStream_t s = T.stream;
-    dim3 g1(n2, (unsigned)(L * Ld), (unsigned)cs);  // x: columns; the launcher divides by its column tile
+    dim3 g1(n2, (unsigned)(nj * Ld), (unsigned)cs);  // x: columns; the launcher divides by its column tile
     DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.w32, T.lazy, sh.reduce, mul, g1, s, a)));
-    dim3 g2((unsigned)cs, n1 / KS_C2, (unsigned)L);
+    dim3 g2((unsigned)cs, n1 / KS_C2, (unsigned)nj);
     // TMA descriptors: (rho, j2 / gamma, slab) tensors with a [n2][16] box
     KsMaps maps;
     memset(&maps, 0, sizeof(maps));

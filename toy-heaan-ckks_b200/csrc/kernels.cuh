@@ -434,6 +434,7 @@ struct KsArgs {
     int L;   // target limbs held here (all of them, or this GPU's share in limb-sharded mode)
     int Ld;  // digits = limbs of the whole basis (== L unless limb-sharded)
     int joff, jstep;  // basis index of local target limb j: joff + jstep * j  (0, 1 unless limb-sharded)
+    int j0;           // first local target limb of this launch (the grid covers j0 .. j0 + nj - 1)
     size_t dig_ct_stride, dig_limb_stride;  // words between ciphertexts / digits in `digits`
     int a1, a2;
     int reduce_every;  // digits between 128-bit accumulator reductions
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     WD *sm = reinterpret_cast<WD *>(sm_raw);
     const int L = a.L, Ld = a.Ld;
-    const int j = blockIdx.y / Ld, i = blockIdx.y % Ld;
+    const int j = a.j0 + blockIdx.y / Ld, i = blockIdx.y % Ld;
     if (DIAG && i == a.joff + a.jstep * j) return;  // ks_pass2 takes the NTT-domain limb itself for this digit
     const int tid = threadIdx.x;
     const int c = tid % C, g = tid / C;
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
     const int L = a.L;
     // grid = (ciphertexts, tiles, target limbs): the ciphertext index runs fastest so that the CTAs
     // resident at the same time share the key tiles of one (target limb, tile) through L2.
-    const int j = blockIdx.z;
+    const int j = a.j0 + blockIdx.z;
     const int tid = threadIdx.x;
     const int c = tid % C, g = tid / C;
     const size_t c0 = (size_t)blockIdx.y * C;

@@ -38,8 +38,8 @@ struct LsSym {  // symmetric buffers of one rank: one cudaMalloc block (one IPC 
     bool connected = false;
     unsigned epochA = 0, epochB = 0;  // flag words [0..8) / [16..24): barriers on the auxiliary / main stream
     cudaEvent_t ev = nullptr;         // in-process groups: barrier by events (ckks_lshard_barrier_local)
-    cudaStream_t aux = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
+    cudaStream_t aux = nullptr, aux2 = nullptr;  // aux2: the dropped limb's broadcast, under the rest of phase B
+    cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr}, ev_k = nullptr, ev_l = nullptr;
     unsigned long long timeout_ns = 20ull * 1000000000ull;
     // how the digits reach the peers in the pipelined entry point: 0 = stores from the producing kernel,
     // 1 = copy engines (cudaMemcpyAsync over the peer mappings: no SM is held while NVLink is busy, so the
@@ -56,9 +56,10 @@ struct LsSym {  // symmetric buffers of one rank: one cudaMalloc block (one IPC 
     ~LsSym() {
         cudaSetDevice(device);
         if (ev) cudaEventDestroy(ev);
-        for (cudaEvent_t e : {ev_start, ev_a[0], ev_a[1], ev_c[0], ev_c[1]})
+        for (cudaEvent_t e : {ev_start, ev_a[0], ev_a[1], ev_c[0], ev_c[1], ev_k, ev_l})
             if (e) cudaEventDestroy(e);
         if (aux) cudaStreamDestroy(aux);
+        if (aux2) cudaStreamDestroy(aux2);
         for (int p = 0; p < 8; ++p)
             if (ipc_base[p]) cudaIpcCloseMemHandle(ipc_base[p]);
         if (block) cudaFree(block);
@@ -173,7 +174,8 @@ extern "C" int ckks_lshard_create(uint64_t n, const uint64_t *moduli, size_t l, 
             for (u64 **b : {&sym->set[k].A0, &sym->set[k].A1, &sym->set[k].B0, &sym->set[k].B1, &sym->set[k].TMP}) CU(cudaMalloc((void **)b, W));
         CU(cudaMalloc((void **)&sym->SCR, W * l));
         CU(cudaStreamCreateWithFlags(&sym->aux, cudaStreamNonBlocking));
-        for (cudaEvent_t *e : {&sym->ev_start, &sym->ev_a[0], &sym->ev_a[1], &sym->ev_c[0], &sym->ev_c[1]})
+        CU(cudaStreamCreateWithFlags(&sym->aux2, cudaStreamNonBlocking));
+        for (cudaEvent_t *e : {&sym->ev_start, &sym->ev_a[0], &sym->ev_a[1], &sym->ev_c[0], &sym->ev_c[1], &sym->ev_k, &sym->ev_l})
             CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         CU(cudaDeviceSynchronize());
         sym->base_p[rank] = sym->block;
@@ -496,6 +498,27 @@ static int ls_mul_phase(ckks_lshard *s, int k, int phase, size_t s0, size_t cs, 
     }
     if (phase == 1) {
         KsShard ks{Lg, s->rank, s->world, n, y.cs_max * n, s->digit_reduce};
+        if (rescale && s->rank == owner && peer_stores && y.world > 1 && Ll > 1) {
+            // The owner of the limb rescale drops key-switches that limb FIRST and sends it to the peers (one GPU
+            // feeding world-1 others: the longest transfer of the step) on a side stream while the key-switch of
+            // its other limbs runs; the barrier that follows phase B finds the broadcast already done.
+            Tables &Tm = *s->local->T;
+            const cudaStream_t cur = Tm.stream;
+            TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(k), w.B0, rlk, w.A0, w.A1, y.SCR, w.TMP, w.B1, true, Ll - 1, 1));
+            CU(cudaEventRecord(y.ev_k, cur));
+            CU(cudaStreamWaitEvent(y.aux2, y.ev_k, 0));
+            Tm.stream = y.aux2;
+            g_cur_stream = y.aux2;
+            int rc = ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, w.TMP, pl0, np, s->rank + 1, 0, 0, y.cs_max);
+            if (rc == CKKS_OK) rc = ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, w.B1, pl1, np, s->rank + 1, 0, 0, y.cs_max);
+            Tm.stream = cur;
+            g_cur_stream = cur;
+            TRY(rc);
+            CU(cudaEventRecord(y.ev_l, y.aux2));
+            TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(k), w.B0, rlk, w.A0, w.A1, y.SCR, w.TMP, w.B1, true, 0, Ll - 1));
+            CU(cudaStreamWaitEvent(cur, y.ev_l, 0));
+            return CKKS_OK;
+        }
         TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(k), w.B0, rlk, w.A0, w.A1, y.SCR, w.TMP, w.B1, true));
         if (!rescale) {
             const size_t ooff = s0 * Ll * n;
