@@ -200,3 +200,5 @@ extern "C" uint64_t emul_shoup_lazy8(uint64_t x, uint64_t w, uint64_t q) {
 // index of (row r, column c) in ks_pass2's tile shape (E = 3, C = 4); swz = 1 for the bit-weighted layout of its
 // digit loop, 0 for the padded layout.
 extern "C" int emul_tile_addr(int swz, int r, int c) { return swz ? tile_addr<3, 5, 1>(r, c) : tile_addr<3, 5, 0>(r, c); }
+// Row permutation of the resident gadget keys (ntt_tile.cuh perm_row) for tests/test_emul.py.
+extern "C" uint64_t emul_perm_row(uint64_t row, int a2, int pe) { return (uint64_t)perm_row((size_t)row, a2, pe); }

@@ -141,3 +141,21 @@ def test_ks_pass2_exchange_layout_is_conflict_free(emul, size):
         for e0 in range(0, c_cols << a, 32):  # transposed read on the padded layout: lane = consecutive rows of one column
             lanes = [pad[x & (rows - 1)][x >> a] * size for x in range(e0, e0 + 32)]
             assert _wavefronts(lanes, size) == ideal, (a, "transposed", e0)
+
+
+def test_key_row_permutation_matches_ks_pass2_indexing(emul):
+    """ksk_finalize stores row (g * 2^E + k) of every key limb at (k * G + g), G = 2^(a2-E): exactly the index
+    `(k * GM::G + g)` ks_pass2 uses for its key tiles, and a bijection on the rows of a limb."""
+    emul.emul_perm_row.argtypes = [C.c_uint64, C.c_int, C.c_int]
+    emul.emul_perm_row.restype = C.c_uint64
+    e = 3
+    for a2 in range(4, 9):
+        rows, groups = 1 << a2, 1 << (a2 - e)
+        seen = set()
+        for g in range(groups):
+            for k in range(1 << e):
+                p = emul.emul_perm_row(g * (1 << e) + k, a2, e)
+                assert p == k * groups + g
+                seen.add(p)
+        assert seen == set(range(rows))
+    assert emul.emul_perm_row(5, 8, -1) == 5  # natural order when the key is not permuted (small-N path)

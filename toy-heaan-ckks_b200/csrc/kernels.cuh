@@ -353,13 +353,7 @@ __global__ void digit_broadcast_kernel(EwArgs a, const u64 *__restrict__ src, u6
         out[i] = (limb == digit) ? v : barrett_word(v, a.lc[limb]);
     }
 }
-// Row permutation of the resident gadget keys on the four-step path: within every limb ([2^a2 rows][2^a1]
-// words, internal NTT order) row (g * 2^pe + k) moves to row (k * 2^(a2-pe) + g), pe = ks_pass2's register
-// window.  perm_row() maps a logical row to where it is stored; pe < 0: not permuted.
-__host__ __device__ __forceinline__ size_t perm_row(size_t row, int a2, int pe) {
-    if (pe < 0 || a2 <= pe) return row;
-    return ((row & (((size_t)1 << pe) - 1)) << (a2 - pe)) | (row >> pe);
-}
+// (perm_row: ntt_tile.cuh)
 template <typename KT>
 __global__ void key_permute_kernel(const u64 *__restrict__ src, KT *__restrict__ dst, size_t total, int logn, int a1, int a2, int pe) {
     const size_t n = (size_t)1 << logn;

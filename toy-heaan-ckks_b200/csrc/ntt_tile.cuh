@@ -169,6 +169,14 @@ __device__ __forceinline__ void tile_get(const WD *sm, WD (&v)[1 << E], int g, i
     for (int k = 0; k < (1 << E); ++k) v[k] = sm[tile_idx<E>(g, k, lo) * CP + c];
 }
 
+// Row permutation of the resident gadget keys on the four-step path: within every limb ([2^a2 rows][2^a1]
+// words, internal NTT order) row (g * 2^pe + k) moves to row (k * 2^(a2-pe) + g), pe = ks_pass2's register
+// window.  perm_row() maps a logical row to where it is stored; pe < 0: not permuted.
+__host__ __device__ __forceinline__ size_t perm_row(size_t row, int a2, int pe) {
+    if (pe < 0 || a2 <= pe) return row;
+    return ((row & (((size_t)1 << pe) - 1)) << (a2 - pe)) | (row >> pe);
+}
+
 enum { XF_NEG_FWD = 0, XF_CYC_FWD = 1, XF_CYC_INV = 2, XF_NEG_INV = 3 };
 
 template <int KIND, int A, int E, int T, int LAZY, typename WD, typename TW>
