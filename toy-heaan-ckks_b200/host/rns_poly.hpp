@@ -43,6 +43,8 @@ class RnsBasis {
     };
     std::shared_ptr<ckks_ctx> h_;
     explicit RnsBasis(ckks_ctx *c) : h_(c, Del()) {}
+    RnsBasis(ckks_ctx *c, std::shared_ptr<void> owner) : h_(std::move(owner), c) {}  // borrowed (kept alive by `owner`)
+    friend class LimbShard;
 
   public:
     RnsBasis() = default;
@@ -80,6 +82,7 @@ class RnsPoly {
     RnsPoly(ckks_poly *p, RnsBasis b) : p_(p), basis_(std::move(b)) {}
     friend struct engine;
     friend class GadgetKey;
+    friend class LimbShard;
 
   public:
     RnsPoly() = default;
@@ -177,6 +180,7 @@ struct Ciphertext {  // types.rs:22-35
 class GadgetKey {  // engine.rs:225-253
     ckks_ksk *k_ = nullptr;
     friend struct engine;
+    friend class LimbShard;
 
   public:
     int32_t rotation = 0;
@@ -233,6 +237,72 @@ struct engine {
         check(ckks_ct_decrypt(ct.c0.p_, ct.c1.p_, s.p_, &p));
         return RnsPoly(p, ct.c0.basis());
     }
+};
+
+// Optional limb-sharded mode (include/ckks_b200.h, ckks_lshard_*): this GPU's share -- limbs j = rank (mod world)
+// -- of one batch and of the gadget keys; every rank of the group makes the same calls.
+class LimbShard {
+    struct Del {
+        void operator()(ckks_lshard *s) const { ckks_lshard_destroy(s); }
+    };
+    std::shared_ptr<ckks_lshard> h_;
+    std::shared_ptr<ckks_lshard> parent_;  // a child level shares its parent's exchange buffers
+    int rank_ = 0, world_ = 1;
+    explicit LimbShard(ckks_lshard *s, int rank, int world, std::shared_ptr<ckks_lshard> parent = nullptr)
+        : h_(s, Del()), parent_(std::move(parent)), rank_(rank), world_(world) {}
+
+  public:
+    LimbShard() = default;
+    static LimbShard create(uint64_t degree, const std::vector<uint64_t> &moduli, int rank, int world, int device = 0, size_t chunk = 0) {
+        ckks_lshard *s = nullptr;
+        check(ckks_lshard_create(degree, moduli.data(), moduli.size(), rank, world, device, chunk, &s));
+        return LimbShard(s, rank, world);
+    }
+    LimbShard drop_last() const {
+        ckks_lshard *c = nullptr;
+        check(ckks_lshard_drop_last(h_.get(), &c));
+        return LimbShard(c, rank_, world_, h_);
+    }
+    // RnsBasis over the limbs held here (local limb jl = basis limb rank + world * jl)
+    RnsBasis local_basis() const { return RnsBasis(ckks_lshard_local_ctx(h_.get()), std::static_pointer_cast<void>(h_)); }
+    size_t channel_count() const { return ckks_lshard_channel_count(h_.get()); }
+    std::vector<unsigned char> ipc_handle() const {
+        std::vector<unsigned char> b(ckks_lshard_ipc_size());
+        check(ckks_lshard_ipc_export(h_.get(), b.data()));
+        return b;
+    }
+    void connect(const std::vector<unsigned char> &handles_in_rank_order) { check(ckks_lshard_ipc_import(h_.get(), handles_in_rank_order.data())); }
+    // a, b: [L][L_own][N], the rows of the key restricted to this GPU's limbs
+    GadgetKey upload_key(const std::vector<uint64_t> &a, const std::vector<uint64_t> &b, int32_t rotation = 0) const {
+        GadgetKey k;
+        check(ckks_lshard_ksk_upload(h_.get(), a.data(), b.data(), &k.k_));
+        k.rotation = rotation;
+        return k;
+    }
+    // mul_ciphertexts_gadget (+ rescale_ciphertext into `child`'s level), engine.rs:473-539, 263-282
+    Ciphertext mul_relin_rescale(const Ciphertext &a, const Ciphertext &b, const GadgetKey &rlk, const LimbShard *child = nullptr) const {
+        if (a.logq != b.logq) throw RnsNttError(CKKS_LEVEL_MISMATCH);
+        ckks_poly *p0, *p1;
+        check(ckks_lshard_ct_mul_relin_rescale(h_.get(), a.c0.p_, a.c1.p_, b.c0.p_, b.c1.p_, rlk.k_, child ? child->h_.get() : nullptr, &p0, &p1));
+        Ciphertext c;
+        RnsBasis ob = child ? child->local_basis() : local_basis();
+        c.c0 = RnsPoly(p0, ob);
+        c.c1 = RnsPoly(p1, ob);
+        c.logp = a.logp + b.logp;
+        c.logq = a.logq;
+        return c;  // the caller subtracts bit_length(q_last) from logp/logq when rescaling, as engine.rs:266-270 does
+    }
+    Ciphertext rotate_ciphertext(const Ciphertext &ct, const GadgetKey &rotk) const {  // engine.rs:412-463
+        ckks_poly *p0, *p1;
+        check(ckks_lshard_ct_rotate(h_.get(), ct.c0.p_, ct.c1.p_, rotk.k_, rotk.rotation, &p0, &p1));
+        Ciphertext c;
+        c.c0 = RnsPoly(p0, local_basis());
+        c.c1 = RnsPoly(p1, local_basis());
+        c.logp = ct.logp;
+        c.logq = ct.logq;
+        return c;
+    }
+    void check_peers() const { check(ckks_lshard_check(h_.get())); }  // sync + "no peer was lost"
 };
 
 }  // namespace ckks
