@@ -259,12 +259,12 @@ def _ipc_worker(rank, world, port, q):
         ck = importlib.import_module("toy-heaan-ckks_b200")
         import oracle as orc
 
-        n, l, batch = 2048, 4, 2
+        n, l, batch = 2048, 4, 5
         moduli = orc.generate_primes(61, l, n)
         rng = np.random.default_rng(555)  # the same global batch on every rank
         a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
         ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
-        sh = ck.LimbShard(n, moduli, rank, world, device=0, chunk=4)
+        sh = ck.LimbShard(n, moduli, rank, world, device=0, chunk=2)  # chunks of 1, 2, 2 through the pipeline
         sh.set_timeout_ms(60000)
         sh.connect_process_group()
         kid = sh.drop_last()
