@@ -264,7 +264,7 @@ def _ipc_worker(rank, world, port, q):
         rng = np.random.default_rng(555)  # the same global batch on every rank
         a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
         ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
-        sh = ck.LimbShard(n, moduli, rank, world, device=0, chunk=2)  # chunks of 1, 2, 2 through the pipeline
+        sh = ck.LimbShard(n, moduli, rank, world, device=0, chunk=2)  # three chunks through the pipeline
         sh.set_timeout_ms(60000)
         sh.connect_process_group()
         kid = sh.drop_last()
