@@ -54,6 +54,7 @@ pub mod ffi {
         pub fn ckks_poly_to_coeff_domain(p: *mut CkksPoly) -> i32;
         pub fn ckks_poly_add_assign(a: *mut CkksPoly, rhs: *const CkksPoly) -> i32;
         pub fn ckks_poly_mul_assign(a: *mut CkksPoly, rhs: *const CkksPoly) -> i32;
+        pub fn ckks_poly_mul_assign_naive(a: *mut CkksPoly, rhs: *const CkksPoly) -> i32;
         pub fn ckks_poly_neg(a: *mut CkksPoly) -> i32;
         pub fn ckks_poly_mod_drop_last(p: *const CkksPoly, child: *mut CkksCtx, out: *mut *mut CkksPoly) -> i32;
         pub fn ckks_poly_rescale_into(p: *const CkksPoly, child: *mut CkksCtx, out: *mut *mut CkksPoly) -> i32;
@@ -212,6 +213,11 @@ impl<const N: usize> RnsPoly<N> {
     }
     pub fn to_coeff_domain(&mut self) {
         check(unsafe { ffi::ckks_poly_to_coeff_domain(self.h.as_ptr()) });
+        self.mirror.take();
+    }
+    /// Schoolbook O(N^2) product (poly.rs:339-367); both operands in the coefficient domain.
+    pub fn mul_assign_naive(&mut self, rhs: &RnsPoly<N>) {
+        check(unsafe { ffi::ckks_poly_mul_assign_naive(self.h.as_ptr(), rhs.h.as_ptr()) });
         self.mirror.take();
     }
     pub fn rescale_into(&self, new_basis: Arc<RnsBasis<N>>) -> Result<Self, RnsNttError> {

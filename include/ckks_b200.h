@@ -134,6 +134,9 @@ int ckks_poly_neg(ckks_poly *a);                                 /* Neg poly.rs:
 /* MulAssign poly.rs:277-331: both NTT domain -> pointwise; both coefficient domain -> negacyclic
  * product returned in the coefficient domain. */
 int ckks_poly_mul_assign(ckks_poly *a, const ckks_poly *rhs);
+/* mul_assign_naive poly.rs:339-367: O(N^2) schoolbook product in Z_q[X]/(X^N+1), coefficient domain only
+ * (CKKS_DOMAIN_MISMATCH otherwise); the reference keeps it as the yardstick for the NTT path. */
+int ckks_poly_mul_assign_naive(ckks_poly *a, const ckks_poly *rhs);
 /* RnsPoly::mod_drop_last(k) poly.rs:169-177; `child` must be ckks_ctx_drop_last(ctx, k). */
 int ckks_poly_mod_drop_last(const ckks_poly *p, ckks_ctx *child, ckks_poly **out);
 /* RnsPoly::rescale_into(new_basis) poly.rs:187-228 (floor division by the last prime; result in

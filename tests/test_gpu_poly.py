@@ -244,3 +244,31 @@ def test_to_coeffs_centered(gpu, orc):
     assert np.array_equal(p.to_coeffs(), co)
     p.to_ntt_domain()
     assert np.array_equal(p.to_coeffs(), co)
+
+
+@pytest.mark.parametrize("n,bits,l", [(8, 0, 3), (64, 40, 2), (256, 61, 3), (1024, 30, 2)])
+def test_mul_assign_naive_matches_ntt_multiply_and_oracle(gpu, orc, n, bits, l):
+    """poly.rs:960-975 (`ntt_mul_matches_naive`): the NTT-based `*=` equals the O(N^2) schoolbook product, here both
+    on the device and against the oracle's restatement of mul_assign_naive (poly.rs:339-367)."""
+    moduli = [17, 97, 113] if bits == 0 else orc.generate_primes(bits, l, n)
+    gb, ob = gpu.RnsBasis(n, moduli), orc.Basis(n, moduli)
+    rng = np.random.default_rng(n)
+    a, b = uniform_limbs(rng, moduli, n, 3), uniform_limbs(rng, moduli, n, 3)
+    fast = gpu.RnsPoly.from_channels(a, gb)
+    fast *= gpu.RnsPoly.from_channels(b, gb)
+    slow = gpu.RnsPoly.from_channels(a, gb)
+    slow.mul_assign_naive(gpu.RnsPoly.from_channels(b, gb))
+    assert not slow.is_ntt_domain()
+    got = slow.channels()
+    assert np.array_equal(got, fast.channels())
+    for i in range(3):
+        assert np.array_equal(got[i], ob.mul_naive(a[i], b[i]))
+    # rhs broadcast over the batch, and the domain rule of the reference's debug_assert
+    one = gpu.RnsPoly.from_channels(a, gb)
+    one.mul_assign_naive(gpu.RnsPoly.from_channels(b[:1], gb))
+    assert np.array_equal(one.channels()[2], ob.mul_naive(a[2], b[0]))
+    ntt = gpu.RnsPoly.from_channels(a, gb)
+    ntt.to_ntt_domain()
+    with pytest.raises(gpu.RnsNttError) as e:
+        ntt.mul_assign_naive(ntt)
+    assert e.value.kind == "DomainMismatch"

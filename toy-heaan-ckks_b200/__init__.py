@@ -114,6 +114,7 @@ _sig("ckks_poly_add_assign", C.c_int, _vp, _vp)
 _sig("ckks_poly_sub_assign", C.c_int, _vp, _vp)
 _sig("ckks_poly_neg", C.c_int, _vp)
 _sig("ckks_poly_mul_assign", C.c_int, _vp, _vp)
+_sig("ckks_poly_mul_assign_naive", C.c_int, _vp, _vp)
 _sig("ckks_poly_mod_drop_last", C.c_int, _vp, _vp, _pp)
 _sig("ckks_poly_rescale_into", C.c_int, _vp, _vp, _pp)
 _sig("ckks_poly_automorphism", C.c_int, _vp, C.c_uint64, _pp)
@@ -400,6 +401,10 @@ class RnsPoly:
     def __imul__(self, rhs: "RnsPoly"):
         _check(_lib.ckks_poly_mul_assign(self._h, rhs._h))
         return self
+
+    def mul_assign_naive(self, rhs: "RnsPoly"):
+        """Schoolbook O(N^2) product (poly.rs:339-367), coefficient domain only."""
+        _check(_lib.ckks_poly_mul_assign_naive(self._h, rhs._h))
 
     def __neg__(self) -> "RnsPoly":
         r = self.clone()

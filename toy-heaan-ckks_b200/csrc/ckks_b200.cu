@@ -815,6 +815,23 @@ extern "C" int ckks_poly_mul_assign(ckks_poly *a, const ckks_poly *b) {
     return rc;
 }
 
+// mul_assign_naive (poly.rs:339-367): coefficient-domain operands only (the reference debug_asserts it).
+extern "C" int ckks_poly_mul_assign_naive(ckks_poly *a, const ckks_poly *b) {
+    TRY(check_pair(a, b, true));
+    if (a->ntt) return CKKS_DOMAIN_MISMATCH;
+    const Tables &T = *a->ctx->T;
+    CU(cudaSetDevice(T.device));
+    EwArgs e = ew_args(T, a->ctx->L, a->batch);
+    if (!e.total) return CKKS_OK;
+    u64 *tmp = nullptr;
+    TRY(dev_alloc(T, e.total, &tmp));
+    KLV("mul_naive", (mul_naive_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, a->d, b->d, b->batch == 1 && a->batch != 1 ? 0 : e.poly, tmp)));
+    cudaMemcpyAsync(a->d, tmp, e.total * 8, cudaMemcpyDeviceToDevice, T.stream);
+    dev_free(T, tmp);
+    if (cudaPeekAtLastError() != cudaSuccess) return cuda_fail(cudaGetLastError(), "mul_naive");
+    return CKKS_OK;
+}
+
 extern "C" int ckks_poly_mod_drop_last(const ckks_poly *p, ckks_ctx *child, ckks_poly **out) {
     if (!out) return CKKS_BAD_ARGUMENT;
     *out = nullptr;

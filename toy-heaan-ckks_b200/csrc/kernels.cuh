@@ -292,6 +292,22 @@ __global__ void rescale_kernel(EwArgs a /* of the OUTPUT: L-1 limbs */, const u6
         out[i] = shoup(submod(ci, cl, m.q), ldg_tw(qlinv + limb), m.q);
     }
 }
+// mul_assign_naive (poly.rs:339-367): the reference's O(N^2) schoolbook product in Z_q[X]/(X^N + 1), kept there as
+// the correctness yardstick of the NTT path and kept here for the same purpose.  One thread per output
+// coefficient: out[k] = sum_{i<=k} a[i] b[k-i] - sum_{i>k} a[i] b[N+k-i]  (X^N = -1).  y_bstride = 0 broadcasts rhs.
+__global__ void mul_naive_kernel(EwArgs a, const u64 *__restrict__ x, const u64 *__restrict__ y, size_t y_bstride, u64 *__restrict__ out) {
+    const size_t n = (size_t)1 << a.logn;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.total; t += (size_t)gridDim.x * blockDim.x) {
+        const LimbConst &m = a.lc[ew_limb(a, t)];
+        const size_t k = t & (n - 1), b = t / a.poly, limb_off = (t % a.poly) - k;
+        const u64 *xa = x + t - k, *yb = y + b * y_bstride + limb_off;
+        u64 pos = 0, neg = 0;
+        for (size_t i = 0; i <= k; ++i) pos = mulmod_add(xa[i], yb[k - i], pos, m);
+        for (size_t i = k + 1; i < n; ++i) neg = mulmod_add(xa[i], yb[n + k - i], neg, m);
+        out[t] = submod(pos, neg, m.q);
+    }
+}
+
 // automorphism (poly.rs:515-538) for odd exponents (a signed permutation), as a gather:
 // out[j] = +-in[i] with i = j * e^-1 mod 2N (sign from i*e mod 2N >= N).
 __global__ void automorphism_kernel(EwArgs a, const u64 *__restrict__ src, u64 *__restrict__ out, u64 e, u64 einv) {

@@ -169,6 +169,7 @@ class RnsPoly {
         check(ckks_poly_to_coeffs(p_, out.data()));
         return out;
     }
+    void mul_assign_naive(const RnsPoly &rhs) { check(ckks_poly_mul_assign_naive(p_, rhs.p_)); }  // poly.rs:339-367
     ckks_poly *raw() const { return p_; }
 };
 
