@@ -85,6 +85,9 @@ int ckks_ctx_moduli(const ckks_ctx *ctx, uint64_t *out);         /* basis.rs:109
 uint32_t ckks_ctx_total_bits(const ckks_ctx *ctx);               /* basis.rs:140-145 */
 uint64_t ckks_ctx_psi(const ckks_ctx *ctx, size_t channel);      /* NttTable psi, basis.rs:33 */
 /* RnsBasis::reconstruct_centered_coeff basis.rs:158-180 (host, u128 CRT, Q < 2^128). */
+/* RnsBasis::ntt_table(channel) basis.rs:112-114 in the reference's NttTable layout (basis.rs:6-17): which = 0
+ * forward_roots, 1 inverse_roots, 2 twist_factors, 3 untwist_factors (N words), 4 n_inv (1 word). */
+int ckks_ctx_ntt_table(const ckks_ctx *ctx, size_t channel, int which, uint64_t *out);
 int ckks_ctx_reconstruct_centered_coeff(const ckks_ctx *ctx, const uint64_t *residues, int64_t *out);
 /* Selects the small-N single-CTA NTT (1) or the four-step NTT (2) for contexts created afterwards;
  * 0 = automatic.  Test hook: both paths must agree with the oracle. */

@@ -272,3 +272,19 @@ def test_mul_assign_naive_matches_ntt_multiply_and_oracle(gpu, orc, n, bits, l):
     with pytest.raises(gpu.RnsNttError) as e:
         ntt.mul_assign_naive(ntt)
     assert e.value.kind == "DomainMismatch"
+
+
+@pytest.mark.parametrize("n,moduli", [(8, [17, 97, 113]), (1024, None)])
+def test_ntt_table_accessor_matches_reference_layout(gpu, orc, n, moduli):
+    """RnsBasis::ntt_table (basis.rs:112-114): forward/inverse roots, twist/untwist factors and n_inv exactly as
+    NttTable::new builds them (basis.rs:21-84), although the device keeps its own table layout."""
+    moduli = moduli or orc.generate_primes(40, 2, n)
+    gb, ob = gpu.RnsBasis(n, moduli), orc.Basis(n, moduli)
+    for ch, q in enumerate(moduli):
+        t = gb.ntt_table(ch)
+        assert t["modulus"] == q and t["n_inv"] == int(ob.table(ch, "n_inv")[0]) and (t["n_inv"] * n) % q == 1
+        assert np.array_equal(t["forward_roots"], ob.table(ch, "forward_roots"))
+        assert np.array_equal(t["inverse_roots"], ob.table(ch, "inverse_roots"))
+        assert np.array_equal(t["twist_factors"], ob.table(ch, "twist"))
+        assert np.array_equal(t["untwist_factors"], ob.table(ch, "untwist"))
+        assert int(t["twist_factors"][1]) == gb.psi(ch)

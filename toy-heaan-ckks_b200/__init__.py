@@ -88,6 +88,7 @@ _sig("ckks_ctx_moduli", C.c_int, _vp, _u64p)
 _sig("ckks_ctx_total_bits", C.c_uint32, _vp)
 _sig("ckks_ctx_psi", C.c_uint64, _vp, C.c_size_t)
 _sig("ckks_ctx_reconstruct_centered_coeff", C.c_int, _vp, _u64p, _i64p)
+_sig("ckks_ctx_ntt_table", C.c_int, _vp, C.c_size_t, C.c_int, _u64p)
 _sig("ckks_set_ntt_path", C.c_int, C.c_int)
 _sig("ckks_set_unfused", C.c_int, C.c_int)
 _sig("ckks_set_word32", C.c_int, C.c_int)
@@ -298,6 +299,19 @@ class RnsBasis:
 
     def psi(self, channel: int) -> int:
         return int(_lib.ckks_ctx_psi(self._h, channel))
+
+    def ntt_table(self, channel: int) -> dict:
+        """`NttTable<N>` of one channel in the reference's layout (basis.rs:6-17)."""
+        out = {}
+        for idx, name in enumerate(("forward_roots", "inverse_roots", "twist_factors", "untwist_factors")):
+            a = np.zeros(self.degree, dtype=np.uint64)
+            _check(_lib.ckks_ctx_ntt_table(self._h, channel, idx, _ptr(a)))
+            out[name] = a
+        a = np.zeros(1, dtype=np.uint64)
+        _check(_lib.ckks_ctx_ntt_table(self._h, channel, 4, _ptr(a)))
+        out["n_inv"] = int(a[0])
+        out["modulus"] = self.moduli()[channel]
+        return out
 
     def reconstruct_centered_coeff(self, residues) -> int:
         r = _u64(residues)

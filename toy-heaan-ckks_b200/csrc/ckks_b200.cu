@@ -375,6 +375,27 @@ extern "C" uint32_t ckks_ctx_total_bits(const ckks_ctx *c) {
     return s;
 }
 extern "C" uint64_t ckks_ctx_psi(const ckks_ctx *c, size_t ch) { return (ok_ctx(c) && ch < c->L) ? c->T->psi[ch] : 0; }
+// NttTable<N> of one channel in the REFERENCE's layout (basis.rs:6-17, 61-83), rebuilt on the host from psi for
+// callers that read `basis.ntt_table(ch)`: which = 0 forward_roots[i] = omega^i, 1 inverse_roots[i] = omega^-i,
+// 2 twist_factors[j] = psi^j, 3 untwist_factors[j] = psi^-j (N words each), 4 n_inv (one word).  The device
+// tables are laid out differently (tables_host.hpp); this accessor is the drop-in view.
+extern "C" int ckks_ctx_ntt_table(const ckks_ctx *c, size_t channel, int which, uint64_t *out) {
+    if (!ok_ctx(c)) return CKKS_BAD_HANDLE;
+    if (channel >= c->L || !out || which < 0 || which > 4) return CKKS_BAD_ARGUMENT;
+    const u64 q = c->T->moduli[channel], n = c->T->n, psi = c->T->psi[channel];
+    if (which == 4) {
+        out[0] = hm::inv_mod(n % q, q);
+        return CKKS_OK;
+    }
+    u64 base = which < 2 ? hm::mul_mod(psi, psi, q) : psi;  // omega = psi^2 (basis.rs:36)
+    if (which & 1) base = hm::inv_mod(base, q);
+    u64 v = 1;
+    for (u64 i = 0; i < n; ++i) {
+        out[i] = v;
+        v = hm::mul_mod(v, base, q);
+    }
+    return CKKS_OK;
+}
 extern "C" int ckks_ctx_reconstruct_centered_coeff(const ckks_ctx *c, const uint64_t *res, int64_t *out) {
     if (!ok_ctx(c) || !res || !out) return CKKS_BAD_HANDLE;
     std::vector<u64> m(c->T->moduli.begin(), c->T->moduli.begin() + c->L);
