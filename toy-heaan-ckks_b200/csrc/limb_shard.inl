@@ -417,6 +417,7 @@ extern "C" int ckks_lshard_check(ckks_lshard *s) {
     CU(cudaMemcpyAsync(&e, y.flags() + 8, sizeof(e), cudaMemcpyDeviceToHost, s->local->T->stream));
     CU(cudaStreamSynchronize(s->local->T->stream));
     if (e) {
+        cudaMemsetAsync(y.flags() + 8, 0, sizeof(unsigned), s->local->T->stream);  // report a lost peer once
         g_err = "limb-sharded barrier " + std::to_string(e) + " timed out waiting for a peer GPU";
         return CKKS_NCCL_ERROR;
     }
