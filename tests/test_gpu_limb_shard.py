@@ -309,3 +309,22 @@ def test_limb_sharded_two_processes_cuda_ipc(gpu):
         assert p.exitcode == 0
     got = sorted(q.get(timeout=10) for _ in range(world))
     assert got == [(0, True), (1, True)]
+
+
+def test_lost_peer_is_an_error_not_a_hang(gpu, orc):
+    """Only rank 0 of a group of two makes the call: its flag barriers give up after the time limit, the stream
+    drains, and check() reports the lost peer (once) instead of leaving a kernel spinning on the GPU."""
+    n, l = 1024, 4
+    moduli = orc.generate_primes(40, l, n)
+    rng = np.random.default_rng(3)
+    shards = [gpu.LimbShard(n, moduli, r, 2, chunk=2) for r in range(2)]
+    gpu.LimbShard.connect_local(shards)
+    shards[0].set_timeout_ms(200)
+    a0, a1 = uniform_limbs(rng, moduli, n, 2), uniform_limbs(rng, moduli, n, 2)
+    key = shards[0].upload_key(uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l))
+    ct = _ct(gpu, shards[0], a0, a1)
+    shards[0].mul_relin_rescale(ct, ct, key)  # enqueues; nobody answers
+    with pytest.raises(gpu.RnsNttError) as e:
+        shards[0].check()
+    assert e.value.kind == "NcclError" and "timed out" in str(e.value)
+    shards[0].check()  # reported once
