@@ -35,6 +35,10 @@ pub mod ffi {
     pub struct CkksKsk {
         _p: [u8; 0],
     }
+    #[repr(C)]
+    pub struct CkksLshard {
+        _p: [u8; 0],
+    }
     extern "C" {
         pub fn ckks_status_str(status: i32) -> *const std::os::raw::c_char;
         pub fn ckks_ctx_create(n: u64, moduli: *const u64, l: usize, device: i32, out: *mut *mut CkksCtx) -> i32;
@@ -71,6 +75,23 @@ pub mod ffi {
                                          rlk: *const CkksKsk, child: *mut CkksCtx, o0: *mut *mut CkksPoly, o1: *mut *mut CkksPoly) -> i32;
         pub fn ckks_ct_rotate(c0: *const CkksPoly, c1: *const CkksPoly, rotk: *const CkksKsk, k: i32,
                               o0: *mut *mut CkksPoly, o1: *mut *mut CkksPoly) -> i32;
+        pub fn ckks_ctx_ntt_table(ctx: *const CkksCtx, channel: usize, which: i32, out: *mut u64) -> i32;
+        // Optional limb-sharded mode (one process per GPU; INTEGRATION.md section 3b shows the call sequence).
+        pub fn ckks_lshard_create(n: u64, moduli: *const u64, l: usize, rank: i32, world: i32, device: i32, chunk: usize,
+                                  out: *mut *mut CkksLshard) -> i32;
+        pub fn ckks_lshard_destroy(s: *mut CkksLshard) -> i32;
+        pub fn ckks_lshard_drop_last(s: *mut CkksLshard, child: *mut *mut CkksLshard) -> i32;
+        pub fn ckks_lshard_local_ctx(s: *mut CkksLshard) -> *mut CkksCtx;
+        pub fn ckks_lshard_ipc_size() -> usize;
+        pub fn ckks_lshard_ipc_export(s: *mut CkksLshard, blob: *mut std::os::raw::c_void) -> i32;
+        pub fn ckks_lshard_ipc_import(s: *mut CkksLshard, blobs: *const std::os::raw::c_void) -> i32;
+        pub fn ckks_lshard_ksk_upload(s: *mut CkksLshard, a: *const u64, b: *const u64, out: *mut *mut CkksKsk) -> i32;
+        pub fn ckks_lshard_ct_mul_relin_rescale(s: *mut CkksLshard, a0: *const CkksPoly, a1: *const CkksPoly, b0: *const CkksPoly,
+                                                b1: *const CkksPoly, rlk: *const CkksKsk, child: *mut CkksLshard,
+                                                o0: *mut *mut CkksPoly, o1: *mut *mut CkksPoly) -> i32;
+        pub fn ckks_lshard_ct_rotate(s: *mut CkksLshard, c0: *const CkksPoly, c1: *const CkksPoly, rotk: *const CkksKsk, k: i32,
+                                     o0: *mut *mut CkksPoly, o1: *mut *mut CkksPoly) -> i32;
+        pub fn ckks_lshard_check(s: *mut CkksLshard) -> i32;
         pub fn ckks_ct_mul_relin_rescale_host(ctx: *mut CkksCtx, child: *mut CkksCtx, rlk: *const CkksKsk, batch: usize,
                                               a0: *const u64, a1: *const u64, b0: *const u64, b1: *const u64,
                                               o0: *mut u64, o1: *mut u64) -> i32;
