@@ -172,34 +172,165 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(config, budget_note=""):
-    import numpy as np
-
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
 
+    return orc
+
+
+def cpu_baseline(config, op, sample, single_thread=True):
+    """The oracle (C++ restatement of the reference schedule) on this box's host cores, fed the SAME inputs as the
+    first pairs of the timed GPU batch (`sample`: host copies), so that its outputs double as the parity check.
+    Returns (record, outputs)."""
+    orc = _oracle()
     logn, l, bits, _, _ = CONFIGS[config]
     n = 1 << logn
     cores = os.cpu_count() or 1
-    moduli = orc.generate_primes(bits, l, n)
-    ob = orc.Basis(n, moduli)
-    rng = np.random.default_rng(4321)
-    q = np.array(moduli, dtype=np.uint64)
-    count = max(1, cores // l)
+    ob = orc.Basis(n, orc.generate_primes(bits, l, n))
+    ins, ka, kb = sample["inputs"], sample["ka"], sample["kb"]
+    count = ins[0].shape[0]
 
-    def uni(*lead):
-        return (rng.integers(0, 1 << 63, size=(*lead, l, n), dtype=np.uint64) % q[:, None]).astype(np.uint64)
+    def run(threads, k):
+        if op == "rotate":
+            return ob.bench_rotate(threads, ins[0][:k], ins[1][:k], ka, kb, 1)
+        return ob.bench_mul_rescale(threads, ins[0][:k], ins[1][:k], ins[2][:k], ins[3][:k], ka, kb)
 
-    a0, a1, b0, b1 = uni(count), uni(count), uni(count), uni(count)
-    ka, kb = uni(l), uni(l)
-    sec, _, _ = ob.bench_mul_rescale(cores, a0, a1, b0, b1, ka, kb)
-    return {
-        "value": count / sec,
-        "unit": "ct-mult/s",
+    timed = max(1, count - 1)  # the last sample is the last pair of the batch: parity only, untimed
+    sec, o0, o1 = run(cores, timed)
+    outs = [(o0, o1)]
+    if count > timed:
+        if op == "rotate":
+            _, p0, p1 = ob.bench_rotate(cores, ins[0][timed:], ins[1][timed:], ka, kb, 1)
+        else:
+            _, p0, p1 = ob.bench_mul_rescale(cores, ins[0][timed:], ins[1][timed:], ins[2][timed:], ins[3][timed:], ka, kb)
+        outs.append((p0, p1))
+    unit = "ct-mult/s" if op == "mul" else "rotation/s"
+    rec = {
+        "value": timed / sec,
+        "unit": unit,
         "cores": cores,
         "kind": "port",
-        "sample": f"{count} ciphertext pair(s) at full size N={n}, L={l} ({sec:.1f} s of wall time on {cores} threads); "
-        "oracle = C++ restatement of the reference schedule (the Rust crate cannot be built here)",
+        "sample": f"{timed} ciphertext pair(s) of the timed GPU batch at full size N={n}, L={l} ({sec:.1f} s of wall time on {cores} threads: "
+        "the limbs of each unit are spread over the threads); oracle = C++ restatement of the reference schedule (the Rust crate cannot "
+        "be built here).  The reference itself is single-threaded: `single_thread` is the like-for-like figure, `value` flatters the CPU",
+    }
+    if single_thread:
+        s1, _, _ = run(1, 1)
+        rec["single_thread"] = {"value": 1.0 / s1, "unit": unit, "cores": 1, "sample": f"1 pair, {s1:.1f} s"}
+    return rec, (np_cat([o[0] for o in outs]), np_cat([o[1] for o in outs]))
+
+
+def np_cat(xs):
+    import numpy as np
+
+    return np.concatenate(xs, axis=0)
+
+
+# Algorithmic modmuls per launch of the key-switch kernels (SURVEY 8d counts a limb transform as N/2 log2 N + N:
+# at N = 2^16 that is 5 N in the first pass -- 256-point negacyclic transform + four-step twiddle -- and 4 N in the
+# second), plus one modmul per key multiply-accumulate.
+def _ks1_modmuls(n, logn, l, batch):
+    a1 = (logn + 1) // 2
+    return _cs(n, l, batch) * l * (l - 1) * n * (a1 / 2 + 1)
+
+
+def _ks2_modmuls(n, logn, l, batch):
+    a2 = logn - (logn + 1) // 2
+    cs = _cs(n, l, batch)
+    return cs * l * (l - 1) * n * (a2 / 2) + 2 * cs * l * l * n + 2 * cs * l * n * (a2 / 2 + 1)
+
+
+def ntt_point(ck, torch, dev, stream, hbm_peak, bits, logn, l, steps, warmup):
+    """One point of BASELINE.json configs[4] (the metric's second half): limb-batched forward / inverse transforms of
+    ~1 GiB of limbs (> L2), CUDA events around each call, median; 16 N algorithmic bytes per limb transform."""
+    n = 1 << logn
+    moduli = ck.generate_primes(bits, l, n)
+    basis = ck.RnsBasis(n, moduli, device=dev.index)
+    basis.set_stream(stream.cuda_stream)
+    batch = max(1, (1 << 30) // (l * n * 8))
+    qt = torch.tensor(moduli, dtype=torch.int64, device=dev)[:, None]
+    t = torch.randint(0, 1 << 62, (batch, l, n), dtype=torch.int64, device=dev) % qt
+    h = ck._vp()
+    ck._check(ck._lib.ckks_poly_from_device(basis._h, batch, ck.C.cast(t.data_ptr(), ck._u64p), 0, ck.C.byref(h)))
+    p = ck.RnsPoly(h, basis)
+    del t
+    rec = {"N": n, "L": l, "bits": bits, "batch": batch, "word": "u32" if bits <= 31 else "u64"}
+    for name in ("fwd", "inv"):
+        fn = p.to_ntt_domain if name == "fwd" else p.to_coeff_domain
+        other = p.to_coeff_domain if name == "fwd" else p.to_ntt_domain
+        if name == "inv":
+            p.to_ntt_domain()
+        for _ in range(max(1, warmup)):
+            fn()
+            other()
+        times = []
+        for _ in range(max(steps, 5)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+            other()
+        ms = sorted(times)[len(times) // 2]
+        tr = batch * l / (ms * 1e-3)
+        rec[name] = {"ms": ms, "transforms_per_s": tr, "gbs": tr * 16.0 * n / 1e9, "hbm_frac": tr * 16.0 * n / 1e9 / hbm_peak}
+        if name == "inv":
+            p.to_coeff_domain()
+    del p, basis
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, passes=2):
+    """BASELINE.json configs[3] as worded: the horner_chain workload (examples/horner_chain.rs:211-278), x <- x * alpha
+    + beta from L limbs down to 2, on a RESIDENT batch: per level one mul_ciphertexts_gadget + rescale_ciphertext with
+    that level's gadget key and one add_ciphertexts.  Ciphertexts and keys are synthetic uniform limbs (the reference
+    regenerates keys per level on the host; key generation is not part of the timed hot path)."""
+    levels = list(range(l, 2, -1))  # limb count before each multiplication: L .. 3 -> ends with 2 primes
+    bases = {l: basis}
+    for k in range(l - 1, 1, -1):
+        bases[k] = bases[k + 1].drop_last(1)
+    keys, alphas, betas = {}, {}, {}
+    for k in levels:
+        ka, kb = uni_poly_at(bases[k], k, k), uni_poly_at(bases[k], k, k)
+        keys[k] = ck.GadgetKey.from_polys(ka, kb)
+        del ka, kb
+    alpha_top = ck.Ciphertext(uni_poly_at(basis, l, batch), uni_poly_at(basis, l, batch), bits, bits * l)
+    beta_top = ck.Ciphertext(uni_poly_at(basis, l, batch), uni_poly_at(basis, l, batch), bits, bits * l)
+    for k in levels:
+        alphas[k] = alpha_top if k == l else ck.Ciphertext(alpha_top.c0.mod_drop_last(basis=bases[k]), alpha_top.c1.mod_drop_last(basis=bases[k]), bits, bits * k)
+        betas[k - 1] = ck.Ciphertext(beta_top.c0.mod_drop_last(basis=bases[k - 1]), beta_top.c1.mod_drop_last(basis=bases[k - 1]), bits, bits * (k - 1))
+    x0 = ck.Ciphertext(uni_poly_at(basis, l, batch), uni_poly_at(basis, l, batch), bits, bits * l)
+    torch.cuda.empty_cache()
+    per_level = {k: [] for k in levels}
+    totals = []
+    for it in range(passes + 1):  # first pass is the warm-up
+        ct = x0
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(levels) + 1)]
+        torch.cuda.synchronize()
+        evs[0].record(stream)
+        for t, k in enumerate(levels):
+            ct = ck.CkksEngine.mul_relin_rescale(ct, alphas[k], keys[k], bases[k - 1])
+            ct.logp = bits
+            ct = ck.CkksEngine.add_ciphertexts(ct, betas[k - 1])
+            evs[t + 1].record(stream)
+        torch.cuda.synchronize()
+        assert ct.c0.channel_count() == 2
+        if it:
+            for t, k in enumerate(levels):
+                per_level[k].append(evs[t].elapsed_time(evs[t + 1]))
+            totals.append(evs[0].elapsed_time(evs[-1]))
+        del ct
+    ms_chain = sum(totals) / len(totals)
+    return {
+        "workload": f"horner_chain x <- x*alpha + beta, N={n}, L={l} -> 2 ({len(levels)} levels), resident batch of {batch} ciphertexts, "
+        "per level: mul_ciphertexts_gadget + rescale_ciphertext + add_ciphertexts",
+        "ms_per_chain": ms_chain,
+        "chains_per_s": batch / (ms_chain * 1e-3),
+        "ct_mults_per_s": batch * len(levels) / (ms_chain * 1e-3),
+        "per_level": {str(k): {"ms": sum(v) / len(v), "ct_mults_per_s": batch / (sum(v) / len(v) * 1e-3)} for k, v in per_level.items()},
     }
 
 
@@ -242,21 +373,36 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     gen = torch.Generator(device=dev)
     gen.manual_seed(99 + rank)
-    qt = torch.tensor(moduli, dtype=torch.int64, device=dev)[:, None]
+    op = args.op or ("rotate" if args.config == "cfg3" else "mul")
+    n_in = 4 if op == "mul" else 2
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+    cores = os.cpu_count() or 1
+    # pairs whose host copies feed the oracle (timing sample + parity): the first `count` and the last of the batch
+    count = max(1, cores // l)
+    keep_idx = sorted(set(list(range(min(count, batch))) + [batch - 1])) if want_cpu else []
 
-    def uni_poly(b):
-        t = torch.randint(0, 1 << 62, (b, l, n), dtype=torch.int64, device=dev, generator=gen) % qt
+    def uni_poly_at(b, limbs, nb, keep=None):
+        qt = torch.tensor(moduli[:limbs], dtype=torch.int64, device=dev)[:, None]
+        t = torch.randint(0, 1 << 62, (nb, limbs, n), dtype=torch.int64, device=dev, generator=gen) % qt
         h = ck._vp()
-        ck._check(ck._lib.ckks_poly_from_device(basis._h, b, ck.C.cast(t.data_ptr(), ck._u64p), 0, ck.C.byref(h)))
-        p = ck.RnsPoly(h, basis)
+        ck._check(ck._lib.ckks_poly_from_device(b._h, nb, ck.C.cast(t.data_ptr(), ck._u64p), 0, ck.C.byref(h)))
+        p = ck.RnsPoly(h, b)
+        if keep is not None:
+            keep.append(t[keep_idx].cpu().numpy().view(np.uint64) if keep_idx and nb == batch else t.cpu().numpy().view(np.uint64))
         del t
         return p
 
-    ka, kb = uni_poly(l), uni_poly(l)
+    def uni_poly(nb, keep=None):
+        return uni_poly_at(basis, l, nb, keep)
+
+    host_keys, host_in = [], []
+    ka, kb = uni_poly(l, host_keys if want_cpu else None), uni_poly(l, host_keys if want_cpu else None)
     rlk = ck.GadgetKey.from_polys(ka, kb)
     del ka, kb
-    cta = ck.Ciphertext(uni_poly(batch), uni_poly(batch), bits, bits * l)
-    ctb = ck.Ciphertext(uni_poly(batch), uni_poly(batch), bits, bits * l)
+    polys = [uni_poly(batch, host_in if want_cpu else None) for _ in range(4)]
+    cta = ck.Ciphertext(polys[0], polys[1], bits, bits * l)
+    ctb = ck.Ciphertext(polys[2], polys[3], bits, bits * l)
+    del polys
     torch.cuda.empty_cache()
 
     def barrier():
@@ -271,7 +417,6 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    op = args.op or ("rotate" if args.config == "cfg3" else "mul")
     rlk.rotation = 1
 
     def step():
@@ -279,40 +424,62 @@ def run_b200(args):
             return ck.CkksEngine.rotate_ciphertext(cta, rlk)
         return ck.CkksEngine.mul_relin_rescale(cta, ctb, rlk, child)
 
+    out = None
     for _ in range(args.warmup):
-        step()
+        out = step()
     barrier()
+    # ---- timed region: K steps, profiler hooks OFF, CUDA events on the library's stream ------------
     sampler = ClockSampler(local)
-    ck._lib.ckks_prof_enable(1 if args.prof else 0)
+    ck._lib.ckks_prof_enable(0)
     launches0 = ck.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
-        step()
+        out = step()
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
     launches = ck.launch_count() - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    ck._lib.ckks_prof_enable(0)
+    ms_per_step = ms_total / args.steps
+    value = world * batch / (ms_per_step * 1e-3)
+
+    # device words of the pairs the oracle will recompute (taken from the last timed step's output)
+    dev_rows = None
+    if want_cpu and out is not None:
+        outL = l - 1 if op == "mul" else l
+        rows = []
+        for comp in (out.c0, out.c1):
+            ptr = ck.C.POINTER(ck.C.c_uint64)()
+            ck._check(ck._lib.ckks_poly_device_ptr(comp._h, ck.C.byref(ptr)))
+            addr = ck.C.cast(ptr, ck.C.c_void_p).value
+            tt = torch.as_tensor(_DevBuf(addr, batch * outL * n), device=dev).view(batch, outL, n)
+            rows.append(tt[keep_idx].cpu().numpy().view(np.uint64))
+        dev_rows = rows
+    del out
+
+    # ---- per-kernel breakdown: a SEPARATE, untimed pass with every launch bracketed by CUDA events ----
     prof = {}
     if args.prof:
+        ck._lib.ckks_prof_enable(1)
+        for _ in range(max(1, min(args.steps, 3))):
+            step()
+        torch.cuda.synchronize()
+        ck._lib.ckks_prof_enable(0)
         buf = ck.C.create_string_buffer(1 << 20)  # collect() drains the records: one call
         ck._lib.ckks_prof_collect(buf, len(buf))
         for ln in buf.value.decode().splitlines():
             name, rest = ln.split("=")
             cnt, ms = rest.split(",")
             prof[name] = (int(cnt), float(ms))
-    ms_per_step = ms_total / args.steps
-    value = world * batch / (ms_per_step * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------
     while True:  # page-locked staging buffers; halve the e2e batch if the host cannot pin that much
         wi, wo = (e2e_batch, l, n), (e2e_batch, l - 1 if op == "mul" else l, n)
         try:
-            hin = [ck.PinnedBuffer(wi) for _ in range(4)]
+            hin = [ck.PinnedBuffer(wi) for _ in range(n_in)]
             hout = [ck.PinnedBuffer(wo) for _ in range(2)]
             break
         except ck.RnsNttError:
@@ -320,14 +487,11 @@ def run_b200(args):
             if e2e_batch <= 1:
                 raise
             e2e_batch //= 2
-    e2e_polys = [uni_poly(e2e_batch) for _ in range(4)]
+    e2e_polys = [uni_poly(e2e_batch) for _ in range(n_in)]
     for hb, p in zip(hin, e2e_polys):  # host copies of the e2e inputs (outside the timed region)
         ck._check(ck._lib.ckks_poly_download(p._h, ck._ptr(hb.array)))
-    h2d = 4 * hin[0].array.nbytes
+    h2d = n_in * hin[0].array.nbytes
     d2h = 2 * hout[0].array.nbytes
-
-    if op == "rotate":
-        h2d //= 2
 
     def e2e_step():
         if op == "rotate":
@@ -346,15 +510,37 @@ def run_b200(args):
     e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)) / args.steps
     e2e_value = world * e2e_batch / (e2e_ms * 1e-3)
 
-    # parity spot check of the e2e output against the device-resident path (same inputs)
-    ea, eb = ck.Ciphertext(e2e_polys[0], e2e_polys[1], bits, bits * l), ck.Ciphertext(e2e_polys[2], e2e_polys[3], bits, bits * l)
-    ref = ck.CkksEngine.rotate_ciphertext(ea, rlk) if op == "rotate" else ck.CkksEngine.mul_relin_rescale(ea, eb, rlk, child)
-    assert np.array_equal(ref.c0.channels(), hout[0].array), "host-buffer path and device path disagree"
+    # the host-buffer path must agree with the device-resident path on the same inputs
+    if op == "rotate":
+        ref = ck.CkksEngine.rotate_ciphertext(ck.Ciphertext(e2e_polys[0], e2e_polys[1], bits, bits * l), rlk)
+    else:
+        ref = ck.CkksEngine.mul_relin_rescale(ck.Ciphertext(e2e_polys[0], e2e_polys[1], bits, bits * l), ck.Ciphertext(e2e_polys[2], e2e_polys[3], bits, bits * l), rlk, child)
+    assert np.array_equal(ref.c0.channels(), hout[0].array) and np.array_equal(ref.c1.channels(), hout[1].array), "host-buffer path and device path disagree"
     del ref, e2e_polys
+
+    # ---- what the host's copy path alone sustains: the same bytes as one e2e step, H2D and D2H concurrently on two
+    # streams in the pipeline's chunk size, all ranks at once (max over ranks) -> the ceiling of `e2e` on this box
+    barrier()
+    sec = float(ck._lib.ckks_bench_host_copy(local, ck._ptr(hin[0].array), hin[0].array.nbytes, n_in, ck._ptr(hout[0].array), hout[0].array.nbytes, 2, 3))
+    copy_ms = max_over_ranks(sec * 1e3)
+    barrier()
+    copy_probe = {
+        "ms_per_step_bytes": copy_ms,
+        "h2d_gbs_per_gpu": h2d / (copy_ms * 1e-3) / 1e9,
+        "d2h_gbs_per_gpu": d2h / (copy_ms * 1e-3) / 1e9,
+        "aggregate_gbs": world * (h2d + d2h) / (copy_ms * 1e-3) / 1e9,
+        "e2e_ceiling": world * e2e_batch / (copy_ms * 1e-3),
+        "what": f"plain cudaMemcpyAsync of one e2e step's bytes ({h2d} B in, {d2h} B out per GPU), both directions concurrently, "
+        f"{world} rank(s) at once, no kernels: the rate the host side alone allows",
+    }
+    del hin, hout
 
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     bytes_ct = algorithmic_bytes_per_ctmult(n, l, batch)
+    mm_ct = modmuls_per_ctmult(n, logn, l)
+    imad_peak = ck.modmul_peak(local, 4096)  # measured in this run: dependent-free exact Shoup modmuls
+    imad_peak = max_over_ranks(imad_peak) if world > 1 else imad_peak
     line = {
         "metric": "ct-mults/sec (mul+relin+rescale)" if op == "mul" else "rotations/sec (automorphism + gadget key-switch)",
         "value": value,
@@ -374,18 +560,29 @@ def run_b200(args):
             "batch_per_gpu": batch,
             "e2e_batch_per_gpu": e2e_batch,
             "parallelism": f"batch-sharded x{world}, no data-path collective",
-            "l2": f"inputs are {4 * batch * l * n * 8 / 2**30:.1f} GiB per step (> 126 MB L2); no flush needed",
+            "l2": f"inputs are {n_in * batch * l * n * 8 / 2**30:.1f} GiB per step (> 126 MB L2); no flush needed",
+            "timing": "CUDA events on the library's stream, per-kernel event hooks off in the timed region (the kernel breakdown is a separate pass)",
         },
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "ct-mult/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+        "e2e": {"value": e2e_value, "unit": "ct-mult/s" if op == "mul" else "rotation/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "host_copy_probe": copy_probe},
         "gpu_launches": launches,
-        "ctmult": {
-            "algorithmic_bytes": bytes_ct,
-            "hbm_frac": value / world * bytes_ct / (hbm_peak * 1e9),
-            "modmuls": modmuls_per_ctmult(n, logn, l),
-            "modmul_rate": value / world * modmuls_per_ctmult(n, logn, l),
+        "imad": {
+            "peak_modmul_per_s": imad_peak,
+            "peak_kind": "measured in this run (ckks_bench_modmul_peak: dependent-free exact 64-bit Shoup multiplies on every SM)",
         },
     }
+    if op == "mul":
+        rate = value / world
+        line["ctmult"] = {
+            "algorithmic_bytes": bytes_ct,
+            "hbm_frac": rate * bytes_ct / (hbm_peak * 1e9),
+            "modmuls": mm_ct,
+            "modmul_rate": rate * mm_ct,
+            "imad_frac": (rate * mm_ct / imad_peak) if imad_peak else None,
+            "binding_roof": "imad",
+        }
+        line["imad"]["step_frac"] = line["ctmult"]["imad_frac"]
     if args.prof and prof:
         tot = sum(ms for _, ms in prof.values())
         top = max(prof.items(), key=lambda kv: kv[1][1])
@@ -396,15 +593,31 @@ def run_b200(args):
         per_launch = KERNEL_BYTES.get(name, lambda **kw: None)(n=n, l=l, batch=batch)
         dur_s = ms * 1e-3 / cnt
         ach = per_launch / dur_s / 1e9 if per_launch else None
+        kmm = {}
+        if op == "mul" and logn >= 8:
+            for kname, fn in (("ks_pass1", _ks1_modmuls), ("ks_pass2_tma", _ks2_modmuls), ("ks_pass2", _ks2_modmuls)):
+                if kname in prof and imad_peak:
+                    c, m = prof[kname]
+                    kmm[kname] = {"modmuls_per_launch": fn(n, logn, l, batch), "modmul_per_s": fn(n, logn, l, batch) / (m * 1e-3 / c),
+                                  "imad_frac": fn(n, logn, l, batch) / (m * 1e-3 / c) / imad_peak}
+        line["imad"]["kernels"] = kmm
+        traffic, traffic_src = ncu_traffic(name, args.config, op, batch)
+        top_imad = kmm.get(name, {}).get("imad_frac")
+        hbm_frac = (ach / hbm_peak if ach else None)
         line["roofline"] = {
             "kernel": name,
-            "bound": "hbm",
+            # the binding roof of the dominant kernel: the integer (IMAD) pipe for the key-switch kernels, HBM otherwise
+            "bound": "imad" if (top_imad is not None and hbm_frac is not None and top_imad > hbm_frac) else "hbm",
             "achieved": ach,
             "peak": hbm_peak,
             "unit": "GB/s",
-            "frac": (ach / hbm_peak if ach else None),
-            # the ncu capture was taken at cfg4 with 14 ciphertexts per launch (the default chunk): null elsewhere
-            "traffic": TRAFFIC_NCU.get(name) if (args.config == "cfg4" and op == "mul" and batch >= 14) else None,
+            "frac": hbm_frac,
+            "hbm_frac": hbm_frac,
+            "imad_frac": top_imad,
+            "imad_achieved_modmul_per_s": kmm.get(name, {}).get("modmul_per_s"),
+            "imad_peak_modmul_per_s": imad_peak,
+            "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_kind": peak_kind,
             "share_of_step": ms / tot,
             "avg_launch_ms": ms / cnt,
@@ -412,14 +625,55 @@ def run_b200(args):
             "algorithmic_bytes_per_launch": per_launch,
         }
         line["kernels"] = {k: {"launches": c, "ms": round(m, 3), "share": round(m / tot, 4)} for k, (c, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.config)
-    if args.imad and rank == 0:
-        line["modmul_peak_per_s"] = ck.modmul_peak(local, 4096)
+    # ---- the metric's second half: limb NTT achieved HBM GB/s vs peak, at the metric's shape ----------
+    if rank == 0 and not args.no_ntt and logn >= 12:
+        del cta, ctb
+        torch.cuda.empty_cache()
+        line["ntt"] = {
+            "what": "standalone limb-batched to_ntt_domain / to_coeff_domain, ~1 GiB of limbs per call, 16 N algorithmic bytes per limb transform, "
+            f"fractions of the {peak_kind} HBM peak {hbm_peak} GB/s",
+            "points": [ntt_point(ck, torch, dev, stream, hbm_peak, b_, logn, l, args.steps, 2) for b_ in (61, 30)],
+        }
+        if not args.no_chain and op == "mul" and world == 1 and args.config == "cfg4":
+            line["chain"] = run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, min(batch, 256))
+    if want_cpu:
+        sample = {"inputs": host_in, "ka": host_keys[0], "kb": host_keys[1]}
+        rec, (o0, o1) = cpu_baseline(args.config, op, sample, single_thread=not args.no_single_thread)
+        line["cpu_baseline"] = rec
+        equal = bool(np.array_equal(o0, dev_rows[0]) and np.array_equal(o1, dev_rows[1]))
+        line["parity"] = {"checked_pairs": len(keep_idx), "pair_indices": keep_idx, "equal": equal,
+                          "what": "every output word of these pairs of the TIMED batch (last timed step) against the oracle on the same inputs"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if want_cpu and not line["parity"]["equal"]:
+        raise SystemExit("bench.py: PARITY FAILURE -- the GPU output differs from the oracle on the timed batch")
+
+
+def ncu_traffic(kernel, config, op, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, read from the committed `ncu --set full`
+    summary (profiles/*.json, newest round first) of the same configuration; (None, reason) if there is none."""
+    if not (config == "cfg4" and op == "mul" and batch >= 14):
+        return None, "no capture for this configuration"
+    import glob
+
+    want = {"ks_pass2_tma": "ks_pass2_kernel", "ks_pass2": "ks_pass2_kernel", "ks_pass1": "ks_pass1_kernel"}.get(kernel)
+    if not want:
+        return None, "no capture of this kernel"
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_ks_kernels*final*.json")), reverse=True):
+        try:
+            with open(path) as f:
+                rows = json.load(f)
+            for r in rows:
+                if want in r.get("Kernel Name", ""):
+                    def gb(v):
+                        x, u = v.split()
+                        return float(x) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+                    return gb(r["dram__bytes_read.sum"]) + gb(r["dram__bytes_write.sum"]), os.path.relpath(path, ROOT) + " (14 ciphertexts per launch)"
+        except Exception:
+            continue
+    return None, "no capture found under profiles/"
 
 
 class _DevBuf:
@@ -681,9 +935,6 @@ KERNEL_BYTES = {
     "tensor": lambda n, l, batch: 8.0 * n * l * _cs(n, l, batch) * 7,
     "rescale": lambda n, l, batch: 8.0 * n * batch * (2 * l - 1),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at cfg4, from the
-# committed `ncu --set full` capture (profiles/); None until measured.
-TRAFFIC_NCU = {"ks_pass2_tma": 5229823000 + 370285000}  # profiles/r01_ncu_full_ks_kernels_final.json (14 ciphertexts per launch)
 
 
 def main():
@@ -697,6 +948,9 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prof", dest="prof", action="store_false")
+    ap.add_argument("--no-ntt", action="store_true", help="skip the limb-NTT record (the metric's second half)")
+    ap.add_argument("--no-chain", action="store_true", help="skip the horner_chain sub-record (cfg4, 1 GPU)")
+    ap.add_argument("--no-single-thread", action="store_true", help="skip the single-threaded oracle timing (~40 s at cfg4)")
     ap.add_argument("--imad", action="store_true", help="also run the integer-pipe microbenchmark")
     ap.add_argument("--op", default="", choices=["", "mul", "rotate"], help="hot-path operation (default: mul; rotate for cfg3)")
     ap.add_argument("--host-chunk-mib", type=int, default=0, help="pipeline chunk of the host-buffer entry point")

@@ -155,7 +155,8 @@ int ckks_poly_to_coeffs(const ckks_poly *p, int64_t *out);
 
 /* ---- gadget keys  (engine.rs:225-253, generated by engine.rs:288-399 on the host) -------------- */
 /* a, b: [digit i < L][limb j < L][N] coefficient domain, as `rlk.a[i].channels()`.  The key is
- * transformed once and stays resident in HBM. */
+ * transformed once and stays resident in HBM.  Words must be canonical, as in every RnsPoly the reference
+ * builds (from_channels poly.rs:83-93): CKKS_NON_REDUCED_COEFFICIENT otherwise (scanned on the device). */
 int ckks_ksk_upload(ckks_ctx *ctx, const uint64_t *a, const uint64_t *b, ckks_ksk **out);
 /* Same, from device polynomials of batch L (digit-major), e.g. produced by ckks_gen_gadget_key. */
 int ckks_ksk_from_polys(const ckks_poly *a, const ckks_poly *b, ckks_ksk **out);
@@ -202,7 +203,9 @@ int ckks_decode(const ckks_poly *p, uint32_t scale_bits, size_t nslots, double *
 /* ---- host-buffer entry points (what a reference-side caller with `Vec<[u64;N]>` data uses) ------ */
 /* mul_ciphertexts_gadget + rescale_ciphertext on `batch` ciphertext pairs held in HOST memory in
  * the reference layout ([batch][L][N] per component; outputs [batch][L-1][N]).  Copies are chunked
- * through pinned staging buffers and overlapped with compute. */
+ * through pinned staging buffers and overlapped with compute.  Every staged chunk goes through the reducedness
+ * scan from_channels applies (poly.rs:83-93): a word >= its modulus makes the call return
+ * CKKS_NON_REDUCED_COEFFICIENT (the outputs are then unspecified); the same holds for ckks_ct_rotate_host. */
 int ckks_ct_mul_relin_rescale_host(ckks_ctx *ctx, ckks_ctx *child, const ckks_ksk *rlk, size_t batch,
                                    const uint64_t *a0, const uint64_t *a1, const uint64_t *b0,
                                    const uint64_t *b1, uint64_t *o0, uint64_t *o1);
@@ -211,6 +214,30 @@ int ckks_ct_rotate_host(ckks_ctx *ctx, const ckks_ksk *rotk, int32_t k, size_t b
 /* Pinned host allocation helpers for the callers of the *_host entry points. */
 int ckks_host_alloc(size_t bytes, void **out);
 int ckks_host_free(void *p);
+
+/* ---- batch-sharded multi-GPU group (SURVEY.md 8b "multi-GPU", 8e default mode) -----------------------------
+ * Replaces the reference's serial loop over a `Vec<Ciphertext>` (examples/horner_chain.rs:211-278 calling
+ * engine.rs:473-539 / :263-282 per ciphertext): ONE process spreads a host batch over the GPUs of a box.
+ * Ciphertexts are independent, so there is no inter-GPU traffic; the gadget key is replicated once per device.
+ * Every *_host call cuts the batch into contiguous shares (sizes differ by at most one) and runs the
+ * single-GPU host pipeline on each device from its own host thread.  Output words equal the single-GPU ones. */
+typedef struct ckks_comm ckks_comm;
+typedef struct ckks_comm_ksk ckks_comm_ksk;
+/* devices: `ndev` CUDA ordinals (NULL = 0..ndev-1; an ordinal may repeat).  Validates like RnsBasis::new. */
+int ckks_comm_init(int ndev, const int *devices, uint64_t n, const uint64_t *moduli, size_t l, ckks_comm **out);
+int ckks_comm_destroy(ckks_comm *c);
+int ckks_comm_drop_last(ckks_comm *c, size_t drop_count, ckks_comm **out);  /* basis.rs:121-134 on every device */
+int ckks_comm_size(const ckks_comm *c);
+ckks_ctx *ckks_comm_ctx(ckks_comm *c, int i);  /* borrowed: the context of device slot i */
+/* One host key (layout of ckks_ksk_upload) -> a transformed replica per device, uploaded concurrently. */
+int ckks_comm_ksk_upload(ckks_comm *c, const uint64_t *a, const uint64_t *b, ckks_comm_ksk **out);
+int ckks_comm_ksk_free(ckks_comm_ksk *k);
+/* Same contracts as ckks_ct_mul_relin_rescale_host / ckks_ct_rotate_host (reducedness scan included). */
+int ckks_comm_ct_mul_relin_rescale_host(ckks_comm *c, const ckks_comm_ksk *rlk, size_t batch, const uint64_t *a0,
+                                        const uint64_t *a1, const uint64_t *b0, const uint64_t *b1, uint64_t *o0,
+                                        uint64_t *o1);
+int ckks_comm_ct_rotate_host(ckks_comm *c, const ckks_comm_ksk *rotk, int32_t k, size_t batch, const uint64_t *c0,
+                             const uint64_t *c1, uint64_t *o0, uint64_t *o1);
 
 /* ---- optional limb-sharded mode (north_star "limb-sharded mode at N=2^16 / L>=24") ------
  * Replaces nothing in the reference (it is single-threaded and single-device); it is the multi-GPU form
@@ -298,6 +325,11 @@ int ckks_poly_from_device(ckks_ctx *ctx, size_t batch, const uint64_t *dev_chann
 int ckks_poly_device_ptr(ckks_poly *p, uint64_t **out);
 /* Integer-pipe microbenchmark: dependent-free 64-bit Shoup modmuls; returns modmul/s (0 on error). */
 double ckks_bench_modmul_peak(int device, int iters);
+/* Host-side copy ceiling of the *_host entry points: n_src H2D copies of [hsrc, +src_bytes) and n_dst D2H copies
+ * into [hdst, +dst_bytes), both directions concurrently, in the pipeline's chunk size, no kernels; seconds per
+ * iteration (0 on error). */
+double ckks_bench_host_copy(int device, const void *hsrc, size_t src_bytes, int n_src, void *hdst, size_t dst_bytes,
+                            int n_dst, int iters);
 
 #ifdef __cplusplus
 }

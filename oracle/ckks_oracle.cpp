@@ -759,6 +759,17 @@ extern "C" double orc_bench_mul_rescale(const orc_basis *b, size_t count, int th
         orc_rescale_ciphertext(b, m0.data(), m1.data(), o0 + k * wo, o1 + k * wo, nullptr);
     });
 }
+// mul_ciphertexts_gadget alone (engine.rs:473-539), same threading: lets the parity tests check the
+// unrescaled limbs at N = 2^16, L = 24 in seconds instead of minutes.
+extern "C" double orc_bench_mul_gadget(const orc_basis *b, size_t count, int threads, const u64 *a0, const u64 *a1,
+                                       const u64 *b0, const u64 *b1, const u64 *rlk_a, const u64 *rlk_b, u64 *o0,
+                                       u64 *o1) {
+    size_t w = b->moduli.size() * b->n;
+    return run_parallel(count, threads, [&](size_t k) {
+        orc_mul_ciphertexts_gadget(b, a0 + k * w, a1 + k * w, b0 + k * w, b1 + k * w, rlk_a, rlk_b, o0 + k * w,
+                                   o1 + k * w);
+    });
+}
 extern "C" double orc_bench_rotate(const orc_basis *b, size_t count, int threads, const u64 *c0, const u64 *c1,
                                    const u64 *rotk_a, const u64 *rotk_b, int32_t rotation, u64 *o0, u64 *o1) {
     size_t w = b->moduli.size() * b->n;

@@ -121,6 +121,9 @@ void orc_decode(uint64_t n, uint32_t scale_bits, const int64_t *coeffs, size_t s
 double orc_bench_mul_rescale(const orc_basis *b, size_t count, int threads, const uint64_t *a0,
                              const uint64_t *a1, const uint64_t *b0, const uint64_t *b1,
                              const uint64_t *rlk_a, const uint64_t *rlk_b, uint64_t *o0, uint64_t *o1);
+double orc_bench_mul_gadget(const orc_basis *b, size_t count, int threads, const uint64_t *a0,
+                            const uint64_t *a1, const uint64_t *b0, const uint64_t *b1, const uint64_t *rlk_a,
+                            const uint64_t *rlk_b, uint64_t *o0, uint64_t *o1);
 double orc_bench_rotate(const orc_basis *b, size_t count, int threads, const uint64_t *c0,
                         const uint64_t *c1, const uint64_t *rotk_a, const uint64_t *rotk_b,
                         int32_t rotation, uint64_t *o0, uint64_t *o1);

@@ -119,6 +119,8 @@ def lib():
         L.orc_decode.restype = None
         L.orc_bench_mul_rescale.restype = C.c_double
         L.orc_bench_mul_rescale.argtypes = [C.c_void_p, C.c_size_t, C.c_int] + [_u64p] * 8
+        L.orc_bench_mul_gadget.restype = C.c_double
+        L.orc_bench_mul_gadget.argtypes = [C.c_void_p, C.c_size_t, C.c_int] + [_u64p] * 8
         L.orc_bench_rotate.restype = C.c_double
         L.orc_bench_rotate.argtypes = [C.c_void_p, C.c_size_t, C.c_int] + [_u64p] * 4 + [C.c_int32, _u64p, _u64p]
         L.orc_bench_ntt.restype = C.c_double
@@ -344,6 +346,16 @@ class Basis:
         o1 = np.zeros_like(o0)
         sec = lib().orc_bench_mul_rescale(self._h, count, threads, _p(a0), _p(_u(a1)), _p(_u(b0)), _p(_u(b1)),
                                           _p(_u(rlk_a)), _p(_u(rlk_b)), _p(o0), _p(o1))
+        return float(sec), o0, o1
+
+    def bench_mul_gadget(self, threads, a0, a1, b0, b1, rlk_a, rlk_b):
+        """mul_ciphertexts_gadget of `count` pairs, unrescaled outputs [count][L][N]."""
+        a0 = _u(a0)
+        count = a0.shape[0]
+        o0 = np.zeros((count, self.l, self.n), dtype=np.uint64)
+        o1 = np.zeros_like(o0)
+        sec = lib().orc_bench_mul_gadget(self._h, count, threads, _p(a0), _p(_u(a1)), _p(_u(b0)), _p(_u(b1)),
+                                         _p(_u(rlk_a)), _p(_u(rlk_b)), _p(o0), _p(o1))
         return float(sec), o0, o1
 
     def bench_rotate(self, threads, c0, c1, rotk_a, rotk_b, rotation):

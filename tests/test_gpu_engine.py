@@ -471,9 +471,9 @@ def test_horner_chain_example(gpu, orc):
 
 
 def test_full_size_properties_n65536_l24(gpu, orc):
-    """BASELINE configs[3] shape (N=2^16, L=24, 61-bit chain): size-independent properties, since
-    one oracle ct-mult at this size costs minutes.
-      * linearity of the key-switch: rotate(ct1 + ct2) == rotate(ct1) + rotate(ct2);
+    """BASELINE configs[3] shape (N=2^16, L=24, 61-bit chain): size-independent properties
+    (the word-for-word comparison with the oracle at this size is test_cfg4_parity_with_oracle_two_chunks).
+      * rotate_ciphertext: ks1 depends on c1 only and o0 - o0' = rotate_slots(c0 - c0') for equal c1;
       * mul by the encryption-free ciphertext (1, 0) with a zero key is the identity before rescale;
       * NTT round trip and schoolbook-free check p * X^k = signed shift."""
     n, l = 65536, 24
@@ -485,15 +485,18 @@ def test_full_size_properties_n65536_l24(gpu, orc):
     rotk = gpu.GadgetKey.upload(gb, ka, kb, rotation=1)
     ct1, ct2 = _ct(gpu, gb, c[0], c[1], 61, 0), _ct(gpu, gb, c[2], c[3], 61, 0)
     r1 = gpu.CkksEngine.rotate_ciphertext(ct1, rotk)
-    r2 = gpu.CkksEngine.rotate_ciphertext(ct2, rotk)
-    rs = gpu.CkksEngine.rotate_ciphertext(gpu.CkksEngine.add_ciphertexts(ct1, ct2), rotk)
-    # alpha_i is a lift, not a ring homomorphism: linearity holds for c0's permutation and modulo the
-    # carry of each digit; compare instead through the exact identity on digits without carry.
-    s0 = r1.c0.clone()
-    s0 += r2.c0
-    carry_free = np.all((c[1].astype(np.float64) + c[3].astype(np.float64)) < np.array(moduli, dtype=np.float64)[:, None])
-    if carry_free:
-        assert np.array_equal(rs.c0.channels(), s0.channels())
+    # c1 of rotate_ciphertext is the key-switch of automorphism(c1) alone; alpha_i is a lift, not a ring homomorphism
+    # (each digit of c1 + c1' may wrap), so the key-switch is linear exactly up to the key applied to the wrap
+    # indicator.  What IS linear without conditions is the automorphism half: o0 - ks0 = rotate_slots(c0), and
+    # ks0 depends on c1 only.  Check it: two ciphertexts with the same c1 and different c0.
+    ct3 = _ct(gpu, gb, c[2], c[1], 61, 0)
+    r3 = gpu.CkksEngine.rotate_ciphertext(ct3, rotk)
+    assert np.array_equal(r3.c1.channels(), r1.c1.channels())  # ks1 sees c1 only
+    d_out = r1.c0.clone()
+    d_out -= r3.c0  # = rotate_slots(c0) - rotate_slots(c0')
+    d_in = gpu.RnsPoly.from_channels(c[0], gb)
+    d_in -= gpu.RnsPoly.from_channels(c[2], gb)
+    assert np.array_equal(d_out.channels(), d_in.rotate_slots(1).channels())
     # multiplication by (1, 0): d0 = a0, d1 = a1, d2 = 0 -> output equals the input (no key contribution)
     one = np.zeros((1, l, n), dtype=np.uint64)
     one[:, :, 0] = 1
@@ -539,3 +542,145 @@ def test_one_oracle_ct_mult_n65536_l3(gpu, orc):
     m0, m1 = ob.mul_ciphertexts_gadget(a0[0], a1[0], b0[0], b1[0], ka, kb)
     r0, r1, _ = ob.rescale_ciphertext(m0, m1)
     assert np.array_equal(out.c0.channels()[0], r0) and np.array_equal(out.c1.channels()[0], r1)
+
+
+def test_cfg4_parity_with_oracle_two_chunks(gpu, orc):
+    """BASELINE configs[3] at full size: N=2^16, L=24, generate_primes(61, 24, 65536), batch 15 = two chunks of the
+    fused pipeline (14 + 1 ciphertexts: 276 MiB of key-switch scratch each).  mul_ciphertexts_gadget
+    (engine.rs:473-539), mul + rescale_ciphertext (engine.rs:263-282) and rotate_ciphertext (engine.rs:412-463),
+    k = 1 and k = -3, are compared WORD FOR WORD with the oracle for the first ciphertext, the last one of the first
+    chunk and the one in the second chunk.  The oracle spreads the limbs of each unit over the host threads
+    (same arithmetic): about 10 s on 16 threads."""
+    import os
+
+    n, l, batch = 65536, 24, 15
+    check = [0, 13, 14]
+    moduli = orc.generate_primes(61, l, n)
+    assert moduli == gpu.generate_primes(61, l, n)
+    gb, ob = gpu.RnsBasis(n, moduli), orc.Basis(n, moduli)
+    rng = np.random.default_rng(2024)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    threads = os.cpu_count() or 1
+    rlk = gpu.GadgetKey.upload(gb, ka, kb)
+    cta, ctb = _ct(gpu, gb, a0, a1, 61, 61 * l), _ct(gpu, gb, b0, b1, 61, 61 * l)
+    # oracle: unrescaled product of the three checked pairs, then the (cheap) rescale of each
+    _, m0, m1 = ob.bench_mul_gadget(threads, a0[check], a1[check], b0[check], b1[check], ka, kb)
+    prod = gpu.CkksEngine.mul_ciphertexts_gadget(cta, ctb, rlk)
+    g0, g1 = prod.c0.channels(), prod.c1.channels()
+    for t, i in enumerate(check):
+        assert np.array_equal(g0[i], m0[t]) and np.array_equal(g1[i], m1[t]), f"mul_ciphertexts_gadget, ciphertext {i}"
+    del prod, g0, g1
+    fused = gpu.CkksEngine.mul_relin_rescale(cta, ctb, rlk)
+    f0, f1 = fused.c0.channels(), fused.c1.channels()
+    assert fused.c0.channel_count() == l - 1 and fused.logp == 122 - 61
+    for t, i in enumerate(check):
+        r0, r1, bits = ob.rescale_ciphertext(m0[t], m1[t])
+        assert bits == 61
+        assert np.array_equal(f0[i], r0) and np.array_equal(f1[i], r1), f"mul+relin+rescale, ciphertext {i}"
+    del fused, f0, f1, ctb, rlk
+    for k in (1, -3):
+        rotk = gpu.GadgetKey.upload(gb, ka, kb, rotation=k)
+        rot = gpu.CkksEngine.rotate_ciphertext(cta, rotk)
+        h0, h1 = rot.c0.channels(), rot.c1.channels()
+        sel = [0, 14]
+        _, r0, r1 = ob.bench_rotate(threads, a0[sel], a1[sel], ka, kb, k)
+        for t, i in enumerate(sel):
+            assert np.array_equal(h0[i], r0[t]) and np.array_equal(h1[i], r1[t]), f"rotate_ciphertext k={k}, ciphertext {i}"
+        del rot, rotk
+
+
+@pytest.mark.parametrize("n,bits,l", [(16, 31, 4), (4096, 30, 3), (4096, 61, 3)])
+def test_host_entry_points_reject_non_reduced_words(gpu, orc, n, bits, l):
+    """from_channels' scan (poly.rs:83-93) also guards the host-buffer entry points and the key upload: a word >= q
+    is RnsNttError::NonReducedCoefficient (code 6), never silent garbage out of the lazy butterflies -- on the small
+    path, the 32-bit word path (where a u64 word >= 2^32 would otherwise be truncated) and the 64-bit path."""
+    moduli = orc.generate_primes(bits, l, n)
+    gb = gpu.RnsBasis(n, moduli)
+    rng = np.random.default_rng(77)
+    batch = 3
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    rlk = gpu.GadgetKey.upload(gb, ka, kb)
+    rotk = gpu.GadgetKey.upload(gb, ka, kb, rotation=1)
+    o0 = np.zeros((batch, l - 1, n), dtype=np.uint64)
+    o1 = np.zeros_like(o0)
+    r0, r1 = np.zeros_like(a0), np.zeros_like(a0)
+    gpu.mul_relin_rescale_host(gb, gb.drop_last(1), rlk, a0, a1, b0, b1, o0, o1)  # clean inputs pass
+    gpu.rotate_host(gb, rotk, a0, a1, r0, r1)
+    for which, bad_word in ((0, moduli[1]), (3, (1 << 32) + 5 if bits < 32 else moduli[l - 1] + 12345), (1, (1 << 64) - 1)):
+        ins = [a0.copy(), a1.copy(), b0.copy(), b1.copy()]
+        limb = 1 if which == 0 else l - 1
+        ins[which][batch - 1, limb, n - 1] = bad_word
+        with pytest.raises(gpu.RnsNttError) as ei:
+            gpu.mul_relin_rescale_host(gb, gb.drop_last(1), rlk, *ins, o0, o1)
+        assert ei.value.code == 6
+        if which < 2:
+            with pytest.raises(gpu.RnsNttError) as ei:
+                gpu.rotate_host(gb, rotk, ins[0], ins[1], r0, r1)
+            assert ei.value.code == 6
+    bad = ka.copy()
+    bad[l - 1, 0, 0] = moduli[0]
+    with pytest.raises(gpu.RnsNttError) as ei:
+        gpu.GadgetKey.upload(gb, bad, kb)
+    assert ei.value.code == 6
+    with pytest.raises(gpu.RnsNttError) as ei:
+        gpu.GadgetKey.upload(gb, ka, bad)
+    assert ei.value.code == 6
+    # the pipeline is reusable after a rejected call
+    gpu.mul_relin_rescale_host(gb, gb.drop_last(1), rlk, a0, a1, b0, b1, o0, o1)
+    fused = gpu.CkksEngine.mul_relin_rescale(_ct(gpu, gb, a0, a1, bits, bits * l), _ct(gpu, gb, b0, b1, bits, bits * l), rlk)
+    assert np.array_equal(fused.c0.channels(), o0) and np.array_equal(fused.c1.channels(), o1)
+
+
+@pytest.mark.parametrize("n,bits,l,batch", [(4096, 40, 3, 7), (16384, 30, 4, 5)])
+def test_batch_sharded_group_matches_single_gpu_and_oracle(gpu, orc, n, bits, l, batch):
+    """ckks_comm_*: ONE process spreads a host batch over the devices of a box.  With fewer than two
+    GPUs both slots of the group sit on device 0 (the share arithmetic, the per-device pipelines and threads are the
+    same); on a multi-GPU box the slots are distinct devices.  Ragged shares (7 over 2 and 3 slots, 5 over 4) and an
+    empty share (batch < slots) are covered; every word equals the oracle's."""
+    moduli = orc.generate_primes(bits, l, n)
+    ob = orc.Basis(n, moduli)
+    rng = np.random.default_rng(4242)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    exp0 = np.zeros((batch, l - 1, n), dtype=np.uint64)
+    exp1 = np.zeros_like(exp0)
+    rot0, rot1 = np.zeros_like(a0), np.zeros_like(a0)
+    for i in range(batch):
+        m0, m1 = ob.mul_ciphertexts_gadget(a0[i], a1[i], b0[i], b1[i], ka, kb)
+        exp0[i], exp1[i], _ = ob.rescale_ciphertext(m0, m1)
+        rot0[i], rot1[i] = ob.rotate_ciphertext(a0[i], a1[i], ka, kb, 2)
+    ndev = gpu.device_count()
+    for slots in (2, 3, 4, 9):
+        devices = [i % ndev for i in range(slots)]
+        grp = gpu.BatchShard(n, moduli, devices)
+        assert grp.size() == slots and grp.basis(slots - 1).channel_count() == l
+        key = grp.upload_key(ka, kb)
+        o0, o1 = np.zeros_like(exp0), np.zeros_like(exp1)
+        grp.mul_relin_rescale_host(key, a0, a1, b0, b1, o0, o1)
+        assert np.array_equal(o0, exp0) and np.array_equal(o1, exp1), f"{slots} slots"
+        rkey = grp.upload_key(ka, kb, rotation=2)
+        r0, r1 = np.zeros_like(a0), np.zeros_like(a0)
+        grp.rotate_host(rkey, a0, a1, r0, r1)
+        assert np.array_equal(r0, rot0) and np.array_equal(r1, rot1), f"rotate, {slots} slots"
+        # one level down through the group's drop_last
+        if slots == 2 and l >= 3:
+            kid = grp.drop_last(1)
+            ob2 = ob.drop_last(1)
+            key2 = kid.upload_key(ka[: l - 1, : l - 1], kb[: l - 1, : l - 1])
+            p0, p1 = np.zeros((batch, l - 2, n), dtype=np.uint64), np.zeros((batch, l - 2, n), dtype=np.uint64)
+            kid.mul_relin_rescale_host(key2, exp0, exp1, exp0, exp1, p0, p1)
+            m0, m1 = ob2.mul_ciphertexts_gadget(exp0[0], exp1[0], exp0[0], exp1[0], np.ascontiguousarray(ka[: l - 1, : l - 1]), np.ascontiguousarray(kb[: l - 1, : l - 1]))
+            e0, e1, _ = ob2.rescale_ciphertext(m0, m1)
+            assert np.array_equal(p0[0], e0) and np.array_equal(p1[0], e1)
+            del key2, kid
+        # a non-reduced word in the LAST share is reported by the group call
+        bad = b1.copy()
+        bad[batch - 1, 0, 5] = moduli[0]
+        with pytest.raises(gpu.RnsNttError) as ei:
+            grp.mul_relin_rescale_host(key, a0, a1, b0, bad, o0, o1)
+        assert ei.value.code == 6
+        del key, rkey, grp
+    with pytest.raises(gpu.RnsNttError):
+        gpu.BatchShard(n, [moduli[0] + 2], [0])  # validation as RnsBasis::new

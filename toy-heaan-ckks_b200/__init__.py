@@ -141,6 +141,16 @@ _sig("ckks_host_free", C.c_int, _vp)
 _sig("ckks_launch_count", C.c_uint64)
 _sig("ckks_launch_table", C.c_size_t, C.c_char_p, C.c_size_t)
 _sig("ckks_bench_modmul_peak", C.c_double, C.c_int, C.c_int)
+_sig("ckks_bench_host_copy", C.c_double, C.c_int, _vp, C.c_size_t, C.c_int, _vp, C.c_size_t, C.c_int, C.c_int)
+_sig("ckks_comm_init", C.c_int, C.c_int, C.POINTER(C.c_int), C.c_uint64, _u64p, C.c_size_t, _pp)
+_sig("ckks_comm_destroy", C.c_int, _vp)
+_sig("ckks_comm_drop_last", C.c_int, _vp, C.c_size_t, _pp)
+_sig("ckks_comm_size", C.c_int, _vp)
+_sig("ckks_comm_ctx", _vp, _vp, C.c_int)
+_sig("ckks_comm_ksk_upload", C.c_int, _vp, _u64p, _u64p, _pp)
+_sig("ckks_comm_ksk_free", C.c_int, _vp)
+_sig("ckks_comm_ct_mul_relin_rescale_host", C.c_int, _vp, _vp, C.c_size_t, _u64p, _u64p, _u64p, _u64p, _u64p, _u64p)
+_sig("ckks_comm_ct_rotate_host", C.c_int, _vp, _vp, C.c_int32, C.c_size_t, _u64p, _u64p, _u64p, _u64p)
 _sig("ckks_lshard_create", C.c_int, C.c_uint64, _u64p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_size_t, _pp)
 _sig("ckks_lshard_destroy", C.c_int, _vp)
 _sig("ckks_lshard_drop_last", C.c_int, _vp, _pp)
@@ -645,6 +655,74 @@ def mul_relin_rescale_host(basis: RnsBasis, child: RnsBasis, rlk: GadgetKey, a0,
 
 def rotate_host(basis: RnsBasis, rotk: GadgetKey, c0, c1, o0, o1):
     _check(_lib.ckks_ct_rotate_host(basis._h, rotk._h, rotk.rotation, c0.shape[0], _ptr(c0), _ptr(c1), _ptr(o0), _ptr(o1)))
+
+
+class BatchShard:
+    """The batch-sharded multi-GPU group (`ckks_comm_*`): one process, one context per device, a host batch cut into
+    contiguous shares.  Replaces the reference's serial loop over a Vec<Ciphertext> (horner_chain.rs:211-278)."""
+
+    def __init__(self, degree: int, moduli, devices=None, _handle=None, _parent=None):
+        self._parent = _parent
+        if _handle is not None:
+            self._h = _handle
+            return
+        if devices is None:
+            devices = list(range(max(1, device_count())))
+        devs = (C.c_int * len(devices))(*devices)
+        arr = (C.c_uint64 * len(moduli))(*moduli)
+        h = _vp()
+        _check(_lib.ckks_comm_init(len(devices), devs, degree, arr, len(moduli), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.ckks_comm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def size(self) -> int:
+        return int(_lib.ckks_comm_size(self._h))
+
+    def basis(self, i: int = 0) -> "RnsBasis":
+        """Borrowed view of device slot i's context."""
+        h = _lib.ckks_comm_ctx(self._h, i)
+        if not h:
+            raise RnsNttError(30)
+        b = RnsBasis(int(_lib.ckks_ctx_degree(h)), [], _handle=_vp(h), _owned=False)
+        b._keepalive = self
+        return b
+
+    def drop_last(self, k: int = 1) -> "BatchShard":
+        h = _vp()
+        _check(_lib.ckks_comm_drop_last(self._h, k, C.byref(h)))
+        return BatchShard(0, [], _handle=h, _parent=self)
+
+    def upload_key(self, a, b, rotation: int = 0) -> "BatchShardKey":
+        a, b = _u64(a), _u64(b)
+        h = _vp()
+        _check(_lib.ckks_comm_ksk_upload(self._h, _ptr(a), _ptr(b), C.byref(h)))
+        return BatchShardKey(h, self, rotation)
+
+    def mul_relin_rescale_host(self, rlk: "BatchShardKey", a0, a1, b0, b1, o0, o1):
+        _check(_lib.ckks_comm_ct_mul_relin_rescale_host(self._h, rlk._h, a0.shape[0], _ptr(a0), _ptr(a1), _ptr(b0), _ptr(b1), _ptr(o0), _ptr(o1)))
+
+    def rotate_host(self, rotk: "BatchShardKey", c0, c1, o0, o1):
+        _check(_lib.ckks_comm_ct_rotate_host(self._h, rotk._h, rotk.rotation, c0.shape[0], _ptr(c0), _ptr(c1), _ptr(o0), _ptr(o1)))
+
+
+class BatchShardKey:
+    def __init__(self, handle, comm: BatchShard, rotation: int = 0):
+        self._h, self._comm, self.rotation = handle, comm, rotation
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.ckks_comm_ksk_free(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 # ── optional limb-sharded mode (SURVEY.md 8e) ────────────────────────────────────────────────────

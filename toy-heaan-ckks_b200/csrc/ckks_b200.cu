@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -419,6 +420,28 @@ static unsigned ew_grid(size_t total) {
     size_t g = (total + 255) / 256;
     size_t cap = 148 * 32;
     return (unsigned)(g < cap ? (g ? g : 1) : cap);
+}
+
+// from_channels' reducedness scan (poly.rs:83-93) of [batch][L][N] device words: ORs 1 into *flag on a word >= q.
+static int scan_reduced(const Tables &T, size_t L, size_t batch, const u64 *d, int *flag, cudaStream_t s) {
+    EwArgs a = ew_args(T, L, batch);
+    if (!a.total) return CKKS_OK;
+    KL("check_reduced", (check_reduced_kernel<<<ew_grid(a.total), 256, 0, s>>>(a, d, flag)));
+    return CKKS_OK;
+}
+
+// The same scan for two freshly uploaded buffers, synchronous: CKKS_NON_REDUCED_COEFFICIENT on a hit.
+static int scan_reduced_pair_sync(const Tables &T, size_t L, size_t batch, const u64 *x, const u64 *y) {
+    int *flag = nullptr, hflag = 0;
+    CU(cudaMallocAsync((void **)&flag, sizeof(int), T.stream));
+    cudaMemsetAsync(flag, 0, sizeof(int), T.stream);
+    int rc = scan_reduced(T, L, batch, x, flag, T.stream);
+    if (rc == CKKS_OK && y) rc = scan_reduced(T, L, batch, y, flag, T.stream);
+    cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, T.stream);
+    if (cudaStreamSynchronize(T.stream) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "reducedness scan");
+    cudaFreeAsync(flag, T.stream);
+    if (rc == CKKS_OK && hflag) rc = CKKS_NON_REDUCED_COEFFICIENT;  // poly.rs:83-93
+    return rc;
 }
 
 // Dispatch on the lazy mode (0 strict, 1 Harvey, 2 lazy8); 32-bit words never use mode 2.
@@ -1067,6 +1090,8 @@ extern "C" int ckks_ksk_upload(ckks_ctx *ctx, const uint64_t *a, const uint64_t 
     if (cudaMemcpyAsync(k->a, a, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess ||
         cudaMemcpyAsync(k->b, b, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess)
         rc = cuda_fail(cudaGetLastError(), "ksk h2d");
+    // the key polynomials are RnsPoly values on the reference side (engine.rs:225-253): same canonical-word rule
+    if (rc == CKKS_OK) rc = scan_reduced_pair_sync(T, ctx->L, ctx->L, k->a, k->b);
     if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, false);
     if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, false);
     if (rc == CKKS_OK) rc = ksk_finalize(T, k);
@@ -1809,6 +1834,7 @@ struct HostPipe {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
     u64 *in[2][4] = {{nullptr}}, *out[2][2] = {{nullptr}};
+    int *flag = nullptr;  // set by the reducedness scan of the staged inputs (poly.rs:83-93)
     int init(const Tables &T, int n_in, size_t in_words, size_t out_words) {
         CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
@@ -1819,6 +1845,7 @@ struct HostPipe {
             for (int t = 0; t < n_in; ++t) CU(cudaMalloc((void **)&in[b][t], in_words * 8));
             for (int t = 0; t < 2; ++t) CU(cudaMalloc((void **)&out[b][t], out_words * 8));
         }
+        CU(cudaMalloc((void **)&flag, sizeof(int)));
         (void)T;
         return CKKS_OK;
     }
@@ -1832,6 +1859,7 @@ struct HostPipe {
             if (comp_done[b]) cudaEventDestroy(comp_done[b]);
             if (out_done[b]) cudaEventDestroy(out_done[b]);
         }
+        if (flag) cudaFree(flag);
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
     }
@@ -1861,11 +1889,8 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
             size_t nb = batch - s < chunk ? batch - s : chunk;
             ckks_poly *P[4] = {nullptr, nullptr, nullptr, nullptr}, *R0 = nullptr, *R1 = nullptr;
             int rc = CKKS_OK;
-            for (int t = 0; t < n_in && rc == CKKS_OK; ++t) {
-                rc = poly_new(ctx, nb, false, &P[t]);
-                if (rc == CKKS_OK && cudaMemcpyAsync(P[t]->d, hin[t] + s * wi, nb * wi * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess)
-                    rc = cuda_fail(cudaGetLastError(), "h2d");
-            }
+            for (int t = 0; t < n_in && rc == CKKS_OK; ++t)  // from_channels: reducedness scan included (poly.rs:83-93)
+                rc = ckks_poly_from_channels(ctx, nb, (const uint64_t *)(hin[t] + s * wi), L, 0, &P[t]);
             ckks_ctx *child = nullptr;
             if (rc == CKKS_OK && kind == 0) rc = ckks_ctx_drop_last(ctx, 1, &child);
             if (rc == CKKS_OK) rc = kind == 0 ? ckks_ct_mul_relin_rescale(P[0], P[1], P[2], P[3], key, child, &R0, &R1) : ckks_ct_rotate(P[0], P[1], key, rot, &R0, &R1);
@@ -1892,6 +1917,7 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
         TM.pipe_out_words = chunk * wo;
     }
     HostPipe &hp = *TM.pipe;
+    if (rc == CKKS_OK && cudaMemsetAsync(hp.flag, 0, sizeof(int), T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "memset");
     const u64 e1 = rot >= 0 ? rot_exponent(n, rot) : (rot_exponent(n, rot) * (2 * n - 1)) % (2 * n);
     size_t c = 0;
     for (size_t s = 0; s < batch && rc == CKKS_OK; s += chunk, ++c) {
@@ -1904,6 +1930,9 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
             CU(cudaEventRecord(hp.in_done[b], hp.s_in));
             CU(cudaStreamWaitEvent(T.stream, hp.in_done[b], 0));
             if (c >= 2) CU(cudaStreamWaitEvent(T.stream, hp.out_done[b], 0));  // D2H of chunk c-2 has drained out[b]
+            // what from_channels checks on every polynomial the reference builds from raw words (poly.rs:83-93): the
+            // lazy butterflies assume canonical inputs, so a word >= q must be an error, not silent garbage
+            for (int t = 0; t < n_in; ++t) TRY(scan_reduced(T, L, nb, hp.in[b][t], hp.flag, T.stream));
             if (kind == 0) {
                 TRY(fused_mul_relin(T, L, nb, hp.in[b][0], hp.in[b][1], hp.in[b][2], hp.in[b][3], key, true, hp.out[b][0], hp.out[b][1]));
             } else {
@@ -1920,9 +1949,12 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
         };
         rc = step();
     }
+    int hflag = 0;
+    if (rc == CKKS_OK && cudaMemcpyAsync(&hflag, hp.flag, sizeof(int), cudaMemcpyDeviceToHost, T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "flag");
     cudaStreamSynchronize(hp.s_in);
     if (cudaStreamSynchronize(T.stream) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
     if (cudaStreamSynchronize(hp.s_out) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
+    if (rc == CKKS_OK && hflag) return CKKS_NON_REDUCED_COEFFICIENT;  // outputs are unspecified in that case
     if (rc != CKKS_OK) {  // do not keep a pipeline whose events may be in an unknown state
         destroy_host_pipe(TM.pipe);
         TM.pipe = nullptr;
@@ -2162,4 +2194,5 @@ extern "C" int ckks_decode(const ckks_poly *p, uint32_t scale_bits, size_t nslot
     return rc;
 }
 
+#include "batch_shard.inl"
 #include "limb_shard.inl"

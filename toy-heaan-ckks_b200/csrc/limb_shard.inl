@@ -334,6 +334,7 @@ extern "C" int ckks_lshard_ksk_upload(ckks_lshard *s, const uint64_t *a, const u
     if (cudaMemcpyAsync(k->a, a, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess ||
         cudaMemcpyAsync(k->b, b, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess)
         rc = cuda_fail(cudaGetLastError(), "ksk h2d");
+    if (rc == CKKS_OK) rc = scan_reduced_pair_sync(T, s->Ll, s->Lg, k->a, k->b);  // canonical words only (poly.rs:83-93)
     if (rc == CKKS_OK) rc = ntt_inplace(T, s->Ll, s->Lg, k->a, false);
     if (rc == CKKS_OK) rc = ntt_inplace(T, s->Ll, s->Lg, k->b, false);
     if (rc == CKKS_OK) rc = ksk_finalize(T, k);
