@@ -299,34 +299,43 @@ def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, pas
         del ka, kb
     alpha_top = ck.Ciphertext(uni_poly_at(basis, l, batch), uni_poly_at(basis, l, batch), bits, bits * l)
     beta_top = ck.Ciphertext(uni_poly_at(basis, l, batch), uni_poly_at(basis, l, batch), bits, bits * l)
-    for k in levels:
-        alphas[k] = alpha_top if k == l else ck.Ciphertext(alpha_top.c0.mod_drop_last(basis=bases[k]), alpha_top.c1.mod_drop_last(basis=bases[k]), bits, bits * k)
-        betas[k - 1] = ck.Ciphertext(beta_top.c0.mod_drop_last(basis=bases[k - 1]), beta_top.c1.mod_drop_last(basis=bases[k - 1]), bits, bits * (k - 1))
     x0 = ck.Ciphertext(uni_poly_at(basis, l, batch), uni_poly_at(basis, l, batch), bits, bits * l)
     torch.cuda.empty_cache()
+
+    def at_level(ct_top, k):  # the reference re-encrypts alpha / beta at every level (horner_chain.rs:211-250): untimed here
+        if k == l:
+            return ct_top
+        return ck.Ciphertext(ct_top.c0.mod_drop_last(basis=bases[k]), ct_top.c1.mod_drop_last(basis=bases[k]), bits, bits * k)
+
     per_level = {k: [] for k in levels}
     totals = []
     for it in range(passes + 1):  # first pass is the warm-up
         ct = x0
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(levels) + 1)]
-        torch.cuda.synchronize()
-        evs[0].record(stream)
-        for t, k in enumerate(levels):
-            ct = ck.CkksEngine.mul_relin_rescale(ct, alphas[k], keys[k], bases[k - 1])
+        total = 0.0
+        for k in levels:
+            alpha_k, beta_k = at_level(alpha_top, k), at_level(beta_top, k - 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            ct = ck.CkksEngine.mul_relin_rescale(ct, alpha_k, keys[k], bases[k - 1])
             ct.logp = bits
-            ct = ck.CkksEngine.add_ciphertexts(ct, betas[k - 1])
-            evs[t + 1].record(stream)
-        torch.cuda.synchronize()
+            ct = ck.CkksEngine.add_ciphertexts(ct, beta_k)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            total += ms
+            if it:
+                per_level[k].append(ms)
+            del alpha_k, beta_k
         assert ct.c0.channel_count() == 2
         if it:
-            for t, k in enumerate(levels):
-                per_level[k].append(evs[t].elapsed_time(evs[t + 1]))
-            totals.append(evs[0].elapsed_time(evs[-1]))
+            totals.append(total)
         del ct
     ms_chain = sum(totals) / len(totals)
     return {
         "workload": f"horner_chain x <- x*alpha + beta, N={n}, L={l} -> 2 ({len(levels)} levels), resident batch of {batch} ciphertexts, "
-        "per level: mul_ciphertexts_gadget + rescale_ciphertext + add_ciphertexts",
+        "per level: mul_ciphertexts_gadget + rescale_ciphertext + add_ciphertexts (CUDA events around each level; the level's alpha / beta "
+        "ciphertexts are produced between the timed levels, as the reference re-encrypts them per level)",
         "ms_per_chain": ms_chain,
         "chains_per_s": batch / (ms_chain * 1e-3),
         "ct_mults_per_s": batch * len(levels) / (ms_chain * 1e-3),

@@ -10,10 +10,9 @@
 //! built in (no Rust toolchain there).
 #![allow(clippy::missing_safety_doc)]
 
-use std::cell::OnceCell;
 use std::ops::{AddAssign, MulAssign, Neg};
 use std::ptr::{self, NonNull};
-use std::sync::Arc;
+use std::sync::{Arc, OnceLock};
 
 use rand::Rng;
 use rand_distr::{Distribution, Normal};
@@ -37,6 +36,14 @@ pub mod ffi {
     }
     #[repr(C)]
     pub struct CkksLshard {
+        _p: [u8; 0],
+    }
+    #[repr(C)]
+    pub struct CkksComm {
+        _p: [u8; 0],
+    }
+    #[repr(C)]
+    pub struct CkksCommKsk {
         _p: [u8; 0],
     }
     extern "C" {
@@ -92,6 +99,17 @@ pub mod ffi {
         pub fn ckks_lshard_ct_rotate(s: *mut CkksLshard, c0: *const CkksPoly, c1: *const CkksPoly, rotk: *const CkksKsk, k: i32,
                                      o0: *mut *mut CkksPoly, o1: *mut *mut CkksPoly) -> i32;
         pub fn ckks_lshard_check(s: *mut CkksLshard) -> i32;
+        // Batch-sharded multi-GPU group: one process, a host batch cut into one contiguous share per device.
+        pub fn ckks_comm_init(ndev: i32, devices: *const i32, n: u64, moduli: *const u64, l: usize, out: *mut *mut CkksComm) -> i32;
+        pub fn ckks_comm_destroy(c: *mut CkksComm) -> i32;
+        pub fn ckks_comm_drop_last(c: *mut CkksComm, k: usize, out: *mut *mut CkksComm) -> i32;
+        pub fn ckks_comm_size(c: *const CkksComm) -> i32;
+        pub fn ckks_comm_ksk_upload(c: *mut CkksComm, a: *const u64, b: *const u64, out: *mut *mut CkksCommKsk) -> i32;
+        pub fn ckks_comm_ksk_free(k: *mut CkksCommKsk) -> i32;
+        pub fn ckks_comm_ct_mul_relin_rescale_host(c: *mut CkksComm, rlk: *const CkksCommKsk, batch: usize, a0: *const u64, a1: *const u64,
+                                                   b0: *const u64, b1: *const u64, o0: *mut u64, o1: *mut u64) -> i32;
+        pub fn ckks_comm_ct_rotate_host(c: *mut CkksComm, rotk: *const CkksCommKsk, k: i32, batch: usize, c0: *const u64, c1: *const u64,
+                                        o0: *mut u64, o1: *mut u64) -> i32;
         pub fn ckks_ct_mul_relin_rescale_host(ctx: *mut CkksCtx, child: *mut CkksCtx, rlk: *const CkksKsk, batch: usize,
                                               a0: *const u64, a1: *const u64, b0: *const u64, b1: *const u64,
                                               o0: *mut u64, o1: *mut u64) -> i32;
@@ -127,10 +145,30 @@ impl<const N: usize> Drop for RnsBasis<N> {
         unsafe { ffi::ckks_ctx_destroy(self.ctx.as_ptr()) };
     }
 }
+/// `NttTable<N>` (basis.rs:6-17) of one channel, read back from the library in the reference's layout; `Vec`s instead
+/// of the reference's `[u64; N]` stack arrays so that it also exists at N = 2^16.
+pub struct NttTable<const N: usize> {
+    pub modulus: u64,
+    pub n_inv: u64,
+    pub forward_roots: Vec<u64>,
+    pub inverse_roots: Vec<u64>,
+    pub twist_factors: Vec<u64>,
+    pub untwist_factors: Vec<u64>,
+}
+
+/// CUDA ordinal used by `RnsBasis::new`: `CKKS_B200_DEVICE` if set, else 0.  `new_on` takes it explicitly.
+pub fn default_device() -> i32 {
+    std::env::var("CKKS_B200_DEVICE").ok().and_then(|v| v.parse().ok()).unwrap_or(0)
+}
+
 impl<const N: usize> RnsBasis<N> {
     pub fn new(moduli: Vec<u64>) -> Result<Self, RnsNttError> {
+        Self::new_on(moduli, default_device())
+    }
+    /// `RnsBasis::new` (basis.rs:97-106) with the tables built on CUDA device `device`.
+    pub fn new_on(moduli: Vec<u64>, device: i32) -> Result<Self, RnsNttError> {
         let mut ctx = ptr::null_mut();
-        let rc = unsafe { ffi::ckks_ctx_create(N as u64, moduli.as_ptr(), moduli.len(), 0, &mut ctx) };
+        let rc = unsafe { ffi::ckks_ctx_create(N as u64, moduli.as_ptr(), moduli.len(), device, &mut ctx) };
         if rc == 3 {
             let bad = moduli.iter().copied().find(|&q| !toy_heaan_ckks::math::is_ntt_friendly_prime(q, N as u64)).unwrap_or(0);
             return Err(RnsNttError::NonNttFriendlyModulus { modulus: bad, degree: N });
@@ -161,6 +199,22 @@ impl<const N: usize> RnsBasis<N> {
     pub fn total_bits(&self) -> u32 {
         unsafe { ffi::ckks_ctx_total_bits(self.ctx.as_ptr()) }
     }
+    /// `RnsBasis::ntt_table(channel)` (basis.rs:112-114).
+    pub fn ntt_table(&self, channel: usize) -> NttTable<N> {
+        let get = |which: i32, len: usize| -> Vec<u64> {
+            let mut v = vec![0u64; len];
+            check(unsafe { ffi::ckks_ctx_ntt_table(self.ctx.as_ptr(), channel, which, v.as_mut_ptr()) });
+            v
+        };
+        NttTable {
+            modulus: self.moduli[channel],
+            n_inv: get(4, 1)[0],
+            forward_roots: get(0, N),
+            inverse_roots: get(1, N),
+            twist_factors: get(2, N),
+            untwist_factors: get(3, N),
+        }
+    }
     pub fn reconstruct_centered_coeff(&self, residues: &[u64]) -> i64 {
         let mut v = 0i64;
         check(unsafe { ffi::ckks_ctx_reconstruct_centered_coeff(self.ctx.as_ptr(), residues.as_ptr(), &mut v) });
@@ -173,8 +227,14 @@ impl<const N: usize> RnsBasis<N> {
 pub struct RnsPoly<const N: usize> {
     h: NonNull<ffi::CkksPoly>,
     basis: Arc<RnsBasis<N>>,
-    mirror: OnceCell<Vec<[u64; N]>>,
+    mirror: OnceLock<Vec<[u64; N]>>,
 }
+// The reference's RnsPoly is plain data (Vec + Arc), hence Send + Sync; so is this one: the device handle is only
+// mutated through `&mut self`, `&self` methods enqueue reads on the context's stream (the CUDA stream API and the
+// library's own bookkeeping are thread-safe; the host-buffer pipeline of a context tree is serialised by a mutex in
+// the library), and the host mirror is a OnceLock.
+unsafe impl<const N: usize> Send for RnsPoly<N> {}
+unsafe impl<const N: usize> Sync for RnsPoly<N> {}
 impl<const N: usize> Drop for RnsPoly<N> {
     fn drop(&mut self) {
         unsafe { ffi::ckks_poly_free(self.h.as_ptr()) };
@@ -189,7 +249,7 @@ impl<const N: usize> Clone for RnsPoly<N> {
 }
 impl<const N: usize> RnsPoly<N> {
     fn wrap(h: *mut ffi::CkksPoly, basis: Arc<RnsBasis<N>>) -> Self {
-        Self { h: NonNull::new(h).unwrap(), basis, mirror: OnceCell::new() }
+        Self { h: NonNull::new(h).unwrap(), basis, mirror: OnceLock::new() }
     }
     pub fn zero(basis: Arc<RnsBasis<N>>) -> Self {
         let mut h = ptr::null_mut();
@@ -248,6 +308,11 @@ impl<const N: usize> RnsPoly<N> {
             return Err(to_err(rc, N));
         }
         Ok(Self::wrap(h, new_basis))
+    }
+    /// `RnsPoly::rescale` (poly.rs:246-249): rescale_into a fresh `drop_last(1)` basis.
+    pub fn rescale(&self) -> Result<Self, RnsNttError> {
+        let child = Arc::new(self.basis.drop_last(1)?);
+        self.rescale_into(child)
     }
     pub fn mod_drop_last(&self, drop_count: usize) -> Result<Self, RnsNttError> {
         let child = Arc::new(self.basis.drop_last(drop_count)?);
@@ -381,4 +446,61 @@ pub fn rotate<const N: usize>(ct: (&RnsPoly<N>, &RnsPoly<N>), rotk: &DeviceGadge
     let (mut o0, mut o1) = (ptr::null_mut(), ptr::null_mut());
     check(unsafe { ffi::ckks_ct_rotate(ct.0.handle(), ct.1.handle(), rotk.handle(), rotk.rotation, &mut o0, &mut o1) });
     (RnsPoly::wrap(o0, ct.0.basis().clone()), RnsPoly::wrap(o1, ct.0.basis().clone()))
+}
+
+/// A `Vec<Ciphertext>` worth of host limbs spread over the GPUs of the box in ONE call (`ckks_comm_*`): what replaces
+/// the reference's serial loop over ciphertexts (examples/horner_chain.rs:211-278).  `cts`: (c0, c1) channel vectors
+/// per ciphertext, level L; returns the rescaled ciphertexts at level L-1.
+pub struct BatchShard<const N: usize> {
+    comm: NonNull<ffi::CkksComm>,
+    channel_count: usize,
+}
+unsafe impl<const N: usize> Send for BatchShard<N> {}
+impl<const N: usize> Drop for BatchShard<N> {
+    fn drop(&mut self) {
+        unsafe { ffi::ckks_comm_destroy(self.comm.as_ptr()) };
+    }
+}
+impl<const N: usize> BatchShard<N> {
+    pub fn new(moduli: &[u64], devices: &[i32]) -> Result<Self, RnsNttError> {
+        let mut c = ptr::null_mut();
+        let rc = unsafe { ffi::ckks_comm_init(devices.len() as i32, devices.as_ptr(), N as u64, moduli.as_ptr(), moduli.len(), &mut c) };
+        if rc != 0 {
+            return Err(to_err(rc, N));
+        }
+        Ok(Self { comm: NonNull::new(c).unwrap(), channel_count: moduli.len() })
+    }
+    pub fn mul_relin_rescale(
+        &self,
+        rlk: (&[RnsPoly<N>], &[RnsPoly<N>]),
+        a: &[(Vec<[u64; N]>, Vec<[u64; N]>)],
+        b: &[(Vec<[u64; N]>, Vec<[u64; N]>)],
+    ) -> Result<Vec<(Vec<[u64; N]>, Vec<[u64; N]>)>, RnsNttError> {
+        assert_eq!(a.len(), b.len());
+        let l = self.channel_count;
+        let flat_key = |v: &[RnsPoly<N>]| -> Vec<u64> { v.iter().flat_map(|p| p.channels().iter().flatten().copied()).collect() };
+        let (ka, kb) = (flat_key(rlk.0), flat_key(rlk.1));
+        let mut key = ptr::null_mut();
+        let rc = unsafe { ffi::ckks_comm_ksk_upload(self.comm.as_ptr(), ka.as_ptr(), kb.as_ptr(), &mut key) };
+        if rc != 0 {
+            return Err(to_err(rc, N));
+        }
+        let gather = |cts: &[(Vec<[u64; N]>, Vec<[u64; N]>)], second: bool| -> Vec<u64> {
+            cts.iter().flat_map(|ct| (if second { &ct.1 } else { &ct.0 }).iter().flatten().copied()).collect()
+        };
+        let (a0, a1, b0, b1) = (gather(a, false), gather(a, true), gather(b, false), gather(b, true));
+        let out_words = a.len() * (l - 1) * N;
+        let (mut o0, mut o1) = (vec![0u64; out_words], vec![0u64; out_words]);
+        let rc = unsafe {
+            ffi::ckks_comm_ct_mul_relin_rescale_host(self.comm.as_ptr(), key, a.len(), a0.as_ptr(), a1.as_ptr(), b0.as_ptr(), b1.as_ptr(), o0.as_mut_ptr(), o1.as_mut_ptr())
+        };
+        unsafe { ffi::ckks_comm_ksk_free(key) };
+        if rc != 0 {
+            return Err(to_err(rc, N));
+        }
+        let split = |flat: &[u64]| -> Vec<Vec<[u64; N]>> {
+            flat.chunks((l - 1) * N).map(|ct| ct.chunks(N).map(|limb| <[u64; N]>::try_from(limb).unwrap()).collect()).collect()
+        };
+        Ok(split(&o0).into_iter().zip(split(&o1)).collect())
+    }
 }

@@ -77,6 +77,9 @@ int ckks_ctx_create(uint64_t n, const uint64_t *moduli, size_t l, int device, ck
 int ckks_ctx_drop_last(ckks_ctx *ctx, size_t drop_count, ckks_ctx **out);
 int ckks_ctx_destroy(ckks_ctx *ctx);
 int ckks_ctx_sync(ckks_ctx *ctx);
+/* Device scratch freed by the library stays cached in the context's PRIVATE memory pool (the device's default
+ * pool, which other libraries of the process share, is never touched); this returns the cached memory. */
+int ckks_ctx_trim(ckks_ctx *ctx);
 /* Run this context's work on a caller-owned cudaStream_t (e.g. torch's current stream). */
 int ckks_ctx_set_stream(ckks_ctx *ctx, void *cuda_stream);
 uint64_t ckks_ctx_degree(const ckks_ctx *ctx);
@@ -152,6 +155,12 @@ int ckks_poly_automorphism(const ckks_poly *p, uint64_t exponent, ckks_poly **ou
 int ckks_poly_rotate_slots(const ckks_poly *p, int32_t k, ckks_poly **out);
 /* PolyRing::to_coeffs poly.rs:404-427: centred CRT into [batch][N] i64 (Q < 2^128). */
 int ckks_poly_to_coeffs(const ckks_poly *p, int64_t *out);
+/* The same for a basis of ANY size: RnsBasis::reconstruct_centered_coeff (basis.rs:158-180) forms Q
+ * in a u128 and stops working at Q >= 2^128; this runs Garner's mixed-radix CRT on the device (no big integers).
+ * out_i64 [batch][N]: the centred value truncated to 64 bits like the reference's `as i64` -- for Q < 2^128 the
+ * reference's result bit for bit, the true value whenever |x| < 2^63 (*overflow = 1 if some |x| >= 2^63);
+ * out_f64 [batch][N]: the centred value rounded to double.  Either output may be NULL; L <= 64. */
+int ckks_poly_to_coeffs_wide(const ckks_poly *p, int64_t *out_i64, double *out_f64, int *overflow);
 
 /* ---- gadget keys  (engine.rs:225-253, generated by engine.rs:288-399 on the host) -------------- */
 /* a, b: [digit i < L][limb j < L][N] coefficient domain, as `rlk.a[i].channels()`.  The key is
@@ -196,8 +205,10 @@ int ckks_ct_decrypt(const ckks_poly *c0, const ckks_poly *c1, const ckks_poly *s
  * the reference asserts); scaled by 2^scale_bits, conjugate-symmetric slots, inverse canonical embedding, rounding
  * (f64::round), from_coeffs.  f64 summation order differs from the reference: tolerance-checked, not bit-exact. */
 int ckks_encode(ckks_ctx *ctx, uint32_t scale_bits, size_t batch, const double *values, size_t nvals, ckks_poly **out);
-/* decode_complex: centred CRT (Q < 2^128 as in the reference), canonical embedding, first `nslots` slots divided
- * by 2^scale_bits; out [batch][nslots] complex. */
+/* decode_complex: centred CRT, canonical embedding, first `nslots` slots divided by 2^scale_bits; out
+ * [batch][nslots] complex.  Q < 2^128: the CRT is the reference's u128 arithmetic (basis.rs:158-180); Q >= 2^128,
+ * where the reference cannot decode: the mixed-radix CRT of ckks_poly_to_coeffs_wide, so a ciphertext at any level
+ * (e.g. cfg4, 24 x 61 bits) decodes without mod_drop_last. */
 int ckks_decode(const ckks_poly *p, uint32_t scale_bits, size_t nslots, double *out);
 
 /* ---- host-buffer entry points (what a reference-side caller with `Vec<[u64;N]>` data uses) ------ */
@@ -299,12 +310,19 @@ int ckks_lshard_barrier_local(ckks_lshard **shards, int world);
  * last: [2][chunk][N] (finished last limb of c0 and c1). */
 int ckks_lshard_buffers(ckks_lshard *s, uint64_t **gather, size_t *gather_words, uint64_t **last,
                         size_t *last_words);
-/* Synchronise and report a barrier that gave up waiting for a peer (CKKS_NCCL_ERROR). */
+/* Synchronise and report a barrier that gave up waiting for a peer (CKKS_NCCL_ERROR).
+ * Failure model (fail closed): a barrier that times out writes an error word the host sees at once.  The kernels
+ * behind it in the same call have consumed buffers the lost peer never filled, so a guard kernel at the end of every
+ * entry point overwrites the outputs with all-ones words (never canonical: rejected by every reducedness scan); the
+ * first blocking call on the local context (ckks_poly_download, ckks_ctx_sync, ckks_lshard_check) and EVERY later
+ * ckks_lshard_* call return CKKS_NCCL_ERROR.  The error is sticky: the epochs of this rank are out of step with its
+ * peers for good.  To recover, destroy every shard of the group on every rank and build the group again
+ * (ckks_lshard_create + ipc export/import or connect_local): that re-creates buffers, flag words and epochs. */
 int ckks_lshard_check(ckks_lshard *s);
 int ckks_lshard_set_timeout_ms(ckks_lshard *s, uint64_t ms);
 /* How the digits travel in the one-call entry points: 0 (default) = stores into peer HBM from the producing
- * kernel; 1 = that kernel stores locally and copy engines push the limbs to the peers (no SM held while
- * NVLink is busy: the better choice when a batch spans several chunks and the exchange hides behind compute). */
+ * kernel; 1 = that kernel stores locally and copy engines push the limbs to the peers (no SM is held while
+ * NVLink is busy, but measured SLOWER on B200: 5126 vs 5427 ct-mult/s at 4 GPUs, DESIGN 5b -- kept as a knob). */
 int ckks_lshard_set_exchange(ckks_lshard *s, int mode);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */

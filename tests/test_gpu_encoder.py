@@ -83,3 +83,109 @@ def test_encrypt_mul_decrypt_entirely_on_device(gpu, orc):
     dec = gpu.CkksEngine.decrypt(out, s.mod_drop_last(1, out.c0.basis()))
     got = enc.decode(gpu.Plaintext(dec, out.logp, 4))[0]
     assert np.max(np.abs(got - va * vb)) <= 1e-4
+
+
+def _centred(x, q):
+    x %= q
+    return x - q if x > q // 2 else x
+
+
+def _wrap64(x):
+    return ((x + (1 << 63)) % (1 << 64)) - (1 << 63)
+
+
+def test_wide_crt_equals_reference_semantics_below_2_128(gpu, orc):
+    """ckks_poly_to_coeffs_wide vs RnsBasis::reconstruct_centered_coeff (basis.rs:158-180) while Q < 2^128: the i64
+    words are identical on uniform limbs -- including the reference's `as i64` truncation of values that do not fit --
+    and equal Python's exact centred CRT; KATs of basis.rs:310-324."""
+    for n, bits, l in ((256, 62, 2), (1024, 40, 3), (256, 30, 4)):
+        moduli = orc.generate_primes(bits, l, n)
+        gb, ob = gpu.RnsBasis(n, moduli), orc.Basis(n, moduli)
+        rng = np.random.default_rng(n + bits)
+        q = np.array(moduli, dtype=np.uint64)
+        ch = (rng.integers(0, 1 << 63, size=(2, l, n), dtype=np.uint64) % q[:, None]).astype(np.uint64)
+        p = gpu.RnsPoly.from_channels(ch, gb)
+        wi, wf, ov = p.to_coeffs_wide()
+        assert np.array_equal(wi, p.to_coeffs())  # the product's u128 path = the reference's arithmetic
+        Q = 1
+        for m in moduli:
+            Q *= m
+        for b, k in ((0, 0), (1, 17), (1, n - 1)):
+            res = [int(ch[b, i, k]) for i in range(l)]
+            x = sum(r * (Q // m) * pow(Q // m, -1, m) for r, m in zip(res, moduli))
+            c = _centred(x, Q)
+            assert int(wi[b, k]) == _wrap64(c) == ob.reconstruct_centered_coeff(res)
+            assert abs(wf[b, k] - float(c)) <= abs(float(c)) * 1e-14
+        assert ov == (bits * l > 64)
+    gb = gpu.RnsBasis(8, [17, 97])
+    kat = np.zeros((1, 2, 8), dtype=np.uint64)
+    kat[0, :, 0] = [3, 3]
+    kat[0, :, 1] = [10, 90]
+    wi, _, ov = gpu.RnsPoly.from_channels(kat, gb).to_coeffs_wide()
+    assert wi[0, 0] == 3 and wi[0, 1] == -7 and not ov
+
+
+@pytest.mark.parametrize("n,bits,l", [(256, 61, 24), (512, 30, 8), (256, 61, 3)])
+def test_wide_crt_beyond_2_128_matches_python_big_integers(gpu, orc, n, bits, l):
+    """Q >= 2^128 (the reference's u128 product overflows there: basis.rs:152-160): Garner's mixed radix on the device
+    against Python's arbitrary-precision centred CRT, for planted values from +-1 to +-Q/2 and for uniform limbs."""
+    moduli = orc.generate_primes(bits, l, n)
+    gb = gpu.RnsBasis(n, moduli)
+    Q = 1
+    for m in moduli:
+        Q *= m
+    rng = np.random.default_rng(5)
+    planted = [0, 1, -1, 2, -2, (1 << 40) + 3, -(1 << 40) - 3, (1 << 62) + 12345, -(1 << 62) - 12345, (1 << 63) - 1, -(1 << 63), (1 << 63), -(1 << 63) - 1,
+               (1 << 100) + 7, -(1 << 100) - 7, Q // 2, -(Q // 2), Q // 2 - 1, Q // 3, -(Q // 3), moduli[0], -moduli[0], moduli[0] * moduli[1], -moduli[0] * moduli[1] - 1]
+    planted = [v for v in planted if abs(v) <= Q // 2]
+    vals = planted + [int(rng.integers(-(1 << 62), 1 << 62)) * int(rng.integers(1, 1 << 62)) % Q - Q // 2 for _ in range(n - len(planted))]
+    ch = np.zeros((1, l, n), dtype=np.uint64)
+    for k, v in enumerate(vals):
+        for i, m in enumerate(moduli):
+            ch[0, i, k] = v % m
+    p = gpu.RnsPoly.from_channels(ch, gb)
+    wi, wf, ov = p.to_coeffs_wide()
+    for k, v in enumerate(vals):
+        c = _centred(v, Q)
+        assert int(wi[0, k]) == _wrap64(c), (k, v)
+        assert abs(wf[0, k] - float(c)) <= abs(float(c)) * l * 2.0 ** -52, (k, v)
+    assert ov  # values beyond 2^63 were planted
+    small = np.zeros((1, l, n), dtype=np.uint64)
+    for k in range(n):
+        v = int(rng.integers(-(1 << 62), 1 << 62))
+        for i, m in enumerate(moduli):
+            small[0, i, k] = v % m
+    _, _, ov = gpu.RnsPoly.from_channels(small, gb).to_coeffs_wide()
+    assert not ov
+    # the NTT-domain polynomial gives the same values (poly.rs:405-411: to_coeffs transforms a clone first)
+    p.to_ntt_domain()
+    wi2, _, _ = p.to_coeffs_wide()
+    assert np.array_equal(wi, wi2)
+
+
+def test_decode_at_full_level_without_mod_drop(gpu, orc):
+    """A ciphertext at a level where Q >= 2^128 (5 x 61 bits here; 24 x 61 at cfg4) decrypts AND decodes directly:
+    the reference has to mod_drop_last down to two primes first (horner_chain.rs:21-35, basis.rs:152-160).  Checked
+    against the plain values within north_star's 2^-(scale_bits-10) and against the decode after mod_drop_last."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_gpu_engine import Party
+
+    n, l, sb = 256, 5, 40
+    moduli = orc.generate_primes(61, l, n)
+    party = Party(orc, n, moduli, seed=11, hw=16)
+    gb = gpu.RnsBasis(n, moduli)
+    rng = np.random.default_rng(12)
+    vals = rng.uniform(-0.9, 0.9, n // 2)
+    c0, c1 = party.encrypt(vals, sb)
+    ct = gpu.Ciphertext(gpu.RnsPoly.from_channels(c0, gb), gpu.RnsPoly.from_channels(c1, gb), sb, gb.total_bits())
+    s = gpu.RnsPoly.from_channels(party.s, gb)
+    dec = gpu.CkksEngine.decrypt(ct, s)
+    enc = gpu.CkksEncoder(n, sb)
+    got = enc.decode(gpu.Plaintext(dec, sb, n // 2))[0]  # 305-bit Q: the wide CRT
+    assert np.max(np.abs(got - vals)) <= 2.0 ** -(sb - 10)  # north_star's bound
+    assert np.max(np.abs(got - vals)) <= (10 * 3.2 * (16 * n) ** 0.5 + 4) / 2.0**sb  # the reference's own (encrypt_add.rs:122-131)
+    low = enc.decode(gpu.Plaintext(dec.mod_drop_last(l - 2), sb, n // 2))[0]  # the reference's route: two primes left
+    assert np.max(np.abs(got - low)) <= 1e-9
+    wi, _, ov = dec.to_coeffs_wide()
+    assert not ov and np.array_equal(wi, dec.mod_drop_last(l - 2).to_coeffs())

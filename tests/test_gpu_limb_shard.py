@@ -312,8 +312,10 @@ def test_limb_sharded_two_processes_cuda_ipc(gpu):
 
 
 def test_lost_peer_is_an_error_not_a_hang(gpu, orc):
-    """Only rank 0 of a group of two makes the call: its flag barriers give up after the time limit, the stream
-    drains, and check() reports the lost peer (once) instead of leaving a kernel spinning on the GPU."""
+    """Only rank 0 of a group of two makes the call: its flag barriers give up after the time limit and the stream
+    drains instead of leaving a kernel spinning on the GPU.  The failure is CLOSED: the outputs are poisoned with
+    all-ones words (never canonical), the first blocking call on the local context (download) returns NcclError, so
+    do check() and every later call on the group (sticky) -- nothing that looks like ciphertext limbs gets out."""
     n, l = 1024, 4
     moduli = orc.generate_primes(40, l, n)
     rng = np.random.default_rng(3)
@@ -323,8 +325,34 @@ def test_lost_peer_is_an_error_not_a_hang(gpu, orc):
     a0, a1 = uniform_limbs(rng, moduli, n, 2), uniform_limbs(rng, moduli, n, 2)
     key = shards[0].upload_key(uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l))
     ct = _ct(gpu, shards[0], a0, a1)
-    shards[0].mul_relin_rescale(ct, ct, key)  # enqueues; nobody answers
+    out = shards[0].mul_relin_rescale(ct, ct, key)  # enqueues; nobody answers
+    with pytest.raises(gpu.RnsNttError) as e:
+        out.c0.channels()  # the first sync point sees the failure
+    assert e.value.kind == "NcclError"
     with pytest.raises(gpu.RnsNttError) as e:
         shards[0].check()
     assert e.value.kind == "NcclError" and "timed out" in str(e.value)
-    shards[0].check()  # reported once
+    with pytest.raises(gpu.RnsNttError) as e:  # sticky: the group is dead until it is rebuilt
+        shards[0].mul_relin_rescale(ct, ct, key)
+    assert e.value.kind == "NcclError" and "re-create" in str(e.value)
+    with pytest.raises(gpu.RnsNttError):
+        shards[0].check()
+    # the words behind the failed barrier were overwritten: read them through the raw device pointer
+    import ctypes as C
+
+    ptr = C.POINTER(C.c_uint64)()
+    gpu._check(gpu._lib.ckks_poly_device_ptr(out.c0._h, C.byref(ptr)))
+    import torch
+
+    class _Buf:
+        def __init__(self, addr, words):
+            self.__cuda_array_interface__ = {"shape": (words,), "typestr": "<i8", "data": (addr, False), "version": 3}
+
+    words = 2 * out.c0.channel_count() * n
+    raw = torch.as_tensor(_Buf(C.cast(ptr, C.c_void_p).value, words), device="cuda:0").cpu().numpy().view(np.uint64)
+    assert np.all(raw == np.uint64(0xFFFFFFFFFFFFFFFF))
+    # recovery = a new group
+    del out, ct, key, shards
+    fresh = [gpu.LimbShard(n, moduli, r, 2, chunk=2) for r in range(2)]
+    gpu.LimbShard.connect_local(fresh)
+    fresh[0].check()

@@ -81,6 +81,7 @@ _sig("ckks_ctx_create", C.c_int, C.c_uint64, _u64p, C.c_size_t, C.c_int, _pp)
 _sig("ckks_ctx_drop_last", C.c_int, _vp, C.c_size_t, _pp)
 _sig("ckks_ctx_destroy", C.c_int, _vp)
 _sig("ckks_ctx_sync", C.c_int, _vp)
+_sig("ckks_ctx_trim", C.c_int, _vp)
 _sig("ckks_ctx_set_stream", C.c_int, _vp, _vp)
 _sig("ckks_ctx_degree", C.c_uint64, _vp)
 _sig("ckks_ctx_channel_count", C.c_size_t, _vp)
@@ -121,6 +122,7 @@ _sig("ckks_poly_rescale_into", C.c_int, _vp, _vp, _pp)
 _sig("ckks_poly_automorphism", C.c_int, _vp, C.c_uint64, _pp)
 _sig("ckks_poly_rotate_slots", C.c_int, _vp, C.c_int32, _pp)
 _sig("ckks_poly_to_coeffs", C.c_int, _vp, _i64p)
+_sig("ckks_poly_to_coeffs_wide", C.c_int, _vp, _i64p, C.POINTER(C.c_double), C.POINTER(C.c_int))
 _sig("ckks_ksk_upload", C.c_int, _vp, _u64p, _u64p, _pp)
 _sig("ckks_ksk_from_polys", C.c_int, _vp, _vp, _pp)
 _sig("ckks_ksk_free", C.c_int, _vp)
@@ -332,6 +334,10 @@ class RnsBasis:
     def sync(self):
         _check(_lib.ckks_ctx_sync(self._h))
 
+    def trim(self):
+        """Return the scratch cached in the context's private memory pool to the device."""
+        _check(_lib.ckks_ctx_trim(self._h))
+
     def set_stream(self, cuda_stream: int):
         _check(_lib.ckks_ctx_set_stream(self._h, _vp(cuda_stream)))
 
@@ -468,6 +474,20 @@ class RnsPoly:
 
 
 # ── keys and ciphertexts ─────────────────────────────────────────────────────────────────────────
+def _to_coeffs_wide(self):
+    """Centred CRT for a basis of any size (Garner mixed radix on the device): (i64 [batch, N], f64 [batch, N],
+    overflow).  i64 equals `to_coeffs` (basis.rs:158-180) bit for bit while Q < 2^128."""
+    n = self._basis.degree
+    oi = np.zeros((self.batch(), n), dtype=np.int64)
+    of = np.zeros((self.batch(), n), dtype=np.float64)
+    ov = C.c_int(0)
+    _check(_lib.ckks_poly_to_coeffs_wide(self._h, oi.ctypes.data_as(_i64p), of.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ov)))
+    return oi, of, bool(ov.value)
+
+
+RnsPoly.to_coeffs_wide = _to_coeffs_wide
+
+
 class GadgetKey:
     """`RnsGadgetRelinKey` / `RnsGadgetRotationKey` (engine.rs:225-253), transformed and resident."""
 

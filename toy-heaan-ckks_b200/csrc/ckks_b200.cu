@@ -17,6 +17,7 @@
 #include "host_math.hpp"
 #include "tables_host.hpp"
 #include "encoder.cuh"
+#include "crt_wide.cuh"
 #include "kernels.cuh"
 
 // -------------------------------------------------------------------------------------------------
@@ -99,6 +100,23 @@ struct ProfScope {
     }
 };
 static thread_local cudaStream_t g_cur_stream = nullptr;  // stream of the context whose call is running on this thread
+// Every launch / allocation helper enqueues on S(T): the context's stream, unless the CALLING THREAD has redirected
+// its own launches with a StreamScope (the limb-sharded chunk pipeline runs phase A on an auxiliary stream).  The
+// redirection is thread-local: the shared Tables object is never modified, so other threads using the same
+// context tree keep launching on the context's stream.
+static thread_local cudaStream_t g_stream_override = nullptr;
+static inline cudaStream_t S(const Tables &T) { return g_stream_override ? g_stream_override : T.stream; }
+struct StreamScope {
+    cudaStream_t prev_override, prev_cur;
+    explicit StreamScope(cudaStream_t s) : prev_override(g_stream_override), prev_cur(g_cur_stream) {
+        g_stream_override = s;
+        g_cur_stream = s;
+    }
+    ~StreamScope() {
+        g_stream_override = prev_override;
+        g_cur_stream = prev_cur;
+    }
+};
 #define KL(name, ...)                                            \
     do {                                                         \
         count_launch(name);                                      \
@@ -212,12 +230,13 @@ Tables::~Tables() {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     destroy_host_pipe(pipe);
+    if (pool) cudaMemPoolDestroy(pool);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
 static bool ok_ctx(const ckks_ctx *c) {
     if (!(c && c->magic == MAGIC_CTX)) return false;
-    g_cur_stream = c->T->stream;
+    g_cur_stream = S(*c->T);
     return true;
 }
 static bool ok_poly(const ckks_poly *p) { return p && p->magic == MAGIC_POLY && ok_ctx(p->ctx); }
@@ -231,6 +250,14 @@ static void ctx_unref(ckks_ctx *c) {
     }
 }
 static bool same_basis(const ckks_ctx *a, const ckks_ctx *b) { return a->T.get() == b->T.get() && a->L == b->L; }
+
+// Every stream-ordered allocation of the library comes from the context's PRIVATE memory pool (created in
+// ckks_ctx_create, released with the tables): freed scratch stays cached there for the next call instead of in the
+// device's default pool, which other libraries in the process (e.g. PyTorch) share; ckks_ctx_trim returns it.
+static cudaError_t pool_malloc(const Tables &T, void **p, size_t bytes) {
+    if (T.pool) return cudaMallocFromPoolAsync(p, bytes, T.pool, S(T));
+    return cudaMallocAsync(p, bytes, S(T));
+}
 
 template <class T>
 static int upload_vec(T **dst, const std::vector<T> &v) {
@@ -317,10 +344,17 @@ extern "C" int ckks_ctx_create(uint64_t n, const uint64_t *moduli, size_t l, int
     for (size_t i = 0; i < l; ++i) T->psi.push_back(hm::find_primitive_root(moduli[i], 2 * n));
     CU(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
     T->own_stream = true;
-    cudaMemPool_t pool;
-    CU(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = ~0ull;
-    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        CU(cudaMemPoolCreate(&T->pool, &props));
+        uint64_t thr = ~0ull;  // keep freed scratch cached in OUR pool; the device's default pool is left untouched
+        CU(cudaMemPoolSetAttribute(T->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
     TRY(build_tables(*T));
     ckks_ctx *c = new ckks_ctx();
     c->magic = MAGIC_CTX;
@@ -348,18 +382,34 @@ extern "C" int ckks_ctx_destroy(ckks_ctx *ctx) {
     ctx_unref(ctx);
     return CKKS_OK;
 }
+// A context that is the local share of a limb-sharded group: non-zero once one of its barriers lost a peer.
+static int group_failed(const Tables &T) {
+    if (T.fail_word && *T.fail_word) {
+        g_err = "a limb-sharded barrier on this context timed out waiting for a peer GPU: results are poisoned";
+        return CKKS_NCCL_ERROR;
+    }
+    return CKKS_OK;
+}
 extern "C" int ckks_ctx_sync(ckks_ctx *ctx) {
     if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
     CU(cudaStreamSynchronize(ctx->T->stream));
-    return CKKS_OK;
+    return group_failed(*ctx->T);
 }
 extern "C" int ckks_ctx_set_stream(ckks_ctx *ctx, void *s) {
     if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
     Tables &T = *ctx->T;
-    CU(cudaStreamSynchronize(T.stream));
-    if (T.own_stream) cudaStreamDestroy(T.stream);
+    CU(cudaStreamSynchronize(S(T)));
+    if (T.own_stream) cudaStreamDestroy(S(T));
     T.stream = (cudaStream_t)s;
     T.own_stream = false;
+    return CKKS_OK;
+}
+extern "C" int ckks_ctx_trim(ckks_ctx *ctx) {
+    if (!ok_ctx(ctx)) return CKKS_BAD_HANDLE;
+    Tables &T = *ctx->T;
+    CU(cudaSetDevice(T.device));
+    CU(cudaStreamSynchronize(S(T)));
+    if (T.pool) CU(cudaMemPoolTrimTo(T.pool, 0));
     return CKKS_OK;
 }
 extern "C" uint64_t ckks_ctx_degree(const ckks_ctx *c) { return ok_ctx(c) ? c->T->n : 0; }
@@ -433,13 +483,13 @@ static int scan_reduced(const Tables &T, size_t L, size_t batch, const u64 *d, i
 // The same scan for two freshly uploaded buffers, synchronous: CKKS_NON_REDUCED_COEFFICIENT on a hit.
 static int scan_reduced_pair_sync(const Tables &T, size_t L, size_t batch, const u64 *x, const u64 *y) {
     int *flag = nullptr, hflag = 0;
-    CU(cudaMallocAsync((void **)&flag, sizeof(int), T.stream));
-    cudaMemsetAsync(flag, 0, sizeof(int), T.stream);
-    int rc = scan_reduced(T, L, batch, x, flag, T.stream);
-    if (rc == CKKS_OK && y) rc = scan_reduced(T, L, batch, y, flag, T.stream);
-    cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, T.stream);
-    if (cudaStreamSynchronize(T.stream) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "reducedness scan");
-    cudaFreeAsync(flag, T.stream);
+    CU(pool_malloc(T, (void **)&flag, sizeof(int)));
+    cudaMemsetAsync(flag, 0, sizeof(int), S(T));
+    int rc = scan_reduced(T, L, batch, x, flag, S(T));
+    if (rc == CKKS_OK && y) rc = scan_reduced(T, L, batch, y, flag, S(T));
+    cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, S(T));
+    if (cudaStreamSynchronize(S(T)) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "reducedness scan");
+    cudaFreeAsync(flag, S(T));
     if (rc == CKKS_OK && hflag) rc = CKKS_NON_REDUCED_COEFFICIENT;  // poly.rs:83-93
     return rc;
 }
@@ -506,7 +556,7 @@ static int run_pass(const Tables &T, int which, Span sp, const void *src_, void 
     const char *src = (const char *)src_;
     char *dst = (char *)dst_;
     const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
-    cudaStream_t s = T.stream;
+    cudaStream_t s = S(T);
     for (size_t b0 = 0; b0 < sp.nb; b0 += 32768) {
         size_t nb = sp.nb - b0 < 32768 ? sp.nb - b0 : 32768;
         PassArgs a;
@@ -570,7 +620,7 @@ static int launch_fused_w(const Tables &T, size_t L, size_t batch, u64 *d, bool 
     do {                                                                                                               \
         if (smem > 48 * 1024)                                                                                          \
             CU(cudaFuncSetAttribute(ntt_fused_kernel<WD, A1, A2, LZ, IV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        KL(IV ? "ntt_fused_inv" : "ntt_fused_fwd", (ntt_fused_kernel<WD, A1, A2, LZ, IV><<<grid, block, smem, T.stream>>>(a)));       \
+        KL(IV ? "ntt_fused_inv" : "ntt_fused_fwd", (ntt_fused_kernel<WD, A1, A2, LZ, IV><<<grid, block, smem, S(T)>>>(a)));       \
     } while (0)
 #define M(LZ)                                                           \
     do {                                                                \
@@ -595,7 +645,7 @@ static int ntt_fused_run(const Tables &T, size_t L, size_t batch, u64 *d, bool i
 // Forward / inverse transform of [batch][L][N] words in place (tmp: same size, four-step only).
 static int ntt_run(const Tables &T, size_t L, size_t batch, u64 *d, u64 *tmp, bool inverse) {
     if (batch == 0) return CKKS_OK;
-    cudaStream_t s = T.stream;
+    cudaStream_t s = S(T);
     if (T.path == 1) {
         SmallArgs a;
         a.data = d;
@@ -638,11 +688,11 @@ static int ntt_run(const Tables &T, size_t L, size_t batch, u64 *d, u64 *tmp, bo
 static int dev_alloc(const Tables &T, size_t words, u64 **out) {
     *out = nullptr;
     if (words == 0) words = 1;
-    CU(cudaMallocAsync((void **)out, words * sizeof(u64), T.stream));
+    CU(pool_malloc(T, (void **)out, words * sizeof(u64)));
     return CKKS_OK;
 }
 static void dev_free(const Tables &T, void *p) {
-    if (p) cudaFreeAsync(p, T.stream);
+    if (p) cudaFreeAsync(p, S(T));
 }
 static int ntt_inplace(const Tables &T, size_t L, size_t batch, u64 *d, bool inverse) {
     u64 *tmp = nullptr;
@@ -712,18 +762,18 @@ extern "C" int ckks_poly_from_coeffs(ckks_ctx *ctx, size_t batch, const int64_t 
     TRY(poly_new(ctx, batch, false, out));
     if (batch == 0) return CKKS_OK;
     i64 *dc;
-    CU(cudaMallocAsync((void **)&dc, batch * clen * sizeof(i64), T.stream));
-    CU(cudaMemcpyAsync(dc, coeffs, batch * clen * sizeof(i64), cudaMemcpyHostToDevice, T.stream));
+    CU(pool_malloc(T, (void **)&dc, batch * clen * sizeof(i64)));
+    CU(cudaMemcpyAsync(dc, coeffs, batch * clen * sizeof(i64), cudaMemcpyHostToDevice, S(T)));
     EwArgs a = ew_args(T, ctx->L, batch);
-    KL("from_coeffs", (from_coeffs_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, dc, clen, (*out)->d)));
+    KL("from_coeffs", (from_coeffs_kernel<<<ew_grid(a.total), 256, 0, S(T)>>>(a, dc, clen, (*out)->d)));
     dev_free(T, dc);
-    CU(cudaStreamSynchronize(T.stream));  // `coeffs` may be pageable and reused by the caller
+    CU(cudaStreamSynchronize(S(T)));  // `coeffs` may be pageable and reused by the caller
     return CKKS_OK;
 }
 
 static int permute(const Tables &T, const u64 *src, u64 *dst, size_t words, bool to_internal) {
     if (!words) return CKKS_OK;
-    KL("permute_ntt", (permute_ntt_kernel<<<(unsigned)((words + 255) / 256), 256, 0, T.stream>>>(src, dst, words, T.logn, T.a1,
+    KL("permute_ntt", (permute_ntt_kernel<<<(unsigned)((words + 255) / 256), 256, 0, S(T)>>>(src, dst, words, T.logn, T.a1,
                                                                                                T.a2, to_internal ? 1 : 0)));
     return CKKS_OK;
 }
@@ -745,19 +795,19 @@ extern "C" int ckks_poly_from_channels(ckks_ctx *ctx, size_t batch, const uint64
         int hflag = 0;
         u64 *stage = nullptr;
         do {
-            if (cudaMallocAsync((void **)&flag, sizeof(int), T.stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "malloc"); break; }
-            cudaMemsetAsync(flag, 0, sizeof(int), T.stream);
+            if (pool_malloc(T, (void **)&flag, sizeof(int)) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "malloc"); break; }
+            cudaMemsetAsync(flag, 0, sizeof(int), S(T));
             u64 *land = p->d;
             if (in_ntt) {
                 if ((rc = dev_alloc(T, words, &stage)) != CKKS_OK) break;
                 land = stage;
             }
-            if (cudaMemcpyAsync(land, ch, words * sizeof(u64), cudaMemcpyHostToDevice, T.stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "h2d"); break; }
+            if (cudaMemcpyAsync(land, ch, words * sizeof(u64), cudaMemcpyHostToDevice, S(T)) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "h2d"); break; }
             EwArgs a = ew_args(T, ctx->L, batch);
-            KLV("check_reduced", (check_reduced_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, land, flag)));
+            KLV("check_reduced", (check_reduced_kernel<<<ew_grid(a.total), 256, 0, S(T)>>>(a, land, flag)));
             if (in_ntt && (rc = permute(T, stage, p->d, words, true)) != CKKS_OK) break;
-            cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, T.stream);
-            if (cudaStreamSynchronize(T.stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "sync"); break; }
+            cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, S(T));
+            if (cudaStreamSynchronize(S(T)) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "sync"); break; }
             if (hflag) rc = CKKS_NON_REDUCED_COEFFICIENT;  // poly.rs:83-93
         } while (0);
         dev_free(T, flag);
@@ -782,13 +832,13 @@ extern "C" int ckks_poly_download(ckks_poly *p, uint64_t *out) {
         u64 *stage;
         TRY(dev_alloc(T, words, &stage));
         TRY(permute(T, p->d, stage, words, false));
-        CU(cudaMemcpyAsync(out, stage, words * sizeof(u64), cudaMemcpyDeviceToHost, T.stream));
+        CU(cudaMemcpyAsync(out, stage, words * sizeof(u64), cudaMemcpyDeviceToHost, S(T)));
         dev_free(T, stage);
     } else {
-        CU(cudaMemcpyAsync(out, p->d, words * sizeof(u64), cudaMemcpyDeviceToHost, T.stream));
+        CU(cudaMemcpyAsync(out, p->d, words * sizeof(u64), cudaMemcpyDeviceToHost, S(T)));
     }
-    CU(cudaStreamSynchronize(T.stream));
-    return CKKS_OK;
+    CU(cudaStreamSynchronize(S(T)));
+    return group_failed(T);
 }
 
 extern "C" int ckks_poly_to_ntt_domain(ckks_poly *p) {
@@ -823,7 +873,7 @@ static int ew_binary(const char *name, ckks_poly *a, const ckks_poly *b) {
     EwArgs e = ew_args(T, a->ctx->L, a->batch);
     if (!e.total) return CKKS_OK;
     size_t bs = (b->batch == a->batch) ? e.poly : 0;
-    KL(name, (ew_binary_kernel<OP><<<ew_grid(e.total), 256, 0, T.stream>>>(e, a->d, b->d, bs)));
+    KL(name, (ew_binary_kernel<OP><<<ew_grid(e.total), 256, 0, S(T)>>>(e, a->d, b->d, bs)));
     return CKKS_OK;
 }
 extern "C" int ckks_poly_add_assign(ckks_poly *a, const ckks_poly *b) {
@@ -840,7 +890,7 @@ extern "C" int ckks_poly_neg(ckks_poly *a) {
     CU(cudaSetDevice(T.device));
     EwArgs e = ew_args(T, a->ctx->L, a->batch);
     if (!e.total) return CKKS_OK;
-    KL("ew_neg", (ew_neg_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, a->d)));
+    KL("ew_neg", (ew_neg_kernel<<<ew_grid(e.total), 256, 0, S(T)>>>(e, a->d)));
     return CKKS_OK;
 }
 extern "C" int ckks_poly_mul_assign(ckks_poly *a, const ckks_poly *b) {
@@ -869,8 +919,8 @@ extern "C" int ckks_poly_mul_assign_naive(ckks_poly *a, const ckks_poly *b) {
     if (!e.total) return CKKS_OK;
     u64 *tmp = nullptr;
     TRY(dev_alloc(T, e.total, &tmp));
-    KLV("mul_naive", (mul_naive_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, a->d, b->d, b->batch == 1 && a->batch != 1 ? 0 : e.poly, tmp)));
-    cudaMemcpyAsync(a->d, tmp, e.total * 8, cudaMemcpyDeviceToDevice, T.stream);
+    KLV("mul_naive", (mul_naive_kernel<<<ew_grid(e.total), 256, 0, S(T)>>>(e, a->d, b->d, b->batch == 1 && a->batch != 1 ? 0 : e.poly, tmp)));
+    cudaMemcpyAsync(a->d, tmp, e.total * 8, cudaMemcpyDeviceToDevice, S(T));
     dev_free(T, tmp);
     if (cudaPeekAtLastError() != cudaSuccess) return cuda_fail(cudaGetLastError(), "mul_naive");
     return CKKS_OK;
@@ -887,14 +937,14 @@ extern "C" int ckks_poly_mod_drop_last(const ckks_poly *p, ckks_ctx *child, ckks
     TRY(poly_new(child, p->batch, p->ntt, out));
     if (p->batch)
         CU(cudaMemcpy2DAsync((*out)->d, child->L * T.n * sizeof(u64), p->d, p->ctx->L * T.n * sizeof(u64),
-                             child->L * T.n * sizeof(u64), p->batch, cudaMemcpyDeviceToDevice, T.stream));
+                             child->L * T.n * sizeof(u64), p->batch, cudaMemcpyDeviceToDevice, S(T)));
     return CKKS_OK;
 }
 
 static int rescale_dev(const Tables &T, size_t L, size_t batch, const u64 *src, u64 *dst) {
     EwArgs e = ew_args(T, L - 1, batch);
     if (!e.total) return CKKS_OK;
-    KL("rescale", (rescale_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, src, dst, T.d_qlinv + (L - 1) * T.L)));
+    KL("rescale", (rescale_kernel<<<ew_grid(e.total), 256, 0, S(T)>>>(e, src, dst, T.d_qlinv + (L - 1) * T.L)));
     return CKKS_OK;
 }
 
@@ -957,14 +1007,14 @@ extern "C" int ckks_poly_automorphism(const ckks_poly *p, uint64_t exponent, ckk
     EwArgs a = ew_args(T, p->ctx->L, p->batch);
     if (rc == CKKS_OK && a.total) {
         if (e & 1) {
-            KLV("automorphism", (automorphism_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, (*out)->d, e, inv_mod_pow2(e, two_n))));
+            KLV("automorphism", (automorphism_kernel<<<ew_grid(a.total), 256, 0, S(T)>>>(a, src, (*out)->d, e, inv_mod_pow2(e, two_n))));
         } else {
             unsigned *win = nullptr;
-            if (cudaMallocAsync((void **)&win, a.total * sizeof(unsigned), T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "malloc");
+            if (pool_malloc(T, (void **)&win, a.total * sizeof(unsigned)) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "malloc");
             if (rc == CKKS_OK) {
-                cudaMemsetAsync(win, 0, a.total * sizeof(unsigned), T.stream);
-                KLV("automorphism_even_mark", (automorphism_even_mark_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, win, e)));
-                KLV("automorphism_even_fill", (automorphism_even_fill_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, src, win, (*out)->d, e)));
+                cudaMemsetAsync(win, 0, a.total * sizeof(unsigned), S(T));
+                KLV("automorphism_even_mark", (automorphism_even_mark_kernel<<<ew_grid(a.total), 256, 0, S(T)>>>(a, src, win, e)));
+                KLV("automorphism_even_fill", (automorphism_even_fill_kernel<<<ew_grid(a.total), 256, 0, S(T)>>>(a, src, win, (*out)->d, e)));
                 dev_free(T, win);
             }
         }
@@ -1019,6 +1069,109 @@ extern "C" int ckks_poly_to_coeffs(const ckks_poly *p, int64_t *out) {
     return CKKS_OK;
 }
 
+// Multi-word floor(Q / 2) in Garner's mixed radix: digit j = (floor(Q/2) div q_0 ... q_{j-1}) mod q_j.
+static std::vector<u64> half_q_digits(const std::vector<u64> &mod) {
+    std::vector<u64> big(1, 1);  // little-endian words of Q
+    for (u64 q : mod) {
+        hm::u128 carry = 0;
+        for (u64 &w : big) {
+            hm::u128 t = (hm::u128)w * q + carry;
+            w = (u64)t;
+            carry = t >> 64;
+        }
+        if (carry) big.push_back((u64)carry);
+    }
+    u64 c = 0;  // big >>= 1
+    for (size_t i = big.size(); i-- > 0;) {
+        u64 w = big[i];
+        big[i] = (w >> 1) | (c << 63);
+        c = w & 1;
+    }
+    std::vector<u64> digits;
+    for (u64 q : mod) {  // big, rem = divmod(big, q)
+        hm::u128 rem = 0;
+        for (size_t i = big.size(); i-- > 0;) {
+            hm::u128 cur = (rem << 64) | big[i];
+            big[i] = (u64)(cur / q);
+            rem = cur % q;
+        }
+        digits.push_back((u64)rem);
+    }
+    return digits;
+}
+// Centred CRT of every coefficient for a basis of any size (device, Garner mixed radix: crt_wide.cuh).
+// d_i64 / d_f64: device buffers [batch][N] or null; *overflow: some |x| >= 2^63.
+static int crt_wide_dev(const ckks_poly *p, long long *d_i64, double *d_f64, int *overflow) {
+    const Tables &T = *p->ctx->T;
+    const size_t L = p->ctx->L;
+    if (L > (size_t)CRT_MAX_L) return CKKS_UNSUPPORTED;
+    std::vector<u64> mod(T.moduli.begin(), T.moduli.begin() + L);
+    std::vector<tw_t> inv(L * L, mk_tw(0, mod[0]));
+    for (size_t i = 0; i < L; ++i)
+        for (size_t j = i + 1; j < L; ++j) inv[i * L + j] = mk_tw(hm::inv_mod(mod[i] % mod[j], mod[j]), mod[j]);
+    std::vector<u64> half = half_q_digits(mod);
+    ckks_poly *c = nullptr;
+    TRY(ckks_poly_clone(const_cast<ckks_poly *>(p), &c));
+    tw_t *dinv = nullptr;
+    u64 *dhalf = nullptr;
+    int *dflag = nullptr, hflag = 0;
+    auto body = [&]() -> int {
+        TRY(ckks_poly_to_coeff_domain(c));  // poly.rs:405-411
+        CU(pool_malloc(T, (void **)&dinv, inv.size() * sizeof(tw_t)));
+        CU(pool_malloc(T, (void **)&dhalf, half.size() * sizeof(u64)));
+        CU(pool_malloc(T, (void **)&dflag, sizeof(int)));
+        CU(cudaMemcpyAsync(dinv, inv.data(), inv.size() * sizeof(tw_t), cudaMemcpyHostToDevice, S(T)));
+        CU(cudaMemcpyAsync(dhalf, half.data(), half.size() * sizeof(u64), cudaMemcpyHostToDevice, S(T)));
+        CU(cudaMemsetAsync(dflag, 0, sizeof(int), S(T)));
+        CrtWideArgs a;
+        a.src = c->d;
+        a.lc = T.d_lc;
+        a.inv = dinv;
+        a.half = dhalf;
+        a.out_i64 = d_i64;
+        a.out_f64 = d_f64;
+        a.overflow = dflag;
+        a.total = p->batch * T.n;
+        a.L = (int)L;
+        a.logn = T.logn;
+        KL("crt_wide", (crt_wide_kernel<<<ew_grid(a.total), 256, 0, S(T)>>>(a)));
+        CU(cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, S(T)));
+        CU(cudaStreamSynchronize(S(T)));  // inv / half leave scope
+        return CKKS_OK;
+    };
+    int rc = body();
+    dev_free(T, dinv);
+    dev_free(T, dhalf);
+    dev_free(T, dflag);
+    ckks_poly_free(c);
+    if (overflow) *overflow = hflag;
+    return rc;
+}
+extern "C" int ckks_poly_to_coeffs_wide(const ckks_poly *p, int64_t *out_i64, double *out_f64, int *overflow) {
+    if (overflow) *overflow = 0;
+    if (!ok_poly(p)) return CKKS_BAD_HANDLE;
+    const Tables &T = *p->ctx->T;
+    if (!p->batch) return CKKS_OK;
+    if (!out_i64 && !out_f64) return CKKS_BAD_ARGUMENT;
+    CU(cudaSetDevice(T.device));
+    const size_t words = p->batch * T.n;
+    long long *di = nullptr;
+    double *dd = nullptr;
+    auto body = [&]() -> int {
+        if (out_i64) CU(pool_malloc(T, (void **)&di, words * sizeof(long long)));
+        if (out_f64) CU(pool_malloc(T, (void **)&dd, words * sizeof(double)));
+        TRY(crt_wide_dev(p, di, dd, overflow));
+        if (out_i64) CU(cudaMemcpyAsync(out_i64, di, words * sizeof(long long), cudaMemcpyDeviceToHost, S(T)));
+        if (out_f64) CU(cudaMemcpyAsync(out_f64, dd, words * sizeof(double), cudaMemcpyDeviceToHost, S(T)));
+        CU(cudaStreamSynchronize(S(T)));
+        return CKKS_OK;
+    };
+    int rc = body();
+    dev_free(T, di);
+    dev_free(T, dd);
+    return rc;
+}
+
 // -------------------------------------------------------------------------------------------------
 // gadget keys
 // -------------------------------------------------------------------------------------------------
@@ -1063,11 +1216,11 @@ static int ksk_finalize(const Tables &T, ckks_ksk *k) {
     TRY(dev_alloc(T, words, &tmp));
     for (u64 *p : {k->a, k->b}) {
         if (T.w32) {
-            KLV("key_permute", (key_permute_kernel<u32><<<ew_grid(words), 256, 0, T.stream>>>(p, reinterpret_cast<u32 *>(tmp), words, T.logn, T.a1, T.a2, KS_E2)));
-            cudaMemcpyAsync(p, tmp, words * 4, cudaMemcpyDeviceToDevice, T.stream);
+            KLV("key_permute", (key_permute_kernel<u32><<<ew_grid(words), 256, 0, S(T)>>>(p, reinterpret_cast<u32 *>(tmp), words, T.logn, T.a1, T.a2, KS_E2)));
+            cudaMemcpyAsync(p, tmp, words * 4, cudaMemcpyDeviceToDevice, S(T));
         } else {
-            KLV("key_permute", (key_permute_kernel<u64><<<ew_grid(words), 256, 0, T.stream>>>(p, tmp, words, T.logn, T.a1, T.a2, KS_E2)));
-            cudaMemcpyAsync(p, tmp, words * 8, cudaMemcpyDeviceToDevice, T.stream);
+            KLV("key_permute", (key_permute_kernel<u64><<<ew_grid(words), 256, 0, S(T)>>>(p, tmp, words, T.logn, T.a1, T.a2, KS_E2)));
+            cudaMemcpyAsync(p, tmp, words * 8, cudaMemcpyDeviceToDevice, S(T));
         }
     }
     dev_free(T, tmp);
@@ -1087,15 +1240,15 @@ extern "C" int ckks_ksk_upload(ckks_ctx *ctx, const uint64_t *a, const uint64_t 
     TRY(ksk_new(ctx, &k));
     size_t words = ctx->L * ctx->L * T.n;
     int rc = CKKS_OK;
-    if (cudaMemcpyAsync(k->a, a, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess ||
-        cudaMemcpyAsync(k->b, b, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess)
+    if (cudaMemcpyAsync(k->a, a, words * 8, cudaMemcpyHostToDevice, S(T)) != cudaSuccess ||
+        cudaMemcpyAsync(k->b, b, words * 8, cudaMemcpyHostToDevice, S(T)) != cudaSuccess)
         rc = cuda_fail(cudaGetLastError(), "ksk h2d");
     // the key polynomials are RnsPoly values on the reference side (engine.rs:225-253): same canonical-word rule
     if (rc == CKKS_OK) rc = scan_reduced_pair_sync(T, ctx->L, ctx->L, k->a, k->b);
     if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, false);
     if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, false);
     if (rc == CKKS_OK) rc = ksk_finalize(T, k);
-    if (rc == CKKS_OK && cudaStreamSynchronize(T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ksk sync");
+    if (rc == CKKS_OK && cudaStreamSynchronize(S(T)) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ksk sync");
     if (rc != CKKS_OK) {
         ckks_ksk_free(k);
         return rc;
@@ -1115,8 +1268,8 @@ extern "C" int ckks_ksk_from_polys(const ckks_poly *a, const ckks_poly *b, ckks_
     ckks_ksk *k;
     TRY(ksk_new(ctx, &k));
     size_t words = ctx->L * ctx->L * T.n;
-    cudaMemcpyAsync(k->a, a->d, words * 8, cudaMemcpyDeviceToDevice, T.stream);
-    cudaMemcpyAsync(k->b, b->d, words * 8, cudaMemcpyDeviceToDevice, T.stream);
+    cudaMemcpyAsync(k->a, a->d, words * 8, cudaMemcpyDeviceToDevice, S(T));
+    cudaMemcpyAsync(k->b, b->d, words * 8, cudaMemcpyDeviceToDevice, S(T));
     int rc = CKKS_OK;
     if (!a->ntt) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, false);
     if (rc == CKKS_OK && !b->ntt) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, false);
@@ -1158,7 +1311,7 @@ extern "C" int ckks_gen_gadget_key_b(const ckks_poly *s, const ckks_poly *target
     if (rc == CKKS_OK) rc = ckks_poly_add_assign(b, e);
     if (rc == CKKS_OK) {
         EwArgs ea = ew_args(T, ctx->L, ctx->L);
-        KLV("add_gadget_target", (add_gadget_target_kernel<<<ew_grid((size_t)ctx->L * T.n), 256, 0, T.stream>>>(ea, b->d, target->d)));
+        KLV("add_gadget_target", (add_gadget_target_kernel<<<ew_grid((size_t)ctx->L * T.n), 256, 0, S(T)>>>(ea, b->d, target->d)));
         if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "add_gadget_target");
     }
     if (rc != CKKS_OK) {
@@ -1183,10 +1336,10 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
     int rc = dev_alloc(T, e.total, &alpha);
     if (rc == CKKS_OK && T.path == 2) rc = dev_alloc(T, e.total, &tmp);
     for (size_t i = 0; i < L && rc == CKKS_OK; ++i) {
-        KLV("digit_broadcast", (digit_broadcast_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, digits, alpha, (int)i)));
+        KLV("digit_broadcast", (digit_broadcast_kernel<<<ew_grid(e.total), 256, 0, S(T)>>>(e, digits, alpha, (int)i)));
         rc = ntt_run(T, L, batch, alpha, tmp, false);
         if (rc != CKKS_OK) break;
-        KLV("ks_mac", (ks_mac_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, alpha, key->k32 ? (const void *)((const u32 *)key->b + i * e.poly) : (const void *)(key->b + i * e.poly),
+        KLV("ks_mac", (ks_mac_kernel<<<ew_grid(e.total), 256, 0, S(T)>>>(e, alpha, key->k32 ? (const void *)((const u32 *)key->b + i * e.poly) : (const void *)(key->b + i * e.poly),
                                                                                    key->k32 ? (const void *)((const u32 *)key->a + i * e.poly) : (const void *)(key->a + i * e.poly), acc0, acc1, T.a1,
                                                                                    T.a2, key->perm_e, key->k32 ? 1 : 0)));
         if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "keyswitch");
@@ -1377,7 +1530,7 @@ static int ks_fused_ex(const Tables &T, size_t L, const KsShard &sh, size_t cs, 
     a.N = T.n;
     const size_t Ld = sh.Ld;
     const unsigned n1 = 1u << T.a1, n2 = 1u << T.a2;
-    cudaStream_t s = T.stream;
+    cudaStream_t s = S(T);
     dim3 g1(n2, (unsigned)(nj * Ld), (unsigned)cs);  // x: columns; the launcher divides by its column tile
     DISPATCH_A(T.a1, TRY(launch_ks1_a<AA>(T.w32, T.lazy, sh.reduce, mul, g1, s, a)));
     dim3 g2((unsigned)cs, n1 / KS_C2, (unsigned)nj);
@@ -1434,7 +1587,7 @@ static int fused_mul_relin(const Tables &T, size_t L, size_t batch, const u64 *a
                 TRY(run_pass(T, P_FWD2, sp, TMP, nt[t]));
             }
             EwArgs e = ew_args(T, L, cs);
-            KL("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, A0, A1, B0, B1, A0, A1, B0)));  // d0,d1,d2
+            KL("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, S(T)>>>(e, A0, A1, B0, B1, A0, A1, B0)));  // d0,d1,d2
             // d2 -> coefficient domain (engine.rs:493); B0 keeps NTT(d2), B1 receives the digits
             TRY(run_pass(T, P_INV2, sp, B0, TMP));
             TRY(run_pass(T, P_INV1, sp, TMP, B1));
@@ -1465,10 +1618,10 @@ static int fused_mul_relin(const Tables &T, size_t L, size_t batch, const u64 *a
             const void *ql = T.w32 ? (const void *)((const tw32_t *)T.d_qlinv_w + (L - 1) * T.L) : (const void *)(T.d_qlinv + (L - 1) * T.L);
             pa.src = TMP;
             pa.dst = d0;
-            DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, LAST, ql)));
+            DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, S(T), pa, LAST, ql)));
             pa.src = B1;
             pa.dst = d1;
-            DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, LAST + cs * n, ql)));
+            DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, S(T), pa, LAST + cs * n, ql)));
             return CKKS_OK;
         };
         rc = step();
@@ -1543,7 +1696,7 @@ static int fused_rotate(const Tables &T, size_t L, size_t batch, const u64 *c0, 
         const size_t off = s0 * L * n;
         auto step = [&]() -> int {
             EwArgs ea = ew_args(T, L, cs);
-            KL("automorphism", (automorphism_kernel<<<ew_grid(ea.total), 256, 0, T.stream>>>(ea, c1 + off, D, e, einv)));
+            KL("automorphism", (automorphism_kernel<<<ew_grid(ea.total), 256, 0, S(T)>>>(ea, c1 + off, D, e, einv)));
             TRY(ks_fused(T, L, cs, D, nullptr, key, nullptr, nullptr, SCR, T0, T1, false));
             TRY(run_pass(T, P_INV1, whole(cs, L), T1, o1 + off));
             PassArgs a;
@@ -1560,7 +1713,7 @@ static int fused_rotate(const Tables &T, size_t L, size_t batch, const u64 *c0, 
             a.rot_src = c0 + off;
             a.rot_einv = einv;
             dim3 g(1, (unsigned)L, (unsigned)cs);
-            DISPATCH_A(T.a1, TRY(launch_inv1_addrot_a<AA>(T.w32, T.lazy, g, T.stream, a)));
+            DISPATCH_A(T.a1, TRY(launch_inv1_addrot_a<AA>(T.w32, T.lazy, g, S(T), a)));
             return CKKS_OK;
         };
         rc = step();
@@ -1646,7 +1799,7 @@ static int ct_mul_relin_impl(const ckks_poly *a0, const ckks_poly *a1, const ckk
     EwArgs e = ew_args(T, L, batch);
     if (rc == CKKS_OK && e.total) {
         // d0 -> A0, d1 -> A1, d2 -> B0
-        KLV("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, A0->d, A1->d, B0->d, B1->d, A0->d, A1->d, B0->d)));
+        KLV("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, S(T)>>>(e, A0->d, A1->d, B0->d, B1->d, A0->d, A1->d, B0->d)));
         if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "tensor");
     }
     if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(B0);  // engine.rs:493
@@ -1894,10 +2047,10 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
             ckks_ctx *child = nullptr;
             if (rc == CKKS_OK && kind == 0) rc = ckks_ctx_drop_last(ctx, 1, &child);
             if (rc == CKKS_OK) rc = kind == 0 ? ckks_ct_mul_relin_rescale(P[0], P[1], P[2], P[3], key, child, &R0, &R1) : ckks_ct_rotate(P[0], P[1], key, rot, &R0, &R1);
-            if (rc == CKKS_OK && (cudaMemcpyAsync(hout[0] + s * wo, R0->d, nb * wo * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess ||
-                                  cudaMemcpyAsync(hout[1] + s * wo, R1->d, nb * wo * 8, cudaMemcpyDeviceToHost, T.stream) != cudaSuccess))
+            if (rc == CKKS_OK && (cudaMemcpyAsync(hout[0] + s * wo, R0->d, nb * wo * 8, cudaMemcpyDeviceToHost, S(T)) != cudaSuccess ||
+                                  cudaMemcpyAsync(hout[1] + s * wo, R1->d, nb * wo * 8, cudaMemcpyDeviceToHost, S(T)) != cudaSuccess))
                 rc = cuda_fail(cudaGetLastError(), "d2h");
-            if (cudaStreamSynchronize(T.stream) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
+            if (cudaStreamSynchronize(S(T)) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
             for (int t = 0; t < 4; ++t)
                 if (P[t]) ckks_poly_free(P[t]);
             free2(R0, R1);
@@ -1907,6 +2060,7 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
         return CKKS_OK;
     }
     Tables &TM = *ctx->T;
+    std::lock_guard<std::mutex> pipe_lock(TM.pipe_mu);
     int rc = CKKS_OK;
     if (!TM.pipe || TM.pipe_nin < n_in || TM.pipe_in_words < chunk * wi || TM.pipe_out_words < chunk * wo) {
         destroy_host_pipe(TM.pipe);
@@ -1917,7 +2071,7 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
         TM.pipe_out_words = chunk * wo;
     }
     HostPipe &hp = *TM.pipe;
-    if (rc == CKKS_OK && cudaMemsetAsync(hp.flag, 0, sizeof(int), T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "memset");
+    if (rc == CKKS_OK && cudaMemsetAsync(hp.flag, 0, sizeof(int), S(T)) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "memset");
     const u64 e1 = rot >= 0 ? rot_exponent(n, rot) : (rot_exponent(n, rot) * (2 * n - 1)) % (2 * n);
     size_t c = 0;
     for (size_t s = 0; s < batch && rc == CKKS_OK; s += chunk, ++c) {
@@ -1928,11 +2082,11 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
             for (int t = 0; t < n_in; ++t)
                 CU(cudaMemcpyAsync(hp.in[b][t], hin[t] + s * wi, nb * wi * 8, cudaMemcpyHostToDevice, hp.s_in));
             CU(cudaEventRecord(hp.in_done[b], hp.s_in));
-            CU(cudaStreamWaitEvent(T.stream, hp.in_done[b], 0));
-            if (c >= 2) CU(cudaStreamWaitEvent(T.stream, hp.out_done[b], 0));  // D2H of chunk c-2 has drained out[b]
+            CU(cudaStreamWaitEvent(S(T), hp.in_done[b], 0));
+            if (c >= 2) CU(cudaStreamWaitEvent(S(T), hp.out_done[b], 0));  // D2H of chunk c-2 has drained out[b]
             // what from_channels checks on every polynomial the reference builds from raw words (poly.rs:83-93): the
             // lazy butterflies assume canonical inputs, so a word >= q must be an error, not silent garbage
-            for (int t = 0; t < n_in; ++t) TRY(scan_reduced(T, L, nb, hp.in[b][t], hp.flag, T.stream));
+            for (int t = 0; t < n_in; ++t) TRY(scan_reduced(T, L, nb, hp.in[b][t], hp.flag, S(T)));
             if (kind == 0) {
                 TRY(fused_mul_relin(T, L, nb, hp.in[b][0], hp.in[b][1], hp.in[b][2], hp.in[b][3], key, true, hp.out[b][0], hp.out[b][1]));
             } else {
@@ -1940,7 +2094,7 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
                 // the last inverse pass
                 TRY(fused_rotate(T, L, nb, hp.in[b][0], hp.in[b][1], e1, key, hp.out[b][0], hp.out[b][1]));
             }
-            CU(cudaEventRecord(hp.comp_done[b], T.stream));
+            CU(cudaEventRecord(hp.comp_done[b], S(T)));
             CU(cudaStreamWaitEvent(hp.s_out, hp.comp_done[b], 0));
             CU(cudaMemcpyAsync(hout[0] + s * wo, hp.out[b][0], nb * wo * 8, cudaMemcpyDeviceToHost, hp.s_out));
             CU(cudaMemcpyAsync(hout[1] + s * wo, hp.out[b][1], nb * wo * 8, cudaMemcpyDeviceToHost, hp.s_out));
@@ -1950,9 +2104,9 @@ static int host_pipeline(ckks_ctx *ctx, int kind, const ckks_ksk *key, int32_t r
         rc = step();
     }
     int hflag = 0;
-    if (rc == CKKS_OK && cudaMemcpyAsync(&hflag, hp.flag, sizeof(int), cudaMemcpyDeviceToHost, T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "flag");
+    if (rc == CKKS_OK && cudaMemcpyAsync(&hflag, hp.flag, sizeof(int), cudaMemcpyDeviceToHost, S(T)) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "flag");
     cudaStreamSynchronize(hp.s_in);
-    if (cudaStreamSynchronize(T.stream) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
+    if (cudaStreamSynchronize(S(T)) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
     if (cudaStreamSynchronize(hp.s_out) != cudaSuccess && rc == CKKS_OK) rc = cuda_fail(cudaGetLastError(), "sync");
     if (rc == CKKS_OK && hflag) return CKKS_NON_REDUCED_COEFFICIENT;  // outputs are unspecified in that case
     if (rc != CKKS_OK) {  // do not keep a pipeline whose events may be in an unknown state
@@ -2067,15 +2221,15 @@ extern "C" int ckks_poly_from_device(ckks_ctx *ctx, size_t batch, const uint64_t
     int rc = CKKS_OK;
     if (words) {
         int *flag = nullptr, hflag = 0;
-        if (cudaMallocAsync((void **)&flag, sizeof(int), T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "malloc");
+        if (pool_malloc(T, (void **)&flag, sizeof(int)) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "malloc");
         if (rc == CKKS_OK) {
-            cudaMemsetAsync(flag, 0, sizeof(int), T.stream);
+            cudaMemsetAsync(flag, 0, sizeof(int), S(T));
             EwArgs a = ew_args(T, ctx->L, batch);
-            KLV("check_reduced", (check_reduced_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, (const u64 *)dev, flag)));
+            KLV("check_reduced", (check_reduced_kernel<<<ew_grid(a.total), 256, 0, S(T)>>>(a, (const u64 *)dev, flag)));
             if (in_ntt) rc = permute(T, (const u64 *)dev, p->d, words, true);
-            else if (cudaMemcpyAsync(p->d, dev, words * 8, cudaMemcpyDeviceToDevice, T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "d2d");
-            cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, T.stream);
-            if (cudaStreamSynchronize(T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "sync");
+            else if (cudaMemcpyAsync(p->d, dev, words * 8, cudaMemcpyDeviceToDevice, S(T)) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "d2d");
+            cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, S(T));
+            if (cudaStreamSynchronize(S(T)) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "sync");
             if (rc == CKKS_OK && hflag) rc = CKKS_NON_REDUCED_COEFFICIENT;
         }
         dev_free(T, flag);
@@ -2099,7 +2253,7 @@ extern "C" int ckks_poly_device_ptr(ckks_poly *p, uint64_t **out) {
 static int fft_run(const Tables &T, cplx *buf, size_t batch, double sign) {
     const size_t work = batch * (T.n / 2);
     for (int lh = 0; lh < T.logn; ++lh)
-        KL("encoder_fft_stage", (fft_stage_kernel<<<(unsigned)((work + 255) / 256), 256, 0, T.stream>>>(buf, T.logn, lh, sign, batch)));
+        KL("encoder_fft_stage", (fft_stage_kernel<<<(unsigned)((work + 255) / 256), 256, 0, S(T)>>>(buf, T.logn, lh, sign, batch)));
     return CKKS_OK;
 }
 static int pow5_table(const Tables &T, unsigned **out) {
@@ -2109,9 +2263,9 @@ static int pow5_table(const Tables &T, unsigned **out) {
         h[i] = (unsigned)v;
         v = (v * 5) % (2 * T.n);
     }
-    CU(cudaMallocAsync((void **)out, h.size() * sizeof(unsigned), T.stream));
-    CU(cudaMemcpyAsync(*out, h.data(), h.size() * sizeof(unsigned), cudaMemcpyHostToDevice, T.stream));
-    CU(cudaStreamSynchronize(T.stream));  // `h` goes out of scope
+    CU(pool_malloc(T, (void **)out, h.size() * sizeof(unsigned)));
+    CU(cudaMemcpyAsync(*out, h.data(), h.size() * sizeof(unsigned), cudaMemcpyHostToDevice, S(T)));
+    CU(cudaStreamSynchronize(S(T)));  // `h` goes out of scope
     return CKKS_OK;
 }
 extern "C" int ckks_encode(ckks_ctx *ctx, uint32_t scale_bits, size_t batch, const double *values, size_t nvals, ckks_poly **out) {
@@ -2130,19 +2284,19 @@ extern "C" int ckks_encode(ckks_ctx *ctx, uint32_t scale_bits, size_t batch, con
     unsigned *p5 = nullptr;
     auto body = [&]() -> int {
         TRY(pow5_table(T, &p5));
-        CU(cudaMallocAsync((void **)&dv, (batch * nvals + 1) * sizeof(cplx), T.stream));
-        CU(cudaMallocAsync((void **)&buf, batch * T.n * sizeof(cplx), T.stream));
-        CU(cudaMallocAsync((void **)&dc, batch * T.n * sizeof(long long), T.stream));
-        if (nvals) CU(cudaMemcpyAsync(dv, values, batch * nvals * sizeof(cplx), cudaMemcpyHostToDevice, T.stream));
+        CU(pool_malloc(T, (void **)&dv, (batch * nvals + 1) * sizeof(cplx)));
+        CU(pool_malloc(T, (void **)&buf, batch * T.n * sizeof(cplx)));
+        CU(pool_malloc(T, (void **)&dc, batch * T.n * sizeof(long long)));
+        if (nvals) CU(cudaMemcpyAsync(dv, values, batch * nvals * sizeof(cplx), cudaMemcpyHostToDevice, S(T)));
         const size_t half = batch * (T.n / 2);
-        KL("encoder_scatter", (enc_scatter_kernel<<<(unsigned)((half + 255) / 256), 256, 0, T.stream>>>(dv, nvals, ldexp(1.0, (int)scale_bits), p5, buf,
+        KL("encoder_scatter", (enc_scatter_kernel<<<(unsigned)((half + 255) / 256), 256, 0, S(T)>>>(dv, nvals, ldexp(1.0, (int)scale_bits), p5, buf,
                                                                                                          T.logn, batch)));
         TRY(fft_run(T, buf, batch, +1.0));
         const size_t tot = batch * T.n;
-        KL("encoder_finish", (enc_finish_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, T.stream>>>(buf, dc, T.logn, batch)));
+        KL("encoder_finish", (enc_finish_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, S(T)>>>(buf, dc, T.logn, batch)));
         EwArgs a = ew_args(T, ctx->L, batch);
-        KL("from_coeffs", (from_coeffs_kernel<<<ew_grid(a.total), 256, 0, T.stream>>>(a, dc, T.n, (*out)->d)));
-        CU(cudaStreamSynchronize(T.stream));  // `values` may be pageable and reused by the caller
+        KL("from_coeffs", (from_coeffs_kernel<<<ew_grid(a.total), 256, 0, S(T)>>>(a, dc, T.n, (*out)->d)));
+        CU(cudaStreamSynchronize(S(T)));  // `values` may be pageable and reused by the caller
         return CKKS_OK;
     };
     int rc = body();
@@ -2163,32 +2317,53 @@ extern "C" int ckks_decode(const ckks_poly *p, uint32_t scale_bits, size_t nslot
     if (!p->batch || !nslots) return CKKS_OK;
     if (!out) return CKKS_BAD_ARGUMENT;
     CU(cudaSetDevice(T.device));
-    // centred CRT exactly as the reference (basis.rs:158-180, Q < 2^128), then the transform on the device
-    std::vector<int64_t> co(p->batch * T.n);
-    TRY(ckks_poly_to_coeffs(p, co.data()));
+    // Q < 2^128: centred CRT exactly as the reference (basis.rs:158-180: u128 arithmetic on the host, `as i64`), then the
+    // transform on the device.  Q >= 2^128 (where the reference's u128 product overflows and it cannot decode at all):
+    // Garner's mixed-radix CRT on the device (crt_wide.cuh), coefficients handed to the transform as doubles.
+    bool fits = true;
+    {
+        hm::u128 q = 1;
+        for (size_t i = 0; i < p->ctx->L && fits; ++i) {
+            if (q > (~(hm::u128)0) / T.moduli[i]) fits = false;
+            else q *= T.moduli[i];
+        }
+    }
+    std::vector<int64_t> co;
+    if (fits) {
+        co.resize(p->batch * T.n);
+        TRY(ckks_poly_to_coeffs(p, co.data()));
+    }
     cplx *buf = nullptr, *dout = nullptr;
     long long *dc = nullptr;
+    double *dcf = nullptr;
     unsigned *p5 = nullptr;
     const size_t batch = p->batch;
     auto body = [&]() -> int {
         TRY(pow5_table(T, &p5));
-        CU(cudaMallocAsync((void **)&buf, batch * T.n * sizeof(cplx), T.stream));
-        CU(cudaMallocAsync((void **)&dc, batch * T.n * sizeof(long long), T.stream));
-        CU(cudaMallocAsync((void **)&dout, batch * nslots * sizeof(cplx), T.stream));
-        CU(cudaMemcpyAsync(dc, co.data(), batch * T.n * sizeof(long long), cudaMemcpyHostToDevice, T.stream));
+        CU(pool_malloc(T, (void **)&buf, batch * T.n * sizeof(cplx)));
+        CU(pool_malloc(T, (void **)&dout, batch * nslots * sizeof(cplx)));
         const size_t tot = batch * T.n;
-        KL("decoder_twist", (dec_twist_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, T.stream>>>(dc, buf, T.logn, batch)));
+        if (fits) {
+            CU(pool_malloc(T, (void **)&dc, batch * T.n * sizeof(long long)));
+            CU(cudaMemcpyAsync(dc, co.data(), batch * T.n * sizeof(long long), cudaMemcpyHostToDevice, S(T)));
+            KL("decoder_twist", (dec_twist_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, S(T)>>>(dc, buf, T.logn, batch)));
+        } else {
+            CU(pool_malloc(T, (void **)&dcf, batch * T.n * sizeof(double)));
+            TRY(crt_wide_dev(p, nullptr, dcf, nullptr));
+            KL("decoder_twist", (dec_twist_f64_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, S(T)>>>(dcf, buf, T.logn, batch)));
+        }
         TRY(fft_run(T, buf, batch, -1.0));
         const size_t ns = batch * nslots;
-        KL("decoder_gather", (dec_gather_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, T.stream>>>(buf, p5, ldexp(1.0, -(int)scale_bits), dout, nslots,
+        KL("decoder_gather", (dec_gather_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, S(T)>>>(buf, p5, ldexp(1.0, -(int)scale_bits), dout, nslots,
                                                                                                      T.logn, batch)));
-        CU(cudaMemcpyAsync(out, dout, ns * sizeof(cplx), cudaMemcpyDeviceToHost, T.stream));
-        CU(cudaStreamSynchronize(T.stream));
+        CU(cudaMemcpyAsync(out, dout, ns * sizeof(cplx), cudaMemcpyDeviceToHost, S(T)));
+        CU(cudaStreamSynchronize(S(T)));
         return CKKS_OK;
     };
     int rc = body();
     dev_free(T, buf);
     dev_free(T, dc);
+    dev_free(T, dcf);
     dev_free(T, dout);
     dev_free(T, p5);
     return rc;

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdint>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "modarith.cuh"
@@ -34,7 +35,12 @@ struct Tables {
     tw_t *d_qlinv = nullptr;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaMemPool_t pool = nullptr;  // private pool of the library's stream-ordered allocations
+    // limb-sharded mode: host-visible word a barrier sets when it gives up waiting for a peer GPU; once non-zero the
+    // blocking calls on this context (download, sync) report CKKS_NCCL_ERROR instead of handing out poisoned words
+    const volatile unsigned *fail_word = nullptr;
     // cached staging buffers / copy streams of the host-buffer entry points
+    std::mutex pipe_mu;  // the *_host entry points of one context tree take turns on the staging pipeline
     struct HostPipe *pipe = nullptr;
     int pipe_nin = 0;
     size_t pipe_in_words = 0, pipe_out_words = 0;

@@ -75,6 +75,18 @@ __global__ void dec_twist_kernel(const long long *__restrict__ coeffs, cplx *__r
     unsigned r = __brev((unsigned)c) >> (32 - logn);
     buf[(b << logn) + r] = cplx{a * co, a * s};
 }
+// the same for coefficients that arrive as doubles (centred CRT of a basis with Q >= 2^128, crt_wide.cuh)
+__global__ void dec_twist_f64_kernel(const double *__restrict__ coeffs, cplx *__restrict__ buf, int logn, size_t batch) {
+    const size_t n = (size_t)1 << logn;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * n) return;
+    size_t b = i >> logn, c = i & (n - 1);
+    double s, co;
+    sincospi(-(double)c / (double)n, &s, &co);
+    double a = coeffs[i];
+    unsigned r = __brev((unsigned)c) >> (32 - logn);
+    buf[(b << logn) + r] = cplx{a * co, a * s};
+}
 // out[b][i] = Y[m_i] / delta,  m_i = (2N - 5^i - 1) / 2   (the reversed slot order of special_dft)
 __global__ void dec_gather_kernel(const cplx *__restrict__ buf, const unsigned *__restrict__ pow5, double inv_delta, cplx *__restrict__ out,
                                   size_t nslots, int logn, size_t batch) {

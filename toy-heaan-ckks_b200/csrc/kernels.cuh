@@ -858,7 +858,8 @@ __global__ void lshard_push_kernel(PushArgs a) {
 struct BarArgs {
     unsigned *peer_flags[8];  // flag arrays of every GPU (own included), [world] words each
     unsigned *my_flags;
-    unsigned *err;
+    unsigned *err;       // device error word of this rank (read by the poison guard)
+    unsigned *host_err;  // the same word in mapped pinned host memory: the host sees a failure without synchronising
     int rank, world;
     unsigned epoch;
     unsigned long long timeout_ns;
@@ -879,11 +880,25 @@ __global__ void lshard_barrier_kernel(BarArgs a) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > a.timeout_ns) {
             atomicExch(a.err, a.epoch);
+            if (a.host_err) {
+                *reinterpret_cast<volatile unsigned *>(a.host_err) = a.epoch;
+                __threadfence_system();
+            }
             break;
         }
         __nanosleep(200);
     }
 #endif
+}
+
+// Fail-closed guard of the limb-sharded entry points: launched after the last kernel of a call.  If a barrier of
+// this rank gave up waiting for a peer, the kernels behind it consumed gather / last buffers that peer never filled,
+// so the outputs are overwritten with all-ones words: not canonical for any modulus (every q < 2^63), i.e. rejected
+// by every reducedness scan, never mistaken for ciphertext limbs.
+__global__ void lshard_poison_kernel(const unsigned *__restrict__ err, u64 *__restrict__ o0, size_t w0, u64 *__restrict__ o1, size_t w1) {
+    if (*err == 0) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < w0; i += (size_t)gridDim.x * blockDim.x) o0[i] = ~0ull;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < w1; i += (size_t)gridDim.x * blockDim.x) o1[i] = ~0ull;
 }
 
 // =================================================================================================

@@ -41,6 +41,7 @@ struct LsSym {  // symmetric buffers of one rank: one cudaMalloc block (one IPC 
     cudaStream_t aux = nullptr, aux2 = nullptr;  // aux2: the dropped limb's broadcast, under the rest of phase B
     cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr}, ev_k = nullptr, ev_l = nullptr;
     unsigned long long timeout_ns = 20ull * 1000000000ull;
+    unsigned *h_fail = nullptr, *d_fail = nullptr;  // mapped pinned word: a barrier's timeout, visible to the host at once
     // how the digits reach the peers in the pipelined entry point: 0 = stores from the producing kernel,
     // 1 = copy engines (cudaMemcpyAsync over the peer mappings: no SM is held while NVLink is busy, so the
     // exchange of chunk k+1 really runs under the key-switch of chunk k)
@@ -60,6 +61,7 @@ struct LsSym {  // symmetric buffers of one rank: one cudaMalloc block (one IPC 
             if (e) cudaEventDestroy(e);
         if (aux) cudaStreamDestroy(aux);
         if (aux2) cudaStreamDestroy(aux2);
+        if (h_fail) cudaFreeHost(h_fail);
         for (int p = 0; p < 8; ++p)
             if (ipc_base[p]) cudaIpcCloseMemHandle(ipc_base[p]);
         if (block) cudaFree(block);
@@ -169,6 +171,10 @@ extern "C" int ckks_lshard_create(uint64_t n, const uint64_t *moduli, size_t l, 
         CU(cudaSetDevice(device));
         CU(cudaMalloc((void **)&sym->block, sym->block_bytes));  // plain cudaMalloc: exportable with cudaIpcGetMemHandle
         CU(cudaMemset(sym->block + sym->off_flags, 0, 256));
+        CU(cudaHostAlloc((void **)&sym->h_fail, sizeof(unsigned), cudaHostAllocMapped));
+        *sym->h_fail = 0;
+        CU(cudaHostGetDevicePointer((void **)&sym->d_fail, sym->h_fail, 0));
+        local->T->fail_word = sym->h_fail;
         const size_t W = cs * sym->Ll0 * n * 8;
         for (int k = 0; k < 2; ++k)
             for (u64 **b : {&sym->set[k].A0, &sym->set[k].A1, &sym->set[k].B0, &sym->set[k].B1, &sym->set[k].TMP}) CU(cudaMalloc((void **)b, W));
@@ -331,14 +337,14 @@ extern "C" int ckks_lshard_ksk_upload(ckks_lshard *s, const uint64_t *a, const u
     TRY(ksk_new(s->local, &k, s->Lg));
     const size_t words = s->Lg * s->Ll * T.n;
     int rc = CKKS_OK;
-    if (cudaMemcpyAsync(k->a, a, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess ||
-        cudaMemcpyAsync(k->b, b, words * 8, cudaMemcpyHostToDevice, T.stream) != cudaSuccess)
+    if (cudaMemcpyAsync(k->a, a, words * 8, cudaMemcpyHostToDevice, S(T)) != cudaSuccess ||
+        cudaMemcpyAsync(k->b, b, words * 8, cudaMemcpyHostToDevice, S(T)) != cudaSuccess)
         rc = cuda_fail(cudaGetLastError(), "ksk h2d");
     if (rc == CKKS_OK) rc = scan_reduced_pair_sync(T, s->Ll, s->Lg, k->a, k->b);  // canonical words only (poly.rs:83-93)
     if (rc == CKKS_OK) rc = ntt_inplace(T, s->Ll, s->Lg, k->a, false);
     if (rc == CKKS_OK) rc = ntt_inplace(T, s->Ll, s->Lg, k->b, false);
     if (rc == CKKS_OK) rc = ksk_finalize(T, k);
-    if (rc == CKKS_OK && cudaStreamSynchronize(T.stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ksk sync");
+    if (rc == CKKS_OK && cudaStreamSynchronize(S(T)) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ksk sync");
     if (rc != CKKS_OK) {
         ckks_ksk_free(k);
         return rc;
@@ -387,7 +393,28 @@ static int ls_inv1_multi(const Tables &T, size_t cs, int L, int limb0, int nl, c
     a.m_step = m_step;
     a.m_cs = m_cs;
     dim3 g(1, (unsigned)nl, (unsigned)cs);
-    DISPATCH_A(T.a1, TRY(launch_inv1_multi_a<AA>(T.w32, T.lazy, g, T.stream, a)));
+    DISPATCH_A(T.a1, TRY(launch_inv1_multi_a<AA>(T.w32, T.lazy, g, S(T), a)));
+    return CKKS_OK;
+}
+// A barrier that timed out leaves this rank's epochs out of step with its peers for good and its buffers half
+// filled: the group is dead.  Every entry point refuses further work (sticky CKKS_NCCL_ERROR) until all shards of the
+// group are destroyed and re-created (ckks_lshard_create + connect): that rebuilds buffers, flags and epochs.
+static int ls_failed(const ckks_lshard *s) {
+    const LsSym &y = *s->sym;
+    if (y.h_fail && *reinterpret_cast<const volatile unsigned *>(y.h_fail)) {
+        g_err = "limb-sharded barrier " + std::to_string(*y.h_fail) +
+                " timed out waiting for a peer GPU: the group is unusable, destroy and re-create every shard of it";
+        return CKKS_NCCL_ERROR;
+    }
+    return CKKS_OK;
+}
+// Enqueued behind the last kernel of a call: all-ones outputs if a barrier of this call (or an earlier one) failed.
+static int ls_poison_guard(ckks_lshard *s, ckks_poly *o0, ckks_poly *o1, cudaStream_t st) {
+    LsSym &y = *s->sym;
+    if (y.world == 1) return CKKS_OK;
+    g_cur_stream = st;
+    KL("lshard_poison_guard", (lshard_poison_kernel<<<148, 256, 0, st>>>(y.flags() + 8, o0 ? o0->d : nullptr, o0 ? poly_words(o0) : 0, o1 ? o1->d : nullptr,
+                                                                         o1 ? poly_words(o1) : 0)));
     return CKKS_OK;
 }
 // which = 0: flag words [0,8) (auxiliary-stream sequence of the chunk pipeline); 1: words [16,24) (main stream).
@@ -401,6 +428,7 @@ static int ls_barrier(ckks_lshard *s, int which, cudaStream_t st) {
     for (int p = 0; p < y.world; ++p) b.peer_flags[p] = y.flags_of(p) + fo;
     b.my_flags = y.flags() + fo;
     b.err = y.flags() + 8;
+    b.host_err = y.d_fail;
     b.rank = y.rank;
     b.world = y.world;
     b.epoch = which ? ++y.epochB : ++y.epochA;
@@ -417,12 +445,8 @@ extern "C" int ckks_lshard_check(ckks_lshard *s) {
     unsigned e = 0;
     CU(cudaMemcpyAsync(&e, y.flags() + 8, sizeof(e), cudaMemcpyDeviceToHost, s->local->T->stream));
     CU(cudaStreamSynchronize(s->local->T->stream));
-    if (e) {
-        cudaMemsetAsync(y.flags() + 8, 0, sizeof(unsigned), s->local->T->stream);  // report a lost peer once
-        g_err = "limb-sharded barrier " + std::to_string(e) + " timed out waiting for a peer GPU";
-        return CKKS_NCCL_ERROR;
-    }
-    return CKKS_OK;
+    if (e && y.h_fail) *y.h_fail = e;  // (the kernel wrote it already; kept for a device without mapped-memory coherence)
+    return ls_failed(s);  // sticky: see ls_failed
 }
 
 static int ls_check_inputs(ckks_lshard *s, const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1,
@@ -459,7 +483,7 @@ static int ls_mul_phase(ckks_lshard *s, int k, int phase, size_t s0, size_t cs, 
     }
     const Tables &T = *s->local->T;
     CU(cudaSetDevice(T.device));
-    g_cur_stream = T.stream;
+    g_cur_stream = S(T);
     const size_t n = T.n, Ll = s->Ll, Lg = s->Lg;
     const size_t off = s0 * Ll * n;
     const bool rescale = child != nullptr;
@@ -480,7 +504,7 @@ static int ls_mul_phase(ckks_lshard *s, int k, int phase, size_t s0, size_t cs, 
             TRY(run_pass(T, P_FWD2, sp, w.TMP, nt[t]));
         }
         EwArgs e = ew_args(T, Ll, cs);
-        KL("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, T.stream>>>(e, w.A0, w.A1, w.B0, w.B1, w.A0, w.A1, w.B0)));  // d0,d1,d2
+        KL("tensor", (tensor_kernel<<<ew_grid(e.total), 256, 0, S(T)>>>(e, w.A0, w.A1, w.B0, w.B1, w.A0, w.A1, w.B0)));  // d0,d1,d2
         TRY(run_pass(T, P_INV2, sp, w.B0, w.TMP));
         // digits: coefficient-domain limbs of d2 (engine.rs:493,507), stored where every GPU will read them
         if (peer_stores && y.exchange == 1 && y.world > 1) {
@@ -490,7 +514,7 @@ static int ls_mul_phase(ckks_lshard *s, int k, int phase, size_t s0, size_t cs, 
                 const int p = (s->rank + t) % y.world;
                 for (size_t jl = 0; jl < Ll; ++jl) {
                     const size_t slot = ((size_t)s->rank + (size_t)s->world * jl) * y.cs_max * n;
-                    CU(cudaMemcpyAsync(y.gather_of(p, k) + slot, y.gather(k) + slot, cs * n * sizeof(u64), cudaMemcpyDefault, T.stream));
+                    CU(cudaMemcpyAsync(y.gather_of(p, k) + slot, y.gather(k) + slot, cs * n * sizeof(u64), cudaMemcpyDefault, S(T)));
                 }
             }
             return CKKS_OK;
@@ -504,18 +528,15 @@ static int ls_mul_phase(ckks_lshard *s, int k, int phase, size_t s0, size_t cs, 
             // The owner of the limb rescale drops key-switches that limb FIRST and sends it to the peers (one GPU
             // feeding world-1 others: the longest transfer of the step) on a side stream while the key-switch of
             // its other limbs runs; the barrier that follows phase B finds the broadcast already done.
-            Tables &Tm = *s->local->T;
-            const cudaStream_t cur = Tm.stream;
+            const cudaStream_t cur = S(T);
             TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(k), w.B0, rlk, w.A0, w.A1, y.SCR, w.TMP, w.B1, true, Ll - 1, 1));
             CU(cudaEventRecord(y.ev_k, cur));
             CU(cudaStreamWaitEvent(y.aux2, y.ev_k, 0));
-            Tm.stream = y.aux2;
-            g_cur_stream = y.aux2;
-            int rc = ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, w.TMP, pl0, np, s->rank + 1, 0, 0, y.cs_max);
-            if (rc == CKKS_OK) rc = ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, w.B1, pl1, np, s->rank + 1, 0, 0, y.cs_max);
-            Tm.stream = cur;
-            g_cur_stream = cur;
-            TRY(rc);
+            {
+                StreamScope side(y.aux2);  // thread-local redirection of the launch helpers (no shared state is touched)
+                TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, w.TMP, pl0, np, s->rank + 1, 0, 0, y.cs_max));
+                TRY(ls_inv1_multi(T, cs, (int)Ll, (int)Ll - 1, 1, w.B1, pl1, np, s->rank + 1, 0, 0, y.cs_max));
+            }
             CU(cudaEventRecord(y.ev_l, y.aux2));
             TRY(ks_fused_ex(T, Ll, ks, cs, y.gather(k), w.B0, rlk, w.A0, w.A1, y.SCR, w.TMP, w.B1, true, 0, Ll - 1));
             CU(cudaStreamWaitEvent(cur, y.ev_l, 0));
@@ -551,10 +572,10 @@ static int ls_mul_phase(ckks_lshard *s, int k, int phase, size_t s0, size_t cs, 
         const size_t ooff = s0 * outL * n;
         pa.src = w.TMP;
         pa.dst = o0->d + ooff;
-        DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, y.last(k), s->d_qlinv_last)));
+        DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, S(T), pa, y.last(k), s->d_qlinv_last)));
         pa.src = w.B1;
         pa.dst = o1->d + ooff;
-        DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, T.stream, pa, y.last(k) + y.cs_max * n, s->d_qlinv_last)));
+        DISPATCH_A(T.a1, TRY(launch_inv1_rescale_a<AA>(T.w32, T.lazy, g, S(T), pa, y.last(k) + y.cs_max * n, s->d_qlinv_last)));
         return CKKS_OK;
     }
     return CKKS_BAD_ARGUMENT;
@@ -565,11 +586,15 @@ extern "C" int ckks_lshard_mul_phase(ckks_lshard *s, int phase, size_t s0, size_
                                      const ckks_poly *b0, const ckks_poly *b1, const ckks_ksk *rlk, ckks_lshard *child, ckks_poly *o0,
                                      ckks_poly *o1, int peer_stores) {
     TRY(ls_check_inputs(s, a0, a1, b0, b1, rlk, child, o0, o1));
-    return ls_mul_phase(s, 0, phase, s0, cs, a0, a1, b0, b1, rlk, child, o0, o1, peer_stores);
+    TRY(ls_failed(s));
+    TRY(ls_mul_phase(s, 0, phase, s0, cs, a0, a1, b0, b1, rlk, child, o0, o1, peer_stores));
+    if (phase == 2 && peer_stores) TRY(ls_poison_guard(s, o0, o1, s->local->T->stream));
+    return CKKS_OK;
 }
 extern "C" int ckks_lshard_barrier(ckks_lshard *s) {
     if (!ok_lshard(s)) return CKKS_BAD_HANDLE;
     if (!s->sym->connected) return CKKS_BAD_ARGUMENT;
+    TRY(ls_failed(s));
     CU(cudaSetDevice(s->sym->device));
     return ls_barrier(s, 1, s->local->T->stream);
 }
@@ -585,6 +610,7 @@ extern "C" int ckks_lshard_ks_phase(ckks_lshard *s, int phase, size_t s0, size_t
     if (digits->ntt) return CKKS_DOMAIN_MISMATCH;
     if (!ok_ksk_slice(key) || key->digits != s->Lg || !same_basis(key->ctx, s->local)) return CKKS_BAD_HANDLE;
     if (ks0->batch != digits->batch || ks1->batch != digits->batch) return CKKS_BATCH_MISMATCH;
+    TRY(ls_failed(s));
     LsSym &y = *s->sym;
     if (cs == 0) return CKKS_OK;
     if (cs > y.cs_max || s0 + cs > digits->batch) return CKKS_BAD_ARGUMENT;
@@ -594,7 +620,7 @@ extern "C" int ckks_lshard_ks_phase(ckks_lshard *s, int phase, size_t s0, size_t
     }
     const Tables &T = *s->local->T;
     CU(cudaSetDevice(T.device));
-    g_cur_stream = T.stream;
+    g_cur_stream = S(T);
     const size_t n = T.n, Ll = s->Ll, off = s0 * Ll * n;
     if (phase == 0) {
         PushArgs a;
@@ -609,7 +635,7 @@ extern "C" int ckks_lshard_ks_phase(ckks_lshard *s, int phase, size_t s0, size_t
         a.L = (int)Ll;
         a.logn = T.logn;
         a.total2 = cs * Ll * n / 2;
-        KL("lshard_push", (lshard_push_kernel<<<ew_grid(a.total2), 256, 0, T.stream>>>(a)));
+        KL("lshard_push", (lshard_push_kernel<<<ew_grid(a.total2), 256, 0, S(T)>>>(a)));
         return CKKS_OK;
     }
     if (phase == 1) {
@@ -619,6 +645,7 @@ extern "C" int ckks_lshard_ks_phase(ckks_lshard *s, int phase, size_t s0, size_t
         TRY(run_pass(T, P_INV1, sp, y.set[0].TMP, ks0->d + off));
         TRY(run_pass(T, P_INV1, sp, y.set[0].B1, ks1->d + off));
         ks0->ntt = ks1->ntt = false;
+        if (peer_stores) TRY(ls_poison_guard(s, ks0, ks1, S(T)));
         return CKKS_OK;
     }
     return CKKS_BAD_ARGUMENT;
@@ -648,6 +675,7 @@ extern "C" int ckks_lshard_ct_rotate(ckks_lshard *s, const ckks_poly *c0, const 
         if (rc == CKKS_OK) rc = ls_barrier(s, 1, s->local->T->stream);  // gather buffers are free again
     }
     if (rc == CKKS_OK) rc = ckks_poly_add_assign(r0, k0);  // engine.rs:454-455
+    if (rc == CKKS_OK) rc = ls_poison_guard(s, r0, k1, s->local->T->stream);
     free2(r1, k0);
     if (rc != CKKS_OK) {
         free2(r0, k1);
@@ -689,9 +717,9 @@ extern "C" int ckks_lshard_barrier_local(ckks_lshard **shards, int world) {
 static int ls_mul_pipeline(ckks_lshard *s, const ckks_poly *a0, const ckks_poly *a1, const ckks_poly *b0, const ckks_poly *b1,
                            const ckks_ksk *rlk, ckks_lshard *child, ckks_poly *r0, ckks_poly *r1) {
     LsSym &y = *s->sym;
-    Tables &T = *s->local->T;
+    const Tables &T = *s->local->T;
     CU(cudaSetDevice(T.device));
-    const cudaStream_t main = T.stream, aux = y.aux;
+    const cudaStream_t main = S(T), aux = y.aux;
     const size_t batch = a0->batch, cs_max = y.cs_max;
     const size_t K = (batch + cs_max - 1) / cs_max;
     if (K == 0) return CKKS_OK;
@@ -700,13 +728,15 @@ static int ls_mul_pipeline(ckks_lshard *s, const ckks_poly *a0, const ckks_poly 
         s0 = k * cs_max;
         cs = batch - s0 < cs_max ? batch - s0 : cs_max;
     };
-    // phase A of chunk k on the auxiliary stream (the launch helpers take the stream from the tables)
+    // phase A of chunk k on the auxiliary stream
     auto phase_a = [&](size_t k) -> int {
         size_t s0, cs;
         span(k, s0, cs);
-        T.stream = aux;
-        int rc = ls_mul_phase(s, (int)(k & 1), 0, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1);
-        T.stream = main;
+        int rc;
+        {
+            StreamScope on_aux(aux);  // thread-local: the shared Tables keep their stream
+            rc = ls_mul_phase(s, (int)(k & 1), 0, s0, cs, a0, a1, b0, b1, rlk, child, r0, r1, 1);
+        }
         if (rc == CKKS_OK) rc = ls_barrier(s, 0, aux);
         if (rc != CKKS_OK) return rc;
         CU(cudaEventRecord(y.ev_a[k & 1], aux));
@@ -747,7 +777,9 @@ extern "C" int ckks_lshard_ct_mul_relin_rescale(ckks_lshard *s, const ckks_poly 
     int rc = poly_new(octx, a0->batch, false, &r0);
     if (rc == CKKS_OK) rc = poly_new(octx, a0->batch, false, &r1);
     if (rc == CKKS_OK) rc = ls_check_inputs(s, a0, a1, b0, b1, rlk, child, r0, r1);
+    if (rc == CKKS_OK) rc = ls_failed(s);
     if (rc == CKKS_OK) rc = ls_mul_pipeline(s, a0, a1, b0, b1, rlk, child, r0, r1);
+    if (rc == CKKS_OK) rc = ls_poison_guard(s, r0, r1, s->local->T->stream);
     if (rc != CKKS_OK) {
         free2(r0, r1);
         return rc;
