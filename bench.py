@@ -343,6 +343,59 @@ def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, pas
     }
 
 
+def run_extra_ops(ck, torch, dev, stream, basis, moduli, bits, l, n, batch, steps, hbm_peak):
+    """BASELINE.json configs[1] as worded: "encrypt + homomorphic add + mul/relin/rescale".  encrypt (engine.rs:84-112,
+    host-sampled u / e0 / e1 / m already resident, as north_star keeps sampling on the host) and add_ciphertexts
+    (engine.rs:131-151) on a resident batch; CUDA events, median of `steps` calls."""
+    qt = torch.tensor(moduli, dtype=torch.int64, device=dev)[:, None]
+
+    def small_poly(nb, lo, hi):  # coefficients in [lo, hi) as canonical residues per limb (what from_coeffs produces)
+        c = torch.randint(lo, hi, (nb, 1, n), dtype=torch.int64, device=dev)
+        t = torch.where(c < 0, c + qt, c.expand(nb, l, n)).contiguous()
+        h = ck._vp()
+        ck._check(ck._lib.ckks_poly_from_device(basis._h, nb, ck.C.cast(t.data_ptr(), ck._u64p), 0, ck.C.byref(h)))
+        return ck.RnsPoly(h, basis)
+
+    def uni(nb):
+        t = torch.randint(0, 1 << 62, (nb, l, n), dtype=torch.int64, device=dev) % qt
+        h = ck._vp()
+        ck._check(ck._lib.ckks_poly_from_device(basis._h, nb, ck.C.cast(t.data_ptr(), ck._u64p), 0, ck.C.byref(h)))
+        return ck.RnsPoly(h, basis)
+
+    pk_b, pk_a = uni(1), uni(1)
+    u, e0, e1 = small_poly(batch, -1, 2), small_poly(batch, -16, 17), small_poly(batch, -16, 17)
+    m = small_poly(batch, -(1 << 28), 1 << 28)  # |m| below every modulus of every config
+    x = ck.Ciphertext(uni(batch), uni(batch), bits, bits * l)
+    y = ck.Ciphertext(uni(batch), uni(batch), bits, bits * l)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(max(steps, 5)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(stream)
+            fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2]
+
+    ms_enc = timed(lambda: ck.CkksEngine.encrypt(pk_b, pk_a, u, e0, e1, m, bits, bits * l))
+    ms_add = timed(lambda: ck.CkksEngine.add_ciphertexts(x, y))
+    poly_bytes = 8.0 * n * l
+    return {
+        "encrypt": {"ms": ms_enc, "per_s": batch / (ms_enc * 1e-3), "unit": "encryption/s",
+                    "algorithmic_bytes": 6 * poly_bytes, "hbm_frac": batch / (ms_enc * 1e-3) * 6 * poly_bytes / (hbm_peak * 1e9),
+                    "what": "c0 = pk_b*u + e0 + m, c1 = pk_a*u + e1 with u, e0, e1, m resident (read 4 polynomials, write 2; pk is shared)"},
+        "add_ciphertexts": {"ms": ms_add, "per_s": batch / (ms_add * 1e-3), "unit": "ct-add/s",
+                            "algorithmic_bytes": 6 * poly_bytes, "hbm_frac": batch / (ms_add * 1e-3) * 6 * poly_bytes / (hbm_peak * 1e9),
+                            "what": "limb-wise add of c0, c1 (read 4 polynomials, write 2)"},
+        "batch": batch,
+    }
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -364,7 +417,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__ as g
 
-    g.build_cuda()
+    if not os.environ.get("CKKS_B200_LIB"):
+        g.build_cuda()
     ck = importlib.import_module("toy-heaan-ckks_b200")
     if args.host_chunk_mib:
         ck._check(ck._lib.ckks_set_host_chunk_mib(args.host_chunk_mib))
@@ -645,6 +699,8 @@ def run_b200(args):
         }
         if not args.no_chain and op == "mul" and world == 1 and args.config == "cfg4":
             line["chain"] = run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, min(batch, 256))
+    if rank == 0 and (args.ops or args.config == "cfg2"):
+        line["ops"] = run_extra_ops(ck, torch, dev, stream, basis, moduli, bits, l, n, batch, args.steps, hbm_peak)
     if want_cpu:
         sample = {"inputs": host_in, "ka": host_keys[0], "kb": host_keys[1]}
         rec, (o0, o1) = cpu_baseline(args.config, op, sample, single_thread=not args.no_single_thread)
@@ -957,6 +1013,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prof", dest="prof", action="store_false")
+    ap.add_argument("--ops", action="store_true", help="also time encrypt and add_ciphertexts on the resident batch (default for cfg2)")
     ap.add_argument("--no-ntt", action="store_true", help="skip the limb-NTT record (the metric's second half)")
     ap.add_argument("--no-chain", action="store_true", help="skip the horner_chain sub-record (cfg4, 1 GPU)")
     ap.add_argument("--no-single-thread", action="store_true", help="skip the single-threaded oracle timing (~40 s at cfg4)")

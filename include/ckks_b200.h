@@ -334,6 +334,9 @@ size_t ckks_launch_table(char *buf, size_t cap);
 /* Per-kernel timing: while enabled every launch is bracketed by CUDA events on the context's stream;
  * collect() synchronises and writes "name=launches,total_ms\n" lines (returns the length needed). */
 int ckks_prof_enable(int on);
+/* NVTX ranges (one per kernel launch, named like the launch table, plus "ckks:<entry point>" around the fused
+ * pipelines) for Nsight timelines: off by default; 1 = on (or CKKS_NVTX=1 in the environment). */
+int ckks_set_nvtx(int on);
 size_t ckks_prof_collect(char *buf, size_t cap);
 /* from_channels with the source already in device memory ([batch][L][N], reference layout), and the
  * raw device pointer of a polynomial (coefficient domain: reference layout; NTT domain: internal

@@ -84,7 +84,9 @@ void pass(const u64 *src, u64 *dst, const LimbConst &m, const TW *tab, const TW 
                     size_t off = (size_t)idx * ncols + c0 + c;
                     WD x = regs[g * C + c][k];
                     // lazy-range audit: CT kinds must stay below 4q, GS kinds below 2q
-                    if (LAZY == 2 && (u64)x >= (CT_RANGE ? 8 * (u64)q : 4 * (u64)q)) *range_bad = 1;
+                    // (lazy8 negacyclic forward with bit-63 range management: any word is in range, see ct_bfly TOPBIT)
+                    constexpr bool FREE_RANGE = (KIND == XF_NEG_FWD && CKKS_NEG_FWD_TOPBIT != 0);
+                    if (LAZY == 2 && !FREE_RANGE && (u64)x >= (CT_RANGE ? 8 * (u64)q : 4 * (u64)q)) *range_bad = 1;
                     if (LAZY == 1 && (u64)x >= (CT_RANGE ? 4 * (u64)q : 2 * (u64)q)) *range_bad = 1;
                     if (!LAZY && x >= q) *range_bad = 1;
                     if (POST) x = mul_tw<LAZY>(x, elt[off], q);

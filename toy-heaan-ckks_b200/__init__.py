@@ -20,7 +20,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libckks_b200.so")
+# CKKS_B200_LIB: load another build of the same library (kernel variants under development, tools/variants.sh)
+LIB_PATH = os.environ.get("CKKS_B200_LIB") or os.path.join(_HERE, "libckks_b200.so")
 
 _ERR_NAMES = {
     1: "InvalidDegree",
@@ -98,6 +99,7 @@ _sig("ckks_set_tma", C.c_int, C.c_int)
 _sig("ckks_set_fused_ntt", C.c_int, C.c_int)
 _sig("ckks_set_host_chunk_mib", C.c_int, C.c_int)
 _sig("ckks_prof_enable", C.c_int, C.c_int)
+_sig("ckks_set_nvtx", C.c_int, C.c_int)
 _sig("ckks_prof_collect", C.c_size_t, C.c_char_p, C.c_size_t)
 _sig("ckks_poly_from_device", C.c_int, _vp, C.c_size_t, _u64p, C.c_int, _pp)
 _sig("ckks_poly_device_ptr", C.c_int, _vp, C.POINTER(_u64p))

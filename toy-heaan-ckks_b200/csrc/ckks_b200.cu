@@ -4,9 +4,11 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -99,6 +101,32 @@ struct ProfScope {
         }
     }
 };
+// NVTX ranges around every kernel launch (and around the entry points that enqueue many), for Nsight Systems /
+// Nsight Compute timelines: off by default, on with ckks_set_nvtx(1) or CKKS_NVTX=1 in the environment.  The
+// header-only NVTX v3 is a no-op unless a profiler has injected its library.
+static std::atomic<int> g_nvtx{-1};
+static bool nvtx_on() {
+    int v = g_nvtx.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("CKKS_NVTX");
+        v = (e && e[0] && e[0] != '0') ? 1 : 0;
+        g_nvtx.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+struct NvtxScope {
+    bool on;
+    explicit NvtxScope(const char *name) : on(nvtx_on()) {
+        if (on) nvtxRangePushA(name);
+    }
+    ~NvtxScope() {
+        if (on) nvtxRangePop();
+    }
+};
+extern "C" int ckks_set_nvtx(int on) {
+    g_nvtx.store(on != 0 ? 1 : 0);
+    return CKKS_OK;
+}
 static thread_local cudaStream_t g_cur_stream = nullptr;  // stream of the context whose call is running on this thread
 // Every launch / allocation helper enqueues on S(T): the context's stream, unless the CALLING THREAD has redirected
 // its own launches with a StreamScope (the limb-sharded chunk pipeline runs phase A on an auxiliary stream).  The
@@ -121,6 +149,7 @@ struct StreamScope {
     do {                                                         \
         count_launch(name);                                      \
         {                                                        \
+            NvtxScope nv__(name);                                \
             ProfScope ps__(name, g_cur_stream);                  \
             __VA_ARGS__;                                         \
         }                                                        \
@@ -131,6 +160,7 @@ struct StreamScope {
 #define KLV(name, ...)                           \
     do {                                         \
         count_launch(name);                      \
+        NvtxScope nv__(name);                    \
         ProfScope ps__(name, g_cur_stream);      \
         __VA_ARGS__;                             \
     } while (0)
@@ -223,6 +253,8 @@ extern "C" int ckks_generate_primes(int bits, int count, uint64_t degree, uint64
 // context
 // -------------------------------------------------------------------------------------------------
 static void destroy_host_pipe(struct HostPipe *p);
+static void ws_release(Tables &T);
+static void cache_release(Tables &T);
 Tables::~Tables() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
@@ -230,6 +262,9 @@ Tables::~Tables() {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     destroy_host_pipe(pipe);
+    ws_release(*this);
+    cache_release(*this);
+    if (stream) cudaStreamSynchronize(stream);
     if (pool) cudaMemPoolDestroy(pool);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
@@ -254,9 +289,79 @@ static bool same_basis(const ckks_ctx *a, const ckks_ctx *b) { return a->T.get()
 // Every stream-ordered allocation of the library comes from the context's PRIVATE memory pool (created in
 // ckks_ctx_create, released with the tables): freed scratch stays cached there for the next call instead of in the
 // device's default pool, which other libraries in the process (e.g. PyTorch) share; ckks_ctx_trim returns it.
-static cudaError_t pool_malloc(const Tables &T, void **p, size_t bytes) {
+static size_t size_class(size_t bytes) {  // smallest m * 2^e >= bytes with m in 8..15
+    int e = 0;
+    while ((bytes >> e) > 15) ++e;
+    size_t m = bytes >> e;
+    if ((m << e) < bytes) ++m;
+    return m << e;
+}
+static cudaError_t raw_pool_malloc(const Tables &T, void **p, size_t bytes) {
     if (T.pool) return cudaMallocFromPoolAsync(p, bytes, T.pool, S(T));
     return cudaMallocAsync(p, bytes, S(T));
+}
+static cudaError_t pool_malloc(const Tables &Tc, void **p, size_t bytes) {
+    // small requests, and calls whose launches are redirected to another stream, go straight to the pool
+    if (bytes < ((size_t)1 << 20) || g_stream_override) return raw_pool_malloc(Tc, p, bytes);
+    Tables &T = const_cast<Tables &>(Tc);  // the cache is internal state guarded by cache_mu
+    const size_t cls = size_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(T.cache_mu);
+        auto it = T.cache_free.find(cls);
+        if (it != T.cache_free.end()) {  // freed on this same stream earlier: reuse is stream-ordered
+            *p = it->second;
+            T.cache_free.erase(it);
+            T.cache_bytes -= cls;
+            T.cache_live[*p] = cls;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = raw_pool_malloc(T, p, cls);
+    if (e != cudaSuccess) {  // out of memory: give the parked blocks back and try once more
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lk(T.cache_mu);
+            for (auto &kv : T.cache_free) cudaFreeAsync(kv.second, T.stream);
+            T.cache_free.clear();
+            T.cache_bytes = 0;
+        }
+        cudaStreamSynchronize(T.stream);
+        if (T.pool) cudaMemPoolTrimTo(T.pool, 0);
+        e = raw_pool_malloc(T, p, cls);
+        if (e != cudaSuccess) return e;
+    }
+    std::lock_guard<std::mutex> lk(T.cache_mu);
+    T.cache_live[*p] = cls;
+    return cudaSuccess;
+}
+static void cache_release(Tables &T) {
+    std::lock_guard<std::mutex> lk(T.cache_mu);
+    for (auto &kv : T.cache_free) cudaFreeAsync(kv.second, T.stream);
+    T.cache_free.clear();
+    T.cache_bytes = 0;
+}
+
+static void dev_free(const Tables &Tc, void *p);
+enum { WS_A0 = 0, WS_A1, WS_B0, WS_B1, WS_TMP, WS_SCR, WS_LAST, WS_COUNT };
+static int ws_get(const Tables &Tc, int slot, size_t bytes, u64 **out) {
+    Tables &T = const_cast<Tables &>(Tc);  // the cache is internal state guarded by ws_mu
+    Tables::WsSlot &w = T.ws[slot];
+    if (w.bytes < bytes || !w.p) {
+        if (w.p) dev_free(T, w.p);  // stream-ordered: the kernels that still use it run first
+        w.p = nullptr;
+        w.bytes = 0;
+        CU(pool_malloc(T, &w.p, bytes ? bytes : 8));
+        w.bytes = bytes;
+    }
+    *out = reinterpret_cast<u64 *>(w.p);
+    return CKKS_OK;
+}
+static void ws_release(Tables &T) {
+    for (auto &w : T.ws) {
+        if (w.p) dev_free(T, w.p);
+        w.p = nullptr;
+        w.bytes = 0;
+    }
 }
 
 template <class T>
@@ -495,12 +600,25 @@ static int scan_reduced_pair_sync(const Tables &T, size_t L, size_t batch, const
 }
 
 // Dispatch on the lazy mode (0 strict, 1 Harvey, 2 lazy8); 32-bit words never use mode 2.
+#ifdef CKKS_ONLY_CFG4
+#define W32_DISPATCH(...) CKKS_UNSUPPORTED
+#else
+#define W32_DISPATCH(...) (__VA_ARGS__)
+#endif
+#ifdef CKKS_ONLY_CFG4  // development builds (tools/variants.sh): only the cfg4 instantiations, compiles in under a minute
+#define LZ_SWITCH(WDT, lazy, M)                                  \
+    do {                                                         \
+        if ((lazy) == 2 && sizeof(WDT) == 8) { M(2); }           \
+        else return CKKS_UNSUPPORTED;                            \
+    } while (0)
+#else
 #define LZ_SWITCH(WDT, lazy, M)                                  \
     do {                                                         \
         if ((lazy) == 2 && sizeof(WDT) == 8) { M(2); }           \
         else if (lazy) { M(1); }                                 \
         else { M(0); }                                           \
     } while (0)
+#endif
 
 // Column tile of the plain passes: 8 for 64-bit words (more, smaller CTAs hide each other's barriers on the
 // IMAD-bound path), 16 for 32-bit words (HBM-bound: wider coalesced segments).
@@ -521,16 +639,18 @@ static int launch_pass_w(const char *name, int lazy, dim3 grid, cudaStream_t s, 
 }
 template <int KIND, int A, bool PRE, bool POST, bool TR>
 static int launch_pass_a(const char *name, bool w32, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
-    if (w32) return launch_pass_w<u32, KIND, A, PRE, POST, TR>(name, lazy, grid, s, a);
+    if (w32) return W32_DISPATCH(launch_pass_w<u32, KIND, A, PRE, POST, TR>(name, lazy, grid, s, a));
     return launch_pass_w<u64, KIND, A, PRE, POST, TR>(name, lazy, grid, s, a);
 }
 template <int KIND, bool PRE, bool POST, bool TR>
 static int launch_pass(const char *name, int A, bool w32, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
     switch (A) {
+#ifndef CKKS_ONLY_CFG4
         case 4: return launch_pass_a<KIND, 4, PRE, POST, TR>(name, w32, lazy, grid, s, a);
         case 5: return launch_pass_a<KIND, 5, PRE, POST, TR>(name, w32, lazy, grid, s, a);
         case 6: return launch_pass_a<KIND, 6, PRE, POST, TR>(name, w32, lazy, grid, s, a);
         case 7: return launch_pass_a<KIND, 7, PRE, POST, TR>(name, w32, lazy, grid, s, a);
+#endif
         case 8: return launch_pass_a<KIND, 8, PRE, POST, TR>(name, w32, lazy, grid, s, a);
     }
     return CKKS_UNSUPPORTED;
@@ -634,7 +754,7 @@ static int launch_fused_w(const Tables &T, size_t L, size_t batch, u64 *d, bool 
     return CKKS_OK;
 }
 static int ntt_fused_run(const Tables &T, size_t L, size_t batch, u64 *d, bool inverse) {
-#define FW(A1v, A2v) (T.w32 ? launch_fused_w<u32, A1v, A2v>(T, L, batch, d, inverse) : launch_fused_w<u64, A1v, A2v>(T, L, batch, d, inverse))
+#define FW(A1v, A2v) (T.w32 ? W32_DISPATCH(launch_fused_w<u32, A1v, A2v>(T, L, batch, d, inverse)) : launch_fused_w<u64, A1v, A2v>(T, L, batch, d, inverse))
     if (T.a1 == 6 && T.a2 == 6) return FW(6, 6);
     if (T.a1 == 7 && T.a2 == 6) return FW(7, 6);
     if (T.a1 == 7 && T.a2 == 7) return FW(7, 7);
@@ -691,8 +811,23 @@ static int dev_alloc(const Tables &T, size_t words, u64 **out) {
     CU(pool_malloc(T, (void **)out, words * sizeof(u64)));
     return CKKS_OK;
 }
-static void dev_free(const Tables &T, void *p) {
-    if (p) cudaFreeAsync(p, S(T));
+static void dev_free(const Tables &Tc, void *p) {
+    if (!p) return;
+    Tables &T = const_cast<Tables &>(Tc);
+    {
+        std::lock_guard<std::mutex> lk(T.cache_mu);
+        auto it = T.cache_live.find(p);
+        if (it != T.cache_live.end()) {
+            const size_t cls = it->second;
+            T.cache_live.erase(it);
+            if (!g_stream_override && T.cache_bytes + cls <= T.cache_cap) {  // park it for the next request of this class
+                T.cache_free.emplace(cls, p);
+                T.cache_bytes += cls;
+                return;
+            }
+        }
+    }
+    cudaFreeAsync(p, S(T));
 }
 static int ntt_inplace(const Tables &T, size_t L, size_t batch, u64 *d, bool inverse) {
     u64 *tmp = nullptr;
@@ -1356,9 +1491,12 @@ template <typename WD>
 constexpr int ks_c1() {
     return sizeof(WD) == 8 ? 8 : 16;
 }
+#ifndef CKKS_KS1_E
+#define CKKS_KS1_E 4
+#endif
 template <typename WD, int A>
 static int launch_ks1_w(int lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
-    constexpr int E = 4, C = ks_c1<WD>();
+    constexpr int E = (sizeof(WD) == 8 && A > CKKS_KS1_E) ? CKKS_KS1_E : 4, C = ks_c1<WD>();
     grid.x /= C;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
@@ -1378,7 +1516,7 @@ static int launch_ks1_w(int lazy, bool reduce, bool diag, dim3 grid, cudaStream_
 }
 template <int A>
 static int launch_ks1_a(bool w32, int lazy, bool reduce, bool diag, dim3 grid, cudaStream_t s, const KsArgs &a) {
-    if (w32) return launch_ks1_w<u32, A>(lazy, reduce, diag, grid, s, a);
+    if (w32) return W32_DISPATCH(launch_ks1_w<u32, A>(lazy, reduce, diag, grid, s, a));
     return launch_ks1_w<u64, A>(lazy, reduce, diag, grid, s, a);
 }
 // Rank-3 tensor map (cols, rows, slabs) with a [rows][C] box for the TMA path of ks_pass2.
@@ -1439,7 +1577,7 @@ static int launch_ks2_w(int lazy, bool mul, bool tma, dim3 grid, cudaStream_t s,
 }
 template <int A>
 static int launch_ks2_a(bool w32, int lazy, bool mul, bool tma, dim3 grid, cudaStream_t s, const KsArgs &a, const KsMaps &maps) {
-    if (w32) return launch_ks2_w<u32, A>(lazy, mul, tma, grid, s, a, maps);
+    if (w32) return W32_DISPATCH(launch_ks2_w<u32, A>(lazy, mul, tma, grid, s, a, maps));
     return launch_ks2_w<u64, A>(lazy, mul, tma, grid, s, a, maps);
 }
 template <typename WD, int A>
@@ -1455,9 +1593,16 @@ static int launch_inv1_rescale_w(int lazy, dim3 grid, cudaStream_t s, const Pass
 }
 template <int A>
 static int launch_inv1_rescale_a(bool w32, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a, const u64 *last, const void *ql) {
-    if (w32) return launch_inv1_rescale_w<u32, A>(lazy, grid, s, a, last, ql);
+    if (w32) return W32_DISPATCH(launch_inv1_rescale_w<u32, A>(lazy, grid, s, a, last, ql));
     return launch_inv1_rescale_w<u64, A>(lazy, grid, s, a, last, ql);
 }
+#ifdef CKKS_ONLY_CFG4
+#define DISPATCH_A(Aval, CALL)                   \
+    switch (Aval) {                              \
+        case 8: { constexpr int AA = 8; CALL; } break; \
+        default: return CKKS_UNSUPPORTED;        \
+    }
+#else
 #define DISPATCH_A(Aval, CALL)                   \
     switch (Aval) {                              \
         case 4: { constexpr int AA = 4; CALL; } break; \
@@ -1467,6 +1612,7 @@ static int launch_inv1_rescale_a(bool w32, int lazy, dim3 grid, cudaStream_t s, 
         case 8: { constexpr int AA = 8; CALL; } break; \
         default: return CKKS_UNSUPPORTED;        \
     }
+#endif
 
 static int reduce_every_for(const Tables &T, size_t L) {
     u64 qmax = 0;
@@ -1563,16 +1709,18 @@ static size_t ks_chunk(const Tables &T, size_t L, size_t batch) {
 static int fused_mul_relin(const Tables &T, size_t L, size_t batch, const u64 *a0, const u64 *a1, const u64 *b0,
                            const u64 *b1, const ckks_ksk *rlk, bool rescale, u64 *o0, u64 *o1) {
     if (!batch) return CKKS_OK;
+    NvtxScope nvtx_call(rescale ? "ckks:mul_relin_rescale" : "ckks:mul_relin");
     const size_t n = T.n, cs_max = ks_chunk(T, L, batch);
     const size_t W = cs_max * L * n;
     u64 *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr, *TMP = nullptr, *SCR = nullptr, *LAST = nullptr;
-    int rc = dev_alloc(T, W, &A0);
-    if (rc == CKKS_OK) rc = dev_alloc(T, W, &A1);
-    if (rc == CKKS_OK) rc = dev_alloc(T, W, &B0);
-    if (rc == CKKS_OK) rc = dev_alloc(T, W, &B1);
-    if (rc == CKKS_OK) rc = dev_alloc(T, W, &TMP);
-    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * L * n, &SCR);
-    if (rc == CKKS_OK && rescale) rc = dev_alloc(T, 2 * cs_max * n, &LAST);
+    std::lock_guard<std::mutex> ws_lock(const_cast<Tables &>(T).ws_mu);
+    int rc = ws_get(T, WS_A0, W * 8, &A0);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_A1, W * 8, &A1);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_B0, W * 8, &B0);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_B1, W * 8, &B1);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_TMP, W * 8, &TMP);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_SCR, cs_max * L * L * n * 8, &SCR);
+    if (rc == CKKS_OK && rescale) rc = ws_get(T, WS_LAST, 2 * cs_max * n * 8, &LAST);
     const size_t outL = rescale ? L - 1 : L;
     for (size_t s0 = 0; s0 < batch && rc == CKKS_OK; s0 += cs_max) {
         const size_t cs = batch - s0 < cs_max ? batch - s0 : cs_max;
@@ -1626,14 +1774,7 @@ static int fused_mul_relin(const Tables &T, size_t L, size_t batch, const u64 *a
         };
         rc = step();
     }
-    dev_free(T, A0);
-    dev_free(T, A1);
-    dev_free(T, B0);
-    dev_free(T, B1);
-    dev_free(T, TMP);
-    dev_free(T, SCR);
-    dev_free(T, LAST);
-    return rc;
+    return rc;  // the scratch stays cached in the context (ws_get)
 }
 
 // Key-switch half of rotate_ciphertext (engine.rs:429-452) on the rotated c1 (coefficient domain):
@@ -1642,9 +1783,10 @@ static int fused_keyswitch(const Tables &T, size_t L, size_t batch, const u64 *c
     if (!batch) return CKKS_OK;
     const size_t n = T.n, cs_max = ks_chunk(T, L, batch);
     u64 *T0 = nullptr, *T1 = nullptr, *SCR = nullptr;
-    int rc = dev_alloc(T, cs_max * L * n, &T0);
-    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * n, &T1);
-    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * L * n, &SCR);
+    std::lock_guard<std::mutex> ws_lock(const_cast<Tables &>(T).ws_mu);
+    int rc = ws_get(T, WS_A0, cs_max * L * n * 8, &T0);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_A1, cs_max * L * n * 8, &T1);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_SCR, cs_max * L * L * n * 8, &SCR);
     for (size_t s0 = 0; s0 < batch && rc == CKKS_OK; s0 += cs_max) {
         const size_t cs = batch - s0 < cs_max ? batch - s0 : cs_max;
         const size_t off = s0 * L * n;
@@ -1653,9 +1795,6 @@ static int fused_keyswitch(const Tables &T, size_t L, size_t batch, const u64 *c
         if (rc == CKKS_OK) rc = run_pass(T, P_INV1, sp, T0, ks0 + off);
         if (rc == CKKS_OK) rc = run_pass(T, P_INV1, sp, T1, ks1 + off);
     }
-    dev_free(T, T0);
-    dev_free(T, T1);
-    dev_free(T, SCR);
     return rc;
 }
 
@@ -1674,7 +1813,7 @@ static int launch_inv1_addrot_w(int lazy, dim3 grid, cudaStream_t s, const PassA
 }
 template <int A>
 static int launch_inv1_addrot_a(bool w32, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
-    if (w32) return launch_inv1_addrot_w<u32, A>(lazy, grid, s, a);
+    if (w32) return W32_DISPATCH(launch_inv1_addrot_w<u32, A>(lazy, grid, s, a));
     return launch_inv1_addrot_w<u64, A>(lazy, grid, s, a);
 }
 
@@ -1684,13 +1823,15 @@ static int launch_inv1_addrot_a(bool w32, int lazy, dim3 grid, cudaStream_t s, c
 static int fused_rotate(const Tables &T, size_t L, size_t batch, const u64 *c0, const u64 *c1, u64 e, const ckks_ksk *key, u64 *o0,
                         u64 *o1) {
     if (!batch) return CKKS_OK;
+    NvtxScope nvtx_call("ckks:rotate");
     const size_t n = T.n, cs_max = ks_chunk(T, L, batch);
     const u64 einv = inv_mod_pow2(e, 2 * n);
     u64 *D = nullptr, *T0 = nullptr, *T1 = nullptr, *SCR = nullptr;
-    int rc = dev_alloc(T, cs_max * L * n, &D);
-    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * n, &T0);
-    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * n, &T1);
-    if (rc == CKKS_OK) rc = dev_alloc(T, cs_max * L * L * n, &SCR);
+    std::lock_guard<std::mutex> ws_lock(const_cast<Tables &>(T).ws_mu);
+    int rc = ws_get(T, WS_B0, cs_max * L * n * 8, &D);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_A0, cs_max * L * n * 8, &T0);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_A1, cs_max * L * n * 8, &T1);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_SCR, cs_max * L * L * n * 8, &SCR);
     for (size_t s0 = 0; s0 < batch && rc == CKKS_OK; s0 += cs_max) {
         const size_t cs = batch - s0 < cs_max ? batch - s0 : cs_max;
         const size_t off = s0 * L * n;
@@ -1718,10 +1859,6 @@ static int fused_rotate(const Tables &T, size_t L, size_t batch, const u64 *c0, 
         };
         rc = step();
     }
-    dev_free(T, D);
-    dev_free(T, T0);
-    dev_free(T, T1);
-    dev_free(T, SCR);
     return rc;
 }
 

@@ -604,9 +604,17 @@ struct KsAcc<u32> {
 
 // Shared memory of ks_pass2 in bytes: two stages of the digit tile (WD), key_b and key_a tiles (WD),
 // exchange tile [2^A][C+1] (WD).
+// CKKS_KS2_PINGPONG = 1: a second exchange tile, so that the digit loop's three-step transform needs one barrier less.
+#ifndef CKKS_KS2_PINGPONG
+#define CKKS_KS2_PINGPONG 0
+#endif
+template <typename WD, int A, int C>
+__host__ __device__ constexpr size_t ks2_exch_bytes() {
+    return (((size_t)(1 << A) * (C + 1) * sizeof(WD) + 15) / 16) * 16;
+}
 template <typename WD, int A, int C>
 __host__ __device__ constexpr size_t ks2_smem_bytes() {
-    return (size_t)(1 << A) * C * (2 * sizeof(WD) + 2 * sizeof(WD)) + (((size_t)(1 << A) * (C + 1) * sizeof(WD) + 15) / 16) * 16 + 64;
+    return (size_t)(1 << A) * C * (2 * sizeof(WD) + 2 * sizeof(WD)) + (1 + CKKS_KS2_PINGPONG) * ks2_exch_bytes<WD, A, C>() + 64;
 }
 
 // TMA = true: the digit tile and the two key tiles are fetched by the copy engine
@@ -638,6 +646,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
     WD *stKa = stKb + TILE;                     // key_a tile
     WD *stS = reinterpret_cast<WD *>(stKa + TILE);  // 2 stages of the digit's pass-1 output
     WD *sm = stS + 2 * TILE;                        // exchange buffer
+    WD *sm2 = CKKS_KS2_PINGPONG ? reinterpret_cast<WD *>(reinterpret_cast<unsigned char *>(sm) + ks2_exch_bytes<WD, A, C>()) : nullptr;
     u64 *bars = reinterpret_cast<u64 *>(sm_raw + ks2_smem_bytes<WD, A, C>() - 64);  // [0,1]: digit stages, [2]: keys
     const int L = a.L;
     // grid = (ciphertexts, tiles, target limbs): the ciphertext index runs fastest so that the CTAs
@@ -724,7 +733,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
         const WD *S = stS + (t & 1) * TILE;
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = S[tile_idx<E>(g, k, lo_in) * C + c];
-        xf_tile<XF_CYC_FWD, A, E, CP, LAZY, SWZ>(v, g, c, sm, W, q, q2);
+        xf_tile<XF_CYC_FWD, A, E, CP, LAZY, SWZ>(v, g, c, sm, W, q, q2, sm2);
         if (TMA) {
             mbar_wait(bars + 2, t & 1);  // keys(t) landed
         } else {

@@ -370,7 +370,7 @@ static int launch_inv1_multi_w(int lazy, dim3 grid, cudaStream_t s, const PassAr
 }
 template <int A>
 static int launch_inv1_multi_a(bool w32, int lazy, dim3 grid, cudaStream_t s, const PassArgs &a) {
-    if (w32) return launch_inv1_multi_w<u32, A>(lazy, grid, s, a);
+    if (w32) return W32_DISPATCH(launch_inv1_multi_w<u32, A>(lazy, grid, s, a));
     return launch_inv1_multi_w<u64, A>(lazy, grid, s, a);
 }
 static int ls_inv1_multi(const Tables &T, size_t cs, int L, int limb0, int nl, const void *src, u64 *const *peers, int npeer, int first,

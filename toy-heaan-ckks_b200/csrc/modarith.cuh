@@ -172,11 +172,29 @@ __device__ __forceinline__ u64 negmod(u64 a, u64 q) { return a ? q - a : 0; }
 // ---- butterflies ---------------------------------------------------------------------------------
 // Cooley-Tukey (decimation in time): (x, y) -> (x + w*y, x - w*y).
 //   LAZY: in/out [0, 4q).  !LAZY: in/out [0, q).
-template <int LAZY, typename W, typename TW>
+//   LAZY == 2 with TOPBIT (the merged negacyclic forward transform, whose butterflies all multiply): the range is
+//   managed by bit 63 alone.  x may be ANY word: if x >= 2^63 (>= 4q because q < 2^61) subtract 4q, which leaves
+//   xx < max(2^63, 2^64 - 4q); then xx + v and xx - v + 4q stay below 2^64 for every v in [0, 4q) -- no overflow, no
+//   64-bit compare, one predicated subtraction (ISETP + 2 predicated adds instead of 2 ISETP + 2 SEL + 2 adds).
+//   Values are no longer below 8q, only below 2^64: every consumer of such a transform multiplies first
+//   (shoup_lazy8 takes any word), so nothing depends on the tighter bound.
+__device__ __forceinline__ u64 csub_topbit(u64 x, u64 q4) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 lo, hi, ql, qh;\n\tmov.b64 {lo, hi}, %0;\n\tmov.b64 {ql, qh}, %1;\n\t"
+        "setp.lt.s32 p, hi, 0;\n\t@p sub.cc.u32 lo, lo, ql;\n\t@p subc.u32 hi, hi, qh;\n\tmov.b64 %0, {lo, hi};\n\t}"
+        : "+l"(x)
+        : "l"(q4));
+    return x;
+#else
+    return (x >> 63) ? x - q4 : x;
+#endif
+}
+__device__ __forceinline__ u32 csub_topbit(u32 x, u32 q4) { return csub(x, q4); }  // (32-bit words have no lazy8 mode)
+template <int LAZY, bool TOPBIT = false, typename W, typename TW>
 __device__ __forceinline__ void ct_bfly(W &x, W &y, TW t, W q, W q2) {
-    if (LAZY == 2) {  // in/out [0, 8q)
+    if (LAZY == 2) {  // in/out [0, 8q)  (TOPBIT: any word in, [0, 2^64) out)
         const W q4 = q2 + q2;
-        W xx = csub(x, q4);
+        W xx = TOPBIT ? csub_topbit(x, q4) : csub(x, q4);
         W v = shoup_lazy8(y, t, (W)(0 - q));
         x = xx + v;
         y = xx - v + q4;

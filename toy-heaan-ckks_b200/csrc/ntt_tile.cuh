@@ -20,6 +20,12 @@
 #pragma once
 #include "modarith.cuh"
 
+// 1 (default): the butterflies of the merged negacyclic forward transform manage their range by bit 63 alone
+// (modarith.cuh, ct_bfly TOPBIT); 0: one exact conditional subtraction per butterfly ([0, 8q) invariant).
+#ifndef CKKS_NEG_FWD_TOPBIT
+#define CKKS_NEG_FWD_TOPBIT 1
+#endif
+
 template <int A, int E>
 struct TileGeom {
     static constexpr int NS = (A + E - 1) / E;  // number of register steps
@@ -50,7 +56,7 @@ __device__ __forceinline__ void neg_fwd_step(WD (&v)[1 << E], int g, const TW *_
         for (int k = 0; k < (1 << E); ++k) {
             if (k & (1 << rb)) continue;
             TW tw = ldg_tw(P + base + (k >> (rb + 1)));
-            ct_bfly<LAZY>(v[k], v[k | (1 << rb)], tw, q, q2);
+            ct_bfly<LAZY, CKKS_NEG_FWD_TOPBIT != 0>(v[k], v[k | (1 << rb)], tw, q, q2);
         }
     }
 }
@@ -191,10 +197,14 @@ __device__ __forceinline__ void xf_step(WD (&v)[1 << E], int g, const TW *__rest
 // kinds: step 0; inverse kinds: step NS-1); on exit it holds the window of the LAST step
 // (forward: NS-1; inverse: 0).  `sm` is the [2^A][CP] exchange buffer (unused if NS == 1).
 template <int KIND, int A, int E, int CP, int LAZY, int SWZ = 0, typename WD, typename TW>
-__device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, const TW *__restrict__ tab, WD q, WD q2) {
+__device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, const TW *__restrict__ tab, WD q, WD q2, WD *sm2 = nullptr) {
+    // sm2 != nullptr: a second exchange buffer for the second exchange of a three-step transform, which makes the
+    // barrier between "everyone has read the first exchange" and "overwrite it" unnecessary (the caller must
+    // separate consecutive transforms by a barrier of its own, as ks_pass2's digit loop does).
     typedef TileGeom<A, E> GM;
     constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);
     static_assert(GM::NS >= 1 && GM::NS <= 3, "1..3 register steps supported");
+    WD *smb = sm2 ? sm2 : sm;
     if (FWD) {
         xf_step<KIND, A, E, 0, LAZY>(v, g, tab, q, q2);
         if (GM::NS >= 2) {
@@ -204,10 +214,10 @@ __device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, c
             xf_step<KIND, A, E, (GM::NS >= 2 ? 1 : 0), LAZY>(v, g, tab, q, q2);
         }
         if (GM::NS >= 3) {
+            if (!sm2) __syncthreads();
+            tile_put<E, CP, SWZ>(smb, v, g, c, GM::lo(1));
             __syncthreads();
-            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(1));
-            __syncthreads();
-            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(2));
+            tile_get<E, CP, SWZ>(smb, v, g, c, GM::lo(2));
             xf_step<KIND, A, E, (GM::NS >= 3 ? 2 : 0), LAZY>(v, g, tab, q, q2);
         }
     } else {
@@ -219,10 +229,10 @@ __device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, c
             xf_step<KIND, A, E, (GM::NS >= 2 ? GM::NS - 2 : 0), LAZY>(v, g, tab, q, q2);
         }
         if (GM::NS >= 3) {
+            if (!sm2) __syncthreads();
+            tile_put<E, CP, SWZ>(smb, v, g, c, GM::lo(1));
             __syncthreads();
-            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(1));
-            __syncthreads();
-            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(0));
+            tile_get<E, CP, SWZ>(smb, v, g, c, GM::lo(0));
             xf_step<KIND, A, E, 0, LAZY>(v, g, tab, q, q2);
         }
     }
