@@ -283,7 +283,7 @@ def ntt_point(ck, torch, dev, stream, hbm_peak, bits, logn, l, steps, warmup):
     return rec
 
 
-def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, passes=2):
+def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, passes=3):
     """BASELINE.json configs[3] as worded: the horner_chain workload (examples/horner_chain.rs:211-278), x <- x * alpha
     + beta from L limbs down to 2, on a RESIDENT batch: per level one mul_ciphertexts_gadget + rescale_ciphertext with
     that level's gadget key and one add_ciphertexts.  Ciphertexts and keys are synthetic uniform limbs (the reference
@@ -309,7 +309,9 @@ def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, pas
 
     per_level = {k: [] for k in levels}
     totals = []
+    alloc = []
     for it in range(passes + 1):  # first pass is the warm-up
+        ck.alloc_stats(reset=True)
         ct = x0
         total = 0.0
         for k in levels:
@@ -328,18 +330,23 @@ def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, pas
                 per_level[k].append(ms)
             del alpha_k, beta_k
         assert ct.c0.channel_count() == 2
+        alloc.append(ck.alloc_stats())
         if it:
             totals.append(total)
         del ct
     ms_chain = sum(totals) / len(totals)
+    ms_best = sum(min(v) for v in per_level.values())
     return {
+        "allocator_per_pass": alloc,
+        "ms_per_chain_best_levels": ms_best,
+        "ct_mults_per_s_best_levels": batch * len(levels) / (ms_best * 1e-3),
         "workload": f"horner_chain x <- x*alpha + beta, N={n}, L={l} -> 2 ({len(levels)} levels), resident batch of {batch} ciphertexts, "
         "per level: mul_ciphertexts_gadget + rescale_ciphertext + add_ciphertexts (CUDA events around each level; the level's alpha / beta "
         "ciphertexts are produced between the timed levels, as the reference re-encrypts them per level)",
         "ms_per_chain": ms_chain,
         "chains_per_s": batch / (ms_chain * 1e-3),
         "ct_mults_per_s": batch * len(levels) / (ms_chain * 1e-3),
-        "per_level": {str(k): {"ms": sum(v) / len(v), "ct_mults_per_s": batch / (sum(v) / len(v) * 1e-3)} for k, v in per_level.items()},
+        "per_level": {str(k): {"ms": sum(v) / len(v), "ms_min": min(v), "ct_mults_per_s": batch / (sum(v) / len(v) * 1e-3)} for k, v in per_level.items()},
     }
 
 
@@ -596,6 +603,40 @@ def run_b200(args):
         "what": f"plain cudaMemcpyAsync of one e2e step's bytes ({h2d} B in, {d2h} B out per GPU), both directions concurrently, "
         f"{world} rank(s) at once, no kernels: the rate the host side alone allows",
     }
+    # ---- N > 1: the same e2e metric through the SINGLE-PROCESS batch-sharded group (ckks_comm_*): rank 0 alone drives
+    # every GPU of the job from one host batch (one pipeline thread per device); the other ranks wait at the barrier.
+    e2e_single = None
+    if world > 1 and op == "mul" and not args.no_e2e_single:
+        barrier()
+        if rank == 0:
+            try:
+                per_dev = max(1, min(e2e_batch, 32))
+                tot = per_dev * world
+                grp = ck.BatchShard(n, moduli, list(range(world)))
+                rngk = np.random.default_rng(5)
+                qn = np.array(moduli, dtype=np.uint64)[None, :, None]
+                gka = rngk.integers(0, 1 << 62, size=(l, l, n), dtype=np.uint64) % qn
+                gkb = rngk.integers(0, 1 << 62, size=(l, l, n), dtype=np.uint64) % qn
+                gkey = grp.upload_key(gka, gkb)
+                del gka, gkb
+                gin = [ck.PinnedBuffer((tot, l, n)) for _ in range(4)]
+                gout = [ck.PinnedBuffer((tot, l - 1, n)) for _ in range(2)]
+                for gb_ in gin:  # replicate the per-rank e2e inputs: canonical words
+                    for r0 in range(0, tot, e2e_batch):
+                        m = min(e2e_batch, tot - r0)
+                        gb_.array[r0 : r0 + m] = hin[gin.index(gb_)].array[:m]
+                grp.mul_relin_rescale_host(gkey, gin[0].array, gin[1].array, gin[2].array, gin[3].array, gout[0].array, gout[1].array)
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    grp.mul_relin_rescale_host(gkey, gin[0].array, gin[1].array, gin[2].array, gin[3].array, gout[0].array, gout[1].array)
+                dt = (time.perf_counter() - t0) / args.steps
+                e2e_single = {"value": tot / dt, "unit": "ct-mult/s", "devices": world, "batch": tot, "ms_per_step": dt * 1e3,
+                              "h2d_bytes_per_step": 4 * gin[0].array.nbytes, "d2h_bytes_per_step": 2 * gout[0].array.nbytes,
+                              "what": "ckks_comm_ct_mul_relin_rescale_host: ONE process, one host batch, every GPU of the job (host wall clock; the call blocks until the results are in host memory)"}
+                del gkey, grp, gin, gout
+            except Exception as exc:  # never lose the main line to the optional leg
+                e2e_single = {"error": repr(exc)[:300]}
+        barrier()
     del hin, hout
 
     peaks, peak_kind = measured_peaks()
@@ -628,7 +669,7 @@ def run_b200(args):
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "ct-mult/s" if op == "mul" else "rotation/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                "host_copy_probe": copy_probe},
+                "host_copy_probe": copy_probe, "single_process_group": e2e_single},
         "gpu_launches": launches,
         "imad": {
             "peak_modmul_per_s": imad_peak,
@@ -1014,6 +1055,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prof", dest="prof", action="store_false")
     ap.add_argument("--ops", action="store_true", help="also time encrypt and add_ciphertexts on the resident batch (default for cfg2)")
+    ap.add_argument("--no-e2e-single", action="store_true", help="N > 1: skip the single-process ckks_comm_* e2e leg on rank 0")
     ap.add_argument("--no-ntt", action="store_true", help="skip the limb-NTT record (the metric's second half)")
     ap.add_argument("--no-chain", action="store_true", help="skip the horner_chain sub-record (cfg4, 1 GPU)")
     ap.add_argument("--no-single-thread", action="store_true", help="skip the single-threaded oracle timing (~40 s at cfg4)")

@@ -334,6 +334,9 @@ size_t ckks_launch_table(char *buf, size_t cap);
 /* Per-kernel timing: while enabled every launch is bracketed by CUDA events on the context's stream;
  * collect() synchronises and writes "name=launches,total_ms\n" lines (returns the length needed). */
 int ckks_prof_enable(int on);
+/* Allocator statistics since the last reset, for requests of 1 MiB and more: served by the library's block cache,
+ * sent to the driver's pool, host microseconds spent there in total and in the slowest call. */
+int ckks_alloc_stats(uint64_t *cache_hits, uint64_t *pool_allocs, uint64_t *pool_us, uint64_t *pool_max_us, int reset);
 /* NVTX ranges (one per kernel launch, named like the launch table, plus "ckks:<entry point>" around the fused
  * pipelines) for Nsight timelines: off by default; 1 = on (or CKKS_NVTX=1 in the environment). */
 int ckks_set_nvtx(int on);

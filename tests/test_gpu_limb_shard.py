@@ -356,3 +356,49 @@ def test_lost_peer_is_an_error_not_a_hang(gpu, orc):
     fresh = [gpu.LimbShard(n, moduli, r, 2, chunk=2) for r in range(2)]
     gpu.LimbShard.connect_local(fresh)
     fresh[0].check()
+
+
+def test_limb_sharded_parity_on_every_gpu_of_the_box(gpu):
+    """The limb-sharded mode on REAL peers: one process per GPU under torchrun (tests/run_limb_shard.py --full):
+    every limb against the oracle (N=4096 61-bit, N=16384 30-bit) and, at N=65536, L=24, against the unsharded device
+    path, with the fused peer-store exchange and with NCCL between the phases.  Needs at least two GPUs; on a
+    one-GPU box the same code paths run with the ranks sharing the device (the tests above)."""
+    import socket
+    import subprocess
+    import sys
+
+    ndev = min(gpu.device_count(), 8)
+    if ndev < 2:
+        pytest.skip("one GPU: covered by the shared-device tests above")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ndev}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "run_limb_shard.py"), "--full"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert f"LIMB_SHARD_PARITY ok world={ndev}" in r.stdout, r.stdout[-2000:]
+
+
+def test_batch_sharded_group_on_every_gpu_of_the_box(gpu, orc):
+    """ckks_comm_* with one slot per physical GPU (skipped on a one-GPU box, where tests/test_gpu_engine.py runs the
+    same entry points with the slots sharing the device): N=2^14, L=4, ragged batch, every word against the oracle."""
+    ndev = min(gpu.device_count(), 8)
+    if ndev < 2:
+        pytest.skip("one GPU: covered by test_batch_sharded_group_matches_single_gpu_and_oracle")
+    n, l, batch = 16384, 4, 2 * ndev + 1
+    moduli = orc.generate_primes(30, l, n)
+    ob = orc.Basis(n, moduli)
+    rng = np.random.default_rng(99)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    grp = gpu.BatchShard(n, moduli, list(range(ndev)))
+    key = grp.upload_key(ka, kb)
+    o0 = np.zeros((batch, l - 1, n), dtype=np.uint64)
+    o1 = np.zeros_like(o0)
+    grp.mul_relin_rescale_host(key, a0, a1, b0, b1, o0, o1)
+    for i in range(batch):
+        m0, m1 = ob.mul_ciphertexts_gadget(a0[i], a1[i], b0[i], b1[i], ka, kb)
+        e0, e1, _ = ob.rescale_ciphertext(m0, m1)
+        assert np.array_equal(o0[i], e0) and np.array_equal(o1[i], e1), i

@@ -100,6 +100,7 @@ _sig("ckks_set_fused_ntt", C.c_int, C.c_int)
 _sig("ckks_set_host_chunk_mib", C.c_int, C.c_int)
 _sig("ckks_prof_enable", C.c_int, C.c_int)
 _sig("ckks_set_nvtx", C.c_int, C.c_int)
+_sig("ckks_alloc_stats", C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_int)
 _sig("ckks_prof_collect", C.c_size_t, C.c_char_p, C.c_size_t)
 _sig("ckks_poly_from_device", C.c_int, _vp, C.c_size_t, _u64p, C.c_int, _pp)
 _sig("ckks_poly_device_ptr", C.c_int, _vp, C.POINTER(_u64p))
@@ -201,6 +202,13 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(_lib.ckks_launch_count())
+
+
+def alloc_stats(reset: bool = False) -> dict:
+    """Block-cache hits, driver-pool allocations and the host time the latter took (requests >= 1 MiB)."""
+    v = [C.c_uint64(0) for _ in range(4)]
+    _check(_lib.ckks_alloc_stats(C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), C.byref(v[3]), 1 if reset else 0))
+    return {"cache_hits": v[0].value, "pool_allocs": v[1].value, "pool_ms": v[2].value / 1e3, "pool_max_ms": v[3].value / 1e3}
 
 
 def launch_table() -> dict:

@@ -296,9 +296,35 @@ static size_t size_class(size_t bytes) {  // smallest m * 2^e >= bytes with m in
     if ((m << e) < bytes) ++m;
     return m << e;
 }
+// allocator statistics (ckks_alloc_stats): requests served by the block cache, requests that went to the driver's
+// pool, and the host time the latter took (the pool growing or re-mapping shows up here)
+static std::atomic<uint64_t> g_alloc_hits{0}, g_alloc_pool{0}, g_alloc_pool_us{0}, g_alloc_pool_max_us{0};
 static cudaError_t raw_pool_malloc(const Tables &T, void **p, size_t bytes) {
-    if (T.pool) return cudaMallocFromPoolAsync(p, bytes, T.pool, S(T));
-    return cudaMallocAsync(p, bytes, S(T));
+    const bool big = bytes >= ((size_t)1 << 20);
+    auto t0 = std::chrono::steady_clock::now();
+    cudaError_t e = T.pool ? cudaMallocFromPoolAsync(p, bytes, T.pool, S(T)) : cudaMallocAsync(p, bytes, S(T));
+    if (big) {
+        uint64_t us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        g_alloc_pool.fetch_add(1);
+        g_alloc_pool_us.fetch_add(us);
+        uint64_t m = g_alloc_pool_max_us.load();
+        while (us > m && !g_alloc_pool_max_us.compare_exchange_weak(m, us)) {
+        }
+    }
+    return e;
+}
+extern "C" int ckks_alloc_stats(uint64_t *cache_hits, uint64_t *pool_allocs, uint64_t *pool_us, uint64_t *pool_max_us, int reset) {
+    if (cache_hits) *cache_hits = g_alloc_hits.load();
+    if (pool_allocs) *pool_allocs = g_alloc_pool.load();
+    if (pool_us) *pool_us = g_alloc_pool_us.load();
+    if (pool_max_us) *pool_max_us = g_alloc_pool_max_us.load();
+    if (reset) {
+        g_alloc_hits = 0;
+        g_alloc_pool = 0;
+        g_alloc_pool_us = 0;
+        g_alloc_pool_max_us = 0;
+    }
+    return CKKS_OK;
 }
 static cudaError_t pool_malloc(const Tables &Tc, void **p, size_t bytes) {
     // small requests, and calls whose launches are redirected to another stream, go straight to the pool
@@ -313,6 +339,7 @@ static cudaError_t pool_malloc(const Tables &Tc, void **p, size_t bytes) {
             T.cache_free.erase(it);
             T.cache_bytes -= cls;
             T.cache_live[*p] = cls;
+            g_alloc_hits.fetch_add(1);
             return cudaSuccess;
         }
     }
@@ -632,7 +659,17 @@ static int launch_pass_w(const char *name, int lazy, dim3 grid, cudaStream_t s, 
     grid.x = a.ncols / C;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
-#define M(LZ) KL(name, (ntt_pass_kernel<WD, KIND, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), PRE, POST, TR><<<grid, block, smem, s>>>(a)))
+// FIX_OF(A): the compile-time ring degree this pass size is specialised for (N = 2^16 with 2^8-point passes, N = 2^14
+// with 2^7-point passes); the specialisation is used when the context's N matches, the generic kernel otherwise.
+#define FIX_OF(Aval) ((Aval) == 8 ? 16 : ((Aval) == 7 ? 14 : 0))
+#define FIX_MATCH(Aval, Nval) (FIX_OF(Aval) != 0 && (Nval) == ((size_t)1 << FIX_OF(Aval)))
+#define M(LZ)                                                                                                                                  \
+    do {                                                                                                                                       \
+        if (FIX_MATCH(A, a.N))                                                                                                                 \
+            KL(name, (ntt_pass_kernel<WD, KIND, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), PRE, POST, TR, false, false, FIX_OF(A)><<<grid, block, smem, s>>>(a))); \
+        else                                                                                                                                   \
+            KL(name, (ntt_pass_kernel<WD, KIND, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), PRE, POST, TR><<<grid, block, smem, s>>>(a)));       \
+    } while (0)
     LZ_SWITCH(WD, lazy, M);
 #undef M
     return CKKS_OK;
@@ -1500,7 +1537,11 @@ static int launch_ks1_w(int lazy, bool reduce, bool diag, dim3 grid, cudaStream_
     grid.x /= C;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
-#define KS1(LZ, RD, DG) KL("ks_pass1", (ks_pass1_kernel<WD, A, E, C, LZ, RD, DG><<<grid, block, smem, s>>>(a)))
+#define KS1(LZ, RD, DG)                                                                                               \
+    do {                                                                                                              \
+        if (FIX_MATCH(A, a.N) && a.a1 == A) KL("ks_pass1", (ks_pass1_kernel<WD, A, E, C, LZ, RD, DG, FIX_OF(A)><<<grid, block, smem, s>>>(a))); \
+        else KL("ks_pass1", (ks_pass1_kernel<WD, A, E, C, LZ, RD, DG><<<grid, block, smem, s>>>(a)));                  \
+    } while (0)
     if (lazy == 2 && sizeof(WD) == 8) {
         constexpr int LZ2 = sizeof(WD) == 8 ? 2 : 1;
         if (reduce) { if (diag) KS1(LZ2, true, true); else KS1(LZ2, true, false); }
@@ -1586,7 +1627,13 @@ static int launch_inv1_rescale_w(int lazy, dim3 grid, cudaStream_t s, const Pass
     grid.x = a.ncols / C;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
-#define M(LZ) KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<WD, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0))><<<grid, block, smem, s>>>(a, last, ql)))
+#define M(LZ)                                                                                                                                         \
+    do {                                                                                                                                              \
+        if (FIX_MATCH(A, a.N))                                                                                                                        \
+            KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<WD, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), FIX_OF(A)><<<grid, block, smem, s>>>(a, last, ql))); \
+        else                                                                                                                                          \
+            KL("ntt_inv_pass1_rescale", (inv_pass1_rescale_kernel<WD, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0))><<<grid, block, smem, s>>>(a, last, ql)));    \
+    } while (0)
     LZ_SWITCH(WD, lazy, M);
 #undef M
     return CKKS_OK;
@@ -1806,7 +1853,12 @@ static int launch_inv1_addrot_w(int lazy, dim3 grid, cudaStream_t s, const PassA
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(WD);
     const int block = C << (A - E);
 #define M(LZ) \
-    KL("ntt_inv_pass1_addrot", (ntt_pass_kernel<WD, XF_NEG_INV, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), false, false, false, false, true><<<grid, block, smem, s>>>(a)))
+    do {                                                                                                                                                  \
+        if (FIX_MATCH(A, a.N))                                                                                                                            \
+            KL("ntt_inv_pass1_addrot", (ntt_pass_kernel<WD, XF_NEG_INV, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), false, false, false, false, true, FIX_OF(A)><<<grid, block, smem, s>>>(a))); \
+        else                                                                                                                                              \
+            KL("ntt_inv_pass1_addrot", (ntt_pass_kernel<WD, XF_NEG_INV, A, E, C, (sizeof(WD) == 8 ? LZ : (LZ ? 1 : 0)), false, false, false, false, true><<<grid, block, smem, s>>>(a)));            \
+    } while (0)
     LZ_SWITCH(WD, lazy, M);
 #undef M
     return CKKS_OK;

@@ -47,8 +47,16 @@ struct PassArgs {
 // Inverse  to_coeff_domain(poly.rs:154-166, 582-591) = <CYC_INV,POSTMUL,TRANSPOSE> then <NEG_INV>.
 // WD = u64 (any q < 2^63) or u32 (all q < 2^31: 32-bit butterflies, 32-bit internal scratch; the words
 // that cross the boundary stay u64).
-template <typename WD, int KIND, int A, int E, int C, int LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE, bool MULTI = false, bool ADDROT = false>
+// FIXLOGN != 0: the ring degree is the compile-time constant 2^FIXLOGN (the launchers pick it for N = 2^16 and 2^14):
+// ncols and N fold into the load / store immediates, which removes the per-access 64-bit address arithmetic --
+// 10 % of the instructions of a 64-bit pass, 10 - 28 % of a 32-bit one (cuobjdump counts).
+template <typename WD, int KIND, int A, int E, int C, int LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE, bool MULTI = false, bool ADDROT = false,
+          int FIXLOGN = 0>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a) {
+    if (FIXLOGN) {
+        a.ncols = 1u << (FIXLOGN > A ? FIXLOGN - A : 0);
+        a.N = (size_t)1 << FIXLOGN;
+    }
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
     constexpr int CP = C + 1;
@@ -451,8 +459,13 @@ struct KsArgs {
     size_t N;
 };
 
-template <typename WD, int A, int E, int C, int LAZY, bool REDUCE, bool DIAG>
+template <typename WD, int A, int E, int C, int LAZY, bool REDUCE, bool DIAG, int FIXLOGN = 0>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
+    if (FIXLOGN) {  // compile-time ring degree (see ntt_pass_kernel)
+        a.a1 = A;
+        a.a2 = FIXLOGN > A ? FIXLOGN - A : 0;
+        a.N = (size_t)1 << FIXLOGN;
+    }
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
     constexpr int CP = C + 1;
@@ -795,9 +808,13 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
 // (poly.rs:214-225): limb i < L-1 of the result is (c_i - (c_last % q_i)) * q_last^-1 mod q_i, where
 // c_last is the already finished coefficient-domain last limb.  src: [cts][L][N] transposed
 // inverse-pass-2 output (WD); last: [cts][N] coefficient domain (u64); dst: [cts][L-1][N] (u64).
-template <typename WD, int A, int E, int C, int LAZY>
+template <typename WD, int A, int E, int C, int LAZY, int FIXLOGN = 0>
 __global__ void __launch_bounds__(C *(1 << (A - E))) inv_pass1_rescale_kernel(PassArgs a, const u64 *__restrict__ last,
                                                                                const void *__restrict__ qlinv_) {
+    if (FIXLOGN) {  // compile-time ring degree (see ntt_pass_kernel)
+        a.ncols = 1u << (FIXLOGN > A ? FIXLOGN - A : 0);
+        a.N = (size_t)1 << FIXLOGN;
+    }
     typedef TileGeom<A, E> GM;
     typedef typename TwOf<WD>::type TW;
     constexpr int CP = C + 1;
