@@ -429,6 +429,10 @@ def run_b200(args):
     ck = importlib.import_module("toy-heaan-ckks_b200")
     if args.host_chunk_mib:
         ck._check(ck._lib.ckks_set_host_chunk_mib(args.host_chunk_mib))
+    if args.ks_scratch_mib:
+        global KS_SCRATCH_MIB
+        KS_SCRATCH_MIB = args.ks_scratch_mib
+        ck._check(ck._lib.ckks_set_ks_scratch_mib(args.ks_scratch_mib))
     logn, l, bits, batch, e2e_batch = CONFIGS[args.config]
     if args.batch:
         batch = args.batch
@@ -730,7 +734,7 @@ def run_b200(args):
         }
         line["kernels"] = {k: {"launches": c, "ms": round(m, 3), "share": round(m / tot, 4)} for k, (c, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     # ---- the metric's second half: limb NTT achieved HBM GB/s vs peak, at the metric's shape ----------
-    if rank == 0 and not args.no_ntt and logn >= 12:
+    if rank == 0 and world == 1 and not args.no_ntt and logn >= 12:
         del cta, ctb
         torch.cuda.empty_cache()
         line["ntt"] = {
@@ -1015,8 +1019,11 @@ def run_ntt_sweep(args):
 # Algorithmic bytes per launch of each kernel as launched by the batched ct-mult.
 # The fused pipeline works on chunks of cs = min(batch, 4 GiB / (L^2 N 8)) ciphertexts (ks_chunk in
 # csrc/ckks_b200.cu); w = 8-byte words (61-bit chain; 4 for the internal scratch of the 32-bit path).
+KS_SCRATCH_MIB = 4096  # the library's default (ckks_set_ks_scratch_mib); --ks-scratch-mib changes both
+
+
 def _cs(n, l, batch):
-    return max(1, min(batch, (4 << 30) // (l * l * n * 8)))
+    return max(1, min(batch, (KS_SCRATCH_MIB << 20) // (l * l * n * 8)))
 
 
 def _ks2(n, l, batch, w=8):
@@ -1062,6 +1069,7 @@ def main():
     ap.add_argument("--imad", action="store_true", help="also run the integer-pipe microbenchmark")
     ap.add_argument("--op", default="", choices=["", "mul", "rotate"], help="hot-path operation (default: mul; rotate for cfg3)")
     ap.add_argument("--host-chunk-mib", type=int, default=0, help="pipeline chunk of the host-buffer entry point")
+    ap.add_argument("--ks-scratch-mib", type=int, default=0, help="key-switch scratch per chunk of ciphertexts (default 4096)")
     ap.add_argument("--ntt-sweep", action="store_true", help="BASELINE.json configs[4]: limb-batched NTT/INTT sweep instead of the ct-mult bench")
     ap.add_argument("--limb-sharded", action="store_true", help="optional limb-sharded mode (one batch, limbs spread over the GPUs)")
     ap.add_argument("--comm", default="peer", choices=["peer", "ce", "nccl"],

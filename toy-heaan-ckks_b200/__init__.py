@@ -98,6 +98,8 @@ _sig("ckks_set_lazy8", C.c_int, C.c_int)
 _sig("ckks_set_tma", C.c_int, C.c_int)
 _sig("ckks_set_fused_ntt", C.c_int, C.c_int)
 _sig("ckks_set_host_chunk_mib", C.c_int, C.c_int)
+_sig("ckks_set_ks_scratch_mib", C.c_int, C.c_int)
+_sig("ckks_ks_chunk", C.c_size_t, _vp, C.c_size_t)
 _sig("ckks_prof_enable", C.c_int, C.c_int)
 _sig("ckks_set_nvtx", C.c_int, C.c_int)
 _sig("ckks_alloc_stats", C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_int)

@@ -1743,13 +1743,22 @@ static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, con
     return ks_fused_ex(T, L, sh, cs, digits, dig_ntt, key, add0, add1, scratch, out0t, out1t, mul);
 }
 
+static size_t g_ks_scratch_mib = 4096;  // key-switch scratch per chunk of ciphertexts (tuning knob)
+extern "C" int ckks_set_ks_scratch_mib(int mib) {
+    if (mib < 1) return CKKS_BAD_ARGUMENT;
+    g_ks_scratch_mib = (size_t)mib;
+    return CKKS_OK;
+}
+extern "C" size_t ckks_ks_chunk(const ckks_ctx *ctx, size_t batch);
 static size_t ks_chunk(const Tables &T, size_t L, size_t batch) {
     size_t per = L * L * T.n * sizeof(u64);
-    size_t c = ((size_t)4 << 30) / per;
+    size_t c = (g_ks_scratch_mib << 20) / per;
     if (c < 1) c = 1;
     if (c > 32768) c = 32768;  // the ciphertext index is a grid dimension (y/z limit 65535)
     return c < batch ? c : batch;
 }
+
+extern "C" size_t ckks_ks_chunk(const ckks_ctx *ctx, size_t batch) { return ok_ctx(ctx) ? ks_chunk(*ctx->T, ctx->L, batch) : 0; }
 
 // mul_ciphertexts_gadget (+ rescale_ciphertext) on coefficient-domain device inputs, four-step path.
 // o0/o1: [batch][L or L-1][N].
