@@ -1019,7 +1019,7 @@ def run_ntt_sweep(args):
 # Algorithmic bytes per launch of each kernel as launched by the batched ct-mult.
 # The fused pipeline works on chunks of cs = min(batch, 4 GiB / (L^2 N 8)) ciphertexts (ks_chunk in
 # csrc/ckks_b200.cu); w = 8-byte words (61-bit chain; 4 for the internal scratch of the 32-bit path).
-KS_SCRATCH_MIB = 4096  # the library's default (ckks_set_ks_scratch_mib); --ks-scratch-mib changes both
+KS_SCRATCH_MIB = 8192  # the library's default (ckks_set_ks_scratch_mib); --ks-scratch-mib changes both
 
 
 def _cs(n, l, batch):
@@ -1069,7 +1069,7 @@ def main():
     ap.add_argument("--imad", action="store_true", help="also run the integer-pipe microbenchmark")
     ap.add_argument("--op", default="", choices=["", "mul", "rotate"], help="hot-path operation (default: mul; rotate for cfg3)")
     ap.add_argument("--host-chunk-mib", type=int, default=0, help="pipeline chunk of the host-buffer entry point")
-    ap.add_argument("--ks-scratch-mib", type=int, default=0, help="key-switch scratch per chunk of ciphertexts (default 4096)")
+    ap.add_argument("--ks-scratch-mib", type=int, default=0, help="key-switch scratch per chunk of ciphertexts (default 8192)")
     ap.add_argument("--ntt-sweep", action="store_true", help="BASELINE.json configs[4]: limb-batched NTT/INTT sweep instead of the ct-mult bench")
     ap.add_argument("--limb-sharded", action="store_true", help="optional limb-sharded mode (one batch, limbs spread over the GPUs)")
     ap.add_argument("--comm", default="peer", choices=["peer", "ce", "nccl"],

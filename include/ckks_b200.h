@@ -110,7 +110,7 @@ int ckks_set_tma(int on);
 /* Test hook: 1 (default) = 2^12 <= N <= 2^14 transforms run as one kernel with the limb resident in shared
  * memory; 0 = two passes through global memory.  Same results. */
 int ckks_set_fused_ntt(int on);
-/* Tuning knob of the fused key-switch: MiB of scratch per chunk of ciphertexts (default 4096: 14 ciphertexts at
+/* Tuning knob of the fused key-switch: MiB of scratch per chunk of ciphertexts (default 8192: 28 ciphertexts at
  * N=2^16, L=24); ckks_ks_chunk reports the ciphertexts per chunk a batch of `batch` is cut into at ctx's level. */
 int ckks_set_ks_scratch_mib(int mib);
 size_t ckks_ks_chunk(const ckks_ctx *ctx, size_t batch);

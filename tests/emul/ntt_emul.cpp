@@ -204,3 +204,112 @@ extern "C" uint64_t emul_shoup_lazy8(uint64_t x, uint64_t w, uint64_t q) {
 extern "C" int emul_tile_addr(int swz, int r, int c) { return swz ? tile_addr<3, 5, 1>(r, c) : tile_addr<3, 5, 0>(r, c); }
 // Row permutation of the resident gadget keys (ntt_tile.cuh perm_row) for tests/test_emul.py.
 extern "C" uint64_t emul_perm_row(uint64_t row, int a2, int pe) { return (uint64_t)perm_row((size_t)row, a2, pe); }
+
+// ---- csrc/arena.hpp: the device-memory arena's bookkeeping, driven on the CPU with fake segments -----------------
+#include <set>
+
+#include "../../toy-heaan-ckks_b200/csrc/arena.hpp"
+// Random take / give stress with `ops` operations over sizes between 1 MiB and `max_mib` MiB.  Segments are fake
+// address ranges (never touched).  Checks after every operation: live ranges are disjoint, aligned and inside a
+// segment; free + live bytes == segment bytes; no two free ranges of one segment are adjacent (coalescing);
+// every give() of a live pointer succeeds and a second one fails.  With `cap_gib` > 0 the fake device refuses segments
+// beyond that total, which exercises the exact-size and release-and-retry fallbacks.  Returns 0, or a failure code;
+// *peak_bytes = the largest total segment size seen, *new_segments = segments requested after the first `ops / 2`
+// operations (a steady-state workload must not need any).
+extern "C" int emul_arena_stress(uint64_t seed, int ops, int max_mib, int cap_gib, uint64_t *peak_bytes, int *new_segments) {
+    Arena ar;
+    uint64_t next_base = (uint64_t)1 << 40, seg_total = 0, peak = 0;
+    std::map<char *, size_t> segs;
+    int late_segs = 0, op = 0;
+    auto seg_alloc = [&](size_t bytes) -> void * {
+        if (cap_gib > 0 && seg_total + bytes > ((uint64_t)cap_gib << 30)) return nullptr;
+        char *b = (char *)next_base;
+        next_base += bytes + ((uint64_t)1 << 30);  // a gap: separate segments are never contiguous here
+        segs[b] = bytes;
+        seg_total += bytes;
+        if (op > ops / 2) ++late_segs;
+        return b;
+    };
+    auto seg_free = [&](void *b) {
+        seg_total -= segs[(char *)b];
+        segs.erase((char *)b);
+    };
+    std::map<char *, size_t> live;  // our own record of what is out
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() {
+        s ^= s << 13;
+        s ^= s >> 7;
+        s ^= s << 17;
+        return s;
+    };
+    for (op = 0; op < ops; ++op) {
+        const bool do_take = live.empty() || (rnd() % 100 < 52 && live.size() < 24);
+        if (do_take) {
+            size_t bytes = ((size_t)1 << 20) + rnd() % ((size_t)max_mib << 20);
+            void *p = ar.take(bytes, seg_alloc, seg_free);
+            if (!p) {
+                if (cap_gib == 0) return 1;  // an unlimited device cannot run out
+                continue;
+            }
+            const size_t need = (bytes + Arena::ALIGN - 1) / Arena::ALIGN * Arena::ALIGN;
+            char *c = (char *)p;
+            if (((uint64_t)c & (Arena::ALIGN - 1)) != 0) return 2;
+            bool inside = false;
+            for (auto &kv : segs) inside |= (c >= kv.first && c + need <= kv.first + kv.second);
+            if (!inside) return 3;
+            auto nx = live.lower_bound(c);
+            if (nx != live.end() && nx->first < c + need) return 4;  // overlaps the next live range
+            if (nx != live.begin()) {
+                auto pv = std::prev(nx);
+                if (pv->first + pv->second > c) return 5;
+            }
+            live[c] = need;
+        } else {
+            auto it = live.begin();
+            std::advance(it, rnd() % live.size());
+            if (!ar.give(it->first)) return 6;
+            if (ar.give(it->first)) return 7;  // double free must be refused
+            live.erase(it);
+        }
+        size_t live_bytes = 0;
+        for (auto &kv : live) live_bytes += kv.second;
+        if (ar.total_bytes() != seg_total) return 8;
+        if (ar.free_bytes() + live_bytes != seg_total) return 9;
+        if (ar.live_ranges() != live.size()) return 10;
+        // coalescing: free ranges <= live ranges + segments (between two live ranges / segment ends at most one free range)
+        if (ar.free_ranges() > live.size() + segs.size()) return 11;
+        if (seg_total > peak) peak = seg_total;
+    }
+    for (auto &kv : live)
+        if (!ar.give(kv.first)) return 12;
+    ar.release_free_segments(seg_free);
+    if (ar.total_bytes() != 0 || seg_total != 0 || ar.segments() != 0) return 13;
+    if (peak_bytes) *peak_bytes = peak;
+    if (new_segments) *new_segments = late_segs;
+    return 0;
+}
+// A horner_chain-like schedule: per level four polynomials of a level-dependent size are taken and the previous level's
+// given back; `passes` passes.  Returns the number of segments requested after the first pass (must be 0).
+extern "C" int emul_arena_chain(int levels, int passes, uint64_t unit_bytes) {
+    Arena ar;
+    uint64_t next_base = (uint64_t)1 << 40;
+    int segs_after_first = 0, pass = 0;
+    auto seg_alloc = [&](size_t bytes) -> void * {
+        char *b = (char *)next_base;
+        next_base += bytes + ((uint64_t)1 << 30);
+        if (pass > 0) ++segs_after_first;
+        return b;
+    };
+    auto seg_free = [&](void *) {};
+    for (pass = 0; pass < passes; ++pass) {
+        std::vector<void *> prev;
+        for (int l = levels; l >= 2; --l) {
+            std::vector<void *> cur;
+            for (int t = 0; t < 4; ++t) cur.push_back(ar.take((size_t)l * unit_bytes, seg_alloc, seg_free));
+            for (void *p : prev) ar.give(p);
+            prev = cur;
+        }
+        for (void *p : prev) ar.give(p);
+    }
+    return segs_after_first;
+}

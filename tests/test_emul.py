@@ -159,3 +159,20 @@ def test_key_row_permutation_matches_ks_pass2_indexing(emul):
                 seen.add(p)
         assert seen == set(range(rows))
     assert emul.emul_perm_row(5, 8, -1) == 5  # natural order when the key is not permuted (small-N path)
+
+
+def test_device_arena_bookkeeping(emul):
+    """csrc/arena.hpp (the allocator behind every polynomial, key and scratch buffer): random take / give stress on
+    fake segments -- live ranges disjoint, aligned, inside a segment; free + live == total; free ranges coalesce;
+    double frees refused; everything returns to the 'device' at the end -- with and without a memory cap, and a
+    horner_chain-like schedule that must not ask the driver for memory after its first pass."""
+    emul.emul_arena_stress.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    emul.emul_arena_chain.argtypes = [C.c_int, C.c_int, C.c_uint64]
+    for seed in range(6):
+        peak, late = C.c_uint64(0), C.c_int(0)
+        assert emul.emul_arena_stress(seed, 6000, 3200, 0, C.byref(peak), C.byref(late)) == 0
+        assert peak.value <= 80 << 30  # at most 24 live ranges of <= 3.2 GiB: fragmentation stays bounded
+        assert emul.emul_arena_stress(seed, 4000, 3200, 24, C.byref(peak), C.byref(late)) == 0  # 24 GiB device: refusals handled
+        assert peak.value <= 24 << 30
+    assert emul.emul_arena_chain(24, 4, 128 << 20) == 0
+    assert emul.emul_arena_chain(24, 4, (128 << 20) + 4096) == 0

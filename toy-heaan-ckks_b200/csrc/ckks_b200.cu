@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <map>
 #include <mutex>
 #include <string>
@@ -289,13 +290,6 @@ static bool same_basis(const ckks_ctx *a, const ckks_ctx *b) { return a->T.get()
 // Every stream-ordered allocation of the library comes from the context's PRIVATE memory pool (created in
 // ckks_ctx_create, released with the tables): freed scratch stays cached there for the next call instead of in the
 // device's default pool, which other libraries in the process (e.g. PyTorch) share; ckks_ctx_trim returns it.
-static size_t size_class(size_t bytes) {  // smallest m * 2^e >= bytes with m in 8..15
-    int e = 0;
-    while ((bytes >> e) > 15) ++e;
-    size_t m = bytes >> e;
-    if ((m << e) < bytes) ++m;
-    return m << e;
-}
 // allocator statistics (ckks_alloc_stats): requests served by the block cache, requests that went to the driver's
 // pool, and the host time the latter took (the pool growing or re-mapping shows up here)
 static std::atomic<uint64_t> g_alloc_hits{0}, g_alloc_pool{0}, g_alloc_pool_us{0}, g_alloc_pool_max_us{0};
@@ -329,43 +323,35 @@ extern "C" int ckks_alloc_stats(uint64_t *cache_hits, uint64_t *pool_allocs, uin
 static cudaError_t pool_malloc(const Tables &Tc, void **p, size_t bytes) {
     // small requests, and calls whose launches are redirected to another stream, go straight to the pool
     if (bytes < ((size_t)1 << 20) || g_stream_override) return raw_pool_malloc(Tc, p, bytes);
-    Tables &T = const_cast<Tables &>(Tc);  // the cache is internal state guarded by cache_mu
-    const size_t cls = size_class(bytes);
-    {
-        std::lock_guard<std::mutex> lk(T.cache_mu);
-        auto it = T.cache_free.find(cls);
-        if (it != T.cache_free.end()) {  // freed on this same stream earlier: reuse is stream-ordered
-            *p = it->second;
-            T.cache_free.erase(it);
-            T.cache_bytes -= cls;
-            T.cache_live[*p] = cls;
-            g_alloc_hits.fetch_add(1);
-            return cudaSuccess;
-        }
-    }
-    cudaError_t e = raw_pool_malloc(T, p, cls);
-    if (e != cudaSuccess) {  // out of memory: give the parked blocks back and try once more
-        cudaGetLastError();
-        {
-            std::lock_guard<std::mutex> lk(T.cache_mu);
-            for (auto &kv : T.cache_free) cudaFreeAsync(kv.second, T.stream);
-            T.cache_free.clear();
-            T.cache_bytes = 0;
-        }
-        cudaStreamSynchronize(T.stream);
-        if (T.pool) cudaMemPoolTrimTo(T.pool, 0);
-        e = raw_pool_malloc(T, p, cls);
-        if (e != cudaSuccess) return e;
-    }
+    Tables &T = const_cast<Tables &>(Tc);  // the arena is internal state guarded by cache_mu
     std::lock_guard<std::mutex> lk(T.cache_mu);
-    T.cache_live[*p] = cls;
+    cudaError_t last = cudaSuccess;
+    bool hit = false;
+    *p = T.arena.take(
+        bytes,
+        [&](size_t seg) -> void * {
+            void *base = nullptr;
+            last = raw_pool_malloc(T, &base, seg);
+            if (last != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            return base;
+        },
+        [&](void *base) {
+            cudaFreeAsync(base, T.stream);
+            cudaStreamSynchronize(T.stream);
+            if (T.pool) cudaMemPoolTrimTo(T.pool, 0);
+        },
+        &hit);
+    if (!*p) return last != cudaSuccess ? last : cudaErrorMemoryAllocation;
+    if (hit) g_alloc_hits.fetch_add(1);
     return cudaSuccess;
 }
+// Give the segments that are entirely free back to the pool (ckks_ctx_trim, destruction).
 static void cache_release(Tables &T) {
     std::lock_guard<std::mutex> lk(T.cache_mu);
-    for (auto &kv : T.cache_free) cudaFreeAsync(kv.second, T.stream);
-    T.cache_free.clear();
-    T.cache_bytes = 0;
+    T.arena.release_free_segments([&](void *base) { cudaFreeAsync(base, T.stream); });
 }
 
 static void dev_free(const Tables &Tc, void *p);
@@ -853,16 +839,7 @@ static void dev_free(const Tables &Tc, void *p) {
     Tables &T = const_cast<Tables &>(Tc);
     {
         std::lock_guard<std::mutex> lk(T.cache_mu);
-        auto it = T.cache_live.find(p);
-        if (it != T.cache_live.end()) {
-            const size_t cls = it->second;
-            T.cache_live.erase(it);
-            if (!g_stream_override && T.cache_bytes + cls <= T.cache_cap) {  // park it for the next request of this class
-                T.cache_free.emplace(cls, p);
-                T.cache_bytes += cls;
-                return;
-            }
-        }
+        if (T.arena.give(p)) return;  // back into the arena, merged with its free neighbours
     }
     cudaFreeAsync(p, S(T));
 }
@@ -1743,7 +1720,7 @@ static int ks_fused(const Tables &T, size_t L, size_t cs, const u64 *digits, con
     return ks_fused_ex(T, L, sh, cs, digits, dig_ntt, key, add0, add1, scratch, out0t, out1t, mul);
 }
 
-static size_t g_ks_scratch_mib = 4096;  // key-switch scratch per chunk of ciphertexts (tuning knob)
+static size_t g_ks_scratch_mib = 8192;  // key-switch scratch per chunk of ciphertexts (tuning knob)
 extern "C" int ckks_set_ks_scratch_mib(int mib) {
     if (mib < 1) return CKKS_BAD_ARGUMENT;
     g_ks_scratch_mib = (size_t)mib;

@@ -7,9 +7,11 @@
 #include <map>
 #include <memory>
 #include <unordered_map>
+#include <vector>
 #include <mutex>
 #include <vector>
 
+#include "arena.hpp"
 #include "modarith.cuh"
 
 // Everything derived from (N, moduli): the device image of RnsBasis<N> + NttTable<N>
@@ -42,15 +44,10 @@ struct Tables {
     // blocking calls on this context (download, sync) report CKKS_NCCL_ERROR instead of handing out poisoned words
     const volatile unsigned *fail_word = nullptr;
     // cached staging buffers / copy streams of the host-buffer entry points
-    // Block cache on top of the pool (pool_malloc / dev_free): requests of 1 MiB and more are rounded up to a size class
-    // (three mantissa bits: at most 12.5 % slack) and freed blocks are kept per class, so a loop of calls at changing
-    // levels (horner_chain: a different polynomial size at every level) reuses exactly the blocks of its previous
-    // pass instead of making the driver split, merge and re-grow its pool (measured: sporadic 0.3 - 1 s stalls).
+    // Arena on top of the pool (arena.hpp; pool_malloc / dev_free): requests of 1 MiB and more are carved out of
+    // large segments taken from the pool once, so a loop of calls at changing levels never goes back to the driver.
     std::mutex cache_mu;
-    std::multimap<size_t, void *> cache_free;
-    std::unordered_map<void *, size_t> cache_live;
-    size_t cache_bytes = 0;                  // bytes parked in cache_free
-    size_t cache_cap = (size_t)64 << 30;     // beyond this, freed blocks go back to the pool
+    Arena arena;
     // persistent scratch of the fused pipelines (ws_get): slot buffers grow to the largest request and are kept, so
     // a chain of calls at changing levels never goes back to the allocator; ws_mu serialises the calls that use them
     struct WsSlot {
