@@ -484,12 +484,10 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    shard = importlib.import_module("toy-heaan-ckks_b200.shard")  # the package's batch-sharding helpers
+
     def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(ms, device=dev)
 
     rlk.rotation = 1
 
@@ -518,7 +516,7 @@ def run_b200(args):
     launches = ck.launch_count() - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = ms_total / args.steps
-    value = world * batch / (ms_per_step * 1e-3)
+    value = shard.aggregate_rate(batch, world, ms_per_step)
 
     # device words of the pairs the oracle will recompute (taken from the last timed step's output)
     dev_rows = None
@@ -1023,7 +1021,7 @@ KS_SCRATCH_MIB = 8192  # the library's default (ckks_set_ks_scratch_mib); --ks-s
 
 
 def _cs(n, l, batch):
-    return max(1, min(batch, (KS_SCRATCH_MIB << 20) // (l * l * n * 8)))
+    return max(1, min(batch, (KS_SCRATCH_MIB << 20) // (l * l * n * 8)))  # (the library also caps 32-bit-word contexts at 512)
 
 
 def _ks2(n, l, batch, w=8):

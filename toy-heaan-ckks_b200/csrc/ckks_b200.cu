@@ -1499,11 +1499,12 @@ static int keyswitch_accumulate(const Tables &T, size_t L, size_t batch, const u
 }
 
 // ---- fused four-step key-switch pipeline -----------------------------------------------------------
-// ks_pass1 column tile: 8 for 64-bit words (integer-pipe bound: more, smaller CTAs), 16 for 32-bit words (its
-// u64 digit loads and the per-element twiddles are L1-bound there: 128-byte row segments instead of 64)
+// ks_pass1 column tile: 16 for both word sizes.  64-bit words: 128-byte row segments for the digit loads and the
+// per-element twiddles, 256 threads per CTA (measured on cfg4: 8 columns 163.5 ms per 768 ciphertexts, 16 columns
+// 159.2, 4 columns 186.6); 32-bit words: the u64 digit loads were L1-bound with 64-byte segments.
 template <typename WD>
 constexpr int ks_c1() {
-    return sizeof(WD) == 8 ? 8 : 16;
+    return 16;
 }
 #ifndef CKKS_KS1_E
 #define CKKS_KS1_E 4
@@ -1732,6 +1733,9 @@ static size_t ks_chunk(const Tables &T, size_t L, size_t batch) {
     size_t c = (g_ks_scratch_mib << 20) / per;
     if (c < 1) c = 1;
     if (c > 32768) c = 32768;  // the ciphertext index is a grid dimension (y/z limit 65535)
+    // 32-bit word path: ks_pass2 falls off a cliff beyond 512 ciphertexts per launch (cfg3: 9.97 ms per 3072 rotations
+    // with 512 per launch, 14.25 ms with 1024; 12 CTAs per SM all streaming slabs a power-of-two 4 MiB apart)
+    if (T.w32 && c > 512) c = 512;
     return c < batch ? c : batch;
 }
 
