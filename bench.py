@@ -283,7 +283,7 @@ def ntt_point(ck, torch, dev, stream, hbm_peak, bits, logn, l, steps, warmup):
     return rec
 
 
-def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, passes=3):
+def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, passes=2):
     """BASELINE.json configs[3] as worded: the horner_chain workload (examples/horner_chain.rs:211-278), x <- x * alpha
     + beta from L limbs down to 2, on a RESIDENT batch: per level one mul_ciphertexts_gadget + rescale_ciphertext with
     that level's gadget key and one add_ciphertexts.  Ciphertexts and keys are synthetic uniform limbs (the reference
@@ -310,7 +310,8 @@ def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, pas
     per_level = {k: [] for k in levels}
     totals = []
     alloc = []
-    for it in range(passes + 1):  # first pass is the warm-up
+    WARM = 2  # warm-up passes: the arena reaches its steady-state footprint in the second one (one more 2 GiB segment)
+    for it in range(passes + WARM):
         ck.alloc_stats(reset=True)
         ct = x0
         total = 0.0
@@ -326,12 +327,12 @@ def run_chain(ck, torch, dev, stream, uni_poly_at, basis, bits, l, n, batch, pas
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             total += ms
-            if it:
+            if it >= WARM:
                 per_level[k].append(ms)
             del alpha_k, beta_k
         assert ct.c0.channel_count() == 2
         alloc.append(ck.alloc_stats())
-        if it:
+        if it >= WARM:
             totals.append(total)
         del ct
     ms_chain = sum(totals) / len(totals)

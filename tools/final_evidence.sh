@@ -4,6 +4,7 @@
 # command is preceded by the plain run of the same command.
 mkdir -p gpurun_out
 R=${R:-r02}
+timeout 300 python __graft_entry__.py smoke > gpurun_out/${R}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${R}_smoke.log | cut -c1-200
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${R}_final_cfg4.json 2> gpurun_out/${R}_final.err; cut -c1-200 gpurun_out/${R}_final_cfg4.json
 timeout 300 python bench.py --config cfg3 --steps 5 --warmup 3 > gpurun_out/${R}_final_cfg3.json 2>> gpurun_out/${R}_final.err; cut -c1-150 gpurun_out/${R}_final_cfg3.json
 timeout 300 python bench.py --config cfg2 --steps 5 --warmup 3 > gpurun_out/${R}_final_cfg2.json 2>> gpurun_out/${R}_final.err; cut -c1-150 gpurun_out/${R}_final_cfg2.json

@@ -10,7 +10,7 @@ for N in 2 4 8; do
   [ $N -le $G ] || continue
   timeout 300 $TR --nproc-per-node $N --master-port $((29600+N)) bench.py --gpus $N --config cfg3 --steps 5 --warmup 3 --no-ntt > gpurun_out/r02m_cfg3_$N.json 2> gpurun_out/r02m_cfg3_$N.err; echo "cfg3 N=$N rc=$?"
 done
-for N in 8 2; do
+for N in 8; do
   [ $N -le $G ] || continue
   timeout 400 $TR --nproc-per-node $N --master-port $((29700+N)) bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r02m_cfg4_$N.json 2> gpurun_out/r02m_cfg4_$N.err; echo "cfg4 N=$N rc=$?"; tail -c 300 gpurun_out/r02m_cfg4_$N.err
 done
