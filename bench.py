@@ -763,7 +763,7 @@ def run_b200(args):
 def ncu_traffic(kernel, config, op, batch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, read from the committed `ncu --set full`
     summary (profiles/*.json, newest round first) of the same configuration; (None, reason) if there is none."""
-    if not (config == "cfg4" and op == "mul" and batch >= 14):
+    if not (config == "cfg4" and op == "mul" and batch >= _cs(65536, 24, batch) and KS_SCRATCH_MIB == 8192):
         return None, "no capture for this configuration"
     import glob
 
@@ -779,7 +779,7 @@ def ncu_traffic(kernel, config, op, batch):
                     def gb(v):
                         x, u = v.split()
                         return float(x) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
-                    return gb(r["dram__bytes_read.sum"]) + gb(r["dram__bytes_write.sum"]), os.path.relpath(path, ROOT) + " (14 ciphertexts per launch)"
+                    return gb(r["dram__bytes_read.sum"]) + gb(r["dram__bytes_write.sum"]), os.path.relpath(path, ROOT) + " (grid " + r.get("Grid Size", "?") + ")"
         except Exception:
             continue
     return None, "no capture found under profiles/"

@@ -1923,11 +1923,20 @@ extern "C" int ckks_ct_add(const ckks_poly *a0, const ckks_poly *a1, const ckks_
     TRY(check_ct(a0, a1));
     TRY(check_ct(b0, b1));
     TRY(check_pair(a0, b0, false));
+    TRY(check_pair(a1, b1, false));
+    const Tables &T = *a0->ctx->T;
+    CU(cudaSetDevice(T.device));
     ckks_poly *r0 = nullptr, *r1 = nullptr;
-    int rc = ckks_poly_clone(const_cast<ckks_poly *>(a0), &r0);
-    if (rc == CKKS_OK) rc = ckks_poly_clone(const_cast<ckks_poly *>(a1), &r1);
-    if (rc == CKKS_OK) rc = ckks_poly_add_assign(r0, b0);
-    if (rc == CKKS_OK) rc = ckks_poly_add_assign(r1, b1);
+    int rc = poly_new(a0->ctx, a0->batch, a0->ntt, &r0);
+    if (rc == CKKS_OK) rc = poly_new(a0->ctx, a0->batch, a0->ntt, &r1);
+    if (rc == CKKS_OK) {
+        EwArgs e = ew_args(T, a0->ctx->L, a0->batch);
+        if (e.total) {
+            KLV("ew_add3", (ew_add3_kernel<<<ew_grid(e.total), 256, 0, S(T)>>>(e, a0->d, b0->d, r0->d)));
+            KLV("ew_add3", (ew_add3_kernel<<<ew_grid(e.total), 256, 0, S(T)>>>(e, a1->d, b1->d, r1->d)));
+            if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ew_add3");
+        }
+    }
     if (rc != CKKS_OK) {
         free2(r0, r1);
         return rc;
@@ -2112,15 +2121,29 @@ extern "C" int ckks_ct_encrypt(const ckks_poly *pk_b, const ckks_poly *pk_a, con
     if (!c0 || !c1) return CKKS_BAD_ARGUMENT;
     *c0 = *c1 = nullptr;
     if (!ok_poly(pk_b) || !ok_poly(pk_a) || !ok_poly(u) || !ok_poly(e0) || !ok_poly(e1) || !ok_poly(m)) return CKKS_BAD_HANDLE;
-    // engine.rs:96-104: c0 = pk.b.clone(); c0 *= u; c0 += e0; c0 += m;  c1 = pk.a.clone(); c1 *= u; c1 += e1
-    ckks_poly *r0 = nullptr, *r1 = nullptr;
-    int rc = ckks_poly_clone(const_cast<ckks_poly *>(u), &r0);
-    if (rc == CKKS_OK) rc = ckks_poly_mul_assign(r0, pk_b);  // commutative; lets pk broadcast over the batch
+    // engine.rs:96-104: c0 = pk.b.clone(); c0 *= u; c0 += e0; c0 += m;  c1 = pk.a.clone(); c1 *= u; c1 += e1.
+    // Each `*=` of coefficient-domain operands is forward(both), pointwise, inverse (poly.rs:307-329); everything is
+    // exact in Z_q, so u is transformed ONCE for both products (1 batched forward + 2 inverse transforms instead of
+    // 2 + 2, plus the two transforms of the public key, which has batch 1) and the words are the reference's.
+    TRY(check_pair(u, pk_b, true));
+    TRY(check_pair(u, pk_a, true));
+    if (u->ntt) return CKKS_DOMAIN_MISMATCH;
+    ckks_poly *r0 = nullptr, *r1 = nullptr, *pb = nullptr, *pa = nullptr;
+    int rc = ckks_poly_clone(const_cast<ckks_poly *>(u), &r1);
+    if (rc == CKKS_OK) rc = ckks_poly_to_ntt_domain(r1);
+    if (rc == CKKS_OK) rc = ckks_poly_clone(r1, &r0);
+    if (rc == CKKS_OK) rc = ckks_poly_clone(const_cast<ckks_poly *>(pk_b), &pb);
+    if (rc == CKKS_OK) rc = ckks_poly_to_ntt_domain(pb);
+    if (rc == CKKS_OK) rc = ckks_poly_clone(const_cast<ckks_poly *>(pk_a), &pa);
+    if (rc == CKKS_OK) rc = ckks_poly_to_ntt_domain(pa);
+    if (rc == CKKS_OK) rc = ckks_poly_mul_assign(r0, pb);  // NTT domain: pointwise (poly.rs:297-306); pk broadcasts over the batch
+    if (rc == CKKS_OK) rc = ckks_poly_mul_assign(r1, pa);
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(r0);
+    if (rc == CKKS_OK) rc = ckks_poly_to_coeff_domain(r1);
     if (rc == CKKS_OK) rc = ckks_poly_add_assign(r0, e0);
     if (rc == CKKS_OK) rc = ckks_poly_add_assign(r0, m);
-    if (rc == CKKS_OK) rc = ckks_poly_clone(const_cast<ckks_poly *>(u), &r1);
-    if (rc == CKKS_OK) rc = ckks_poly_mul_assign(r1, pk_a);
     if (rc == CKKS_OK) rc = ckks_poly_add_assign(r1, e1);
+    free2(pb, pa);
     if (rc != CKKS_OK) {
         free2(r0, r1);
         return rc;

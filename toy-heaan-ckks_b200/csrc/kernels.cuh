@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
         }
     }
     if (TRANSPOSE) {
-        if (GM::NS >= 2) __syncthreads();
+        // (no barrier before this put: it overwrites exactly the slots this thread read in the transform's last
+        // tile_get, which was at the same window lo_out)
         tile_put<E, CP>(sm, v, g, c, lo_out);
         __syncthreads();
         DST_T *d = dst + dbase + c0 * (size_t)(1 << A);
@@ -245,6 +246,12 @@ __global__ void ew_binary_kernel(EwArgs a, u64 *__restrict__ x, const u64 *__res
         if (OP == EW_SUB) x[i] = submod(xx, yy, m.q);
         if (OP == EW_MUL) x[i] = mulmod(xx, yy, m);
     }
+}
+// add_ciphertexts (engine.rs:131-151) out of place: z = x + y, one pass (read two polynomials, write one) instead of
+// clone + AddAssign (read three, write two).
+__global__ void ew_add3_kernel(EwArgs a, const u64 *__restrict__ x, const u64 *__restrict__ y, u64 *__restrict__ z) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x)
+        z[i] = addmod(x[i], y[i], a.lc[ew_limb(a, i)].q);
 }
 // Neg (poly.rs:370-385)
 __global__ void ew_neg_kernel(EwArgs a, u64 *__restrict__ x) {
@@ -498,8 +505,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
         for (int k = 0; k < (1 << E); ++k)
             v[k] = mul_tw<LAZY>(v[k], ldg_tw(TTt + (size_t)tile_idx<E>(g, k, GM::lo(GM::NS - 1)) * ncols + c0 + c), q);
     }
-    if (GM::NS >= 2) __syncthreads();
-    tile_put<E, CP>(sm, v, g, c, GM::lo(GM::NS - 1));
+    tile_put<E, CP>(sm, v, g, c, GM::lo(GM::NS - 1));  // own slots (last tile_get was at this window): no barrier needed
     __syncthreads();
     WD *d = dst + c0 * (size_t)(1 << A);
     for (int e = tid; e < (C << A); e += NT) {
@@ -617,17 +623,13 @@ struct KsAcc<u32> {
 
 // Shared memory of ks_pass2 in bytes: two stages of the digit tile (WD), key_b and key_a tiles (WD),
 // exchange tile [2^A][C+1] (WD).
-// CKKS_KS2_PINGPONG = 1: a second exchange tile, so that the digit loop's three-step transform needs one barrier less.
-#ifndef CKKS_KS2_PINGPONG
-#define CKKS_KS2_PINGPONG 0
-#endif
 template <typename WD, int A, int C>
 __host__ __device__ constexpr size_t ks2_exch_bytes() {
     return (((size_t)(1 << A) * (C + 1) * sizeof(WD) + 15) / 16) * 16;
 }
 template <typename WD, int A, int C>
 __host__ __device__ constexpr size_t ks2_smem_bytes() {
-    return (size_t)(1 << A) * C * (2 * sizeof(WD) + 2 * sizeof(WD)) + (1 + CKKS_KS2_PINGPONG) * ks2_exch_bytes<WD, A, C>() + 64;
+    return (size_t)(1 << A) * C * (2 * sizeof(WD) + 2 * sizeof(WD)) + ks2_exch_bytes<WD, A, C>() + 64;
 }
 
 // TMA = true: the digit tile and the two key tiles are fetched by the copy engine
@@ -659,7 +661,6 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
     WD *stKa = stKb + TILE;                     // key_a tile
     WD *stS = reinterpret_cast<WD *>(stKa + TILE);  // 2 stages of the digit's pass-1 output
     WD *sm = stS + 2 * TILE;                        // exchange buffer
-    WD *sm2 = CKKS_KS2_PINGPONG ? reinterpret_cast<WD *>(reinterpret_cast<unsigned char *>(sm) + ks2_exch_bytes<WD, A, C>()) : nullptr;
     u64 *bars = reinterpret_cast<u64 *>(sm_raw + ks2_smem_bytes<WD, A, C>() - 64);  // [0,1]: digit stages, [2]: keys
     const int L = a.L;
     // grid = (ciphertexts, tiles, target limbs): the ciphertext index runs fastest so that the CTAs
@@ -746,7 +747,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
         const WD *S = stS + (t & 1) * TILE;
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = S[tile_idx<E>(g, k, lo_in) * C + c];
-        xf_tile<XF_CYC_FWD, A, E, CP, LAZY, SWZ>(v, g, c, sm, W, q, q2, sm2);
+        xf_tile<XF_CYC_FWD, A, E, CP, LAZY, SWZ>(v, g, c, sm, W, q, q2);
         if (TMA) {
             mbar_wait(bars + 2, t & 1);  // keys(t) landed
         } else {
@@ -793,8 +794,7 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
             size_t off = (size_t)tile_idx<E>(g, k, lo_in) * ncols + c0 + c;
             v[k] = mul_tw<LAZY>(v[k], ldg_tw(TTi + off), q);
         }
-        if (GM::NS >= 2) __syncthreads();
-        tile_put<E, CP>(sm, v, g, c, lo_in);
+        tile_put<E, CP>(sm, v, g, c, lo_in);  // own slots (the inverse transform's last tile_get was at window lo_in)
         __syncthreads();
         WD *d = out + c0 * (size_t)(1 << A);
         for (int e = tid; e < (C << A); e += NT) {

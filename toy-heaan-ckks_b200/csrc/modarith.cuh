@@ -34,6 +34,7 @@ struct uint2 {
 static inline uint2 __ldg(const uint2 *p) { return *p; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline void __syncthreads() {}
+static inline void __syncwarp() {}
 #endif
 
 typedef unsigned int u32;

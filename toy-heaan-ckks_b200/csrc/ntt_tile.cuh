@@ -196,15 +196,19 @@ __device__ __forceinline__ void xf_step(WD (&v)[1 << E], int g, const TW *__rest
 // Full transform of the tile.  On entry the thread holds the window of the FIRST step (forward
 // kinds: step 0; inverse kinds: step NS-1); on exit it holds the window of the LAST step
 // (forward: NS-1; inverse: 0).  `sm` is the [2^A][CP] exchange buffer (unused if NS == 1).
+// Barriers of a three-step transform (A = 8 with E = 3: windows over index bits [7:5], [4:2], [2:0]).  Threads are
+// numbered tid = g * C + c (all callers).  The exchange between the two LOWER windows only moves words inside groups of
+// 2^lo(1) thread groups that share the index bits above lo(1) + E - 1: with lo(1) = 2 these are the thread groups
+// 4h .. 4h+3, i.e. 4 * C consecutive threads -- inside one warp when 4 * C <= 32.  That exchange therefore needs
+// __syncwarp(), not a CTA barrier.  And a tile_put that follows a tile_get of the SAME window overwrites exactly the
+// slots the thread itself has just read, so no barrier is needed between them either.  A three-step transform is left
+// with ONE CTA barrier (the exchange that involves the top window) instead of three.
 template <int KIND, int A, int E, int CP, int LAZY, int SWZ = 0, typename WD, typename TW>
-__device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, const TW *__restrict__ tab, WD q, WD q2, WD *sm2 = nullptr) {
-    // sm2 != nullptr: a second exchange buffer for the second exchange of a three-step transform, which makes the
-    // barrier between "everyone has read the first exchange" and "overwrite it" unnecessary (the caller must
-    // separate consecutive transforms by a barrier of its own, as ks_pass2's digit loop does).
+__device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, const TW *__restrict__ tab, WD q, WD q2) {
     typedef TileGeom<A, E> GM;
     constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);
     static_assert(GM::NS >= 1 && GM::NS <= 3, "1..3 register steps supported");
-    WD *smb = sm2 ? sm2 : sm;
+    constexpr bool WARP_LOCAL = GM::NS == 3 && (((CP - 1) << GM::lo(1)) <= 32) && (32 % ((CP - 1) << GM::lo(1)) == 0);
     if (FWD) {
         xf_step<KIND, A, E, 0, LAZY>(v, g, tab, q, q2);
         if (GM::NS >= 2) {
@@ -214,25 +218,29 @@ __device__ __forceinline__ void xf_tile(WD (&v)[1 << E], int g, int c, WD *sm, c
             xf_step<KIND, A, E, (GM::NS >= 2 ? 1 : 0), LAZY>(v, g, tab, q, q2);
         }
         if (GM::NS >= 3) {
-            if (!sm2) __syncthreads();
-            tile_put<E, CP, SWZ>(smb, v, g, c, GM::lo(1));
-            __syncthreads();
-            tile_get<E, CP, SWZ>(smb, v, g, c, GM::lo(2));
+            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(1));  // own slots: the ones tile_get(lo(1)) read
+            if (WARP_LOCAL) __syncwarp();
+            else __syncthreads();
+            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(2));
             xf_step<KIND, A, E, (GM::NS >= 3 ? 2 : 0), LAZY>(v, g, tab, q, q2);
         }
     } else {
         xf_step<KIND, A, E, GM::NS - 1, LAZY>(v, g, tab, q, q2);
-        if (GM::NS >= 2) {
-            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(GM::NS - 1));
+        if (GM::NS == 2) {
+            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(1));
             __syncthreads();
-            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(GM::NS - 2));
-            xf_step<KIND, A, E, (GM::NS >= 2 ? GM::NS - 2 : 0), LAZY>(v, g, tab, q, q2);
+            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(0));
+            xf_step<KIND, A, E, 0, LAZY>(v, g, tab, q, q2);
         }
         if (GM::NS >= 3) {
-            if (!sm2) __syncthreads();
-            tile_put<E, CP, SWZ>(smb, v, g, c, GM::lo(1));
+            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(2));
+            if (WARP_LOCAL) __syncwarp();
+            else __syncthreads();
+            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(1));
+            xf_step<KIND, A, E, (GM::NS >= 3 ? 1 : 0), LAZY>(v, g, tab, q, q2);
+            tile_put<E, CP, SWZ>(sm, v, g, c, GM::lo(1));  // own slots again
             __syncthreads();
-            tile_get<E, CP, SWZ>(smb, v, g, c, GM::lo(0));
+            tile_get<E, CP, SWZ>(sm, v, g, c, GM::lo(0));
             xf_step<KIND, A, E, 0, LAZY>(v, g, tab, q, q2);
         }
     }
