@@ -33,6 +33,7 @@ CONFIGS = {
     "cfg4": (16, 24, 61, 256, 128),   # BASELINE.json configs[3]: the metric's configuration (default)
     "cfg3": (14, 8, 30, 1024, 256),   # configs[2]: rotation (automorphism + key-switch), see --op
     "cfg2": (12, 3, 40, 4096, 1024),  # configs[1]
+    "cfg1": (4, 4, 31, 1, 1),         # configs[0]: examples/encrypt_mul as shipped (N=16, generate_primes(31, 4, 16), one ciphertext)
     "tiny": (12, 3, 40, 8, 8),
 }
 

@@ -72,6 +72,9 @@ pub mod ffi {
         pub fn ckks_poly_automorphism(p: *const CkksPoly, e: u64, out: *mut *mut CkksPoly) -> i32;
         pub fn ckks_poly_rotate_slots(p: *const CkksPoly, k: i32, out: *mut *mut CkksPoly) -> i32;
         pub fn ckks_poly_to_coeffs(p: *const CkksPoly, out: *mut i64) -> i32;
+        pub fn ckks_poly_to_coeffs_wide(p: *const CkksPoly, out_i64: *mut i64, out_f64: *mut f64, overflow: *mut i32) -> i32;
+        pub fn ckks_ctx_trim(ctx: *mut CkksCtx) -> i32;
+        pub fn ckks_set_nvtx(on: i32) -> i32;
         pub fn ckks_ksk_upload(ctx: *mut CkksCtx, a: *const u64, b: *const u64, out: *mut *mut CkksKsk) -> i32;
         pub fn ckks_ksk_free(k: *mut CkksKsk) -> i32;
         pub fn ckks_ct_mul_relin(a0: *const CkksPoly, a1: *const CkksPoly, b0: *const CkksPoly, b1: *const CkksPoly,
@@ -323,6 +326,14 @@ impl<const N: usize> RnsPoly<N> {
         }
         Ok(Self::wrap(h, child))
     }
+    /// Centred CRT for a basis of ANY size (the reference's `reconstruct_centered_coeff`, basis.rs:158-180, stops at
+    /// Q < 2^128): the centred value of every coefficient rounded to f64, and whether some |x| >= 2^63.
+    pub fn to_coeffs_wide(&self) -> (Vec<f64>, bool) {
+        let mut out = vec![0f64; N];
+        let mut overflow = 0i32;
+        check(unsafe { ffi::ckks_poly_to_coeffs_wide(self.h.as_ptr(), ptr::null_mut(), out.as_mut_ptr(), &mut overflow) });
+        (out, overflow != 0)
+    }
     /// Raw handle for the batched / fused entry points (`ckks_ct_*`).
     pub fn handle(&self) -> *mut ffi::CkksPoly {
         self.h.as_ptr()
@@ -344,7 +355,7 @@ impl<'a, const N: usize> MulAssign<&'a RnsPoly<N>> for RnsPoly<N> {
 }
 impl<const N: usize> Neg for RnsPoly<N> {
     type Output = Self;
-    fn neg(self) -> Self {
+    fn neg(mut self) -> Self {
         check(unsafe { ffi::ckks_poly_neg(self.h.as_ptr()) });
         self.mirror.take();
         self

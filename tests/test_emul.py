@@ -174,5 +174,7 @@ def test_device_arena_bookkeeping(emul):
         assert peak.value <= 80 << 30  # at most 24 live ranges of <= 3.2 GiB: fragmentation stays bounded
         assert emul.emul_arena_stress(seed, 4000, 3200, 24, C.byref(peak), C.byref(late)) == 0  # 24 GiB device: refusals handled
         assert peak.value <= 24 << 30
+        assert emul.emul_arena_stress(seed, 3000, 8, 0, C.byref(peak), C.byref(late)) == 0  # small polynomials: a small arena
+        assert peak.value <= 512 << 20
     assert emul.emul_arena_chain(24, 4, 128 << 20) == 0
     assert emul.emul_arena_chain(24, 4, (128 << 20) + 4096) == 0

@@ -8,6 +8,7 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/${R}_smoke.log 2>&1; ec
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${R}_final_cfg4.json 2> gpurun_out/${R}_final.err; cut -c1-200 gpurun_out/${R}_final_cfg4.json
 timeout 300 python bench.py --config cfg3 --steps 5 --warmup 3 > gpurun_out/${R}_final_cfg3.json 2>> gpurun_out/${R}_final.err; cut -c1-150 gpurun_out/${R}_final_cfg3.json
 timeout 300 python bench.py --config cfg2 --steps 5 --warmup 3 > gpurun_out/${R}_final_cfg2.json 2>> gpurun_out/${R}_final.err; cut -c1-150 gpurun_out/${R}_final_cfg2.json
+timeout 120 python bench.py --config cfg1 --steps 20 --warmup 5 > gpurun_out/${R}_final_cfg1.json 2>> gpurun_out/${R}_final.err; cut -c1-150 gpurun_out/${R}_final_cfg1.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${R}_final_reference_arm.json 2>> gpurun_out/${R}_final.err
 CMD="python bench.py --steps 2 --warmup 1 --batch 56 --e2e-batch 4 --no-cpu-baseline --no-ntt --no-chain"
 timeout 200 $CMD > gpurun_out/${R}_final_b56.json 2>> gpurun_out/${R}_final.err && timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_b56.csv $CMD > gpurun_out/ncu_a.log 2>&1

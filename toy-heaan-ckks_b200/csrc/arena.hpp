@@ -17,8 +17,9 @@
 
 class Arena {
 public:
-    static constexpr size_t ALIGN = (size_t)2 << 20;  // ranges are multiples of 2 MiB
-    static constexpr size_t GROW = (size_t)2 << 30;   // segments: at least 2 GiB, rounded up to whole GiB
+    static constexpr size_t ALIGN = (size_t)2 << 20;       // ranges are multiples of 2 MiB
+    static constexpr size_t GROW_MIN = (size_t)64 << 20;   // first segment: 64 MiB (small contexts stay small) ...
+    static constexpr size_t GROW_MAX = (size_t)2 << 30;    // ... then as large as everything held so far, up to 2 GiB
     struct Seg {
         char *base;
         size_t bytes;
@@ -33,8 +34,9 @@ public:
         if (from_arena) *from_arena = true;
         if (void *p = carve(need)) return p;
         if (from_arena) *from_arena = false;
-        size_t seg = need > GROW ? need : GROW;
-        seg = (seg + ((size_t)1 << 30) - 1) >> 30 << 30;
+        size_t grow = total_ < GROW_MIN ? GROW_MIN : (total_ > GROW_MAX ? GROW_MAX : total_);
+        size_t seg = need > grow ? need : grow;
+        seg = (seg + GROW_MIN - 1) / GROW_MIN * GROW_MIN;  // whole multiples of 64 MiB
         void *base = seg_alloc(seg);
         if (!base && seg > need) {  // no room for a rounded segment: exactly what is needed
             seg = need;

@@ -169,6 +169,17 @@ class RnsPoly {
         check(ckks_poly_to_coeffs(p_, out.data()));
         return out;
     }
+    // The same for a basis of any size (Q >= 2^128 too): centred values as i64 (the reference's `as i64` truncation) and
+    // as doubles; returns true if some |x| >= 2^63.  Below Q = 2^128 `wide_i64` == to_coeffs() bit for bit.
+    bool to_coeffs_wide(std::vector<int64_t> *wide_i64, std::vector<double> *wide_f64) const {
+        const size_t n = batch() * basis_.degree();
+        if (wide_i64) wide_i64->assign(n, 0);
+        if (wide_f64) wide_f64->assign(n, 0.0);
+        int overflow = 0;
+        check(ckks_poly_to_coeffs_wide(p_, wide_i64 ? wide_i64->data() : nullptr, wide_f64 ? wide_f64->data() : nullptr, &overflow));
+        return overflow != 0;
+    }
+    RnsPoly rescale() const { return rescale_into(basis_.drop_last(1)); }  // poly.rs:246-249
     void mul_assign_naive(const RnsPoly &rhs) { check(ckks_poly_mul_assign_naive(p_, rhs.p_)); }  // poly.rs:339-367
     ckks_poly *raw() const { return p_; }
 };
@@ -304,6 +315,59 @@ class LimbShard {
         return c;
     }
     void check_peers() const { check(ckks_lshard_check(h_.get())); }  // sync + "no peer was lost"
+};
+
+// The batch-sharded multi-GPU group (ckks_comm_*): ONE process spreads a host batch of ciphertexts over the GPUs of a
+// box; replaces the reference's serial loop over a Vec<Ciphertext> (examples/horner_chain.rs:211-278).
+class BatchShard {
+    struct Del {
+        void operator()(ckks_comm *c) const { ckks_comm_destroy(c); }
+    };
+    std::shared_ptr<ckks_comm> h_;
+    explicit BatchShard(ckks_comm *c) : h_(c, Del()) {}
+
+public:
+    class Key {
+        friend class BatchShard;
+        ckks_comm_ksk *k_ = nullptr;
+        std::shared_ptr<ckks_comm> owner_;
+
+    public:
+        int32_t rotation = 0;
+        Key() = default;
+        Key(const Key &) = delete;
+        Key(Key &&o) noexcept : k_(o.k_), owner_(std::move(o.owner_)), rotation(o.rotation) { o.k_ = nullptr; }
+        ~Key() {
+            if (k_) ckks_comm_ksk_free(k_);
+        }
+    };
+    static BatchShard create(uint64_t degree, const std::vector<uint64_t> &moduli, const std::vector<int> &devices) {
+        ckks_comm *c = nullptr;
+        check(ckks_comm_init((int)devices.size(), devices.data(), degree, moduli.data(), moduli.size(), &c));
+        return BatchShard(c);
+    }
+    BatchShard drop_last(size_t k) const {
+        ckks_comm *c = nullptr;
+        check(ckks_comm_drop_last(h_.get(), k, &c));
+        return BatchShard(c);
+    }
+    int size() const { return ckks_comm_size(h_.get()); }
+    // a, b: [L][L][N] as RnsGadgetRelinKey / RnsGadgetRotationKey hold them (engine.rs:225-253)
+    Key upload_key(const std::vector<uint64_t> &a, const std::vector<uint64_t> &b, int32_t rotation = 0) const {
+        Key k;
+        check(ckks_comm_ksk_upload(h_.get(), a.data(), b.data(), &k.k_));
+        k.owner_ = h_;
+        k.rotation = rotation;
+        return k;
+    }
+    // host [batch][L][N] in, [batch][L-1][N] out: mul_ciphertexts_gadget + rescale_ciphertext
+    void mul_relin_rescale_host(const Key &rlk, size_t batch, const uint64_t *a0, const uint64_t *a1, const uint64_t *b0, const uint64_t *b1, uint64_t *o0,
+                                uint64_t *o1) const {
+        check(ckks_comm_ct_mul_relin_rescale_host(h_.get(), rlk.k_, batch, a0, a1, b0, b1, o0, o1));
+    }
+    void rotate_host(const Key &rotk, size_t batch, const uint64_t *c0, const uint64_t *c1, uint64_t *o0, uint64_t *o1) const {
+        check(ckks_comm_ct_rotate_host(h_.get(), rotk.k_, rotk.rotation, batch, c0, c1, o0, o1));
+    }
 };
 
 }  // namespace ckks
