@@ -192,3 +192,28 @@ def test_decode_at_full_level_without_mod_drop(gpu, orc):
     assert np.max(np.abs(got - low)) <= 1e-9
     wi, _, ov = dec.to_coeffs_wide()
     assert not ov and np.array_equal(wi, dec.mod_drop_last(l - 2).to_coeffs())
+
+
+def test_wide_crt_and_decode_at_cfg4_size(gpu, orc):
+    """N=2^16, L=24, generate_primes(61, 24, 65536) (BASELINE configs[3]): Q has 1464 bits, where the reference can
+    neither run reconstruct_centered_coeff (u128 product, basis.rs:152-160) nor decode.  from_coeffs -> wide CRT returns
+    the coefficients bit for bit (from either domain), and encode -> decode at the full level stays within
+    2^-(scale_bits - 10) without any mod_drop_last."""
+    n, l, sb = 65536, 24, 50
+    moduli = orc.generate_primes(61, l, n)
+    gb = gpu.RnsBasis(n, moduli)
+    rng = np.random.default_rng(2)
+    coeffs = rng.integers(-(1 << 62), 1 << 62, size=(2, n), dtype=np.int64)
+    coeffs[0, :4] = [0, -1, (1 << 63) - 1, -(1 << 63)]
+    p = gpu.RnsPoly.from_coeffs(coeffs, gb)
+    wi, wf, ov = p.to_coeffs_wide()
+    assert not ov and np.array_equal(wi, coeffs)
+    assert np.all(np.abs(wf - coeffs.astype(np.float64)) <= np.abs(coeffs.astype(np.float64)) * 2.0 ** -50)
+    p.to_ntt_domain()
+    wi2, _, _ = p.to_coeffs_wide()
+    assert np.array_equal(wi2, coeffs)
+    enc = gpu.CkksEncoder(n, sb)
+    vals = rng.uniform(-0.9, 0.9, (2, n // 2))
+    pt = enc.encode(vals, gb)
+    got = enc.decode(pt)
+    assert np.max(np.abs(got - vals)) <= 2.0 ** -(sb - 10)
