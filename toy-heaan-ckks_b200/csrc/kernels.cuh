@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
         tile_put<E, CP>(sm, v, g, c, lo_out);
         __syncthreads();
         DST_T *d = dst + dbase + c0 * (size_t)(1 << A);
-        for (int e = tid; e < (C << A); e += NT) {
+#pragma unroll 4
+        for (int i = 0; i < (1 << E); ++i) {  // (C << A) / NT = 2^E words per thread (a full unroll costs 16 registers)
+            const int e = tid + i * NT;
             int cc = e >> A, r = e & ((1 << A) - 1);
             d[e] = (DST_T)sm[r * CP + cc];
         }
@@ -508,7 +510,9 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ks_pass1_kernel(KsArgs a) {
     tile_put<E, CP>(sm, v, g, c, GM::lo(GM::NS - 1));  // own slots (last tile_get was at this window): no barrier needed
     __syncthreads();
     WD *d = dst + c0 * (size_t)(1 << A);
-    for (int e = tid; e < (C << A); e += NT) {
+#pragma unroll 4
+    for (int i = 0; i < (1 << E); ++i) {  // (C << A) / NT = 2^E words per thread (a full unroll costs 16 registers: 78 instead of 62)
+        const int e = tid + i * NT;
         int cc = e >> A, r = e & ((1 << A) - 1);
         d[e] = sm[r * CP + cc];
     }
@@ -797,7 +801,9 @@ __global__ void __launch_bounds__(C *(1 << (A - E)), ks2_min_ctas<WD, C *(1 << (
         tile_put<E, CP>(sm, v, g, c, lo_in);  // own slots (the inverse transform's last tile_get was at window lo_in)
         __syncthreads();
         WD *d = out + c0 * (size_t)(1 << A);
-        for (int e = tid; e < (C << A); e += NT) {
+#pragma unroll 4
+        for (int i = 0; i < R; ++i) {  // (C << A) / NT = 2^E words per thread
+            const int e = tid + i * NT;
             int cc = e >> A, r = e & ((1 << A) - 1);
             d[e] = sm[r * CP + cc];
         }
