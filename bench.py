@@ -435,6 +435,8 @@ def run_b200(args):
         global KS_SCRATCH_MIB
         KS_SCRATCH_MIB = args.ks_scratch_mib
         ck._check(ck._lib.ckks_set_ks_scratch_mib(args.ks_scratch_mib))
+    if args.ks_aux is not None:
+        ck.set_ks_aux(args.ks_aux)
     logn, l, bits, batch, e2e_batch = CONFIGS[args.config]
     if args.batch:
         batch = args.batch
@@ -1069,6 +1071,8 @@ def main():
     ap.add_argument("--imad", action="store_true", help="also run the integer-pipe microbenchmark")
     ap.add_argument("--op", default="", choices=["", "mul", "rotate"], help="hot-path operation (default: mul; rotate for cfg3)")
     ap.add_argument("--host-chunk-mib", type=int, default=0, help="pipeline chunk of the host-buffer entry point")
+    ap.add_argument("--ks-aux", type=int, default=None, choices=[0, 1, 2],
+                    help="gadget product through auxiliary 30-bit primes: 0 never, 1 automatic (library default), 2 whenever possible")
     ap.add_argument("--ks-scratch-mib", type=int, default=0, help="key-switch scratch per chunk of ciphertexts (default 8192)")
     ap.add_argument("--ntt-sweep", action="store_true", help="BASELINE.json configs[4]: limb-batched NTT/INTT sweep instead of the ct-mult bench")
     ap.add_argument("--limb-sharded", action="store_true", help="optional limb-sharded mode (one batch, limbs spread over the GPUs)")

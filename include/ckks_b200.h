@@ -114,6 +114,11 @@ int ckks_set_fused_ntt(int on);
  * N=2^16, L=24); ckks_ks_chunk reports the ciphertexts per chunk a batch of `batch` is cut into at ctx's level. */
 int ckks_set_ks_scratch_mib(int mib);
 size_t ckks_ks_chunk(const ckks_ctx *ctx, size_t batch);
+/* Gadget product of mul_ciphertexts_gadget (engine.rs:501-541) through auxiliary 30-bit NTT primes (exact integer
+ * convolution + Garner reconstruction, csrc/aux_ks.cuh; bit-identical results): 0 = never, 1 (default) = on the 64-bit
+ * four-step path from 11 limbs up, 2 = whenever the path allows it (test hook).  Read when a key is uploaded (the
+ * auxiliary form of the key is derived there) and when a product is computed. */
+int ckks_set_ks_aux(int mode);
 /* Tuning knob of the host-buffer entry points: MiB per component and pipeline chunk (default 64). */
 int ckks_set_host_chunk_mib(int mib);
 

@@ -213,6 +213,52 @@ def test_lazy8_and_harvey_butterflies_agree_with_oracle(gpu, orc, n, bits, l):
         assert np.array_equal(rot.c0.channels()[0], r0) and np.array_equal(rot.c1.channels()[0], r1), f"lazy8={lazy8}"
 
 
+@pytest.mark.parametrize("n,bits,l,batch", [(4096, 61, 4, 3), (1024, 62, 2, 2), (8192, 50, 5, 2), (256, 61, 3, 9), (65536, 61, 3, 1),
+                                              (512, 40, 12, 2)])
+def test_auxiliary_basis_key_switch_matches_oracle(gpu, orc, n, bits, l, batch):
+    """The gadget product through auxiliary 30-bit primes (exact integer convolution + Garner, csrc/aux_ks.cuh) gives
+    the limbs of the per-(digit, target) pipeline and of the oracle, with and without the fused rescale, for keys
+    uploaded from the host and keys built from resident NTT-domain polynomials."""
+    moduli = orc.generate_primes(bits, l, n)
+    ob = orc.Basis(n, moduli)
+    rng = np.random.default_rng(900 + n)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
+    # the extremes of the word range next to the random words: largest digits and key words
+    top = np.array(moduli, dtype=np.uint64)[:, None] - np.uint64(1)
+    a1[0], b1[0] = np.broadcast_to(top, a1[0].shape), np.broadcast_to(top, b1[0].shape)
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    ka[0], kb[-1] = np.broadcast_to(top, ka[0].shape), np.broadcast_to(top, kb[-1].shape)
+    want = []
+    for i in range(batch):
+        m0, m1 = ob.mul_ciphertexts_gadget(a0[i], a1[i], b0[i], b1[i], ka, kb)
+        want.append((m0, m1) + tuple(ob.rescale_ciphertext(m0, m1)[:2]))
+    got = {}
+    for mode in (2, 0):
+        gpu.set_ks_aux(mode)
+        try:
+            gb = gpu.RnsBasis(n, moduli)
+            launches0 = gpu.launch_table().get("aux_mac", 0)
+            keys = [gpu.GadgetKey.upload(gb, ka, kb)]
+            pa, pb = gpu.RnsPoly.from_channels(ka, gb), gpu.RnsPoly.from_channels(kb, gb)
+            pa.to_ntt_domain()
+            keys.append(gpu.GadgetKey.from_polys(pa, pb))
+            cta, ctb = _ct(gpu, gb, a0, a1, 30, 90), _ct(gpu, gb, b0, b1, 30, 90)
+            for key in keys:
+                prod = gpu.CkksEngine.mul_ciphertexts_gadget(cta, ctb, key)
+                fused = gpu.CkksEngine.mul_relin_rescale(cta, ctb, key)
+                g = (prod.c0.channels(), prod.c1.channels(), fused.c0.channels(), fused.c1.channels())
+                for i in range(batch):
+                    for t in range(4):
+                        assert np.array_equal(g[t][i], want[i][t]), f"mode {mode}, ciphertext {i}, output {t}"
+            used = gpu.launch_table().get("aux_mac", 0) - launches0
+            assert (used > 0) == (mode == 2), "the auxiliary-basis kernels ran exactly when asked to"
+            got[mode] = g
+        finally:
+            gpu.set_ks_aux(1)
+    for t in range(4):
+        assert np.array_equal(got[0][t], got[2][t])
+
+
 def test_add_encrypt_decrypt_keygen_match_oracle(gpu, orc):
     n, l = 1024, 3
     moduli = orc.generate_primes(40, l, n)

@@ -99,6 +99,7 @@ _sig("ckks_set_tma", C.c_int, C.c_int)
 _sig("ckks_set_fused_ntt", C.c_int, C.c_int)
 _sig("ckks_set_host_chunk_mib", C.c_int, C.c_int)
 _sig("ckks_set_ks_scratch_mib", C.c_int, C.c_int)
+_sig("ckks_set_ks_aux", C.c_int, C.c_int)
 _sig("ckks_ks_chunk", C.c_size_t, _vp, C.c_size_t)
 _sig("ckks_prof_enable", C.c_int, C.c_int)
 _sig("ckks_set_nvtx", C.c_int, C.c_int)
@@ -247,6 +248,12 @@ def set_lazy8(on: bool):
 def set_tma(on: bool):
     """Test hook: TMA (default) or cp.async staging in the fused key-switch kernel."""
     _check(_lib.ckks_set_tma(int(on)))
+
+
+def set_ks_aux(mode: int):
+    """Gadget product through auxiliary 30-bit NTT primes (csrc/aux_ks.cuh): 0 never, 1 automatic (default: 64-bit
+    four-step path, 11 limbs and more), 2 whenever possible (test hook).  Read at key upload and at every product."""
+    _check(_lib.ckks_set_ks_aux(int(mode)))
 
 
 def set_unfused(on: bool):

@@ -11,7 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <iterator>
+#include <cmath>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -21,6 +23,7 @@
 #include "tables_host.hpp"
 #include "encoder.cuh"
 #include "crt_wide.cuh"
+#include "aux_ks.cuh"
 #include "kernels.cuh"
 
 // -------------------------------------------------------------------------------------------------
@@ -254,6 +257,7 @@ extern "C" int ckks_generate_primes(int bits, int count, uint64_t degree, uint64
 // context
 // -------------------------------------------------------------------------------------------------
 static void destroy_host_pipe(struct HostPipe *p);
+static void destroy_aux(struct AuxKs *a);
 static void ws_release(Tables &T);
 static void cache_release(Tables &T);
 Tables::~Tables() {
@@ -263,6 +267,7 @@ Tables::~Tables() {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     destroy_host_pipe(pipe);
+    destroy_aux(aux);
     ws_release(*this);
     cache_release(*this);
     if (stream) cudaStreamSynchronize(stream);
@@ -385,9 +390,9 @@ static int upload_vec(T **dst, const std::vector<T> &v) {
 }
 static tw_t mk_tw(u64 w, u64 q) { return ht::mk_tw(w, q); }
 
-static int build_tables(Tables &T) {
+static int build_tables(Tables &T, bool allow_w32, bool allow_lazy8) {
     ht::HostTables H;
-    ht::build_host_tables(T.n, T.logn, T.path, T.a1, T.a2, T.moduli, T.psi, H, g_allow_w32 != 0, g_allow_lazy8 != 0);
+    ht::build_host_tables(T.n, T.logn, T.path, T.a1, T.a2, T.moduli, T.psi, H, allow_w32, allow_lazy8);
     T.lazy = H.lazy;
     T.w32 = H.w32;
     T.digit_reduce = H.digit_reduce;
@@ -473,7 +478,7 @@ extern "C" int ckks_ctx_create(uint64_t n, const uint64_t *moduli, size_t l, int
         uint64_t thr = ~0ull;  // keep freed scratch cached in OUR pool; the device's default pool is left untouched
         CU(cudaMemPoolSetAttribute(T->pool, cudaMemPoolAttrReleaseThreshold, &thr));
     }
-    TRY(build_tables(*T));
+    TRY(build_tables(*T, g_allow_w32 != 0, g_allow_lazy8 != 0));
     ckks_ctx *c = new ckks_ctx();
     c->magic = MAGIC_CTX;
     c->T = T;
@@ -1341,6 +1346,8 @@ static int ksk_new(ckks_ctx *ctx, ckks_ksk **out, size_t digits = 0) {
     k->digits = digits;
     k->perm_e = -1;
     k->k32 = false;
+    k->xa = k->xb = nullptr;
+    k->aux_k = 0;
     *out = k;
     return CKKS_OK;
 }
@@ -1349,12 +1356,15 @@ extern "C" int ckks_ksk_free(ckks_ksk *k) {
     cudaSetDevice(k->ctx->T->device);
     dev_free(*k->ctx->T, k->a);
     dev_free(*k->ctx->T, k->b);
+    if (k->xa) dev_free(*k->ctx->T, k->xa);
+    if (k->xb) dev_free(*k->ctx->T, k->xb);
     ckks_ctx *c = k->ctx;
     k->magic = 0;
     delete k;
     ctx_unref(c);
     return CKKS_OK;
 }
+static int ksk_add_aux(const Tables &T, ckks_ksk *k, const u64 *a_coeff, const u64 *b_coeff);  // aux_ks.inl
 // Four-step path: store the transformed key with the rows of every limb in ks_pass2's order (perm_row) and in
 // the transform word type (u32 words on the 32-bit path: the key is the largest stream ks_pass2 stages).
 static int ksk_finalize(const Tables &T, ckks_ksk *k) {
@@ -1394,6 +1404,7 @@ extern "C" int ckks_ksk_upload(ckks_ctx *ctx, const uint64_t *a, const uint64_t 
         rc = cuda_fail(cudaGetLastError(), "ksk h2d");
     // the key polynomials are RnsPoly values on the reference side (engine.rs:225-253): same canonical-word rule
     if (rc == CKKS_OK) rc = scan_reduced_pair_sync(T, ctx->L, ctx->L, k->a, k->b);
+    if (rc == CKKS_OK) rc = ksk_add_aux(T, k, k->a, k->b);  // from the coefficient-domain words
     if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, false);
     if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, false);
     if (rc == CKKS_OK) rc = ksk_finalize(T, k);
@@ -1420,8 +1431,12 @@ extern "C" int ckks_ksk_from_polys(const ckks_poly *a, const ckks_poly *b, ckks_
     cudaMemcpyAsync(k->a, a->d, words * 8, cudaMemcpyDeviceToDevice, S(T));
     cudaMemcpyAsync(k->b, b->d, words * 8, cudaMemcpyDeviceToDevice, S(T));
     int rc = CKKS_OK;
-    if (!a->ntt) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, false);
-    if (rc == CKKS_OK && !b->ntt) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, false);
+    // the auxiliary form is derived from coefficient-domain words
+    if (a->ntt) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, true);
+    if (rc == CKKS_OK && b->ntt) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, true);
+    if (rc == CKKS_OK) rc = ksk_add_aux(T, k, k->a, k->b);
+    if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->a, false);
+    if (rc == CKKS_OK) rc = ntt_inplace(T, ctx->L, ctx->L, k->b, false);
     if (rc == CKKS_OK) rc = ksk_finalize(T, k);
     if (rc != CKKS_OK) {
         ckks_ksk_free(k);
@@ -1741,11 +1756,14 @@ static size_t ks_chunk(const Tables &T, size_t L, size_t batch) {
 
 extern "C" size_t ckks_ks_chunk(const ckks_ctx *ctx, size_t batch) { return ok_ctx(ctx) ? ks_chunk(*ctx->T, ctx->L, batch) : 0; }
 
+#include "aux_ks.inl"
+
 // mul_ciphertexts_gadget (+ rescale_ciphertext) on coefficient-domain device inputs, four-step path.
 // o0/o1: [batch][L or L-1][N].
 static int fused_mul_relin(const Tables &T, size_t L, size_t batch, const u64 *a0, const u64 *a1, const u64 *b0,
                            const u64 *b1, const ckks_ksk *rlk, bool rescale, u64 *o0, u64 *o1) {
     if (!batch) return CKKS_OK;
+    if (rlk->aux_k && aux_wanted(T, L)) return fused_mul_relin_aux(T, L, batch, a0, a1, b0, b1, rlk, rescale, o0, o1);
     NvtxScope nvtx_call(rescale ? "ckks:mul_relin_rescale" : "ckks:mul_relin");
     const size_t n = T.n, cs_max = ks_chunk(T, L, batch);
     const size_t W = cs_max * L * n;

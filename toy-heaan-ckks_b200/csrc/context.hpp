@@ -55,6 +55,8 @@ struct Tables {
         size_t bytes = 0;
     } ws[8];
     std::mutex ws_mu;
+    struct AuxKs *aux = nullptr;  // auxiliary-basis key-switch tables (aux_ks.inl), built on first use
+    std::mutex aux_mu;
     std::mutex pipe_mu;  // the *_host entry points of one context tree take turns on the staging pipeline
     struct HostPipe *pipe = nullptr;
     int pipe_nin = 0;
@@ -82,6 +84,9 @@ struct ckks_ksk {
     size_t digits;  // == ctx->L, except for a limb-sharded key slice (all digits x this GPU's limbs)
     int perm_e;     // >= 0: rows of every limb stored permuted for ks_pass2 (kernels.cuh perm_row), -1: natural
     bool k32;       // words are u32 (32-bit word path: half the key bytes in HBM, L2 and shared memory)
+    // auxiliary-basis form (aux_ks.cuh): NTT_{p_k}(key[i][j] mod p_k), [k][j][i][N] u32; aux_k = 0: not present
+    u32 *xa, *xb;
+    int aux_k;
 };
 
 enum : uint32_t { MAGIC_CTX = 0x434b4358u, MAGIC_POLY = 0x434b504cu, MAGIC_KSK = 0x434b4b53u, MAGIC_LSHARD = 0x434b4c53u };

@@ -35,6 +35,9 @@ struct PassArgs {
     // automorphism(rot_src)[p] added, gathered on the fly: +-rot_src[p * rot_einv mod 2N] (poly.rs:515-538).
     const u64 *rot_src;  // [batch][L][N] coefficient domain
     u64 rot_einv;        // inverse of the (odd) Galois exponent modulo 2N
+    // IO32 (auxiliary-basis key-switch, aux_ks.cuh): the "limbs" of src are (ciphertext limb, auxiliary prime) pairs
+    // and the tables of limb l are those of prime (l / tab_div) % tab_mod
+    int tab_div, tab_mod;
 };
 
 // One pass: a 2^A-point transform along the strided dimension of a [2^A][ncols] limb, for a tile of
@@ -50,8 +53,9 @@ struct PassArgs {
 // FIXLOGN != 0: the ring degree is the compile-time constant 2^FIXLOGN (the launchers pick it for N = 2^16 and 2^14):
 // ncols and N fold into the load / store immediates, which removes the per-access 64-bit address arithmetic --
 // 10 % of the instructions of a 64-bit pass, 10 - 28 % of a 32-bit one (cuobjdump counts).
+// IO32: the words crossing the boundary are of the transform word type too (u32 in, u32 out).
 template <typename WD, int KIND, int A, int E, int C, int LAZY, bool PREMUL, bool POSTMUL, bool TRANSPOSE, bool MULTI = false, bool ADDROT = false,
-          int FIXLOGN = 0>
+          int FIXLOGN = 0, bool IO32 = false>
 __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a) {
     if (FIXLOGN) {
         a.ncols = 1u << (FIXLOGN > A ? FIXLOGN - A : 0);
@@ -63,8 +67,8 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
     constexpr int NT = C * GM::G;
     constexpr bool FWD = (KIND == XF_NEG_FWD || KIND == XF_CYC_FWD);
     constexpr bool SRC_INTERNAL = (KIND == XF_CYC_FWD || KIND == XF_NEG_INV);
-    typedef typename std::conditional<SRC_INTERNAL, WD, u64>::type SRC_T;
-    typedef typename std::conditional<TRANSPOSE, WD, u64>::type DST_T;
+    typedef typename std::conditional<SRC_INTERNAL || IO32, WD, u64>::type SRC_T;
+    typedef typename std::conditional<TRANSPOSE || IO32, WD, u64>::type DST_T;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     WD *sm = reinterpret_cast<WD *>(sm_raw);
     const SRC_T *src = reinterpret_cast<const SRC_T *>(a.src);
@@ -75,10 +79,11 @@ __global__ void __launch_bounds__(C *(1 << (A - E))) ntt_pass_kernel(PassArgs a)
     const size_t c0 = (size_t)blockIdx.x * C;
     const size_t base = ((size_t)blockIdx.z * a.L + limb) * a.N;
     const size_t dbase = ((size_t)blockIdx.z * a.dstL + (limb - a.dst_limb0)) * a.N;
-    const LimbConst m = a.lc[limb];
+    const int tl = IO32 ? (limb / a.tab_div) % a.tab_mod : limb;  // whose tables
+    const LimbConst m = a.lc[tl];
     const WD q = (WD)m.q, q2 = (WD)m.q2;
-    const TW *tab = reinterpret_cast<const TW *>(a.tab) + (size_t)limb * a.tab_stride;
-    const TW *elt = (PREMUL || POSTMUL) ? reinterpret_cast<const TW *>(a.elt) + (size_t)limb * a.N : nullptr;
+    const TW *tab = reinterpret_cast<const TW *>(a.tab) + (size_t)tl * a.tab_stride;
+    const TW *elt = (PREMUL || POSTMUL) ? reinterpret_cast<const TW *>(a.elt) + (size_t)tl * a.N : nullptr;
 
     WD v[1 << E];
     constexpr int lo_in = FWD ? GM::lo(0) : GM::lo(GM::NS - 1);
