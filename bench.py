@@ -691,6 +691,8 @@ def run_b200(args):
             "modmul_rate": rate * mm_ct,
             "imad_frac": (rate * mm_ct / imad_peak) if imad_peak else None,
             "binding_roof": "imad",
+            "note": "modmuls = the reference algorithm's count (SURVEY 8d); with the auxiliary-basis gadget product the library executes fewer, "
+                    "cheaper multiplies for the same result, so imad_frac (reference-algorithm modmul rate / measured 64-bit modmul peak) may exceed 1",
         }
         line["imad"]["step_frac"] = line["ctmult"]["imad_frac"]
     if args.prof and prof:
@@ -700,11 +702,23 @@ def run_b200(args):
         # algorithmic bytes per launch of the dominant kernel (DESIGN.md "Kernels"): an NTT pass is
         # half of a transform (16 N bytes per limb transform) -> 8 N per limb per pass;
         # elementwise kernels: the words they must read and write once.
-        per_launch = KERNEL_BYTES.get(name, lambda **kw: None)(n=n, l=l, batch=batch)
+        aux = "aux_mac" in prof  # the gadget product ran through the auxiliary 30-bit primes (csrc/aux_ks.cuh)
+        global AUX_K
+        AUX_K = _aux_k(logn, l, bits)
+        table = KERNEL_BYTES_AUX if aux else KERNEL_BYTES
+        per_launch = table.get(name, lambda **kw: None)(n=n, l=l, batch=batch)
         dur_s = ms * 1e-3 / cnt
         ach = per_launch / dur_s / 1e9 if per_launch else None
         kmm = {}
-        if op == "mul" and logn >= 8:
+        if aux:
+            mac_peak = ck.mac32_peak(local, 4096)
+            c, m = prof["aux_mac"]
+            macs = 2.0 * _cs_aux(n, l, batch, AUX_K) * AUX_K * l * l * n
+            kmm["aux_mac"] = {"mac32_per_launch": macs, "mac32_per_s": macs / (m * 1e-3 / c), "mac32_peak_per_s": mac_peak,
+                              "imad_frac": macs / (m * 1e-3 / c) / mac_peak if mac_peak else None,
+                              "peak_kind": "measured in this run (ckks_bench_mac32_peak: 32x32->64-bit multiply-accumulates, IMAD.WIDE.U32, every SM)"}
+            line["config"]["gadget_product"] = f"auxiliary basis: {AUX_K} NTT primes below 2^30, exact integer convolution + Garner CRT (csrc/aux_ks.cuh)"
+        elif op == "mul" and logn >= 8:
             for kname, fn in (("ks_pass1", _ks1_modmuls), ("ks_pass2_tma", _ks2_modmuls), ("ks_pass2", _ks2_modmuls)):
                 if kname in prof and imad_peak:
                     c, m = prof[kname]
@@ -725,6 +739,8 @@ def run_b200(args):
             "hbm_frac": hbm_frac,
             "imad_frac": top_imad,
             "imad_achieved_modmul_per_s": kmm.get(name, {}).get("modmul_per_s"),
+            "imad_achieved_mac32_per_s": kmm.get(name, {}).get("mac32_per_s"),
+            "imad_peak_mac32_per_s": kmm.get(name, {}).get("mac32_peak_per_s"),
             "imad_peak_modmul_per_s": imad_peak,
             "traffic": traffic,
             "traffic_source": traffic_src,
@@ -766,11 +782,12 @@ def run_b200(args):
 def ncu_traffic(kernel, config, op, batch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, read from the committed `ncu --set full`
     summary (profiles/*.json, newest round first) of the same configuration; (None, reason) if there is none."""
-    if not (config == "cfg4" and op == "mul" and batch >= _cs(65536, 24, batch) and KS_SCRATCH_MIB == 8192):
+    if not (config == "cfg4" and op == "mul" and batch >= 64 and KS_SCRATCH_MIB == 8192):
         return None, "no capture for this configuration"
     import glob
 
-    want = {"ks_pass2_tma": "ks_pass2_kernel", "ks_pass2": "ks_pass2_kernel", "ks_pass1": "ks_pass1_kernel"}.get(kernel)
+    want = {"ks_pass2_tma": "ks_pass2_kernel", "ks_pass2": "ks_pass2_kernel", "ks_pass1": "ks_pass1_kernel", "aux_mac": "aux_mac_kernel",
+            "aux_crt": "aux_crt_kernel"}.get(kernel)
     if not want:
         return None, "no capture of this kernel"
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_ks_kernels*final*.json")), reverse=True):
@@ -1032,6 +1049,50 @@ def _ks2(n, l, batch, w=8):
     cs = _cs(n, l, batch)
     return cs * l * (l - 1) * n * w + 2 * l * l * n * 8 + cs * l * n * 8 * 3 + 2 * cs * l * n * w
 
+
+def _aux_k(logn, l, bits):
+    """Auxiliary 30-bit primes of the exact multi-modular gadget product (csrc/aux_ks.inl aux_get): enough for
+    P > 2 * L * N * q_max^2."""
+    need = max(0, (l - 1).bit_length()) + logn + 2 * bits + 1.5
+    k = 1
+    while k * 29.99 < need:
+        k += 1
+    return k
+
+
+def _cs_aux(n, l, batch, k):
+    return max(1, min(batch, (KS_SCRATCH_MIB << 20) // (4 * k * l * n * 4)))  # x, rb, ra and the transposed intermediate
+
+
+AUX_K = 5  # set from the configuration in run_b200
+
+
+def _aux_bytes(what):
+    def f(n, l, batch):
+        k = AUX_K
+        cs = _cs_aux(n, l, batch, k)
+        if what == "mac":  # x once, both key halves once per launch, both sums out
+            return 4.0 * n * (cs * k * l + 2 * k * l * l + 2 * cs * l * k)
+        if what == "crt":  # two launches per chunk (last limb, then the others): the average of the two
+            return (4.0 * n * 2 * cs * l * k + 8.0 * n * 2 * cs * l + 8.0 * n * 2 * cs * (l - 1) + 8.0 * n * 4 * cs) / 2
+        if what == "pass":  # one 32-bit pass over cs * l * k rows: half of a transform's read-once + write-once (SURVEY 8d convention)
+            return 4.0 * n * cs * l * k
+        if what == "ks1":  # digits in (u64, once: the K-1 re-reads are L2 hits), first-pass rows out (u32)
+            return 8.0 * n * cs * l + 4.0 * n * cs * l * k
+        if what == "u64pass":
+            return 8.0 * n * l * cs
+        if what == "tensor":
+            return 8.0 * n * l * cs * 7
+        raise KeyError(what)
+    return f
+
+
+KERNEL_BYTES_AUX = {
+    "aux_mac": _aux_bytes("mac"), "aux_crt": _aux_bytes("crt"), "aux_inv_pass1": _aux_bytes("pass"), "aux_inv_pass2": _aux_bytes("pass"),
+    "aux_fwd_pass2": _aux_bytes("pass"), "ks_pass1": _aux_bytes("ks1"), "ntt_fwd_pass1": _aux_bytes("u64pass"),
+    "ntt_fwd_pass2": _aux_bytes("u64pass"), "ntt_inv_pass1": _aux_bytes("u64pass"), "ntt_inv_pass2": _aux_bytes("u64pass"),
+    "tensor": _aux_bytes("tensor"),
+}
 
 KERNEL_BYTES = {
     # an NTT pass is half of a limb transform (16 N bytes per transform, SURVEY 8d) -> 8 N per limb per pass

@@ -34,7 +34,6 @@ __global__ void aux_key_reduce_kernel(const u64 *__restrict__ src, u32 *__restri
 }
 
 struct AuxMacArgs {
-    const u32 *x;          // [cs][K][L][N]
     const u32 *kb, *ka;    // [K][L][L][N]
     u32 *rb, *ra;          // [cs][L][K][N]
     const LimbConst *alc;  // [K] auxiliary primes
@@ -42,20 +41,9 @@ struct AuxMacArgs {
     int jb;                // target limbs per CTA (blockDim.y); the grid's y counts (prime, j-block) pairs
     unsigned cs;
 };
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
-}
-// r[ct][j][k][e] = sum_i x[ct][k][i][e] * key[k][j][i][e] mod p_k for both key halves.
-// One thread: one NTT position e (threadIdx.x, 32 per CTA), one target limb j (threadIdx.y), one auxiliary prime.
-// Its 2 * L key words are loaded ONCE into registers and stay there while the CTA walks over every ciphertext of the
-// launch, so the key -- the largest operand, K * L^2 * N words per half -- crosses HBM once per launch and never
-// touches shared memory.  The x rows of the next two ciphertexts (L rows of 32 words each, shared by the L warps of
-// the CTA) are staged with cp.async into a double buffer laid out [ct][i / 4][e][4], so one 16-byte shared load
-// feeds four digits.  Products are < 2^60 (p < 2^30): 16 of them plus a carried residue fit a 64-bit accumulator, so
-// the accumulators are folded once, after the 16th digit.
-// L4 = ceil(L / 4) (compile time: the key registers); digits L .. 4 L4 - 1 are zero padding.
-constexpr int AUX_MAC_T = 2;  // ciphertexts per stage
+struct AuxMacMap {
+    alignas(64) unsigned char x[128];  // CUtensorMap of x seen as (cols N, rows L, slabs cs * K), box [L][32]
+};
 __device__ __forceinline__ void aux_mad(u64 &acc, u32 x, u32 k) {
 #ifdef __CUDA_ARCH__
     asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x), "r"(k));
@@ -63,21 +51,53 @@ __device__ __forceinline__ void aux_mad(u64 &acc, u32 x, u32 k) {
     acc += (u64)x * k;
 #endif
 }
+// r[ct][j][k][e] = sum_i x[ct][k][i][e] * key[k][j][i][e] mod p_k for both key halves.
+// One thread: one NTT position e (threadIdx.x, 32 per CTA), one target limb j (threadIdx.y), one auxiliary prime.
+// Its 2 * L key words are loaded ONCE into registers and stay there while the CTA walks over every ciphertext of the
+// launch, so the key -- the largest operand, K * L^2 * N words per half -- crosses HBM once per launch and never
+// touches shared memory.  The x rows of a ciphertext (L rows of 32 words, shared by the L warps of the CTA) arrive
+// as one TMA box per ciphertext, AUX_MAC_T ciphertexts per stage, two stages in flight; thread 0 issues the copies,
+// an mbarrier per stage signals their arrival, one __syncthreads per stage releases the buffer.
+// Products are < 2^60 (p < 2^30): 16 of them plus a carried residue fit a 64-bit accumulator, so the accumulators
+// are folded once, after the 16th digit.
+// L4 = ceil(L / 4) (compile time: the key registers); digits L .. 4 L4 - 1 have zero key words (their x rows in
+// shared memory are never written and may hold anything).
+#ifndef CKKS_AUX_MAC_T
+#define CKKS_AUX_MAC_T 4
+#endif
+constexpr int AUX_MAC_T = CKKS_AUX_MAC_T;  // ciphertexts per stage
 template <int L4>
-__global__ void __launch_bounds__(L4 <= 6 ? 768 : 512, 1) aux_mac_kernel(AuxMacArgs a) {
+__global__ void __launch_bounds__(L4 <= 6 ? 768 : 512, 1) aux_mac_kernel(AuxMacArgs a, const __grid_constant__ AuxMacMap map) {
     constexpr int T = AUX_MAC_T;
-    constexpr int STAGE = T * L4 * 32 * 4;  // words per stage
-    __shared__ __align__(16) u32 xs[2 * STAGE];
+    constexpr int TILE = 4 * L4 * 32;  // words per ciphertext tile
+    __shared__ __align__(128) u32 xs[2 * T * TILE];
+    __shared__ __align__(8) u64 bars[2];
     const int L = a.L, K = a.K;
     const size_t n = (size_t)1 << a.logn;
     const int tx = threadIdx.x, jy = threadIdx.y, jb = a.jb;
-    const int nthr = 32 * jb, tid = jy * 32 + tx;
-    const size_t e = (size_t)blockIdx.x * 32 + tx;
+    const int tid = jy * 32 + tx;
+    const int e0 = blockIdx.x * 32;
+    const size_t e = (size_t)e0 + tx;
     const int jblocks = (L + jb - 1) / jb;
     const int k = blockIdx.y / jblocks, j = (blockIdx.y % jblocks) * jb + jy;
     const bool live = j < L;
     const LimbConst m = a.alc[k];
-    for (int w = tid; w < 2 * STAGE; w += nthr) xs[w] = 0;  // the padding digits stay zero for good
+    const unsigned cs = a.cs;
+    const unsigned niter = (cs + T - 1) / T;
+    const unsigned tile_bytes = (unsigned)L * 32 * 4;
+    auto issue = [&](unsigned it) {  // thread 0: the boxes of stage `it`
+        u64 *bar = bars + (it & 1);
+        const unsigned c0 = it * T, nv = cs - c0 < (unsigned)T ? cs - c0 : (unsigned)T;
+        mbar_expect_tx(bar, nv * tile_bytes);
+        for (unsigned c = 0; c < nv; ++c) tma_load_tile(xs + ((it & 1) * T + c) * TILE, map.x, e0, (int)((c0 + c) * K + k), bar);
+    };
+    if (tid == 0) {
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        issue(0);
+        if (niter > 1) issue(1);
+    }
     u32 kb[4 * L4], ka[4 * L4];
     {   // (volatile: one running pointer instead of 8 L4 addresses held in registers at once)
         const u32 *pb = a.kb + (((size_t)k * L + (live ? j : 0)) * L) * n + e;
@@ -95,126 +115,146 @@ __global__ void __launch_bounds__(L4 <= 6 ? 768 : 512, 1) aux_mac_kernel(AuxMacA
             pa += n;
         }
     }
-    __syncthreads();
-    const unsigned cs = a.cs;
-    const unsigned niter = (cs + T - 1) / T;
-    const size_t xct = (size_t)K * L * n;                  // words between ciphertexts in x
-    const u32 *px = a.x + ((size_t)k * L) * n + e;         // row i of ciphertext ct: px + ct * xct + i * n
-    const size_t oct = (size_t)L * K * n;                  // words between ciphertexts in r
-    const size_t o0 = ((size_t)(live ? j : 0) * K + k) * n + e;
-    // thread (tx, jy) stages word tx of rows jy, jy + jb, .. of ciphertexts T*it .. T*it+T-1 (clamped to the last one)
-    auto stage = [&](unsigned it, int buf) {
-#pragma unroll
-        for (int c = 0; c < T; ++c) {
-            unsigned ct = it * T + c;
-            ct = ct < cs ? ct : cs - 1;
-            for (int i = jy; i < L; i += jb)
-                cp_async4(&xs[buf * STAGE + (((c * L4 + (i >> 2)) * 32 + tx) << 2) + (i & 3)], px + (size_t)ct * xct + (size_t)i * n);
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-    };
-    stage(0, 0);
+    __syncthreads();  // the barriers are initialised
+    const size_t oct = (size_t)L * K * n;  // words between ciphertexts in r
+    u32 *prb = a.rb + ((size_t)(live ? j : 0) * K + k) * n + e;
+    u32 *pra = a.ra + ((size_t)(live ? j : 0) * K + k) * n + e;
     for (unsigned it = 0; it < niter; ++it) {
         const int buf = it & 1;
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        __syncthreads();  // stage `it` is visible, and everybody is done with the other buffer
-        if (it + 1 < niter) stage(it + 1, buf ^ 1);
+        mbar_wait(bars + buf, (it >> 1) & 1);
         if (live) {
 #pragma unroll
             for (int c = 0; c < T; ++c) {
-                u64 sb = 0, sa = 0;
+                if (it * T + c < cs) {
+                    const u32 *xc = xs + (buf * T + c) * TILE + tx;
+                    u64 sb = 0, sa = 0;
 #pragma unroll
-                for (int i4 = 0; i4 < L4; ++i4) {
-                    const uint4 xv = *reinterpret_cast<const uint4 *>(&xs[buf * STAGE + (((c * L4 + i4) * 32 + tx) << 2)]);
-                    aux_mad(sb, xv.x, kb[4 * i4]);
-                    aux_mad(sa, xv.x, ka[4 * i4]);
-                    aux_mad(sb, xv.y, kb[4 * i4 + 1]);
-                    aux_mad(sa, xv.y, ka[4 * i4 + 1]);
-                    aux_mad(sb, xv.z, kb[4 * i4 + 2]);
-                    aux_mad(sa, xv.z, ka[4 * i4 + 2]);
-                    aux_mad(sb, xv.w, kb[4 * i4 + 3]);
-                    aux_mad(sa, xv.w, ka[4 * i4 + 3]);
-                    if (i4 == 3 && L4 > 4) {
-                        sb = barrett_word(sb, m);
-                        sa = barrett_word(sa, m);
+                    for (int i = 0; i < 4 * L4; ++i) {
+                        const u32 x = xc[i * 32];
+                        aux_mad(sb, x, kb[i]);
+                        aux_mad(sa, x, ka[i]);
+                        if (i == 15 && L4 > 4) {
+                            sb = barrett_word(sb, m);
+                            sa = barrett_word(sa, m);
+                        }
                     }
-                }
-                const unsigned ct = it * T + c;
-                if (ct < cs) {
-                    a.rb[o0 + (size_t)ct * oct] = (u32)barrett_word(sb, m);
-                    a.ra[o0 + (size_t)ct * oct] = (u32)barrett_word(sa, m);
+                    *prb = (u32)barrett_word(sb, m);
+                    *pra = (u32)barrett_word(sa, m);
+                    prb += oct;
+                    pra += oct;
                 }
             }
         }
+        __syncthreads();  // everybody is done with this buffer
+        if (tid == 0 && it + 2 < niter) issue(it + 2);
     }
 }
 
 constexpr int AUX_MAX_K = 8;
+// Constants of the auxiliary basis, passed by value (kernel parameters live in the constant bank: the unrolled Garner
+// chain reads them with immediate offsets, no loads).
+struct AuxCrtConst {
+    u32 p[AUX_MAX_K];                      // auxiliary primes
+    u32 half[AUX_MAX_K];                   // mixed-radix digits of floor(P / 2)
+    tw32_t inv[AUX_MAX_K * AUX_MAX_K];     // inv[m * AUX_MAX_K + k] = p_m^-1 mod p_k, m < k
+};
 struct AuxCrtArgs {
-    const u32 *rb, *ra;    // [cs][L][K][N] residues of S_j (coefficient domain)
-    const u64 *add0, *add1;  // [cs][L][N] coefficient domain addends (d0, d1) or null
-    u64 *out0, *out1;      // [cs][L][N]
-    const LimbConst *lc;   // [L] ciphertext primes
-    const LimbConst *alc;  // [K] auxiliary primes
-    const tw32_t *inv;     // [K][K]: inv[m * K + k] = p_m^-1 mod p_k, m < k
-    const tw_t *mix;       // [L][K]: prod_{m<k} p_m mod q_j
-    const u64 *pmod;       // [L]: P mod q_j
-    const u32 *half;       // [K]: mixed-radix digits of floor(P / 2)
+    const u32 *rb, *ra;      // [cs][L][K][N] residues of S_j (coefficient domain)
+    const u64 *add0, *add1;  // [cs][L][N] coefficient domain addends (d0, d1)
+    u64 *out0, *out1;        // [cs][outL][N]; limb j lands in slot j - j0
+    const u64 *last0, *last1;  // RESCALE: [cs][N] the finished last limb of c0 / c1
+    const LimbConst *lc;     // [L] ciphertext primes
+    const tw_t *mix;         // [L][K]: prod_{m<k} p_m mod q_j
+    const u64 *pmod;         // [L]: P mod q_j
+    const tw_t *ql;          // RESCALE: [L] q_last^-1 mod q_j
     int L, K, logn;
-    size_t total;          // cs * L * N
+    int j0, nj, outL;        // target limbs j0 .. j0 + nj - 1 of every ciphertext (grid y = cs * nj)
 };
 // Garner mixed-radix digits of the residues (0 <= v_k < p_k, value = sum_k v_k prod_{m<k} p_m in [0, P)), sign by
 // comparison with floor(P/2), image mod q_j: sum_k v_k (prod_{m<k} p_m mod q_j) - [negative] (P mod q_j); then the
-// addend (d0 / d1 in the coefficient domain).  One thread per (ciphertext, target limb, coefficient).
-__global__ void aux_crt_kernel(AuxCrtArgs a) {
+// addend (d0 / d1 in the coefficient domain), and with RESCALE the epilogue of rescale_into (poly.rs:214-225):
+// (c_j - c_last mod q_j) * q_last^-1 mod q_j.  grid = (N / (256 EPT), cs * nj); a thread owns EPT coefficients
+// (independent Garner chains to overlap) of one (ciphertext, target limb); everything that depends only on the
+// limb is loaded once per thread.
+template <int K, int EPT, bool RESCALE>
+__global__ void __launch_bounds__(256) aux_crt_kernel(AuxCrtArgs a, const __grid_constant__ AuxCrtConst cc) {
     const size_t n = (size_t)1 << a.logn;
-    const int L = a.L, K = a.K;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.total; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t e = t & (n - 1), cj = t >> a.logn;  // cj = ct * L + j
-        const int j = (int)(cj % L);
-        const LimbConst mq = a.lc[j];
-        const tw_t *mix = a.mix + (size_t)j * K;
-        const size_t ro = cj * K * n + e;
+    const int L = a.L;
+    const size_t ct = blockIdx.y / a.nj;
+    const int j = a.j0 + (int)(blockIdx.y % a.nj);
+    const LimbConst mq = a.lc[j];
+    tw_t mix[K];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const u32 *r = (h ? a.ra : a.rb) + ro;
-            // digits, sign and image mod q_j
-            u32 v[AUX_MAX_K];
+    for (int k = 1; k < K; ++k) mix[k] = ldg_tw(a.mix + (size_t)j * K + k);
+    const u64 pmod = a.pmod[j];
+    tw_t ql;
+    if (RESCALE) ql = ldg_tw(a.ql + j);
+    const size_t e0 = (size_t)blockIdx.x * (256 * EPT) + threadIdx.x;
+    const size_t ro = (ct * L + j) * K * n + e0;
+    const size_t ao = (ct * L + j) * n + e0;
+    const size_t oo = (ct * a.outL + (j - a.j0)) * n + e0;
 #pragma unroll
-            for (int k = 0; k < AUX_MAX_K; ++k) {
-                if (k < K) {
-                    const u32 p = (u32)a.alc[k].q;
-                    u32 x = r[(size_t)k * n];
+    for (int h = 0; h < 2; ++h) {
+        const u32 *r = (h ? a.ra : a.rb) + ro;
+        u32 v[EPT][K];
 #pragma unroll
-                    for (int mi = 0; mi < AUX_MAX_K; ++mi) {
-                        if (mi < k) {
-                            const u32 vm = csub(v[mi], p);  // auxiliary primes lie in (2^29, 2^30): v_m < p_m < 2 p_k
-                            const u32 d = x >= vm ? x - vm : x + p - vm;
-                            x = shoup(d, ldg_tw(a.inv + mi * K + k), p);
-                        }
-                    }
-                    v[k] = x;
+        for (int u = 0; u < EPT; ++u)
+#pragma unroll
+            for (int k = 0; k < K; ++k) v[u][k] = r[(size_t)k * n + u * 256];
+        u64 addv[EPT], lastv[EPT];
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
+            addv[u] = (h ? a.add1 : a.add0)[ao + u * 256];
+            if (RESCALE) lastv[u] = (h ? a.last1 : a.last0)[ct * n + e0 + u * 256];
+        }
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+            const u32 p = cc.p[k];
+#pragma unroll
+            for (int mi = 0; mi < k; ++mi) {
+                const tw32_t iv = cc.inv[mi * AUX_MAX_K + k];
+#pragma unroll
+                for (int u = 0; u < EPT; ++u) {
+                    const u32 vm = csub(v[u][mi], p);  // auxiliary primes lie in (2^29, 2^30): v_m < p_m < 2 p_k
+                    const u32 x = v[u][k];
+                    const u32 d = x >= vm ? x - vm : x + p - vm;
+                    v[u][k] = shoup(d, iv, p);
                 }
             }
+        }
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
             bool neg = false, decided = false;
 #pragma unroll
-            for (int k = AUX_MAX_K - 1; k >= 0; --k) {
-                if (k < K && !decided) {
-                    const u32 hk = a.half[k];
-                    if (v[k] != hk) {
-                        neg = v[k] > hk;
-                        decided = true;
-                    }
+            for (int k = K - 1; k >= 0; --k) {
+                if (!decided && v[u][k] != cc.half[k]) {
+                    neg = v[u][k] > cc.half[k];
+                    decided = true;
                 }
             }
-            u64 y = barrett_word((u64)v[0], mq);
+            u64 y = barrett_word((u64)v[u][0], mq);
 #pragma unroll
-            for (int k = 1; k < AUX_MAX_K; ++k)
-                if (k < K) y = addmod(y, shoup((u64)v[k], ldg_tw(mix + k), mq.q), mq.q);
-            if (neg) y = submod(y, a.pmod[j], mq.q);
-            const u64 *add = h ? a.add1 : a.add0;
-            if (add) y = addmod(y, add[t], mq.q);
-            (h ? a.out1 : a.out0)[t] = y;
+            for (int k = 1; k < K; ++k) y = addmod(y, shoup((u64)v[u][k], mix[k], mq.q), mq.q);
+            if (neg) y = submod(y, pmod, mq.q);
+            y = addmod(y, addv[u], mq.q);
+            if (RESCALE) y = shoup(submod(y, barrett_word(lastv[u], mq), mq.q), ql, mq.q);
+            (h ? a.out1 : a.out0)[oo + u * 256] = y;
         }
     }
+}
+
+// Throughput of the multiply-accumulate aux_mac_kernel is made of: 32 x 32 -> 64-bit products added into 64-bit
+// accumulators (IMAD.WIDE.U32), eight independent chains per thread, every SM busy (ckks_bench_mac32_peak).
+__global__ void mac32_peak_kernel(u64 *out, int iters, u32 w) {
+    u64 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (u64)threadIdx.x * 977 + k * 31 + blockIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) aux_mad(v[k], (u32)v[k], w);
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s ^= v[k];
+    if (s == 0x123456789abcdefull) out[0] = s;
 }

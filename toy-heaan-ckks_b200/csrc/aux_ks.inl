@@ -8,14 +8,13 @@
 struct AuxKs {
     std::shared_ptr<Tables> X;  // tables of the auxiliary primes (32-bit word path, Harvey lazy)
     int K = 0;
-    tw32_t *d_inv = nullptr;  // [K][K] p_m^-1 mod p_k
     tw_t *d_mix = nullptr;    // [L][K] prod_{m<k} p_m mod q_j
     u64 *d_pmod = nullptr;    // [L] P mod q_j
-    u32 *d_half = nullptr;    // [K] mixed-radix digits of floor(P/2)
+    AuxCrtConst cc;           // primes, Garner inverses and floor(P/2) digits as a kernel parameter
 };
 static void destroy_aux(AuxKs *a) {
     if (!a) return;
-    for (void *p : {(void *)a->d_inv, (void *)a->d_mix, (void *)a->d_pmod, (void *)a->d_half})
+    for (void *p : {(void *)a->d_mix, (void *)a->d_pmod})
         if (p) cudaFree(p);
     delete a;
 }
@@ -90,10 +89,14 @@ static int aux_get(const Tables &Tc, AuxKs **out) {
     }
     std::vector<u64> half64 = half_q_digits(primes);
     std::vector<u32> half(half64.begin(), half64.end());
-    TRY(upload_vec(&A->d_inv, inv));
+    memset(&A->cc, 0, sizeof(A->cc));
+    for (int k = 0; k < K; ++k) {
+        A->cc.p[k] = (u32)primes[k];
+        A->cc.half[k] = half[k];
+        for (int m = 0; m < k; ++m) A->cc.inv[m * AUX_MAX_K + k] = inv[(size_t)m * K + k];
+    }
     TRY(upload_vec(&A->d_mix, mix));
     TRY(upload_vec(&A->d_pmod, pmod));
-    TRY(upload_vec(&A->d_half, half));
     T.aux = A.release();
     *out = T.aux;
     return CKKS_OK;
@@ -210,8 +213,9 @@ static size_t aux_chunk(const Tables &T, const AuxKs &A, size_t L, size_t batch)
     if (c > 32768) c = 32768;
     return c < batch ? c : batch;
 }
+// out0 / out1: [cs][L][N], or with `last` ([2][cs][N] scratch) the rescaled [cs][L-1][N].
 static int aux_keyswitch(const Tables &T, const AuxKs &A, size_t L, size_t cs, const u64 *digits, const ckks_ksk *key, const u64 *add0,
-                         const u64 *add1, u32 *scr, u64 *out0, u64 *out1) {
+                         const u64 *add1, u32 *scr, u64 *out0, u64 *out1, u64 *last) {
     const Tables &X = *A.X;
     const size_t n = T.n, K = (size_t)A.K;
     const size_t W = cs * K * L * n;
@@ -241,7 +245,12 @@ static int aux_keyswitch(const Tables &T, const AuxKs &A, size_t L, size_t cs, c
     TRY(aux_pass(T, A, AUX_FWD2_NOPRE, cs, K * L, (int)L, xs, xs));  // in place: a CTA owns its column tile
     {
         AuxMacArgs m;
-        m.x = xs;
+        AuxMacMap map;
+        memset(&map, 0, sizeof(map));
+        if (!make_tile_map(map.x, xs, 4, n, L, cs * K, 32)) {
+            g_err = "auxiliary-basis key-switch: cannot encode the TMA descriptor of the digit transforms";
+            return CKKS_CUDA_ERROR;
+        }
         m.kb = key->xb;
         m.ka = key->xa;
         m.rb = rb;
@@ -257,7 +266,7 @@ static int aux_keyswitch(const Tables &T, const AuxKs &A, size_t L, size_t cs, c
         dim3 g((unsigned)(n / 32), (unsigned)(K * jblocks)), blk(32, (unsigned)m.jb);
         switch ((L + 3) / 4) {
 #define AUX_MAC_CASE(L4v) \
-    case L4v: KL("aux_mac", (aux_mac_kernel<L4v><<<g, blk, 0, s>>>(m))); break
+    case L4v: KL("aux_mac", (aux_mac_kernel<L4v><<<g, blk, 0, s>>>(m, map))); break
             AUX_MAC_CASE(1);
             AUX_MAC_CASE(2);
             AUX_MAC_CASE(3);
@@ -275,24 +284,71 @@ static int aux_keyswitch(const Tables &T, const AuxKs &A, size_t L, size_t cs, c
         TRY(aux_pass(T, A, AUX_INV1, cs, L * K, 1, rt, r));
     }
     AuxCrtArgs c;
+    memset(&c, 0, sizeof(c));
     c.rb = rb;
     c.ra = ra;
     c.add0 = add0;
     c.add1 = add1;
-    c.out0 = out0;
-    c.out1 = out1;
     c.lc = T.d_lc;
-    c.alc = X.d_lc;
-    c.inv = A.d_inv;
     c.mix = A.d_mix;
     c.pmod = A.d_pmod;
-    c.half = A.d_half;
     c.L = (int)L;
     c.K = (int)K;
     c.logn = T.logn;
-    c.total = cs * L * n;
-    KL("aux_crt", (aux_crt_kernel<<<ew_grid(c.total), 256, 0, s>>>(c)));
-    return CKKS_OK;
+#ifndef CKKS_AUX_CRT_EPT
+#define CKKS_AUX_CRT_EPT 4
+#endif
+    constexpr int EPT = CKKS_AUX_CRT_EPT;  // N >= 2^8 on this path; N = 2^8, 2^9 use one coefficient per thread
+    auto launch = [&](bool rs, int ept) -> int {
+        dim3 g((unsigned)(n / (256 * (size_t)ept)), (unsigned)(cs * c.nj));
+#define AUX_CRT_CASE(Kv)                                                                                      \
+    case Kv:                                                                                                  \
+        if (rs) {                                                                                             \
+            if (ept == EPT) KL("aux_crt", (aux_crt_kernel<Kv, EPT, true><<<g, 256, 0, s>>>(c, A.cc)));        \
+            else KL("aux_crt", (aux_crt_kernel<Kv, 1, true><<<g, 256, 0, s>>>(c, A.cc)));                     \
+        } else {                                                                                              \
+            if (ept == EPT) KL("aux_crt", (aux_crt_kernel<Kv, EPT, false><<<g, 256, 0, s>>>(c, A.cc)));       \
+            else KL("aux_crt", (aux_crt_kernel<Kv, 1, false><<<g, 256, 0, s>>>(c, A.cc)));                    \
+        }                                                                                                     \
+        break
+        switch (K) {
+            AUX_CRT_CASE(2);
+            AUX_CRT_CASE(3);
+            AUX_CRT_CASE(4);
+            AUX_CRT_CASE(5);
+            AUX_CRT_CASE(6);
+            AUX_CRT_CASE(7);
+            AUX_CRT_CASE(8);
+#undef AUX_CRT_CASE
+            default: return CKKS_UNSUPPORTED;
+        }
+        return CKKS_OK;
+    };
+    const int ept = n >= 256 * EPT ? EPT : 1;
+    if (!last) {  // every limb, no rescale
+        c.out0 = out0;
+        c.out1 = out1;
+        c.j0 = 0;
+        c.nj = (int)L;
+        c.outL = (int)L;
+        return launch(false, ept);
+    }
+    // rescale_ciphertext fused in: the last limb first, then the others with the rescale epilogue
+    c.out0 = last;
+    c.out1 = last + cs * n;
+    c.j0 = (int)L - 1;
+    c.nj = 1;
+    c.outL = 1;
+    TRY(launch(false, ept));
+    c.last0 = last;
+    c.last1 = last + cs * n;
+    c.ql = T.d_qlinv + (L - 1) * T.L;
+    c.out0 = out0;
+    c.out1 = out1;
+    c.j0 = 0;
+    c.nj = (int)L - 1;
+    c.outL = (int)L - 1;
+    return launch(true, ept);
 }
 
 static int rescale_dev(const Tables &T, size_t L, size_t batch, const u64 *src, u64 *dst);
@@ -306,7 +362,7 @@ static int fused_mul_relin_aux(const Tables &T, size_t L, size_t batch, const u6
     NvtxScope nvtx_call(rescale ? "ckks:mul_relin_rescale" : "ckks:mul_relin");
     const size_t n = T.n, cs_max = aux_chunk(T, A, L, batch);
     const size_t W = cs_max * L * n;
-    u64 *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr, *TMP = nullptr, *SCR = nullptr;
+    u64 *A0 = nullptr, *A1 = nullptr, *B0 = nullptr, *B1 = nullptr, *TMP = nullptr, *SCR = nullptr, *LAST = nullptr;
     std::lock_guard<std::mutex> ws_lock(const_cast<Tables &>(T).ws_mu);
     int rc = ws_get(T, WS_A0, W * 8, &A0);
     if (rc == CKKS_OK) rc = ws_get(T, WS_A1, W * 8, &A1);
@@ -314,6 +370,7 @@ static int fused_mul_relin_aux(const Tables &T, size_t L, size_t batch, const u6
     if (rc == CKKS_OK) rc = ws_get(T, WS_B1, W * 8, &B1);
     if (rc == CKKS_OK) rc = ws_get(T, WS_TMP, W * 8, &TMP);
     if (rc == CKKS_OK) rc = ws_get(T, WS_SCR, 4 * cs_max * (size_t)A.K * L * n * 4, &SCR);
+    if (rc == CKKS_OK && rescale) rc = ws_get(T, WS_LAST, 2 * cs_max * n * 8, &LAST);
     const size_t outL = rescale ? L - 1 : L;
     for (size_t s0 = 0; s0 < batch && rc == CKKS_OK; s0 += cs_max) {
         const size_t cs = batch - s0 < cs_max ? batch - s0 : cs_max;
@@ -337,11 +394,7 @@ static int fused_mul_relin_aux(const Tables &T, size_t L, size_t batch, const u6
             TRY(run_pass(T, P_INV2, sp, A1, TMP));
             TRY(run_pass(T, P_INV1, sp, TMP, A1));
             u64 *d0 = o0 + s0 * outL * n, *d1 = o1 + s0 * outL * n;
-            if (!rescale) return aux_keyswitch(T, A, L, cs, B1, rlk, A0, A1, reinterpret_cast<u32 *>(SCR), d0, d1);
-            TRY(aux_keyswitch(T, A, L, cs, B1, rlk, A0, A1, reinterpret_cast<u32 *>(SCR), B0, TMP));
-            TRY(rescale_dev(T, L, cs, B0, d0));  // poly.rs:214-225
-            TRY(rescale_dev(T, L, cs, TMP, d1));
-            return CKKS_OK;
+            return aux_keyswitch(T, A, L, cs, B1, rlk, A0, A1, reinterpret_cast<u32 *>(SCR), d0, d1, rescale ? LAST : nullptr);
         };
         rc = step();
     }

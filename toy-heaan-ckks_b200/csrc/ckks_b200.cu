@@ -23,8 +23,8 @@
 #include "tables_host.hpp"
 #include "encoder.cuh"
 #include "crt_wide.cuh"
-#include "aux_ks.cuh"
 #include "kernels.cuh"
+#include "aux_ks.cuh"
 
 // -------------------------------------------------------------------------------------------------
 // errors, launch accounting
@@ -2381,6 +2381,29 @@ extern "C" double ckks_bench_modmul_peak(int device, int iters) {
     modmul_peak_kernel<<<blocks, threads>>>(d, 16, q, t);
     cudaEventRecord(e0);
     KLV("modmul_peak", (modmul_peak_kernel<<<blocks, threads>>>(d, iters, q, t)));
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess || ms <= 0) return 0.0;
+    return (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
+}
+
+extern "C" double ckks_bench_mac32_peak(int device, int iters) {
+    if (ckks_device_count() <= device) return 0.0;
+    if (cudaSetDevice(device) != cudaSuccess) return 0.0;
+    u64 *d;
+    if (cudaMalloc((void **)&d, 64) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = 148 * 8, threads = 256;
+    mac32_peak_kernel<<<blocks, threads>>>(d, 16, 0x3ffffff1u);
+    cudaEventRecord(e0);
+    KLV("mac32_peak", (mac32_peak_kernel<<<blocks, threads>>>(d, iters, 0x3ffffff1u)));
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms = 0;
