@@ -313,3 +313,49 @@ extern "C" int emul_arena_chain(int levels, int passes, uint64_t unit_bytes) {
     }
     return segs_after_first;
 }
+
+// ---- auxiliary-basis gadget product (csrc/aux_crt.cuh): constants and the per-coefficient reconstruction ----------------
+#include "../../toy-heaan-ckks_b200/csrc/aux_crt.cuh"
+// The auxiliary primes the library picks for (n, moduli): returns K and writes primes[0..K-1] (0: not possible).
+extern "C" int emul_aux_primes(uint64_t n, const uint64_t *moduli, int l, uint64_t *primes) {
+    int logn = 0;
+    while (((u64)1 << logn) < n) ++logn;
+    AuxHost H;
+    if (!aux_host_build(n, logn, std::vector<u64>(moduli, moduli + l), H)) return 0;
+    for (int k = 0; k < H.K; ++k) primes[k] = H.primes[k];
+    return H.K;
+}
+template <int K>
+static void crt_all(const AuxHost &H, const std::vector<LimbConst> &lc, int l, uint64_t count, const uint64_t *res, uint64_t *out, int *negs) {
+    for (int j = 0; j < l; ++j)
+        for (uint64_t e = 0; e < count; ++e) {
+            u32 v[K];
+            for (int k = 0; k < K; ++k) v[k] = (u32)res[((size_t)j * K + k) * count + e];
+            aux_garner<K>(v, H.cc);
+            const bool neg = aux_negative<K>(v, H.cc);
+            out[(size_t)j * count + e] = aux_image<K>(v, neg, H.mix.data() + (size_t)j * K, H.pmod[j], lc[j]);
+            if (negs) negs[(size_t)j * count + e] = neg ? 1 : 0;
+        }
+}
+// res: [l][K][count] residues mod the auxiliary primes of one integer per (j, e); out: [l][count] its centred value
+// mod moduli[j] (the device code of aux_crt_kernel, element by element); negs (optional): the sign decisions.
+extern "C" int emul_aux_crt(uint64_t n, const uint64_t *moduli, int l, uint64_t count, const uint64_t *res, uint64_t *out, int *negs) {
+    int logn = 0;
+    while (((u64)1 << logn) < n) ++logn;
+    std::vector<u64> mod(moduli, moduli + l), psi(l, 1);
+    AuxHost H;
+    if (!aux_host_build(n, logn, mod, H)) return -1;
+    ht::HostTables T;
+    ht::build_host_tables(1, 0, 1, 0, 0, mod, psi, T, false);
+    switch (H.K) {
+        case 2: crt_all<2>(H, T.lc, l, count, res, out, negs); break;
+        case 3: crt_all<3>(H, T.lc, l, count, res, out, negs); break;
+        case 4: crt_all<4>(H, T.lc, l, count, res, out, negs); break;
+        case 5: crt_all<5>(H, T.lc, l, count, res, out, negs); break;
+        case 6: crt_all<6>(H, T.lc, l, count, res, out, negs); break;
+        case 7: crt_all<7>(H, T.lc, l, count, res, out, negs); break;
+        case 8: crt_all<8>(H, T.lc, l, count, res, out, negs); break;
+        default: return -2;
+    }
+    return H.K;
+}

@@ -178,3 +178,92 @@ def test_device_arena_bookkeeping(emul):
         assert peak.value <= 512 << 20
     assert emul.emul_arena_chain(24, 4, 128 << 20) == 0
     assert emul.emul_arena_chain(24, 4, (128 << 20) + 4096) == 0
+
+
+def _negacyclic(a, b, n):
+    """Product of two integer polynomials modulo X^n + 1 (Python integers, schoolbook)."""
+    out = [0] * n
+    for i, ai in enumerate(a):
+        if ai == 0:
+            continue
+        for j, bj in enumerate(b):
+            k = i + j
+            if k < n:
+                out[k] += ai * bj
+            else:
+                out[k - n] -= ai * bj
+    return out
+
+
+@pytest.mark.parametrize("n,bits,l,extreme", [(256, 61, 3, False), (256, 61, 3, True), (256, 40, 4, False), (512, 62, 2, True)])
+def test_auxiliary_basis_gadget_product_is_exact(emul, orc, n, bits, l, extreme):
+    """The algorithm of csrc/aux_ks.cuh on the CPU, with the library's own constants and device arithmetic
+    (csrc/aux_crt.cuh compiled by g++) and the emulated 32-bit four-step transforms: sum_i alpha_i (*) key[i][j] computed
+    in the auxiliary 30-bit primes and reconstructed by Garner equals the integer negacyclic sums reduced mod q_j --
+    including the largest words the reference admits (every digit and key word = q - 1), which sit at the edge of the
+    bound the number of auxiliary primes is derived from."""
+    emul.emul_aux_primes.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_uint64)]
+    emul.emul_aux_crt.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_int)]
+    moduli = [int(q) for q in orc.generate_primes(bits, l, n)]
+    mod_arr = (C.c_uint64 * l)(*moduli)
+    primes_arr = (C.c_uint64 * 8)()
+    K = emul.emul_aux_primes(n, mod_arr, l, primes_arr)
+    primes = [int(primes_arr[k]) for k in range(K)]
+    assert K >= 2 and all((1 << 29) < p < (1 << 30) and (p - 1) % (2 * n) == 0 for p in primes)
+    big_p = 1
+    for p in primes:
+        big_p *= p
+    assert big_p > 2 * l * n * max(moduli) ** 2, "the centred range of P covers every coefficient of the integer sums"
+    rng = random.Random(77 + n + bits)
+    if extreme:
+        digits = [[moduli[i] - 1] * n for i in range(l)]
+        keys = [[[moduli[j] - 1] * n for j in range(l)] for _ in range(l)]
+        if l > 1:  # mixed signs of the wrapped terms too
+            keys[1] = [[(moduli[j] - 1) if (t % 2 == 0) else 0 for t in range(n)] for j in range(l)]
+    else:
+        digits = [[rng.randrange(moduli[i]) for _ in range(n)] for i in range(l)]
+        keys = [[[rng.randrange(moduli[j]) for _ in range(n)] for j in range(l)] for _ in range(l)]
+    # the integer sums S_j and what the reference's per-limb arithmetic gives: S_j mod q_j
+    sums = []
+    for j in range(l):
+        s = [0] * n
+        for i in range(l):
+            s = [x + y for x, y in zip(s, _negacyclic(digits[i], keys[i][j], n))]
+        sums.append(s)
+    assert max(abs(c) for s in sums for c in s) < big_p // 2
+
+    def ntt(words, p, inverse):
+        buf = np.array(words, dtype=np.uint64)
+        rc = emul.emul_ntt_4step32(n, p, buf.ctypes.data_as(C.POINTER(C.c_uint64)), int(inverse), 0)
+        assert rc == 0
+        return buf
+
+    res = np.zeros((l, K, n), dtype=np.uint64)
+    for k, p in enumerate(primes):
+        x = [ntt([d % p for d in digits[i]], p, False) for i in range(l)]
+        for j in range(l):
+            acc = np.zeros(n, dtype=np.uint64)
+            for i in range(l):
+                kk = ntt([w % p for w in keys[i][j]], p, False)
+                acc = (acc + (x[i] * kk) % np.uint64(p)) % np.uint64(p)  # products below 2^60
+            res[j, k] = ntt(acc.tolist(), p, True)
+            assert all(int(res[j, k, e]) == sums[j][e] % p for e in range(0, n, 37)), "residues of the integer sum"
+    out = np.zeros((l, n), dtype=np.uint64)
+    negs = np.zeros((l, n), dtype=np.int32)
+    got_k = emul.emul_aux_crt(n, mod_arr, l, n, res.ctypes.data_as(C.POINTER(C.c_uint64)), out.ctypes.data_as(C.POINTER(C.c_uint64)),
+                              negs.ctypes.data_as(C.POINTER(C.c_int)))
+    assert got_k == K
+    for j in range(l):
+        assert [int(v) for v in out[j]] == [c % moduli[j] for c in sums[j]], f"limb {j}"
+        assert [int(v) for v in negs[j]] == [1 if c < 0 else 0 for c in sums[j]]
+    # and the same words come out of the oracle's NTT-domain arithmetic mod q_j
+    ob = orc.Basis(n, moduli)
+    for j in range(l):
+        want = np.zeros(n, dtype=np.uint64)
+        for i in range(l):
+            a = np.array([[d % q for d in digits[i]] for q in moduli], dtype=np.uint64)
+            b = np.array([[w if jj == j else 0 for w in keys[i][jj]] for jj, q in enumerate(moduli)], dtype=np.uint64)
+            prod = ob.mul(a, b)
+            want = (want.astype(object) + prod[j].astype(object)) % moduli[j]
+        assert [int(v) for v in out[j]] == [int(v) for v in want], f"oracle, limb {j}"

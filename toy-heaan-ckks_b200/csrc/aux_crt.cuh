@@ -1,0 +1,110 @@
+// aux_crt.cuh -- the per-coefficient arithmetic of the auxiliary-basis gadget product's reconstruction (aux_ks.cuh),
+// and the host-side construction of its constants.  No CUDA runtime in this file: tests/emul compiles it with g++ and
+// checks it against Python integers and the oracle on the CPU (tests/test_emul.py).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "host_math.hpp"
+#include "modarith.cuh"
+
+constexpr int AUX_MAX_K = 8;
+// Constants of the auxiliary basis, passed by value (kernel parameters live in the constant bank: the unrolled Garner
+// chain reads them with immediate offsets, no loads).
+struct AuxCrtConst {
+    u32 p[AUX_MAX_K];                      // auxiliary primes
+    u32 half[AUX_MAX_K];                   // mixed-radix digits of floor(P / 2)
+    tw32_t inv[AUX_MAX_K * AUX_MAX_K];     // inv[m * AUX_MAX_K + k] = p_m^-1 mod p_k, m < k
+};
+// Residues r_k of an integer x in [0, P) -> its mixed-radix digits v_k (x = sum_k v_k prod_{m<k} p_m, 0 <= v_k < p_k), in place.
+// Garner: v_k = (..((r_k - v_0) p_0^-1 - v_1) p_1^-1 .. - v_{k-1}) p_{k-1}^-1 mod p_k.  The running value stays in [0, 2 p_k):
+// x + 2 p_k - v_m is positive and below 4 p_k < 2^32 (v_m < p_m < 2^30 < 2 p_k: the auxiliary primes lie in (2^29, 2^30)),
+// and the lazy Shoup product takes any word.
+template <int K>
+__device__ __forceinline__ void aux_garner(u32 (&v)[K], const AuxCrtConst &cc) {
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        const u32 p = cc.p[k], p2 = 2 * p;
+#pragma unroll
+        for (int mi = 0; mi < k; ++mi) v[k] = shoup_lazy((u32)(v[k] + p2 - v[mi]), cc.inv[mi * AUX_MAX_K + k], p);
+        v[k] = csub(v[k], p);
+    }
+}
+// x > floor(P / 2), i.e. x stands for the negative integer x - P: most significant digit first.
+template <int K>
+__device__ __forceinline__ bool aux_negative(const u32 (&v)[K], const AuxCrtConst &cc) {
+    bool neg = false, decided = false;
+#pragma unroll
+    for (int k = K - 1; k >= 0; --k) {
+        if (!decided && v[k] != cc.half[k]) {
+            neg = v[k] > cc.half[k];
+            decided = true;
+        }
+    }
+    return neg;
+}
+// The centred integer mod q: sum_k v_k (prod_{m<k} p_m mod q) - [negative] (P mod q).  mix: K Shoup pairs of this q.
+template <int K>
+__device__ __forceinline__ u64 aux_image(const u32 (&v)[K], bool neg, const tw_t *mix, u64 pmod, const LimbConst &mq) {
+    u64 y = barrett_word((u64)v[0], mq);
+#pragma unroll
+    for (int k = 1; k < K; ++k) y = addmod(y, shoup((u64)v[k], mix[k], mq.q), mq.q);
+    if (neg) y = submod(y, pmod, mq.q);
+    return y;
+}
+
+// Host side: the auxiliary primes of a basis and every constant derived from them.
+struct AuxHost {
+    int K = 0;
+    std::vector<u64> primes;
+    AuxCrtConst cc;
+    std::vector<tw_t> mix;  // [L][K]: prod_{m<k} p_m mod q_j
+    std::vector<u64> pmod;  // [L]: P mod q_j
+};
+// |coefficients of sum_i alpha_i (*) key[i][j]| < L * N * q_max^2 < 2^need; the centred range of P = prod p_k must cover
+// it: P > 2^(need + 1).  The primes are the first NTT-friendly ones below 2^30 (hm::generate_primes), all in (2^29, 2^30).
+inline bool aux_host_build(u64 n, int logn, const std::vector<u64> &moduli, AuxHost &A) {
+    const size_t L = moduli.size();
+    u64 qmax = 0;
+    for (u64 q : moduli) qmax = q > qmax ? q : qmax;
+    int lbits = 0;
+    while (((size_t)1 << lbits) < L) ++lbits;
+    const int qbits = 64 - __builtin_clzll(qmax);
+    const int need = lbits + logn + 2 * qbits;
+    std::vector<u64> primes(AUX_MAX_K);
+    if (!hm::generate_primes(30, AUX_MAX_K, n, primes.data())) return false;
+    int K = 0;
+    double have = 0.0;
+    while (K < AUX_MAX_K && have < need + 1.5) have += std::log2((double)primes[K++]);
+    if (have < need + 1.5 || K < 2) return false;
+    primes.resize(K);
+    for (u64 p : primes)
+        if (p <= (1ull << 29) || p >= (1ull << 30)) return false;
+    A.K = K;
+    A.primes = primes;
+    memset(&A.cc, 0, sizeof(A.cc));
+    const std::vector<u64> half = hm::half_q_digits(primes);
+    for (int k = 0; k < K; ++k) {
+        A.cc.p[k] = (u32)primes[k];
+        A.cc.half[k] = (u32)half[k];
+        for (int m = 0; m < k; ++m) {
+            const u64 w = hm::inv_mod(primes[m] % primes[k], primes[k]);
+            A.cc.inv[m * AUX_MAX_K + k].w = (u32)w;
+            A.cc.inv[m * AUX_MAX_K + k].ws = (u32)((w << 32) / primes[k]);
+        }
+    }
+    A.mix.assign(L * K, tw_t{0, 0});
+    A.pmod.assign(L, 0);
+    for (size_t j = 0; j < L; ++j) {
+        const u64 q = moduli[j];
+        u64 acc = 1 % q;
+        for (int k = 0; k < K; ++k) {
+            A.mix[j * K + k].w = acc;
+            A.mix[j * K + k].ws = hm::shoup_of(acc, q);
+            acc = hm::mul_mod(acc, primes[k] % q, q);
+        }
+        A.pmod[j] = acc;
+    }
+    return true;
+}

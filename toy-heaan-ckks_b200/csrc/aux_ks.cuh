@@ -17,6 +17,7 @@
 //   key    [k][j][i][N]    NTT_{p_k}(key[i][j] mod p_k), same order (ksk->xb / ->xa)
 //   r      [ct][j][k][N]   sum_i x * key  (NTT domain, then transformed back in place to the coefficient domain)
 #pragma once
+#include "aux_crt.cuh"
 #include "modarith.cuh"
 
 // key[i][j][n] mod p_k for every auxiliary prime: src u64 [L(i)][L(j)][N] coefficient domain, dst u32 [K][L(j)][L(i)][N].
@@ -150,14 +151,6 @@ __global__ void __launch_bounds__(L4 <= 6 ? 768 : 512, 1) aux_mac_kernel(AuxMacA
     }
 }
 
-constexpr int AUX_MAX_K = 8;
-// Constants of the auxiliary basis, passed by value (kernel parameters live in the constant bank: the unrolled Garner
-// chain reads them with immediate offsets, no loads).
-struct AuxCrtConst {
-    u32 p[AUX_MAX_K];                      // auxiliary primes
-    u32 half[AUX_MAX_K];                   // mixed-radix digits of floor(P / 2)
-    tw32_t inv[AUX_MAX_K * AUX_MAX_K];     // inv[m * AUX_MAX_K + k] = p_m^-1 mod p_k, m < k
-};
 struct AuxCrtArgs {
     const u32 *rb, *ra;      // [cs][L][K][N] residues of S_j (coefficient domain)
     const u64 *add0, *add1;  // [cs][L][N] coefficient domain addends (d0, d1)
@@ -208,34 +201,9 @@ __global__ void __launch_bounds__(256) aux_crt_kernel(AuxCrtArgs a, const __grid
             if (RESCALE) lastv[u] = (h ? a.last1 : a.last0)[ct * n + e0 + u * 256];
         }
 #pragma unroll
-        for (int k = 1; k < K; ++k) {
-            const u32 p = cc.p[k];
-#pragma unroll
-            for (int mi = 0; mi < k; ++mi) {
-                const tw32_t iv = cc.inv[mi * AUX_MAX_K + k];
-#pragma unroll
-                for (int u = 0; u < EPT; ++u) {
-                    const u32 vm = csub(v[u][mi], p);  // auxiliary primes lie in (2^29, 2^30): v_m < p_m < 2 p_k
-                    const u32 x = v[u][k];
-                    const u32 d = x >= vm ? x - vm : x + p - vm;
-                    v[u][k] = shoup(d, iv, p);
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < EPT; ++u) {
-            bool neg = false, decided = false;
-#pragma unroll
-            for (int k = K - 1; k >= 0; --k) {
-                if (!decided && v[u][k] != cc.half[k]) {
-                    neg = v[u][k] > cc.half[k];
-                    decided = true;
-                }
-            }
-            u64 y = barrett_word((u64)v[u][0], mq);
-#pragma unroll
-            for (int k = 1; k < K; ++k) y = addmod(y, shoup((u64)v[u][k], mix[k], mq.q), mq.q);
-            if (neg) y = submod(y, pmod, mq.q);
+        for (int u = 0; u < EPT; ++u) {  // (independent chains: the unrolled code interleaves them)
+            aux_garner<K>(v[u], cc);
+            u64 y = aux_image<K>(v[u], aux_negative<K>(v[u], cc), mix, pmod, mq);
             y = addmod(y, addv[u], mq.q);
             if (RESCALE) y = shoup(submod(y, barrett_word(lastv[u], mq), mq.q), ql, mq.q);
             (h ? a.out1 : a.out0)[oo + u * 256] = y;

@@ -20,7 +20,7 @@ static void destroy_aux(AuxKs *a) {
 }
 
 static int g_ks_aux = 1;         // 0 never, 1 when it pays (aux_wanted), 2 whenever it is possible (tests)
-static int g_ks_aux_min_l = 11;  // measured crossover on B200 for 61-bit primes
+static int g_ks_aux_min_l = 10;  // measured crossover on B200 for 61-bit primes at N = 2^16 (horner_chain per-level times)
 extern "C" int ckks_set_ks_aux(int mode) {
     if (mode < 0 || mode > 2) return CKKS_BAD_ARGUMENT;
     g_ks_aux = mode;
@@ -40,20 +40,10 @@ static int aux_get(const Tables &Tc, AuxKs **out) {
         *out = T.aux;
         return CKKS_OK;
     }
-    u64 qmax = 0;
-    for (u64 q : T.moduli) qmax = q > qmax ? q : qmax;
-    int lbits = 0;
-    while (((size_t)1 << lbits) < T.L) ++lbits;
-    const int qbits = 64 - __builtin_clzll(qmax);
-    // |coefficients of S_j| < L * N * q_max^2 < 2^need; the centred range of P must cover it: P > 2^(need + 1)
-    const int need = lbits + T.logn + 2 * qbits;
-    std::vector<u64> primes(AUX_MAX_K);
-    if (!hm::generate_primes(30, AUX_MAX_K, T.n, primes.data())) return CKKS_UNSUPPORTED;
-    int K = 0;
-    double have = 0.0;
-    while (K < AUX_MAX_K && have < need + 1.5) have += log2((double)primes[K++]);
-    if (have < need + 1.5) return CKKS_UNSUPPORTED;
-    primes.resize(K);
+    AuxHost H;
+    if (!aux_host_build(T.n, T.logn, T.moduli, H)) return CKKS_UNSUPPORTED;
+    const int K = H.K;
+    const std::vector<u64> &primes = H.primes;
     std::unique_ptr<AuxKs, void (*)(AuxKs *)> A(new AuxKs(), destroy_aux);
     A->K = K;
     A->X = std::make_shared<Tables>();
@@ -69,34 +59,9 @@ static int aux_get(const Tables &Tc, AuxKs **out) {
     for (u64 p : primes) X.psi.push_back(hm::find_primitive_root(p, 2 * T.n));
     TRY(build_tables(X, true, false));  // the auxiliary primes always use the 32-bit word path
     if (!X.w32 || X.lazy != 1) return CKKS_UNSUPPORTED;
-    std::vector<tw32_t> inv((size_t)K * K);
-    for (int m = 0; m < K; ++m)
-        for (int k = 0; k < K; ++k) {
-            tw32_t t{0, 0};
-            if (m < k) t = ht::mk_tw32(hm::inv_mod(primes[m] % primes[k], primes[k]), primes[k]);
-            inv[(size_t)m * K + k] = t;
-        }
-    std::vector<tw_t> mix(T.L * K);
-    std::vector<u64> pmod(T.L);
-    for (size_t j = 0; j < T.L; ++j) {
-        const u64 q = T.moduli[j];
-        u64 acc = 1 % q;
-        for (int k = 0; k < K; ++k) {
-            mix[j * K + k] = mk_tw(acc, q);
-            acc = hm::mul_mod(acc, primes[k] % q, q);
-        }
-        pmod[j] = acc;
-    }
-    std::vector<u64> half64 = half_q_digits(primes);
-    std::vector<u32> half(half64.begin(), half64.end());
-    memset(&A->cc, 0, sizeof(A->cc));
-    for (int k = 0; k < K; ++k) {
-        A->cc.p[k] = (u32)primes[k];
-        A->cc.half[k] = half[k];
-        for (int m = 0; m < k; ++m) A->cc.inv[m * AUX_MAX_K + k] = inv[(size_t)m * K + k];
-    }
-    TRY(upload_vec(&A->d_mix, mix));
-    TRY(upload_vec(&A->d_pmod, pmod));
+    A->cc = H.cc;
+    TRY(upload_vec(&A->d_mix, H.mix));
+    TRY(upload_vec(&A->d_pmod, H.pmod));
     T.aux = A.release();
     *out = T.aux;
     return CKKS_OK;

@@ -1224,35 +1224,7 @@ extern "C" int ckks_poly_to_coeffs(const ckks_poly *p, int64_t *out) {
 }
 
 // Multi-word floor(Q / 2) in Garner's mixed radix: digit j = (floor(Q/2) div q_0 ... q_{j-1}) mod q_j.
-static std::vector<u64> half_q_digits(const std::vector<u64> &mod) {
-    std::vector<u64> big(1, 1);  // little-endian words of Q
-    for (u64 q : mod) {
-        hm::u128 carry = 0;
-        for (u64 &w : big) {
-            hm::u128 t = (hm::u128)w * q + carry;
-            w = (u64)t;
-            carry = t >> 64;
-        }
-        if (carry) big.push_back((u64)carry);
-    }
-    u64 c = 0;  // big >>= 1
-    for (size_t i = big.size(); i-- > 0;) {
-        u64 w = big[i];
-        big[i] = (w >> 1) | (c << 63);
-        c = w & 1;
-    }
-    std::vector<u64> digits;
-    for (u64 q : mod) {  // big, rem = divmod(big, q)
-        hm::u128 rem = 0;
-        for (size_t i = big.size(); i-- > 0;) {
-            hm::u128 cur = (rem << 64) | big[i];
-            big[i] = (u64)(cur / q);
-            rem = cur % q;
-        }
-        digits.push_back((u64)rem);
-    }
-    return digits;
-}
+using hm::half_q_digits;  // mixed-radix digits of floor(Q / 2) (host_math.hpp)
 // Centred CRT of every coefficient for a basis of any size (device, Garner mixed radix: crt_wide.cuh).
 // d_i64 / d_f64: device buffers [batch][N] or null; *overflow: some |x| >= 2^63.
 static int crt_wide_dev(const ckks_poly *p, long long *d_i64, double *d_f64, int *overflow) {

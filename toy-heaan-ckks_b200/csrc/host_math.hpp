@@ -141,4 +141,35 @@ inline int64_t reconstruct_centered(const std::vector<u64> &moduli, const u64 *r
     if (acc > q / 2) return (int64_t)((i128)acc - (i128)q);
     return (int64_t)acc;
 }
+// Mixed-radix digits (radices mod[0], mod[1], ...; least significant first) of floor(prod(mod) / 2): the centring
+// threshold of a Garner reconstruction (crt_wide.cuh, aux_crt.cuh).
+inline std::vector<u64> half_q_digits(const std::vector<u64> &mod) {
+    std::vector<u64> big(1, 1);  // little-endian words of Q
+    for (u64 q : mod) {
+        u128 carry = 0;
+        for (u64 &w : big) {
+            u128 t = (u128)w * q + carry;
+            w = (u64)t;
+            carry = t >> 64;
+        }
+        if (carry) big.push_back((u64)carry);
+    }
+    u64 c = 0;  // big >>= 1
+    for (size_t i = big.size(); i-- > 0;) {
+        u64 w = big[i];
+        big[i] = (w >> 1) | (c << 63);
+        c = w & 1;
+    }
+    std::vector<u64> digits;
+    for (u64 q : mod) {  // big, rem = divmod(big, q)
+        u128 rem = 0;
+        for (size_t i = big.size(); i-- > 0;) {
+            u128 cur = (rem << 64) | big[i];
+            big[i] = (u64)(cur / q);
+            rem = cur % q;
+        }
+        digits.push_back((u64)rem);
+    }
+    return digits;
+}
 }  // namespace hm
