@@ -1055,7 +1055,7 @@ def _aux_k(logn, l, bits):
     P > 2 * L * N * q_max^2."""
     need = max(0, (l - 1).bit_length()) + logn + 2 * bits + 1.5
     k = 1
-    while k * 29.99 < need:
+    while k * 29.49 < need:  # the auxiliary primes lie just below 2^29.5 (csrc/aux_crt.cuh AUX_P_BOUND)
         k += 1
     return k
 

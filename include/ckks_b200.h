@@ -359,8 +359,11 @@ int ckks_poly_device_ptr(ckks_poly *p, uint64_t **out);
 /* Integer-pipe microbenchmark: dependent-free 64-bit Shoup modmuls; returns modmul/s (0 on error). */
 double ckks_bench_modmul_peak(int device, int iters);
 /* The same for the multiply-accumulate of the auxiliary-basis key-switch: 32 x 32 -> 64-bit products added into 64-bit
- * accumulators (IMAD.WIDE.U32), per second on the whole device. */
+ * accumulators (IMAD.WIDE.U32, both factors in general registers), per second on the whole device. */
 double ckks_bench_mac32_peak(int device, int iters);
+/* vary = 0: warp-uniform multiplier (fed from a uniform register); 1: a different multiplier per thread, in a general
+ * register, as in aux_mac_kernel (what ckks_bench_mac32_peak measures). */
+double ckks_bench_mac32_peak_ex(int device, int iters, int vary);
 /* Host-side copy ceiling of the *_host entry points: n_src H2D copies of [hsrc, +src_bytes) and n_dst D2H copies
  * into [hdst, +dst_bytes), both directions concurrently, in the pipeline's chunk size, no kernels; seconds per
  * iteration (0 on error). */

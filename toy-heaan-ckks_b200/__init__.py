@@ -150,6 +150,7 @@ _sig("ckks_launch_count", C.c_uint64)
 _sig("ckks_launch_table", C.c_size_t, C.c_char_p, C.c_size_t)
 _sig("ckks_bench_modmul_peak", C.c_double, C.c_int, C.c_int)
 _sig("ckks_bench_mac32_peak", C.c_double, C.c_int, C.c_int)
+_sig("ckks_bench_mac32_peak_ex", C.c_double, C.c_int, C.c_int, C.c_int)
 _sig("ckks_bench_host_copy", C.c_double, C.c_int, _vp, C.c_size_t, C.c_int, _vp, C.c_size_t, C.c_int, C.c_int)
 _sig("ckks_comm_init", C.c_int, C.c_int, C.POINTER(C.c_int), C.c_uint64, _u64p, C.c_size_t, _pp)
 _sig("ckks_comm_destroy", C.c_int, _vp)
@@ -269,6 +270,10 @@ def modmul_peak(device: int = 0, iters: int = 4096) -> float:
 def mac32_peak(device: int = 0, iters: int = 4096) -> float:
     """32 x 32 -> 64-bit multiply-accumulates per second on the whole device (the roof of aux_mac)."""
     return float(_lib.ckks_bench_mac32_peak(device, iters))
+
+
+def mac32_peak_ex(device: int = 0, iters: int = 4096, vary: bool = True) -> float:
+    return float(_lib.ckks_bench_mac32_peak_ex(device, iters, int(vary)))
 
 
 # ── src/math ─────────────────────────────────────────────────────────────────────────────────────

@@ -10,6 +10,10 @@
 #include "modarith.cuh"
 
 constexpr int AUX_MAX_K = 8;
+// The auxiliary primes lie in (2^29, 2^29.5): 32 p^2 < 2^64, so a sum of up to AUX_MAX_L = 32 products of two residues fits
+// a 64-bit accumulator without an intermediate reduction (aux_mac_kernel), and v < p_m < 2 p_k for any two of them (Garner).
+constexpr unsigned long long AUX_P_BOUND = 759250124ull;  // floor(2^29.5)
+constexpr int AUX_MAX_L = 32;
 // Constants of the auxiliary basis, passed by value (kernel parameters live in the constant bank: the unrolled Garner
 // chain reads them with immediate offsets, no loads).
 struct AuxCrtConst {
@@ -63,7 +67,7 @@ struct AuxHost {
     std::vector<u64> pmod;  // [L]: P mod q_j
 };
 // |coefficients of sum_i alpha_i (*) key[i][j]| < L * N * q_max^2 < 2^need; the centred range of P = prod p_k must cover
-// it: P > 2^(need + 1).  The primes are the first NTT-friendly ones below 2^30 (hm::generate_primes), all in (2^29, 2^30).
+// it: P > 2^(need + 1).
 inline bool aux_host_build(u64 n, int logn, const std::vector<u64> &moduli, AuxHost &A) {
     const size_t L = moduli.size();
     u64 qmax = 0;
@@ -72,15 +76,16 @@ inline bool aux_host_build(u64 n, int logn, const std::vector<u64> &moduli, AuxH
     while (((size_t)1 << lbits) < L) ++lbits;
     const int qbits = 64 - __builtin_clzll(qmax);
     const int need = lbits + logn + 2 * qbits;
-    std::vector<u64> primes(AUX_MAX_K);
-    if (!hm::generate_primes(30, AUX_MAX_K, n, primes.data())) return false;
-    int K = 0;
+    // the NTT-friendly primes below AUX_P_BOUND, largest first
+    std::vector<u64> primes;
     double have = 0.0;
-    while (K < AUX_MAX_K && have < need + 1.5) have += std::log2((double)primes[K++]);
+    for (u64 cur = hm::first_prime_down(AUX_P_BOUND, n); cur > (1ull << 29) && (int)primes.size() < AUX_MAX_K && have < need + 1.5;
+         cur = hm::first_prime_down(cur, n)) {
+        primes.push_back(cur);
+        have += std::log2((double)cur);
+    }
+    const int K = (int)primes.size();
     if (have < need + 1.5 || K < 2) return false;
-    primes.resize(K);
-    for (u64 p : primes)
-        if (p <= (1ull << 29) || p >= (1ull << 30)) return false;
     A.K = K;
     A.primes = primes;
     memset(&A.cc, 0, sizeof(A.cc));

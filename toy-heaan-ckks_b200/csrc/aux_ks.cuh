@@ -59,14 +59,28 @@ __device__ __forceinline__ void aux_mad(u64 &acc, u32 x, u32 k) {
 // touches shared memory.  The x rows of a ciphertext (L rows of 32 words, shared by the L warps of the CTA) arrive
 // as one TMA box per ciphertext, AUX_MAC_T ciphertexts per stage, two stages in flight; thread 0 issues the copies,
 // an mbarrier per stage signals their arrival, one __syncthreads per stage releases the buffer.
-// Products are < 2^60 (p < 2^30): 16 of them plus a carried residue fit a 64-bit accumulator, so the accumulators
-// are folded once, after the 16th digit.
+// Products are below p^2 < 2^59 (AUX_P_BOUND): the L <= 32 of them fit a 64-bit accumulator, reduced once at the end
+// (aux_reduce_sum: the quotient comes from the FP64 pipe, which is idle here; the integer pipe is the one this kernel
+// saturates).
 // L4 = ceil(L / 4) (compile time: the key registers); digits L .. 4 L4 - 1 have zero key words (their x rows in
 // shared memory are never written and may hold anything).
 #ifndef CKKS_AUX_MAC_T
 #define CKKS_AUX_MAC_T 4
 #endif
 constexpr int AUX_MAC_T = CKKS_AUX_MAC_T;  // ciphertexts per stage
+// s mod p for any 64-bit s and p in (2^29, 2^30): floor(s / p) < 2^35 estimated in double precision (relative error
+// below 2^-51: off by at most one either way), exact remainder by one 64-bit multiply-subtract and two corrections.
+__device__ __forceinline__ u32 aux_reduce_sum(u64 s, u32 p, double pinv) {
+#ifdef __CUDA_ARCH__
+    const u64 q = (u64)__double2ull_rz(__ull2double_rz(s) * pinv);
+#else
+    const u64 q = (u64)((double)s * pinv);
+#endif
+    i64 r = (i64)(s - q * (u64)p);  // in (-p, 2p)
+    if (r < 0) r += p;
+    if (r >= (i64)p) r -= p;
+    return (u32)r;
+}
 template <int L4>
 __global__ void __launch_bounds__(L4 <= 6 ? 768 : 512, 1) aux_mac_kernel(AuxMacArgs a, const __grid_constant__ AuxMacMap map) {
     constexpr int T = AUX_MAC_T;
@@ -82,7 +96,8 @@ __global__ void __launch_bounds__(L4 <= 6 ? 768 : 512, 1) aux_mac_kernel(AuxMacA
     const int jblocks = (L + jb - 1) / jb;
     const int k = blockIdx.y / jblocks, j = (blockIdx.y % jblocks) * jb + jy;
     const bool live = j < L;
-    const LimbConst m = a.alc[k];
+    const u32 p = (u32)a.alc[k].q;
+    const double pinv = 1.0 / (double)p;
     const unsigned cs = a.cs;
     const unsigned niter = (cs + T - 1) / T;
     const unsigned tile_bytes = (unsigned)L * 32 * 4;
@@ -134,13 +149,9 @@ __global__ void __launch_bounds__(L4 <= 6 ? 768 : 512, 1) aux_mac_kernel(AuxMacA
                         const u32 x = xc[i * 32];
                         aux_mad(sb, x, kb[i]);
                         aux_mad(sa, x, ka[i]);
-                        if (i == 15 && L4 > 4) {
-                            sb = barrett_word(sb, m);
-                            sa = barrett_word(sa, m);
-                        }
                     }
-                    *prb = (u32)barrett_word(sb, m);
-                    *pra = (u32)barrett_word(sa, m);
+                    *prb = aux_reduce_sum(sb, p, pinv);
+                    *pra = aux_reduce_sum(sa, p, pinv);
                     prb += oct;
                     pra += oct;
                 }
@@ -213,13 +224,20 @@ __global__ void __launch_bounds__(256) aux_crt_kernel(AuxCrtArgs a, const __grid
 
 // Throughput of the multiply-accumulate aux_mac_kernel is made of: 32 x 32 -> 64-bit products added into 64-bit
 // accumulators (IMAD.WIDE.U32), eight independent chains per thread, every SM busy (ckks_bench_mac32_peak).
-__global__ void mac32_peak_kernel(u64 *out, int iters, u32 w) {
+// VARY: the multiplier sits in a general register, different per thread, like the key words of aux_mac_kernel (with a
+// warp-uniform multiplier the compiler feeds it from a uniform register and the product issues faster).
+template <bool VARY>
+__global__ void mac32_peak_kernel(u64 *out, int iters, u32 w0) {
     u64 v[8];
+    u32 w[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = (u64)threadIdx.x * 977 + k * 31 + blockIdx.x;
+    for (int k = 0; k < 8; ++k) {
+        v[k] = (u64)threadIdx.x * 977 + k * 31 + blockIdx.x;
+        w[k] = VARY ? w0 - 2 * (threadIdx.x * 8 + k) : w0;
+    }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) aux_mad(v[k], (u32)v[k], w);
+        for (int k = 0; k < 8; ++k) aux_mad(v[k], (u32)v[k], w[k]);
     }
     u64 s = 0;
 #pragma unroll

@@ -26,7 +26,7 @@ extern "C" int ckks_set_ks_aux(int mode) {
     g_ks_aux = mode;
     return CKKS_OK;
 }
-static bool aux_possible(const Tables &T) { return T.path == 2 && !T.w32 && T.a1 >= 4 && T.a2 >= 4 && T.L <= 32; }
+static bool aux_possible(const Tables &T) { return T.path == 2 && !T.w32 && T.a1 >= 4 && T.a2 >= 4 && T.L <= (size_t)AUX_MAX_L; }
 static bool aux_wanted(const Tables &T, size_t L) {
     if (!aux_possible(T) || g_ks_aux == 0) return false;
     return g_ks_aux == 2 || L >= (size_t)g_ks_aux_min_l;
@@ -225,8 +225,12 @@ static int aux_keyswitch(const Tables &T, const AuxKs &A, size_t L, size_t cs, c
         m.K = (int)K;
         m.logn = T.logn;
         m.cs = (unsigned)cs;
-        // at most 24 target limbs (768 threads) per CTA; deeper bases split the targets over two or more CTAs
-        const int jblocks = (int)((L + 23) / 24);
+        // at most 12 target limbs (384 threads, 80 registers: two CTAs per SM, so the key loads at the start of one overlap
+        // the arithmetic of the other -- measured 38.3 -> 36.6 ms per 512 ct-mults against 24 limbs and one CTA per SM)
+#ifndef CKKS_AUX_MAC_JMAX
+#define CKKS_AUX_MAC_JMAX 12
+#endif
+        const int jblocks = (int)((L + CKKS_AUX_MAC_JMAX - 1) / CKKS_AUX_MAC_JMAX);
         m.jb = (int)((L + jblocks - 1) / jblocks);
         dim3 g((unsigned)(n / 32), (unsigned)(K * jblocks)), blk(32, (unsigned)m.jb);
         switch ((L + 3) / 4) {

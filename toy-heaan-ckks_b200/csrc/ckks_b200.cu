@@ -2364,7 +2364,8 @@ extern "C" double ckks_bench_modmul_peak(int device, int iters) {
     return (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
 }
 
-extern "C" double ckks_bench_mac32_peak(int device, int iters) {
+extern "C" double ckks_bench_mac32_peak(int device, int iters) { return ckks_bench_mac32_peak_ex(device, iters, 1); }
+extern "C" double ckks_bench_mac32_peak_ex(int device, int iters, int vary) {
     if (ckks_device_count() <= device) return 0.0;
     if (cudaSetDevice(device) != cudaSuccess) return 0.0;
     u64 *d;
@@ -2373,9 +2374,11 @@ extern "C" double ckks_bench_mac32_peak(int device, int iters) {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     const int blocks = 148 * 8, threads = 256;
-    mac32_peak_kernel<<<blocks, threads>>>(d, 16, 0x3ffffff1u);
+    if (vary) mac32_peak_kernel<true><<<blocks, threads>>>(d, 16, 0x3ffffff1u);
+    else mac32_peak_kernel<false><<<blocks, threads>>>(d, 16, 0x3ffffff1u);
     cudaEventRecord(e0);
-    KLV("mac32_peak", (mac32_peak_kernel<<<blocks, threads>>>(d, iters, 0x3ffffff1u)));
+    if (vary) KLV("mac32_peak", (mac32_peak_kernel<true><<<blocks, threads>>>(d, iters, 0x3ffffff1u)));
+    else KLV("mac32_peak", (mac32_peak_kernel<false><<<blocks, threads>>>(d, iters, 0x3ffffff1u)));
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms = 0;
