@@ -703,7 +703,9 @@ def run_b200(args):
         # half of a transform (16 N bytes per limb transform) -> 8 N per limb per pass;
         # elementwise kernels: the words they must read and write once.
         aux = "aux_mac" in prof  # the gadget product ran through the auxiliary 30-bit primes (csrc/aux_ks.cuh)
-        global AUX_K
+        global AUX_K, KS_WORD, KS_MUL
+        KS_MUL = op == "mul"
+        KS_WORD = 4 if bits <= 31 and logn >= 8 else 8  # the 32-bit word path (all q < 2^31, four-step transforms)
         AUX_K = _aux_k(logn, l, bits)
         table = KERNEL_BYTES_AUX if aux else KERNEL_BYTES
         per_launch = table.get(name, lambda **kw: None)(n=n, l=l, batch=batch)
@@ -1041,13 +1043,19 @@ def run_ntt_sweep(args):
 KS_SCRATCH_MIB = 8192  # the library's default (ckks_set_ks_scratch_mib); --ks-scratch-mib changes both
 
 
+KS_MUL = True  # ct-mult (NTT-domain digit limb and d0 / d1 are read by ks_pass2) or rotation (they are not)
+KS_WORD = 8  # bytes per word of the key-switch scratch and of the resident key: 4 on the 32-bit word path (set in run_b200)
+
+
 def _cs(n, l, batch):
-    return max(1, min(batch, (KS_SCRATCH_MIB << 20) // (l * l * n * 8)))  # (the library also caps 32-bit-word contexts at 512)
+    c = max(1, min(batch, (KS_SCRATCH_MIB << 20) // (l * l * n * 8)))
+    return min(c, 512) if KS_WORD == 4 else c  # the library caps 32-bit-word contexts at 512 ciphertexts per launch (ks_chunk)
 
 
-def _ks2(n, l, batch, w=8):
+def _ks2(n, l, batch, w=None):
+    w = KS_WORD if w is None else w
     cs = _cs(n, l, batch)
-    return cs * l * (l - 1) * n * w + 2 * l * l * n * 8 + cs * l * n * 8 * 3 + 2 * cs * l * n * w
+    return cs * l * (l - 1 if KS_MUL else l) * n * w + 2 * l * l * n * w + (cs * l * n * 8 * 3 if KS_MUL else 0) + 2 * cs * l * n * w
 
 
 def _aux_k(logn, l, bits):
@@ -1102,7 +1110,7 @@ KERNEL_BYTES = {
     "ntt_inv_pass2": lambda n, l, batch: 8.0 * n * l * _cs(n, l, batch),
     "ntt_inv_pass1_rescale": lambda n, l, batch: 8.0 * n * _cs(n, l, batch) * (3 * (l - 1)),
     # ks_pass1: read each digit limb once (its L-1 re-reads are L2 hits), write the (i, j) scratch slabs
-    "ks_pass1": lambda n, l, batch: 8.0 * n * _cs(n, l, batch) * (l + l * (l - 1)),
+    "ks_pass1": lambda n, l, batch: 1.0 * n * _cs(n, l, batch) * (8 * l + KS_WORD * l * (l - 1)),
     # ks_pass2: scratch slabs + key once per launch + NTT-domain digit limb + d0/d1 in + two outputs
     "ks_pass2": lambda n, l, batch: float(_ks2(n, l, batch)),
     "ks_pass2_tma": lambda n, l, batch: float(_ks2(n, l, batch)),
