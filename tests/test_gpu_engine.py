@@ -214,11 +214,13 @@ def test_lazy8_and_harvey_butterflies_agree_with_oracle(gpu, orc, n, bits, l):
 
 
 @pytest.mark.parametrize("n,bits,l,batch", [(4096, 61, 4, 3), (1024, 62, 2, 2), (8192, 50, 5, 2), (256, 61, 3, 9), (65536, 61, 3, 1),
-                                              (512, 40, 12, 2)])
+                                              (512, 40, 12, 2), (256, 61, 26, 2), (256, 50, 32, 3), (256, 61, 13, 5)])
 def test_auxiliary_basis_key_switch_matches_oracle(gpu, orc, n, bits, l, batch):
     """The gadget product through auxiliary 30-bit primes (exact integer convolution + Garner, csrc/aux_ks.cuh) gives
     the limbs of the per-(digit, target) pipeline and of the oracle, with and without the fused rescale, for keys
-    uploaded from the host and keys built from resident NTT-domain polynomials."""
+    uploaded from the host and keys built from resident NTT-domain polynomials; the same for rotate_ciphertext.  The deep
+    shapes (26 and 32 limbs) exercise the wider key-register variants of the multiply-accumulate kernel and target limbs
+    split over three CTAs."""
     moduli = orc.generate_primes(bits, l, n)
     ob = orc.Basis(n, moduli)
     rng = np.random.default_rng(900 + n)
@@ -231,7 +233,7 @@ def test_auxiliary_basis_key_switch_matches_oracle(gpu, orc, n, bits, l, batch):
     want = []
     for i in range(batch):
         m0, m1 = ob.mul_ciphertexts_gadget(a0[i], a1[i], b0[i], b1[i], ka, kb)
-        want.append((m0, m1) + tuple(ob.rescale_ciphertext(m0, m1)[:2]))
+        want.append((m0, m1) + tuple(ob.rescale_ciphertext(m0, m1)[:2]) + tuple(ob.rotate_ciphertext(a0[i], a1[i], ka, kb, -3)))
     got = {}
     for mode in (2, 0):
         gpu.set_ks_aux(mode)
@@ -246,16 +248,18 @@ def test_auxiliary_basis_key_switch_matches_oracle(gpu, orc, n, bits, l, batch):
             for key in keys:
                 prod = gpu.CkksEngine.mul_ciphertexts_gadget(cta, ctb, key)
                 fused = gpu.CkksEngine.mul_relin_rescale(cta, ctb, key)
-                g = (prod.c0.channels(), prod.c1.channels(), fused.c0.channels(), fused.c1.channels())
+                key.rotation = -3
+                rot = gpu.CkksEngine.rotate_ciphertext(cta, key)
+                g = (prod.c0.channels(), prod.c1.channels(), fused.c0.channels(), fused.c1.channels(), rot.c0.channels(), rot.c1.channels())
                 for i in range(batch):
-                    for t in range(4):
+                    for t in range(6):
                         assert np.array_equal(g[t][i], want[i][t]), f"mode {mode}, ciphertext {i}, output {t}"
             used = gpu.launch_table().get("aux_mac", 0) - launches0
             assert (used > 0) == (mode == 2), "the auxiliary-basis kernels ran exactly when asked to"
             got[mode] = g
         finally:
             gpu.set_ks_aux(1)
-    for t in range(4):
+    for t in range(6):
         assert np.array_equal(got[0][t], got[2][t])
 
 

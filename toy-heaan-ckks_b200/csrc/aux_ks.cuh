@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(L4 <= 6 ? 768 : 512, 1) aux_mac_kernel(AuxMacA
 
 struct AuxCrtArgs {
     const u32 *rb, *ra;      // [cs][L][K][N] residues of S_j (coefficient domain)
-    const u64 *add0, *add1;  // [cs][L][N] coefficient domain addends (d0, d1)
+    const u64 *add0, *add1;  // [cs][L][N] coefficient domain addends (d0, d1; automorphism(c0), none) -- either may be null
     u64 *out0, *out1;        // [cs][outL][N]; limb j lands in slot j - j0
     const u64 *last0, *last1;  // RESCALE: [cs][N] the finished last limb of c0 / c1
     const LimbConst *lc;     // [L] ciphertext primes
@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(256) aux_crt_kernel(AuxCrtArgs a, const __grid
         u64 addv[EPT], lastv[EPT];
 #pragma unroll
         for (int u = 0; u < EPT; ++u) {
-            addv[u] = (h ? a.add1 : a.add0)[ao + u * 256];
+            const u64 *add = h ? a.add1 : a.add0;
+            addv[u] = add ? add[ao + u * 256] : 0ull;  // (rotations: nothing is added to the second sum)
             if (RESCALE) lastv[u] = (h ? a.last1 : a.last0)[ct * n + e0 + u * 256];
         }
 #pragma unroll

@@ -1,9 +1,10 @@
 // aux_ks.inl -- host side of the exact multi-modular gadget key-switch (kernels and the algorithm: aux_ks.cuh).
 // Included by ckks_b200.cu after the four-step launchers.
 //
-// Used for mul_ciphertexts_gadget (engine.rs:474-545) on the 64-bit four-step path once the basis is deep enough for
-// L*K + 2*L*K 32-bit transforms to beat L*(L-1) 64-bit ones (aux_wanted); shallower levels, rotations, the 32-bit
-// word path and the limb-sharded mode keep the per-(digit, target) pipeline of ks_pass1 / ks_pass2.
+// Used for mul_ciphertexts_gadget (engine.rs:474-545) and rotate_ciphertext (engine.rs:412-463) on the 64-bit four-step
+// path once the basis is deep enough for L*K + 2*L*K 32-bit transforms to beat L*(L-1) 64-bit ones (aux_wanted);
+// shallower levels, the 32-bit word path and the limb-sharded mode keep the per-(digit, target) pipeline of
+// ks_pass1 / ks_pass2.
 
 struct AuxKs {
     std::shared_ptr<Tables> X;  // tables of the auxiliary primes (32-bit word path, Harvey lazy)
@@ -364,6 +365,36 @@ static int fused_mul_relin_aux(const Tables &T, size_t L, size_t batch, const u6
             TRY(run_pass(T, P_INV1, sp, TMP, A1));
             u64 *d0 = o0 + s0 * outL * n, *d1 = o1 + s0 * outL * n;
             return aux_keyswitch(T, A, L, cs, B1, rlk, A0, A1, reinterpret_cast<u32 *>(SCR), d0, d1, rescale ? LAST : nullptr);
+        };
+        rc = step();
+    }
+    return rc;
+}
+
+// rotate_ciphertext (engine.rs:412-463) with the auxiliary-basis key-switch; same contract as fused_rotate: the digits are
+// automorphism(c1), automorphism(c0) is the addend of the first sum, the second sum is the new c1 as it is.
+static int fused_rotate_aux(const Tables &T, size_t L, size_t batch, const u64 *c0, const u64 *c1, u64 e, const ckks_ksk *key, u64 *o0,
+                            u64 *o1) {
+    AuxKs *Ap;
+    TRY(aux_get(T, &Ap));
+    const AuxKs &A = *Ap;
+    if (key->aux_k != A.K) return CKKS_BAD_HANDLE;
+    NvtxScope nvtx_call("ckks:rotate");
+    const size_t n = T.n, cs_max = aux_chunk(T, A, L, batch);
+    const u64 einv = inv_mod_pow2(e, 2 * n);
+    u64 *D = nullptr, *R0 = nullptr, *SCR = nullptr;
+    std::lock_guard<std::mutex> ws_lock(const_cast<Tables &>(T).ws_mu);
+    int rc = ws_get(T, WS_B0, cs_max * L * n * 8, &D);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_A0, cs_max * L * n * 8, &R0);
+    if (rc == CKKS_OK) rc = ws_get(T, WS_SCR, 4 * cs_max * (size_t)A.K * L * n * 4, &SCR);
+    for (size_t s0 = 0; s0 < batch && rc == CKKS_OK; s0 += cs_max) {
+        const size_t cs = batch - s0 < cs_max ? batch - s0 : cs_max;
+        const size_t off = s0 * L * n;
+        auto step = [&]() -> int {
+            EwArgs ea = ew_args(T, L, cs);
+            KL("automorphism", (automorphism_kernel<<<ew_grid(ea.total), 256, 0, S(T)>>>(ea, c1 + off, D, e, einv)));
+            KL("automorphism", (automorphism_kernel<<<ew_grid(ea.total), 256, 0, S(T)>>>(ea, c0 + off, R0, e, einv)));
+            return aux_keyswitch(T, A, L, cs, D, key, R0, nullptr, reinterpret_cast<u32 *>(SCR), o0 + off, o1 + off, nullptr);
         };
         rc = step();
     }

@@ -1855,6 +1855,7 @@ static int launch_inv1_addrot_a(bool w32, int lazy, dim3 grid, cudaStream_t s, c
 static int fused_rotate(const Tables &T, size_t L, size_t batch, const u64 *c0, const u64 *c1, u64 e, const ckks_ksk *key, u64 *o0,
                         u64 *o1) {
     if (!batch) return CKKS_OK;
+    if (key->aux_k && aux_wanted(T, L)) return fused_rotate_aux(T, L, batch, c0, c1, e, key, o0, o1);
     NvtxScope nvtx_call("ckks:rotate");
     const size_t n = T.n, cs_max = ks_chunk(T, L, batch);
     const u64 einv = inv_mod_pow2(e, 2 * n);
