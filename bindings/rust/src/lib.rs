@@ -75,6 +75,9 @@ pub mod ffi {
         pub fn ckks_poly_to_coeffs_wide(p: *const CkksPoly, out_i64: *mut i64, out_f64: *mut f64, overflow: *mut i32) -> i32;
         pub fn ckks_ctx_trim(ctx: *mut CkksCtx) -> i32;
         pub fn ckks_set_nvtx(on: i32) -> i32;
+        /// 0 never / 1 automatic (default) / 2 whenever possible: the gadget product through auxiliary 30-bit NTT primes
+        /// (exact).  Read when a key is uploaded and when a product is computed.
+        pub fn ckks_set_ks_aux(mode: i32) -> i32;
         pub fn ckks_ksk_upload(ctx: *mut CkksCtx, a: *const u64, b: *const u64, out: *mut *mut CkksKsk) -> i32;
         pub fn ckks_ksk_free(k: *mut CkksKsk) -> i32;
         pub fn ckks_ct_mul_relin(a0: *const CkksPoly, a1: *const CkksPoly, b0: *const CkksPoly, b1: *const CkksPoly,
