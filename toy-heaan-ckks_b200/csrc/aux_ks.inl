@@ -72,7 +72,11 @@ static int aux_get(const Tables &Tc, AuxKs **out) {
 enum { AUX_FWD1, AUX_FWD2, AUX_FWD2_NOPRE, AUX_INV2, AUX_INV1 };
 template <int KIND, int A, bool PRE, bool POST, bool TR>
 static int launch_aux_pass_a(const char *name, dim3 grid, cudaStream_t s, const PassArgs &a) {
-    constexpr int E = 4, C = 16;
+    // Column tile: 16 words = 64-byte row segments; the last inverse pass, whose canonical rows are the WRITTEN side, does
+    // better with 32 (128-byte segments: 16.7 -> 12.9 ms per 512 ct-mults at cfg4), the passes that READ canonical rows or run
+    // in place do not (inverse pass 2: 15.0 -> 16.5, forward pass 2: 7.6 -> 8.6).
+    constexpr int CW = (KIND == XF_NEG_INV) ? 32 : 16;
+    constexpr int E = 4, C = CW <= (1 << A) ? CW : (1 << A);  // (ncols >= 2^(A-1) >= C for A >= 5; A = 4: 16)
     grid.x = a.ncols / C;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(u32);
     const int block = C << (A - E);
@@ -148,7 +152,7 @@ static int ksk_add_aux(const Tables &T, ckks_ksk *k, const u64 *a_coeff, const u
     const size_t L = k->ctx->L;
     if (k->digits != L || !aux_wanted(T, L)) return CKKS_OK;
     AuxKs *A;
-    TRY(aux_get(T, &A));
+    if (aux_get(T, &A) != CKKS_OK) return CKKS_OK;  // no auxiliary basis for this ring: the key keeps the standard form only
     const size_t words = (size_t)A->K * L * L * T.n;
     u32 *tmp = nullptr;
     CU(pool_malloc(T, (void **)&tmp, words * 4));
