@@ -70,13 +70,9 @@ static int aux_get(const Tables &Tc, AuxKs **out) {
 
 // ---- 32-bit-in / 32-bit-out passes over (limb, auxiliary prime) pairs ------------------------------------------------
 enum { AUX_FWD1, AUX_FWD2, AUX_FWD2_NOPRE, AUX_INV2, AUX_INV1 };
-template <int KIND, int A, bool PRE, bool POST, bool TR>
-static int launch_aux_pass_a(const char *name, dim3 grid, cudaStream_t s, const PassArgs &a) {
-    // Column tile: 16 words = 64-byte row segments; the last inverse pass, whose canonical rows are the WRITTEN side, does
-    // better with 32 (128-byte segments: 16.7 -> 12.9 ms per 512 ct-mults at cfg4), the passes that READ canonical rows or run
-    // in place do not (inverse pass 2: 15.0 -> 16.5, forward pass 2: 7.6 -> 8.6).
-    constexpr int CW = (KIND == XF_NEG_INV) ? 32 : 16;
-    constexpr int E = 4, C = CW <= (1 << A) ? CW : (1 << A);  // (ncols >= 2^(A-1) >= C for A >= 5; A = 4: 16)
+template <int KIND, int A, bool PRE, bool POST, bool TR, int CW>
+static int launch_aux_pass_c(const char *name, dim3 grid, cudaStream_t s, const PassArgs &a) {
+    constexpr int E = 4, C = CW <= (1 << A) ? CW : (1 << A);
     grid.x = a.ncols / C;
     const size_t smem = (size_t)(1 << A) * (C + 1) * sizeof(u32);
     const int block = C << (A - E);
@@ -85,6 +81,14 @@ static int launch_aux_pass_a(const char *name, dim3 grid, cudaStream_t s, const 
     else
         KL(name, (ntt_pass_kernel<u32, KIND, A, E, C, 1, PRE, POST, TR, false, false, 0, true><<<grid, block, smem, s>>>(a)));
     return CKKS_OK;
+}
+// Column tile: 16 words = 64-byte row segments; the last inverse pass, whose canonical rows are the WRITTEN side, does better
+// with 32 (128-byte segments: 16.7 -> 12.9 ms per 512 ct-mults at cfg4) wherever the limb has that many columns; the passes
+// that READ canonical rows or run in place do not (inverse pass 2: 15.0 -> 16.5, forward pass 2: 7.6 -> 8.6).
+template <int KIND, int A, bool PRE, bool POST, bool TR>
+static int launch_aux_pass_a(const char *name, dim3 grid, cudaStream_t s, const PassArgs &a) {
+    if (KIND == XF_NEG_INV && A >= 5 && a.ncols >= 32) return launch_aux_pass_c<KIND, A, PRE, POST, TR, 32>(name, grid, s, a);
+    return launch_aux_pass_c<KIND, A, PRE, POST, TR, 16>(name, grid, s, a);
 }
 template <int KIND, bool PRE, bool POST, bool TR>
 static int launch_aux_pass(const char *name, int A, dim3 grid, cudaStream_t s, const PassArgs &a) {
