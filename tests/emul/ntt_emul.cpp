@@ -359,3 +359,5 @@ extern "C" int emul_aux_crt(uint64_t n, const uint64_t *moduli, int l, uint64_t 
     }
     return H.K;
 }
+// aux_reduce_sum (the final `mod p` of aux_mac_kernel: quotient estimated in double precision, exact remainder).
+extern "C" uint32_t emul_aux_reduce_sum(uint64_t s, uint32_t p) { return aux_reduce_sum((u64)s, (u32)p, 1.0 / (double)p); }

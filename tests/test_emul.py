@@ -267,3 +267,24 @@ def test_auxiliary_basis_gadget_product_is_exact(emul, orc, n, bits, l, extreme)
             prod = ob.mul(a, b)
             want = (want.astype(object) + prod[j].astype(object)) % moduli[j]
         assert [int(v) for v in out[j]] == [int(v) for v in want], f"oracle, limb {j}"
+
+
+def test_auxiliary_sum_reduction_is_exact(emul):
+    """aux_reduce_sum: s mod p for any 64-bit s and every auxiliary prime range the library uses, with the quotient taken
+    from a double-precision estimate: exact at the multiples of p (where an estimate off by one either way must be
+    corrected), at the ends of the 64-bit range and on random words."""
+    emul.emul_aux_reduce_sum.argtypes = [C.c_uint64, C.c_uint32]
+    emul.emul_aux_reduce_sum.restype = C.c_uint32
+    rng = random.Random(4242)
+    primes = [536903681, 759250061, 759169033, 663224321, (1 << 29) + 11, 759250123, (1 << 30) - 35]
+    for p in primes:
+        cases = [0, 1, p - 1, p, p + 1, 2 * p - 1, 2 * p, (1 << 64) - 1, (1 << 64) - p, (1 << 63), (1 << 53) - 1, (1 << 53), (1 << 53) + 1]
+        top = ((1 << 64) - 1) // p
+        for _ in range(2000):
+            m = rng.randrange(top + 1)
+            cases += [m * p, m * p + p - 1, max(0, m * p - 1)]
+        cases += [rng.randrange(1 << 64) for _ in range(4000)]
+        cases += [32 * (p - 1) * (p - 1), 24 * (p - 1) * (p - 1)]  # the largest sums of 32 / 24 products
+        for s in cases:
+            if s < (1 << 64):
+                assert emul.emul_aux_reduce_sum(s, p) == s % p, (s, p)

@@ -58,6 +58,20 @@ __device__ __forceinline__ u64 aux_image(const u32 (&v)[K], bool neg, const tw_t
     return y;
 }
 
+// s mod p for any 64-bit s and p in (2^29, 2^30): floor(s / p) < 2^35 estimated in double precision (relative error
+// below 2^-51: off by at most one either way), exact remainder by one 64-bit multiply-subtract and two corrections.
+__device__ __forceinline__ u32 aux_reduce_sum(u64 s, u32 p, double pinv) {
+#ifdef __CUDA_ARCH__
+    const u64 q = (u64)__double2ull_rz(__ull2double_rz(s) * pinv);
+#else
+    const u64 q = (u64)((double)s * pinv);
+#endif
+    i64 r = (i64)(s - q * (u64)p);  // in (-p, 2p)
+    if (r < 0) r += p;
+    if (r >= (i64)p) r -= p;
+    return (u32)r;
+}
+
 // Host side: the auxiliary primes of a basis and every constant derived from them.
 struct AuxHost {
     int K = 0;

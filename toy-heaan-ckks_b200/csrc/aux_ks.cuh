@@ -68,19 +68,6 @@ __device__ __forceinline__ void aux_mad(u64 &acc, u32 x, u32 k) {
 #define CKKS_AUX_MAC_T 4
 #endif
 constexpr int AUX_MAC_T = CKKS_AUX_MAC_T;  // ciphertexts per stage
-// s mod p for any 64-bit s and p in (2^29, 2^30): floor(s / p) < 2^35 estimated in double precision (relative error
-// below 2^-51: off by at most one either way), exact remainder by one 64-bit multiply-subtract and two corrections.
-__device__ __forceinline__ u32 aux_reduce_sum(u64 s, u32 p, double pinv) {
-#ifdef __CUDA_ARCH__
-    const u64 q = (u64)__double2ull_rz(__ull2double_rz(s) * pinv);
-#else
-    const u64 q = (u64)((double)s * pinv);
-#endif
-    i64 r = (i64)(s - q * (u64)p);  // in (-p, 2p)
-    if (r < 0) r += p;
-    if (r >= (i64)p) r -= p;
-    return (u32)r;
-}
 template <int L4>
 __global__ void __launch_bounds__(L4 <= 6 ? 768 : 512, 1) aux_mac_kernel(AuxMacArgs a, const __grid_constant__ AuxMacMap map) {
     constexpr int T = AUX_MAC_T;
