@@ -263,6 +263,30 @@ def test_auxiliary_basis_key_switch_matches_oracle(gpu, orc, n, bits, l, batch):
         assert np.array_equal(got[0][t], got[2][t])
 
 
+def test_auxiliary_basis_large_batch_small_degree(gpu, orc):
+    """7300 ciphertexts at N=256, L=10 (deep enough for the auxiliary-basis pipeline by default): more (ciphertext, limb)
+    pairs than one grid dimension holds; spot-checked against the oracle at both ends and around the wrap."""
+    n, l, batch = 256, 10, 7300
+    moduli = orc.generate_primes(61, l, n)
+    ob = orc.Basis(n, moduli)
+    rng = np.random.default_rng(4711)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, batch) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    gb = gpu.RnsBasis(n, moduli)
+    before = gpu.launch_table().get("aux_mac", 0)
+    key = gpu.GadgetKey.upload(gb, ka, kb)
+    cta, ctb = _ct(gpu, gb, a0, a1, 30, 90), _ct(gpu, gb, b0, b1, 30, 90)
+    prod = gpu.CkksEngine.mul_ciphertexts_gadget(cta, ctb, key)
+    fused = gpu.CkksEngine.mul_relin_rescale(cta, ctb, key)
+    assert gpu.launch_table().get("aux_mac", 0) > before
+    g = (prod.c0.channels(), prod.c1.channels(), fused.c0.channels(), fused.c1.channels())
+    for i in (0, 1, 3275, 3276, 3277, 6552, 6553, 6554, 7280, 7281, 7282, 7299):
+        m0, m1 = ob.mul_ciphertexts_gadget(a0[i], a1[i], b0[i], b1[i], ka, kb)
+        r0, r1, _ = ob.rescale_ciphertext(m0, m1)
+        for t, w in enumerate((m0, m1, r0, r1)):
+            assert np.array_equal(g[t][i], w), f"ciphertext {i}, output {t}"
+
+
 def test_add_encrypt_decrypt_keygen_match_oracle(gpu, orc):
     n, l = 1024, 3
     moduli = orc.generate_primes(40, l, n)

@@ -159,20 +159,23 @@ struct AuxCrtArgs {
     const u64 *pmod;         // [L]: P mod q_j
     const tw_t *ql;          // RESCALE: [L] q_last^-1 mod q_j
     int L, K, logn;
-    int j0, nj, outL;        // target limbs j0 .. j0 + nj - 1 of every ciphertext (grid y = cs * nj)
+    int j0, nj, outL;        // target limbs j0 .. j0 + nj - 1 of every ciphertext
+    size_t rows;             // cs * nj (ciphertext, limb) pairs
 };
 // Garner mixed-radix digits of the residues (0 <= v_k < p_k, value = sum_k v_k prod_{m<k} p_m in [0, P)), sign by
 // comparison with floor(P/2), image mod q_j: sum_k v_k (prod_{m<k} p_m mod q_j) - [negative] (P mod q_j); then the
 // addend (d0 / d1 in the coefficient domain), and with RESCALE the epilogue of rescale_into (poly.rs:214-225):
-// (c_j - c_last mod q_j) * q_last^-1 mod q_j.  grid = (N / (256 EPT), cs * nj); a thread owns EPT coefficients
+// (c_j - c_last mod q_j) * q_last^-1 mod q_j.  grid = (N / (256 EPT), cs * nj [, continued in z]); a thread owns EPT coefficients
 // (independent Garner chains to overlap) of one (ciphertext, target limb); everything that depends only on the
 // limb is loaded once per thread.
 template <int K, int EPT, bool RESCALE>
 __global__ void __launch_bounds__(256) aux_crt_kernel(AuxCrtArgs a, const __grid_constant__ AuxCrtConst cc) {
     const size_t n = (size_t)1 << a.logn;
     const int L = a.L;
-    const size_t ct = blockIdx.y / a.nj;
-    const int j = a.j0 + (int)(blockIdx.y % a.nj);
+    const size_t row = (size_t)blockIdx.z * gridDim.y + blockIdx.y;  // (ciphertext, limb) pairs: y, continued in z past 32768
+    if (row >= a.rows) return;
+    const size_t ct = row / a.nj;
+    const int j = a.j0 + (int)(row % a.nj);
     const LimbConst mq = a.lc[j];
     tw_t mix[K];
 #pragma unroll

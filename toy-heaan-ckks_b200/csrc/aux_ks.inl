@@ -278,7 +278,9 @@ static int aux_keyswitch(const Tables &T, const AuxKs &A, size_t L, size_t cs, c
 #endif
     constexpr int EPT = CKKS_AUX_CRT_EPT;  // N >= 2^8 on this path; N = 2^8, 2^9 use one coefficient per thread
     auto launch = [&](bool rs, int ept) -> int {
-        dim3 g((unsigned)(n / (256 * (size_t)ept)), (unsigned)(cs * c.nj));
+        c.rows = cs * (size_t)c.nj;
+        const size_t gy = c.rows < 32768 ? c.rows : 32768;
+        dim3 g((unsigned)(n / (256 * (size_t)ept)), (unsigned)gy, (unsigned)((c.rows + gy - 1) / gy));
 #define AUX_CRT_CASE(Kv)                                                                                      \
     case Kv:                                                                                                  \
         if (rs) {                                                                                             \
