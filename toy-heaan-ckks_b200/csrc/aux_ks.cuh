@@ -5,12 +5,14 @@
 // computed there with one NTT mod q_j per (digit, target) pair: L^2 transforms of 61-bit words.  The same ring element
 // is the image mod q_j of the product over the INTEGERS,
 //     S_j = sum_i alpha_i (*) key[i][j]   in Z[X]/(X^N + 1),   |coefficients of S_j| < L * N * q_max^2 =: B,
-// and S_j can be computed exactly in a few word-sized NTT primes p_0 .. p_{K-1} (all < 2^30, prod p_k > 2B) chosen by
+// and S_j can be computed exactly in a few word-sized NTT primes p_0 .. p_{K-1} (all in (2^29, 2^29.5), prod p_k > 2B) chosen by
 // this library: NTT_{p_k}(alpha_i mod p_k) does NOT depend on the target limb, so a ciphertext needs L*K forward and
 // 2*L*K inverse transforms of 32-bit words instead of L*(L-1) forward transforms of 64-bit words (cfg4, L = 24,
 // K = 5: 360 cheap transforms against 552 expensive ones), a multiply-accumulate over the digits in between, and a
-// Garner reconstruction of the centred integer, reduced mod q_j, at the end.  Every step is exact integer arithmetic,
-// so the result is bit-identical to the reference's (tests/test_gpu_engine.py pins it against the oracle).
+// Garner reconstruction of the centred integer, reduced mod q_j, at the end.  Every step is exact integer arithmetic
+// (the one floating-point product, in aux_reduce_sum, only ESTIMATES a quotient whose remainder is then computed and
+// corrected in integers), so the result is bit-identical to the reference's: pinned on the CPU by tests/test_emul.py
+// (the algorithm end to end with this code compiled by g++) and on the GPU by tests/test_gpu_engine.py against the oracle.
 //
 // Layouts (all u32 words):
 //   x      [ct][k][i][N]   NTT_{p_k}(alpha_i mod p_k), device-internal NTT order of the auxiliary tables
@@ -56,7 +58,7 @@ __device__ __forceinline__ void aux_mad(u64 &acc, u32 x, u32 k) {
 // One thread: one NTT position e (threadIdx.x, 32 per CTA), one target limb j (threadIdx.y), one auxiliary prime.
 // Its 2 * L key words are loaded ONCE into registers and stay there while the CTA walks over every ciphertext of the
 // launch, so the key -- the largest operand, K * L^2 * N words per half -- crosses HBM once per launch and never
-// touches shared memory.  The x rows of a ciphertext (L rows of 32 words, shared by the L warps of the CTA) arrive
+// touches shared memory.  The x rows of a ciphertext (L rows of 32 words, shared by the warps of the CTA: one per target limb, at most 12) arrive
 // as one TMA box per ciphertext, AUX_MAC_T ciphertexts per stage, two stages in flight; thread 0 issues the copies,
 // an mbarrier per stage signals their arrival, one __syncthreads per stage releases the buffer.
 // Products are below p^2 < 2^59 (AUX_P_BOUND): the L <= 32 of them fit a 64-bit accumulator, reduced once at the end
