@@ -254,6 +254,17 @@ def test_auxiliary_basis_key_switch_matches_oracle(gpu, orc, n, bits, l, batch):
                 for i in range(batch):
                     for t in range(6):
                         assert np.array_equal(g[t][i], want[i][t]), f"mode {mode}, ciphertext {i}, output {t}"
+            # the host-buffer entry points (pinned staging, chunked pipeline) take the same route
+            o0 = np.zeros((batch, l - 1, n), dtype=np.uint64)
+            o1 = np.zeros_like(o0)
+            gpu.mul_relin_rescale_host(gb, gb.drop_last(1), keys[0], a0, a1, b0, b1, o0, o1)
+            h0 = np.zeros((batch, l, n), dtype=np.uint64)
+            h1 = np.zeros_like(h0)
+            keys[0].rotation = -3
+            gpu.rotate_host(gb, keys[0], a0, a1, h0, h1)
+            for i in range(batch):
+                assert np.array_equal(o0[i], want[i][2]) and np.array_equal(o1[i], want[i][3]), f"mode {mode}: mul_relin_rescale_host, ciphertext {i}"
+                assert np.array_equal(h0[i], want[i][4]) and np.array_equal(h1[i], want[i][5]), f"mode {mode}: rotate_host, ciphertext {i}"
             used = gpu.launch_table().get("aux_mac", 0) - launches0
             assert (used > 0) == (mode == 2), "the auxiliary-basis kernels ran exactly when asked to"
             got[mode] = g
