@@ -331,10 +331,13 @@ static void crt_all(const AuxHost &H, const std::vector<LimbConst> &lc, int l, u
         for (uint64_t e = 0; e < count; ++e) {
             u32 v[K];
             for (int k = 0; k < K; ++k) v[k] = (u32)res[((size_t)j * K + k) * count + e];
+            u64 hps = 0;
+            if constexpr (K <= 5) hps = aux_image_hps<K>(v, H.cc, H.mstar.data() + (size_t)j * K, H.tp.data() + (size_t)j * (AUX_MAX_K + 1), lc[j]);
             aux_garner<K>(v, H.cc);
             const bool neg = aux_negative<K>(v, H.cc);
             out[(size_t)j * count + e] = aux_image<K>(v, neg, H.mix.data() + (size_t)j * K, H.pmod[j], lc[j]);
             if (negs) negs[(size_t)j * count + e] = neg ? 1 : 0;
+            if (K <= 5 && hps != out[(size_t)j * count + e]) negs ? (void)(negs[(size_t)j * count + e] = -1) : (void)0;  // both reconstructions must agree
         }
 }
 // res: [l][K][count] residues mod the auxiliary primes of one integer per (j, e); out: [l][count] its centred value

@@ -20,6 +20,8 @@ struct AuxCrtConst {
     u32 p[AUX_MAX_K];                      // auxiliary primes
     u32 half[AUX_MAX_K];                   // mixed-radix digits of floor(P / 2)
     tw32_t inv[AUX_MAX_K * AUX_MAX_K];     // inv[m * AUX_MAX_K + k] = p_m^-1 mod p_k, m < k
+    tw32_t chat[AUX_MAX_K];                // (P / p_k)^-1 mod p_k
+    double pinv[AUX_MAX_K];                // 1 / p_k
 };
 // Residues r_k of an integer x in [0, P) -> its mixed-radix digits v_k (x = sum_k v_k prod_{m<k} p_m, 0 <= v_k < p_k), in place.
 // Garner: v_k = (..((r_k - v_0) p_0^-1 - v_1) p_1^-1 .. - v_{k-1}) p_{k-1}^-1 mod p_k.  The running value stays in [0, 2 p_k):
@@ -72,6 +74,31 @@ __device__ __forceinline__ u32 aux_reduce_sum(u64 s, u32 p, double pinv) {
     return (u32)r;
 }
 
+// The same image without the sequential Garner chain (K <= 5), in the form of the "fast base conversion with exact
+// correction": with z_k = r_k (P/p_k)^-1 mod p_k,  sum_k z_k (P/p_k) = x + t P  for the centred x and an integer 0 <= t <= K;
+// since |x| < 2^-1.5 P = 0.354 P (aux_host_build takes primes until P > 2^1.5 * 2^need >= 2^1.5 * L N q_max^2), the fractional
+// part of sum_k z_k / p_k = t + x / P stays 0.146 away from one half and t = round(sum_k z_k / p_k) is decided by a
+// double-precision sum whose error is below 1e-14.  The image is (sum_k z_k ((P/p_k) mod q) - (t P mod q)) mod q: the
+// sum is accumulated exactly in 96 bits and reduced once.  mstar: K words (P/p_k) mod q; tp: K + 1 words t P mod q.
+template <int K>
+__device__ __forceinline__ u64 aux_image_hps(const u32 (&r)[K], const AuxCrtConst &cc, const u64 *mstar, const u64 *tp, const LimbConst &mq) {
+    static_assert(K <= 5, "the 64-bit halves of the 96-bit sum hold five terms");
+    u64 lo = 0, mid = 0;  // sum z_k * low32(M_k) < 5 * 2^61.5,  sum z_k * high32(M_k) < 5 * 2^60.5
+    double s = 0.5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const u32 z = shoup(r[k], cc.chat[k], cc.p[k]);
+        s += (double)z * cc.pinv[k];
+        const u64 m = mstar[k];
+        lo += (u64)z * (u32)m;
+        mid += (u64)z * (u32)(m >> 32);
+    }
+    const int t = (int)s;
+    const u64 lo2 = lo + (mid << 32);
+    const u64 hi = (mid >> 32) + (lo2 < lo ? 1ull : 0ull);
+    return submod(reduce128(hi, lo2, mq), tp[t], mq.q);
+}
+
 // Host side: the auxiliary primes of a basis and every constant derived from them.
 struct AuxHost {
     int K = 0;
@@ -79,6 +106,8 @@ struct AuxHost {
     AuxCrtConst cc;
     std::vector<tw_t> mix;  // [L][K]: prod_{m<k} p_m mod q_j
     std::vector<u64> pmod;  // [L]: P mod q_j
+    std::vector<u64> mstar;  // [L][K]: (P / p_k) mod q_j
+    std::vector<u64> tp;     // [L][AUX_MAX_K + 1]: t P mod q_j
 };
 // |coefficients of sum_i alpha_i (*) key[i][j]| < L * N * q_max^2 < 2^need; the centred range of P = prod p_k must cover
 // it: P > 2^(need + 1).
@@ -113,6 +142,17 @@ inline bool aux_host_build(u64 n, int logn, const std::vector<u64> &moduli, AuxH
             A.cc.inv[m * AUX_MAX_K + k].ws = (u32)((w << 32) / primes[k]);
         }
     }
+    for (int k = 0; k < K; ++k) {
+        u64 prod = 1 % primes[k];
+        for (int m = 0; m < K; ++m)
+            if (m != k) prod = hm::mul_mod(prod, primes[m] % primes[k], primes[k]);
+        const u64 w = hm::inv_mod(prod, primes[k]);
+        A.cc.chat[k].w = (u32)w;
+        A.cc.chat[k].ws = (u32)((w << 32) / primes[k]);
+        A.cc.pinv[k] = 1.0 / (double)primes[k];
+    }
+    A.mstar.assign(L * K, 0);
+    A.tp.assign(L * (AUX_MAX_K + 1), 0);
     A.mix.assign(L * K, tw_t{0, 0});
     A.pmod.assign(L, 0);
     for (size_t j = 0; j < L; ++j) {
@@ -124,6 +164,13 @@ inline bool aux_host_build(u64 n, int logn, const std::vector<u64> &moduli, AuxH
             acc = hm::mul_mod(acc, primes[k] % q, q);
         }
         A.pmod[j] = acc;
+        for (int k = 0; k < K; ++k) {
+            u64 prod = 1 % q;
+            for (int m = 0; m < K; ++m)
+                if (m != k) prod = hm::mul_mod(prod, primes[m] % q, q);
+            A.mstar[j * K + k] = prod;
+        }
+        for (int t = 0; t <= AUX_MAX_K; ++t) A.tp[j * (AUX_MAX_K + 1) + t] = hm::mul_mod((u64)t % q, acc, q);
     }
     return true;
 }

@@ -8,10 +8,12 @@
 // and S_j can be computed exactly in a few word-sized NTT primes p_0 .. p_{K-1} (all in (2^29, 2^29.5), prod p_k > 2B) chosen by
 // this library: NTT_{p_k}(alpha_i mod p_k) does NOT depend on the target limb, so a ciphertext needs L*K forward and
 // 2*L*K inverse transforms of 32-bit words instead of L*(L-1) forward transforms of 64-bit words (cfg4, L = 24,
-// K = 5: 360 cheap transforms against 552 expensive ones), a multiply-accumulate over the digits in between, and a
-// Garner reconstruction of the centred integer, reduced mod q_j, at the end.  Every step is exact integer arithmetic
-// (the one floating-point product, in aux_reduce_sum, only ESTIMATES a quotient whose remainder is then computed and
-// corrected in integers), so the result is bit-identical to the reference's: pinned on the CPU by tests/test_emul.py
+// K = 5: 360 cheap transforms against 552 expensive ones), a multiply-accumulate over the digits in between, and the
+// image mod q_j of the centred integer at the end (aux_crt.cuh: base conversion with exact correction, or Garner's
+// mixed radix for deep auxiliary bases).  Every step is exact integer arithmetic -- floating point appears twice, each
+// time only to pick an integer that integer arithmetic then uses or corrects: the quotient estimate of aux_reduce_sum
+// and the multiple of P in aux_image_hps, decided with a margin of 0.146 -- so the result is bit-identical to the
+// reference's: pinned on the CPU by tests/test_emul.py
 // (the algorithm end to end with this code compiled by g++) and on the GPU by tests/test_gpu_engine.py against the oracle.
 //
 // Layouts (all u32 words):
@@ -159,6 +161,8 @@ struct AuxCrtArgs {
     const LimbConst *lc;     // [L] ciphertext primes
     const tw_t *mix;         // [L][K]: prod_{m<k} p_m mod q_j
     const u64 *pmod;         // [L]: P mod q_j
+    const u64 *mstar;        // [L][K]: (P / p_k) mod q_j
+    const u64 *tp;           // [L][AUX_MAX_K + 1]: t P mod q_j
     const tw_t *ql;          // RESCALE: [L] q_last^-1 mod q_j
     int L, K, logn;
     int j0, nj, outL;        // target limbs j0 .. j0 + nj - 1 of every ciphertext
@@ -183,6 +187,13 @@ __global__ void __launch_bounds__(256) aux_crt_kernel(AuxCrtArgs a, const __grid
 #pragma unroll
     for (int k = 1; k < K; ++k) mix[k] = ldg_tw(a.mix + (size_t)j * K + k);
     const u64 pmod = a.pmod[j];
+#ifndef CKKS_AUX_CRT_HPS
+#define CKKS_AUX_CRT_HPS 1
+#endif
+    constexpr bool HPS = CKKS_AUX_CRT_HPS && K <= 5;  // (deeper auxiliary bases keep the Garner chain)
+    u64 ms[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) ms[k] = HPS ? a.mstar[(size_t)j * K + k] : 0;
     tw_t ql;
     if (RESCALE) ql = ldg_tw(a.ql + j);
     const size_t e0 = (size_t)blockIdx.x * (256 * EPT) + threadIdx.x;
@@ -206,8 +217,13 @@ __global__ void __launch_bounds__(256) aux_crt_kernel(AuxCrtArgs a, const __grid
         }
 #pragma unroll
         for (int u = 0; u < EPT; ++u) {  // (independent chains: the unrolled code interleaves them)
-            aux_garner<K>(v[u], cc);
-            u64 y = aux_image<K>(v[u], aux_negative<K>(v[u], cc), mix, pmod, mq);
+            u64 y;
+            if (HPS) {
+                y = aux_image_hps<(HPS ? K : 1)>(reinterpret_cast<const u32(&)[HPS ? K : 1]>(v[u]), cc, ms, a.tp + (size_t)j * (AUX_MAX_K + 1), mq);
+            } else {
+                aux_garner<K>(v[u], cc);
+                y = aux_image<K>(v[u], aux_negative<K>(v[u], cc), mix, pmod, mq);
+            }
             y = addmod(y, addv[u], mq.q);
             if (RESCALE) y = shoup(submod(y, barrett_word(lastv[u], mq), mq.q), ql, mq.q);
             (h ? a.out1 : a.out0)[oo + u * 256] = y;

@@ -11,11 +11,13 @@ struct AuxKs {
     int K = 0;
     tw_t *d_mix = nullptr;    // [L][K] prod_{m<k} p_m mod q_j
     u64 *d_pmod = nullptr;    // [L] P mod q_j
+    u64 *d_mstar = nullptr;   // [L][K] (P / p_k) mod q_j
+    u64 *d_tp = nullptr;      // [L][AUX_MAX_K + 1] t P mod q_j
     AuxCrtConst cc;           // primes, Garner inverses and floor(P/2) digits as a kernel parameter
 };
 static void destroy_aux(AuxKs *a) {
     if (!a) return;
-    for (void *p : {(void *)a->d_mix, (void *)a->d_pmod})
+    for (void *p : {(void *)a->d_mix, (void *)a->d_pmod, (void *)a->d_mstar, (void *)a->d_tp})
         if (p) cudaFree(p);
     delete a;
 }
@@ -63,6 +65,8 @@ static int aux_get(const Tables &Tc, AuxKs **out) {
     A->cc = H.cc;
     TRY(upload_vec(&A->d_mix, H.mix));
     TRY(upload_vec(&A->d_pmod, H.pmod));
+    TRY(upload_vec(&A->d_mstar, H.mstar));
+    TRY(upload_vec(&A->d_tp, H.tp));
     T.aux = A.release();
     *out = T.aux;
     return CKKS_OK;
@@ -270,6 +274,8 @@ static int aux_keyswitch(const Tables &T, const AuxKs &A, size_t L, size_t cs, c
     c.lc = T.d_lc;
     c.mix = A.d_mix;
     c.pmod = A.d_pmod;
+    c.mstar = A.d_mstar;
+    c.tp = A.d_tp;
     c.L = (int)L;
     c.K = (int)K;
     c.logn = T.logn;
