@@ -286,17 +286,41 @@ __global__ void check_reduced_kernel(EwArgs a, const u64 *__restrict__ x, int *f
 }
 // Tensor product of mul_ciphertexts_gadget (engine.rs:481-493) on NTT-domain operands:
 // d0 = a0*b0, d1 = a0*b1 + a1*b0, d2 = a1*b1.  d0/d1/d2 may alias a0/a1/b0 element-wise.
+__device__ __forceinline__ void tensor_one(const LimbConst &m, u64 x0, u64 x1, u64 y0, u64 y1, u64 &t0, u64 &t1, u64 &t2) {
+    t0 = mulmod(x0, y0, m);
+    t2 = mulmod(x1, y1, m);
+    // x0 y1 + x1 y0 as one 128-bit sum (both products are below 2^126: q < 2^63), reduced once
+    const u64 l1 = x0 * y1, l2 = x1 * y0;
+    const u64 lo = l1 + l2;
+    const u64 hi = __umul64hi(x0, y1) + __umul64hi(x1, y0) + (lo < l1 ? 1ull : 0ull);
+    t1 = reduce128(hi, lo, m);
+}
+// Two adjacent words per thread and iteration (16-byte loads and stores: the kernel is HBM-bound, four streams in and three
+// out); a limb has an even number of words, so both words of a pair share their modulus.
 __global__ void tensor_kernel(EwArgs a, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1, u64 *d0, u64 *d1,
                               u64 *d2) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
-        const LimbConst &m = a.lc[ew_limb(a, i)];
-        u64 x0 = a0[i], x1 = a1[i], y0 = b0[i], y1 = b1[i];
-        u64 t0 = mulmod(x0, y0, m);
-        u64 t2 = mulmod(x1, y1, m);
-        u64 t1 = addmod(mulmod(x0, y1, m), mulmod(x1, y0, m), m.q);
-        d0[i] = t0;
-        d1[i] = t1;
-        d2[i] = t2;
+    if (a.logn == 0) {  // N = 1: word by word
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (size_t)gridDim.x * blockDim.x) {
+            u64 t0, t1, t2;
+            tensor_one(a.lc[ew_limb(a, i)], a0[i], a1[i], b0[i], b1[i], t0, t1, t2);
+            d0[i] = t0;
+            d1[i] = t1;
+            d2[i] = t2;
+        }
+        return;
+    }
+    const ulonglong2 *A0 = reinterpret_cast<const ulonglong2 *>(a0), *A1 = reinterpret_cast<const ulonglong2 *>(a1);
+    const ulonglong2 *B0 = reinterpret_cast<const ulonglong2 *>(b0), *B1 = reinterpret_cast<const ulonglong2 *>(b1);
+    ulonglong2 *D0 = reinterpret_cast<ulonglong2 *>(d0), *D1 = reinterpret_cast<ulonglong2 *>(d1), *D2 = reinterpret_cast<ulonglong2 *>(d2);
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.total / 2; p += (size_t)gridDim.x * blockDim.x) {
+        const LimbConst &m = a.lc[ew_limb(a, 2 * p)];
+        const ulonglong2 x0 = A0[p], x1 = A1[p], y0 = B0[p], y1 = B1[p];
+        ulonglong2 t0, t1, t2;
+        tensor_one(m, x0.x, x1.x, y0.x, y1.x, t0.x, t1.x, t2.x);
+        tensor_one(m, x0.y, x1.y, y0.y, y1.y, t0.y, t1.y, t2.y);
+        D0[p] = t0;
+        D1[p] = t1;
+        D2[p] = t2;
     }
 }
 // rescale_into (poly.rs:214-225): out_i = (c_i - (c_last % q_i)) * (q_last^-1 mod q_i) mod q_i.
