@@ -718,12 +718,13 @@ def test_host_entry_points_reject_non_reduced_words(gpu, orc, n, bits, l):
     assert np.array_equal(fused.c0.channels(), o0) and np.array_equal(fused.c1.channels(), o1)
 
 
-@pytest.mark.parametrize("n,bits,l,batch", [(4096, 40, 3, 7), (16384, 30, 4, 5)])
+@pytest.mark.parametrize("n,bits,l,batch", [(4096, 40, 3, 7), (16384, 30, 4, 5), (256, 61, 11, 6)])
 def test_batch_sharded_group_matches_single_gpu_and_oracle(gpu, orc, n, bits, l, batch):
     """ckks_comm_*: ONE process spreads a host batch over the devices of a box.  With fewer than two
     GPUs both slots of the group sit on device 0 (the share arithmetic, the per-device pipelines and threads are the
     same); on a multi-GPU box the slots are distinct devices.  Ragged shares (7 over 2 and 3 slots, 5 over 4) and an
-    empty share (batch < slots) are covered; every word equals the oracle's."""
+    empty share (batch < slots) are covered; every word equals the oracle's.  The 11-limb 61-bit shape runs the
+    auxiliary-basis key-switch from the group's pipeline threads."""
     moduli = orc.generate_primes(bits, l, n)
     ob = orc.Basis(n, moduli)
     rng = np.random.default_rng(4242)
