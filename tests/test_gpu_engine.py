@@ -274,6 +274,25 @@ def test_auxiliary_basis_key_switch_matches_oracle(gpu, orc, n, bits, l, batch):
         assert np.array_equal(got[0][t], got[2][t])
 
 
+def test_auxiliary_basis_six_primes_at_63_bits(gpu, orc):
+    """N=2^16, L=17, 63-bit primes: the bound L N q^2 needs SIX auxiliary primes, which takes the Garner reconstruction
+    (the base conversion with exact correction covers up to five), next to the strict 64-bit butterflies of the main basis."""
+    n, bits, l = 65536, 63, 17
+    moduli = orc.generate_primes(bits, l, n)
+    ob = orc.Basis(n, moduli)
+    rng = np.random.default_rng(5)
+    a0, a1, b0, b1 = (uniform_limbs(rng, moduli, n, 1) for _ in range(4))
+    ka, kb = uniform_limbs(rng, moduli, n, l), uniform_limbs(rng, moduli, n, l)
+    m0, m1 = ob.mul_ciphertexts_gadget(a0[0], a1[0], b0[0], b1[0], ka, kb)
+    r0, r1, _ = ob.rescale_ciphertext(m0, m1)
+    gb = gpu.RnsBasis(n, moduli)
+    before = gpu.launch_table().get("aux_mac", 0)
+    key = gpu.GadgetKey.upload(gb, ka, kb)
+    out = gpu.CkksEngine.mul_relin_rescale(_ct(gpu, gb, a0, a1, 30, 90), _ct(gpu, gb, b0, b1, 30, 90), key)
+    assert gpu.launch_table().get("aux_mac", 0) > before
+    assert np.array_equal(out.c0.channels()[0], r0) and np.array_equal(out.c1.channels()[0], r1)
+
+
 def test_auxiliary_basis_large_batch_small_degree(gpu, orc):
     """7300 ciphertexts at N=256, L=10 (deep enough for the auxiliary-basis pipeline by default): more (ciphertext, limb)
     pairs than one grid dimension holds; spot-checked against the oracle at both ends and around the wrap."""
